@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""Benchmark of the raw basecalling hot path (BASELINE.json: raw samples/s, rgrgr_r94).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle/_ref)
+
+One "step" = one pass of the hot path (network forward + Viterbi decode) over the whole
+workload on each GPU: `--reads` synthetic reads of `--samples` samples, processed in batches
+of `--batch` reads that run concurrently on their own CUDA streams (BASELINE config 2:
+rgrgr_r94, 1024 x 4000-sample reads, batch 256).  With N > 1 (torchrun, one rank per GPU) every
+rank processes its own `--reads` reads (weak scaling); rank 0 loads the weight blob and
+broadcasts it over NCCL at start-up; there is no collective on the per-read path.
+
+  value  samples/s with the signals already resident in HBM; device time from CUDA events on
+         the launching stream (L2 flushed between steps, outside the timed region), max over ranks.
+  e2e    samples/s through the C-ABI batch basecall with HOST buffers: pinned H2D of the
+         signals, forward, decode, D2H of paths/scores, homopolymer fix-up and overlapper on
+         the host, all inside the timed region (wall clock, max over ranks).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_READ_STEP_RECURRENT = {"rgrgr_r94": 55296, "rgrgr_r941": 55296, "rgrgr_r10": 55296, "rnnrf_r94": 75264}
+FLOP_PER_BLOCK_TOTAL = {"rgrgr_r94": 753408, "rnnrf_r94": 760704}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--model", default="rgrgr_r94")
+    ap.add_argument("--reads", type=int, default=1024)
+    ap.add_argument("--samples", type=int, default=4000)
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--cpu-sample-reads", type=int, default=512)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_workload(nreads, nsamples, seed0):
+    from scrappie_b200.synthetic import synthetic_read
+    return [synthetic_read(seed0 + i, nsamples) for i in range(nreads)]
+
+
+# ------------------------------------------------------------------------------------
+# reference arm / cpu baseline (the only place bench.py touches oracle/)
+# ------------------------------------------------------------------------------------
+
+def run_reference(model, sigs, nthreads=0):
+    """Times oracle/_ref (the reference's own C sources + OpenBLAS, one read per OpenMP thread).
+    Returns (seconds, nbases, nblocks, threads)."""
+    import ctypes as C
+    so = os.path.join(ROOT, "oracle", "_ref", "libref_bench.so")
+    if not os.path.exists(so):
+        return None
+    L = C.CDLL(so)
+    L.ref_bench_run.restype = C.c_double
+    L.ref_bench_run.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int,
+                                C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.c_void_p]
+    concat = np.concatenate(sigs).astype(np.float32)
+    lens = np.array([len(s) for s in sigs], dtype=np.uint64)
+    offs = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.uint64)
+    nb, nk = C.c_size_t(0), C.c_size_t(0)
+    threads = nthreads or L.ref_bench_max_threads()
+    secs = L.ref_bench_run(model.encode(), concat.ctypes.data, offs.ctypes.data, lens.ctypes.data, len(sigs),
+                           threads, C.byref(nb), C.byref(nk), None)
+    return secs, nb.value, nk.value, threads
+
+
+def run_oracle_port(model, sigs):
+    """Fallback when oracle/_ref is absent: the scalar C restatement, 1 thread."""
+    from oracle.oracle import Oracle
+    o = Oracle()
+    t0 = time.time()
+    nb = 0
+    for s in sigs:
+        _, _, bases, _ = o.basecall_raw(model, s)
+        nb += len(bases or "")
+    return time.time() - t0, nb, 0, 1
+
+
+def cpu_baseline(model, sigs, nreads_sample):
+    sample = sigs[:nreads_sample]
+    res = run_reference(model, sample)
+    kind = "reference"
+    if res is None:
+        sample = sigs[:max(8, nreads_sample // 16)]
+        res = run_oracle_port(model, sample)
+        kind = "port"
+    secs, nbases, _, threads = res
+    nsamp = sum(len(s) for s in sample)
+    return {"value": nsamp / secs, "unit": "samples/s", "cores": threads, "kind": kind,
+            "kbases_per_s": nbases / secs / 1e3,
+            "sample": "%d of the workload's reads (%d samples), one read per OpenMP thread, 1 BLAS thread, %.2f s wall"
+                      % (len(sample), nsamp, secs)}
+
+
+def main_reference(args, rank, world):
+    if rank != 0:
+        return
+    sigs = make_workload(args.cpu_sample_reads, args.samples, 1000)
+    for _ in range(max(1, min(args.warmup, 1))):
+        run_reference(args.model, sigs[:32]) if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_bench.so")) else None
+    times, kind, threads, nbases = [], "reference", 1, 0
+    for _ in range(args.steps):
+        res = run_reference(args.model, sigs)
+        if res is None:
+            kind = "port"
+            res = run_oracle_port(args.model, sigs[:32])
+            nsamp = sum(len(s) for s in sigs[:32])
+        else:
+            nsamp = sum(len(s) for s in sigs)
+        times.append(res[0]); nbases = res[1]; threads = res[3]
+    ms = 1e3 * float(np.mean(times))
+    value = nsamp / (ms / 1e3)
+    line = {"impl": "reference", "metric": "raw samples/sec (%s)" % args.model, "value": value, "unit": "samples/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "%s raw, synthetic %d-sample reads (bounded sample: %d reads per step), CPU %s"
+                                   % (args.model, args.samples, len(sigs), kind)},
+            "kbases_per_s": nbases / (ms / 1e3) / 1e3,
+            "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "kind": kind,
+                             "sample": "%d reads x %d samples per step" % (len(sigs), args.samples)},
+            "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------
+# this repo's arm
+# ------------------------------------------------------------------------------------
+
+def main_b200(args, rank, world, local_rank):
+    import torch
+    import scrappie_b200 as sb
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    eng = sb.Engine(local_rank)
+    # weights: rank 0 reads the blob, every other rank receives it over NCCL (init only)
+    blob_path = os.path.join(sb.WEIGHTS_DIR, args.model + ".bin")
+    if world > 1:
+        if rank == 0:
+            blob = torch.from_numpy(np.fromfile(blob_path, dtype=np.uint8)).cuda()
+            size = torch.tensor([blob.numel()], device="cuda")
+        else:
+            size = torch.zeros(1, dtype=torch.int64, device="cuda")
+        dist.broadcast(size, 0)
+        if rank != 0:
+            blob = torch.empty(int(size.item()), dtype=torch.uint8, device="cuda")
+        dist.broadcast(blob, 0)
+        eng.load_blob(args.model, blob.cpu().numpy())
+    else:
+        eng.load_blob(args.model, np.fromfile(blob_path, dtype=np.uint8))
+
+    sigs = make_workload(args.reads, args.samples, 1000 + rank * args.reads)
+    nbatch = (args.reads + args.batch - 1) // args.batch
+    groups = [sigs[i * args.batch:(i + 1) * args.batch] for i in range(nbatch)]
+    batches = [eng.batch(args.model, [len(s) for s in g]) for g in groups]
+    pinned = []
+    for b, g in zip(batches, groups):
+        pb = sb.PinnedBuffer(b.total_samples_padded)
+        pb.array[:] = 0
+        for r, s in enumerate(g):
+            pb.array[b.sample_offset[r]:b.sample_offset[r] + len(s)] = s
+        pinned.append(pb)
+        b.upload_concat(pb.ptr, pinned_async=False)
+    params = sb.default_params()
+    total_samples = sum(len(s) for s in sigs)
+    total_blocks = sum(b.total_blocks for b in batches)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    # ---- device-resident throughput ------------------------------------------------
+    sb.multi_time(batches, params, nrep=args.warmup, flush_l2=True)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = eng.launches
+    ms = sb.multi_time(batches, params, nrep=args.steps, flush_l2=True)
+    launches = eng.launches - launches0
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    step_ms = float(np.mean(ms))
+    stage = [b.stage_ms() for b in batches]
+
+    # ---- end to end through the C-ABI batch basecall, host buffers ------------------------
+    results = [None] * nbatch
+
+    def work(i):
+        results[i] = batches[i].basecall(pinned[i].ptr, True, params)
+
+    def e2e_step():
+        th = [threading.Thread(target=work, args=(i,)) for i in range(nbatch)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    nbases = sum(len(c[0] or "") for res in results for c in res)
+    h2d = sum(b.total_samples_padded * 4 for b in batches)
+    d2h = sum((b.total_blocks + b.nread) * 4 + b.nread * 4 for b in batches)
+
+    # ---- reduce over ranks (max time) ------------------------------------------------------
+    if dist is not None:
+        t = torch.tensor([step_ms, e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        step_ms, e2e_s = float(t[0]), float(t[1])
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    pk, pk_src = peaks()
+    scan_ms = [st["scan%d" % l] for st in stage for l in range(1, 6)]
+    scan_avg_ms = float(np.mean(scan_ms))
+    blocks_per_batch = batches[0].total_blocks
+    flop_per_launch = FLOP_PER_READ_STEP_RECURRENT[args.model] * blocks_per_batch
+    achieved = flop_per_launch / (scan_avg_ms * 1e-3) / 1e12
+    peak = pk["bf16_tflops_sustained"]
+    stage_sum = {k: float(np.mean([st[k] for st in stage])) for k in stage[0]}
+    line = {
+        "metric": "raw samples/sec (%s)" % args.model, "value": world * total_samples / (step_ms * 1e-3),
+        "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%s raw, %d synthetic %d-sample reads per GPU, batch=%d (%d concurrent batches), "
+                               "forward + Viterbi decode" % (args.model, args.reads, args.samples, args.batch, nbatch),
+                   "l2": "flushed between timed steps (384 MB overwrite, outside the timed region)",
+                   "scan_impl": os.environ.get("SCRAPPIE_B200_SCAN", "default"),
+                   "parallelism": "reads sharded, %d rank(s), NCCL weight broadcast at init only" % world},
+        "kbases_per_s": world * nbases / e2e_s / 1e3,
+        "blocks_per_s": world * total_blocks / (step_ms * 1e-3),
+        "network_tflops": world * FLOP_PER_BLOCK_TOTAL.get(args.model, 0) * total_blocks / (step_ms * 1e-3) / 1e12,
+        "e2e": {"value": world * total_samples / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"kernel": "gru_scan (recurrent sW/sW2 products + gates), 5 launches per batch",
+                     "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                     "frac": achieved / peak, "traffic": None,
+                     "peak_source": "%s bf16 dense sustained (MEASURED_PEAKS.json); tf32 nominal is half of bf16" % pk_src,
+                     "flop_per_launch": flop_per_launch, "avg_launch_ms": scan_avg_ms,
+                     "stage_ms_per_batch": stage_sum},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args.model, sigs, args.cpu_sample_reads)
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        main_reference(args, rank, world)
+    else:
+        main_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

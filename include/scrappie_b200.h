@@ -1,0 +1,218 @@
+/* libscrappie_b200 -- B200-native drop-in for the `scrappie raw` hot path.
+ *
+ * C-ABI of libscrappie_b200.so.  Part 1 re-exports, with identical names, argument
+ * meaning, ownership and error behaviour, the libscrappie symbols that sit on the raw
+ * basecalling path (reference: interface/scrappie.h:47-52, python/pyscrap.h:1-27,62,
+ * src/networks.h:22-49, src/decode.h:13-30, src/homopolymer.h:13-14,
+ * src/scrappie_matrix.h:31-41, src/scrappie_common.h, src/util.h:262).  Part 2 is the
+ * batch interface the reference does not have: many reads per call, which is what the
+ * GPU needs; the single-read symbols of part 1 are batches of one.
+ *
+ * The network forward pass and both Viterbi decoders run as sm_100a CUDA kernels.
+ * Containers, signal trimming / normalisation and the O(T) integer post-processing
+ * (overlapper, crfpath_to_basecall, homopolymer_path) stay on the host, as in the
+ * reference.  There is no CPU fallback for the GPU stages: without a usable CUDA
+ * device the posterior / decode entry points fail (NULL / NAN) and say so on stderr.
+ */
+#ifndef SCRAPPIE_B200_H
+#define SCRAPPIE_B200_H
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ===================================================================== */
+/* Part 1 -- libscrappie-compatible surface                               */
+/* ===================================================================== */
+
+/* src/scrappie_structures.h:24-30.  Passed BY VALUE, borrowed, never modified by
+ * the posterior functions. */
+typedef struct {
+    char *uuid;
+    size_t n;
+    size_t start;
+    size_t end;
+    float *raw;
+} raw_table;
+
+/* src/scrappie_matrix.h:10-16.  Column-major fp32, every column padded to a multiple
+ * of 4 floats (stride = 4 * nrq), 16-byte aligned, zero initialised.  The reference's
+ * union {__m128 *v; float *f;} is a single pointer; `f` here has the same offset. */
+typedef struct {
+    size_t nr, nrq, nc, stride;
+    union {
+        void *v;
+        float *f;
+    } data;
+} _Mat;
+typedef _Mat *scrappie_matrix;
+typedef _Mat const *const_scrappie_matrix;
+
+/* src/networks.h:8-14 */
+enum raw_model_type {
+    SCRAPPIE_MODEL_RAW = 0,
+    SCRAPPIE_MODEL_RGRGR_R9_4,
+    SCRAPPIE_MODEL_RGRGR_R9_4_1,
+    SCRAPPIE_MODEL_RGRGR_R10,
+    SCRAPPIE_MODEL_RNNRF_R9_4,
+    SCRAPPIE_MODEL_INVALID
+};
+
+/* src/homopolymer.h:6-10 */
+enum homopolymer_calculation {
+    HOMOPOLYMER_NOCHANGE = 0,
+    HOMOPOLYMER_MEAN,
+    HOMOPOLYMER_INVALID
+};
+
+/* -- host containers: src/scrappie_matrix.c:11-136 -- */
+scrappie_matrix make_scrappie_matrix(size_t nr, size_t nc);
+scrappie_matrix remake_scrappie_matrix(scrappie_matrix M, size_t nr, size_t nc);
+scrappie_matrix copy_scrappie_matrix(const_scrappie_matrix M);
+scrappie_matrix free_scrappie_matrix(scrappie_matrix mat);      /* always returns NULL */
+void zero_scrappie_matrix(scrappie_matrix M);
+scrappie_matrix mat_from_array(const float *x, size_t nr, size_t nc);
+float *array_from_scrappie_matrix(const_scrappie_matrix mat);
+
+/* -- signal preparation (host): src/scrappie_common.c:5-73, src/util.c:92-204 -- */
+void medmad_normalise_array(float *x, size_t n);
+float medianf(const float *x, size_t n);
+float madf(const float *x, size_t n, const float *med);
+void quantilef(const float *x, size_t nx, float *p, size_t np);
+/* frees rt.raw and returns a zeroed table when the trimmed range is empty */
+raw_table trim_and_segment_raw(raw_table rt, size_t trim_start, size_t trim_end,
+                               size_t varseg_chunk, float varseg_thresh);
+raw_table trim_raw_by_mad(raw_table rt, size_t chunk_size, float perc);
+
+/* -- model registry: src/networks.c:17-127, python/build.py:34-44 -- */
+typedef scrappie_matrix (*posterior_function_ptr)(const raw_table, float, float, float, bool);
+enum raw_model_type get_raw_model(const char *modelstr);
+const char *raw_model_string(const enum raw_model_type model);
+int get_raw_model_stride(const enum raw_model_type model);
+int get_raw_model_stride_from_string(const char *modelstr);
+posterior_function_ptr get_posterior_function(const enum raw_model_type model);
+
+/* -- network forward (GPU): src/networks.c:250-394, :567-615.
+ *    Returns a new matrix [nstate x nblock] owned by the caller, or NULL. -- */
+scrappie_matrix nanonet_rgrgr_r94_posterior(const raw_table signal, float min_prob,
+                                            float tempW, float tempb, bool return_log);
+scrappie_matrix nanonet_rgrgr_r941_posterior(const raw_table signal, float min_prob,
+                                             float tempW, float tempb, bool return_log);
+scrappie_matrix nanonet_rgrgr_r10_posterior(const raw_table signal, float min_prob,
+                                            float tempW, float tempb, bool return_log);
+scrappie_matrix nanonet_rnnrf_r94_transitions(const raw_table signal, float min_prob,
+                                              float tempW, float tempb, bool return_log);
+
+/* -- decoders (GPU): src/decode.c:123-365, :836-893.  seq / path: nblock + 1 ints,
+ *    caller allocated.  Return the Viterbi score, NAN on failure. -- */
+float decode_transducer(const_scrappie_matrix logpost, float stay_pen, float skip_pen,
+                        float local_pen, int *seq, bool allow_slip);
+float decode_crf(const_scrappie_matrix trans, int *path);
+
+/* -- integer post-processing (host): src/decode.c:449-509, :895-918,
+ *    src/homopolymer.c:175-235.  Returned strings are calloc'd; caller frees. -- */
+char *overlapper(const int *seq, size_t n, int nkmer, int *pos);
+char *crfpath_to_basecall(int const *path, size_t npos, int *pos);
+int homopolymer_path(const_scrappie_matrix post, int *viterbipath,
+                     enum homopolymer_calculation pathCalculationFlag);
+enum homopolymer_calculation get_homopolymer_calculation(const char *calcstr);
+
+/* ===================================================================== */
+/* Part 2 -- batch interface (new)                                        */
+/* ===================================================================== */
+
+typedef struct sb2_engine sb2_engine;   /* one CUDA device + resident model weights */
+typedef struct sb2_batch sb2_batch;     /* device workspace for one batch of reads   */
+
+/* Decode / network parameters; sb2_default_params() = `scrappie raw` defaults
+ * (src/scrappie_raw.c:98-121). */
+typedef struct {
+    float min_prob, tempW, tempb;
+    float stay_pen, skip_pen, local_pen;
+    int allow_slip;
+    int homopolymer;            /* enum homopolymer_calculation */
+} sb2_params;
+sb2_params sb2_default_params(void);
+
+/* Engine for `device`.  Weights are read from `weights_dir` (NULL: $SCRAPPIE_B200_WEIGHTS,
+ * else the `weights/` directory next to the shared library).  NULL on failure. */
+sb2_engine *sb2_engine_create(int device, const char *weights_dir);
+void sb2_engine_destroy(sb2_engine *eng);
+/* Install a model from a weight blob already in host memory (multi-GPU runs broadcast
+ * the blob from rank 0 and never touch the file system on the other ranks). */
+int sb2_engine_load_blob(sb2_engine *eng, enum raw_model_type model, const void *blob, size_t nbytes);
+/* Last error message of the calling thread ("" if none). */
+const char *sb2_last_error(void);
+/* Number of kernel launches this engine has issued so far. */
+uint64_t sb2_engine_launch_count(const sb2_engine *eng);
+
+/* A batch = nread reads of the given lengths (samples fed to the network, i.e.
+ * end - start).  Device buffers are sized here; reuse a batch for equal-or-smaller work
+ * by calling sb2_batch_reset. */
+sb2_batch *sb2_batch_create(sb2_engine *eng, enum raw_model_type model, const size_t *nsample, size_t nread);
+void sb2_batch_destroy(sb2_batch *b);
+size_t sb2_batch_nblock(const sb2_batch *b, size_t read);       /* columns of read's posterior */
+size_t sb2_batch_total_blocks(const sb2_batch *b);
+size_t sb2_batch_nstate(const sb2_batch *b);
+/* host -> device copy of the (already trimmed + normalised) signals: one pointer per read,
+ * or one buffer in the batch's padded layout (read r starts at sb2_batch_sample_offset(b, r),
+ * total sb2_batch_total_samples_padded(b) floats; asynchronous when the buffer is pinned). */
+int sb2_batch_upload(sb2_batch *b, const float *const *signals);
+int sb2_batch_upload_concat(sb2_batch *b, const float *concat, int pinned_async);
+size_t sb2_batch_total_samples_padded(const sb2_batch *b);
+size_t sb2_batch_sample_offset(const sb2_batch *b, size_t read);
+void *sb2_host_alloc_pinned(size_t nbytes);
+void sb2_host_free_pinned(void *p);
+/* keep a copy of every layer's output during forward (parity tests only) */
+int sb2_batch_keep_layers(sb2_batch *b, int keep);
+/* network forward: leaves the posterior / transition matrices in HBM */
+int sb2_batch_forward(sb2_batch *b, const sb2_params *p, bool return_log);
+/* Viterbi decode of the resident posterior: paths + scores stay in HBM */
+int sb2_batch_decode(sb2_batch *b, const sb2_params *p);
+int sb2_batch_sync(sb2_batch *b);
+/* device -> host */
+int sb2_batch_download_posterior(sb2_batch *b, size_t read, float *dst, size_t dst_stride);
+int sb2_batch_download_paths(sb2_batch *b, int *paths_concat /* sum(nblock+1) */, float *scores /* nread */);
+/* Per-layer activations of one read, for layer-wise parity tests: layer 0 = conv+act,
+ * 1..5 = GRU outputs; dst is [nblock][H]. */
+int sb2_batch_download_layer(sb2_batch *b, int layer, size_t read, float *dst);
+/* Time `nrep` repetitions of forward+decode with CUDA events on the batch's own stream;
+ * optionally a buffer larger than L2 is overwritten between repetitions.  ms_out[nrep]. */
+int sb2_batch_time(sb2_batch *b, const sb2_params *p, int nrep, int flush_l2, float *ms_out,
+                   float *ms_forward_out, float *ms_decode_out);
+/* Per-kernel-stage times of the last sb2_batch_time repetition, ms. */
+int sb2_batch_stage_ms(const sb2_batch *b, float *stage_ms, int nstage_max);
+
+/* One basecall, the equivalent of calculate_post (src/scrappie_raw.c:265-315) for many
+ * reads: upload, forward, decode, homopolymer fix-up, overlapper.  signals are trimmed +
+ * normalised.  Outputs (any may be NULL): bases[i] calloc'd string (caller frees),
+ * scores[i], nblock[i]. Returns number of reads called successfully. */
+typedef struct {
+    char *bases;        /* calloc'd, caller frees; NULL on failure */
+    float score;
+    size_t nblock;
+    size_t nbase;
+} sb2_call;
+int sb2_basecall_batch(sb2_engine *eng, enum raw_model_type model, const float *const *signals,
+                       const size_t *nsample, size_t nread, const sb2_params *p, sb2_call *out);
+/* Same on an existing batch workspace (no device allocation per call).  concat: signals in
+ * the batch's padded layout (pinned != 0 if it came from sb2_host_alloc_pinned), or NULL
+ * when the signals are already resident. */
+int sb2_batch_basecall(sb2_batch *b, const float *concat, int pinned, const sb2_params *p, sb2_call *out);
+/* Time forward+decode of several batches running concurrently on their own streams (how a
+ * job larger than one batch executes); CUDA events on the launching stream. */
+int sb2_multi_time(sb2_batch **batches, int nbatch, const sb2_params *p, int nrep, int flush_l2, float *ms_out);
+
+/* Test hook: flat dump of the host-side convolution tail plan, which reproduces the
+ * right-edge behaviour of the reference's strided convolution (src/layers.c:218-241).
+ * out = {first_col, ncol, then 24 x {nseg, (x0, tap0, ntap) x 3}}. */
+int sb2_conv_plan_debug(size_t nsample, size_t winlen, size_t stride, int *out, int nout);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCRAPPIE_B200_H */

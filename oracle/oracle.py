@@ -355,17 +355,8 @@ class Reference:
         return score, path, bases, post
 
 
-def synthetic_read(seed, n=4000):
-    """SURVEY.md section 8(d) config 2 generator: piecewise-constant levels ~U(-1.5,1.5) held for
-    ~Geometric(mean 9) samples + N(0, 0.1^2) noise, then med-MAD normalised (numpy, float32)."""
-    rng = np.random.default_rng(seed)
-    out = np.empty(n + 64, dtype=np.float32)
-    i = 0
-    while i < n:
-        d = int(rng.geometric(1.0 / 9.0))
-        out[i:i + d] = rng.uniform(-1.5, 1.5)
-        i += d
-    x = out[:n] + rng.normal(0.0, 0.1, n).astype(np.float32)
-    med = np.median(x)
-    mad = np.median(np.abs(x - med)) * np.float32(1.4826)
-    return ((x - med) / mad).astype(np.float32)
+# the workload generator lives with the product (numpy only); re-exported for the tests
+import sys as _sys
+if ROOT not in _sys.path:
+    _sys.path.insert(0, ROOT)
+from scrappie_b200.synthetic import synthetic_read  # noqa: E402,F401

@@ -1,0 +1,518 @@
+"""scrappie_b200 -- Python host side of libscrappie_b200.so (ctypes, no torch).
+
+Mirrors the reference's `scrappy` binding for the raw basecalling path
+(python/scrappy/__init__.py: RawTable :47-111, ScrappyMatrix :147-192, calc_post :276-299,
+decode_post :302-366, basecall_raw :403-430, get_model_stride :390-400) with the same
+names, argument meaning and error behaviour, and adds the batch interface
+(`Engine`, `Batch`, `basecall_batch`) that the GPU needs.
+
+All numerical work goes through the C-ABI of include/scrappie_b200.h.  There is no
+Python or CPU implementation of the network or the decoders in this package: if the
+shared library is missing, or no CUDA device is usable, calls raise.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libscrappie_b200.so")
+WEIGHTS_DIR = os.path.join(_HERE, "weights")
+
+MODELS = ("rgrgr_r94", "rgrgr_r941", "rgrgr_r10", "rnnrf_r94")
+_MODEL_ENUM = {"raw_r94": 0, "rgrgr_r94": 1, "rgrgr_r941": 2, "rgrgr_r10": 3, "rnnrf_r94": 4}
+
+_f32p = C.POINTER(C.c_float)
+_i32p = C.POINTER(C.c_int)
+
+
+class _Mat(C.Structure):
+    _fields_ = [("nr", C.c_size_t), ("nrq", C.c_size_t), ("nc", C.c_size_t), ("stride", C.c_size_t),
+                ("f", _f32p)]
+
+
+class _RawTable(C.Structure):
+    _fields_ = [("uuid", C.c_char_p), ("n", C.c_size_t), ("start", C.c_size_t), ("end", C.c_size_t),
+                ("raw", _f32p)]
+
+
+class Params(C.Structure):
+    """sb2_params (include/scrappie_b200.h); defaults = `scrappie raw` CLI defaults."""
+    _fields_ = [("min_prob", C.c_float), ("tempW", C.c_float), ("tempb", C.c_float),
+                ("stay_pen", C.c_float), ("skip_pen", C.c_float), ("local_pen", C.c_float),
+                ("allow_slip", C.c_int), ("homopolymer", C.c_int)]
+
+
+class _Call(C.Structure):
+    _fields_ = [("bases", C.c_void_p), ("score", C.c_float), ("nblock", C.c_size_t), ("nbase", C.c_size_t)]
+
+
+def build_library(verbose=False):
+    """Compile libscrappie_b200.so in-tree with nvcc for sm_100a."""
+    subprocess.run(["make", "-C", os.path.join(_HERE, "csrc")], check=True,
+                   stdout=None if verbose else subprocess.DEVNULL)
+
+
+_lib = None
+
+
+def lib():
+    """The loaded shared library (raises if it has not been built)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("libscrappie_b200.so not built: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    L = C.CDLL(LIB_PATH)
+    mp = C.POINTER(_Mat)
+    sig = {
+        "make_scrappie_matrix": (mp, [C.c_size_t, C.c_size_t]),
+        "free_scrappie_matrix": (mp, [mp]),
+        "mat_from_array": (mp, [_f32p, C.c_size_t, C.c_size_t]),
+        "medmad_normalise_array": (None, [_f32p, C.c_size_t]),
+        "medianf": (C.c_float, [_f32p, C.c_size_t]),
+        "madf": (C.c_float, [_f32p, C.c_size_t, _f32p]),
+        "trim_and_segment_raw": (_RawTable, [_RawTable, C.c_size_t, C.c_size_t, C.c_size_t, C.c_float]),
+        "trim_raw_by_mad": (_RawTable, [_RawTable, C.c_size_t, C.c_float]),
+        "get_raw_model": (C.c_int, [C.c_char_p]),
+        "raw_model_string": (C.c_char_p, [C.c_int]),
+        "get_raw_model_stride": (C.c_int, [C.c_int]),
+        "get_raw_model_stride_from_string": (C.c_int, [C.c_char_p]),
+        "get_posterior_function": (C.c_void_p, [C.c_int]),
+        "decode_transducer": (C.c_float, [mp, C.c_float, C.c_float, C.c_float, _i32p, C.c_bool]),
+        "decode_crf": (C.c_float, [mp, _i32p]),
+        "overlapper": (C.c_void_p, [_i32p, C.c_size_t, C.c_int, _i32p]),
+        "crfpath_to_basecall": (C.c_void_p, [_i32p, C.c_size_t, _i32p]),
+        "homopolymer_path": (C.c_int, [mp, _i32p, C.c_int]),
+        "get_homopolymer_calculation": (C.c_int, [C.c_char_p]),
+        "sb2_default_params": (Params, []),
+        "sb2_engine_create": (C.c_void_p, [C.c_int, C.c_char_p]),
+        "sb2_engine_destroy": (None, [C.c_void_p]),
+        "sb2_engine_load_blob": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
+        "sb2_last_error": (C.c_char_p, []),
+        "sb2_engine_launch_count": (C.c_uint64, [C.c_void_p]),
+        "sb2_batch_create": (C.c_void_p, [C.c_void_p, C.c_int, C.POINTER(C.c_size_t), C.c_size_t]),
+        "sb2_batch_destroy": (None, [C.c_void_p]),
+        "sb2_batch_nblock": (C.c_size_t, [C.c_void_p, C.c_size_t]),
+        "sb2_batch_total_blocks": (C.c_size_t, [C.c_void_p]),
+        "sb2_batch_nstate": (C.c_size_t, [C.c_void_p]),
+        "sb2_batch_upload": (C.c_int, [C.c_void_p, C.POINTER(_f32p)]),
+        "sb2_batch_upload_concat": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+        "sb2_batch_total_samples_padded": (C.c_size_t, [C.c_void_p]),
+        "sb2_batch_sample_offset": (C.c_size_t, [C.c_void_p, C.c_size_t]),
+        "sb2_host_alloc_pinned": (C.c_void_p, [C.c_size_t]),
+        "sb2_host_free_pinned": (None, [C.c_void_p]),
+        "sb2_batch_keep_layers": (C.c_int, [C.c_void_p, C.c_int]),
+        "sb2_batch_forward": (C.c_int, [C.c_void_p, C.POINTER(Params), C.c_bool]),
+        "sb2_batch_decode": (C.c_int, [C.c_void_p, C.POINTER(Params)]),
+        "sb2_batch_sync": (C.c_int, [C.c_void_p]),
+        "sb2_batch_download_posterior": (C.c_int, [C.c_void_p, C.c_size_t, _f32p, C.c_size_t]),
+        "sb2_batch_download_paths": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+        "sb2_batch_download_layer": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, _f32p]),
+        "sb2_batch_time": (C.c_int, [C.c_void_p, C.POINTER(Params), C.c_int, C.c_int, _f32p, _f32p, _f32p]),
+        "sb2_batch_stage_ms": (C.c_int, [C.c_void_p, _f32p, C.c_int]),
+        "sb2_basecall_batch": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(_f32p), C.POINTER(C.c_size_t), C.c_size_t,
+                                         C.POINTER(Params), C.POINTER(_Call)]),
+        "sb2_batch_basecall": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(Params), C.POINTER(_Call)]),
+        "sb2_multi_time": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(Params), C.c_int, C.c_int, _f32p]),
+        "sb2_conv_plan_debug": (C.c_int, [C.c_size_t, C.c_size_t, C.c_size_t, _i32p, C.c_int]),
+    }
+    for name in MODELS:
+        fn = "nanonet_%s_%s" % (name, "transitions" if name == "rnnrf_r94" else "posterior")
+        sig[fn] = (mp, [_RawTable, C.c_float, C.c_float, C.c_float, C.c_bool])
+    for name, (res, args) in sig.items():
+        f = getattr(L, name)
+        f.restype = res
+        f.argtypes = args
+    _lib = L
+    return L
+
+
+EXPORTED_SYMBOLS = None     # filled by tests from include/scrappie_b200.h
+
+
+def last_error():
+    return lib().sb2_last_error().decode()
+
+
+_libc = C.CDLL(None)
+_libc.free.argtypes = [C.c_void_p]
+
+
+def _take_string(ptr):
+    if not ptr:
+        return None
+    s = C.string_at(ptr).decode()
+    _libc.free(ptr)
+    return s
+
+
+def _fp(a):
+    return a.ctypes.data_as(_f32p)
+
+
+def _ip(a):
+    return a.ctypes.data_as(_i32p)
+
+
+def default_params(**kw):
+    p = lib().sb2_default_params()
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise TypeError("unknown parameter %r" % k)
+        setattr(p, k, v)
+    return p
+
+
+# ---------------------------------------------------------------------------
+# scrappy-compatible single-read API
+# ---------------------------------------------------------------------------
+
+class RawTable(object):
+    """A raw signal with trimming bounds (python/scrappy/__init__.py:47-111)."""
+
+    def __init__(self, data, start=0, end=None):
+        self._data = np.ascontiguousarray(data, dtype=np.float32).copy()
+        if end is None:
+            end = len(self._data)
+        self._rt = _RawTable(None, len(self._data), start, end, _fp(self._data))
+
+    def data(self, as_numpy=False):
+        return self._data[self.start:self.end] if as_numpy else self._rt
+
+    @property
+    def start(self):
+        return self._rt.start
+
+    @property
+    def end(self):
+        return self._rt.end
+
+    def trim(self, start=200, end=10, varseg_chunk=100, varseg_thresh=0.0):
+        """Trim by MAD segmentation then fixed amounts (trim_and_segment_raw).  The C
+        routine frees its buffer when nothing is left, so it works on a malloc'd copy."""
+        _libc.malloc.restype = C.c_void_p
+        _libc.malloc.argtypes = [C.c_size_t]
+        buf = _libc.malloc(max(self._data.nbytes, 4))
+        C.memmove(buf, self._data.ctypes.data, self._data.nbytes)
+        rt = _RawTable(None, self._rt.n, self._rt.start, self._rt.end, C.cast(buf, _f32p))
+        out = lib().trim_and_segment_raw(rt, start, end, varseg_chunk, varseg_thresh)
+        if not out.raw:
+            raise RuntimeError("no signal left after trimming")
+        _libc.free(buf)
+        self._rt.start, self._rt.end = out.start, out.end
+        return self
+
+    def scale(self):
+        """med-MAD normalise the trimmed part in place (medmad_normalise_array)."""
+        view = self._data[self.start:self.end]
+        lib().medmad_normalise_array(_fp(view), view.size)
+        return self
+
+
+class ScrappyMatrix(object):
+    """Owner of a C scrappie_matrix (python/scrappy/__init__.py:147-192)."""
+
+    def __init__(self, ptr):
+        self._ptr = ptr
+
+    def __del__(self):
+        if getattr(self, "_ptr", None):
+            lib().free_scrappie_matrix(self._ptr)
+            self._ptr = None
+
+    @property
+    def shape(self):
+        m = self._ptr.contents
+        return int(m.nc), int(m.nr)
+
+    def data(self, as_numpy=False, sloika=False):
+        if not as_numpy:
+            return self._ptr
+        m = self._ptr.contents
+        a = np.ctypeslib.as_array(m.f, shape=(m.nc, m.stride))[:, :m.nr]
+        if sloika:
+            a = np.hstack((a[:, m.nr - 1:m.nr], a[:, :m.nr - 1]))
+        return np.ascontiguousarray(a)
+
+    def padded(self):
+        m = self._ptr.contents
+        return np.ctypeslib.as_array(m.f, shape=(m.nc, m.stride)).copy()
+
+    @classmethod
+    def from_numpy(cls, a, nr=None):
+        """[nblock, >=nr] float32 -> scrappie_matrix with nr rows per column."""
+        a = np.ascontiguousarray(a, dtype=np.float32)
+        nr = a.shape[1] if nr is None else nr
+        packed = np.ascontiguousarray(a[:, :nr])
+        return cls(lib().mat_from_array(_fp(packed), nr, a.shape[0]))
+
+
+def _posterior_fn(model):
+    if model not in MODELS:
+        raise KeyError("Model type '{}' not recognised.".format(model))
+    return getattr(lib(), "nanonet_%s_%s" % (model, "transitions" if model == "rnnrf_r94" else "posterior"))
+
+
+def calc_post(rt, model='rgrgr_r94', min_prob=1e-6, log=True, tempW=1.0, tempb=1.0):
+    if not log and model == 'rnnrf_r94':
+        raise ValueError("Returning non-log transformed matrix not supported for model type 'rnnrf_r94'.")
+    if not isinstance(rt, RawTable):
+        raise TypeError('`rt` should be a RawTable.')
+    ptr = _posterior_fn(model)(rt.data(), min_prob, tempW, tempb, log)
+    if not ptr:
+        raise RuntimeError('An unknown error occurred during posterior calculation. (%s)' % last_error())
+    return ScrappyMatrix(ptr)
+
+
+def _decode_post(post, stay_pen=0.0, skip_pen=0.0, local_pen=2.0, use_slip=False):
+    nblock, nstate = post.shape
+    path = np.zeros(nblock + 1, dtype=np.int32)
+    score = lib().decode_transducer(post.data(), stay_pen, skip_pen, local_pen, _ip(path), use_slip)
+    if score != score:
+        raise RuntimeError("decode_transducer failed: %s" % last_error())
+    pos = np.zeros(nblock + 1, dtype=np.int32)
+    call = _take_string(lib().overlapper(_ip(path), nblock + 1, nstate - 1, _ip(pos)))
+    return call, score, pos
+
+
+def _decode_post_crf(post):
+    nblock, nstate = post.shape
+    path = np.zeros(nblock + 1, dtype=np.int32)
+    score = lib().decode_crf(post.data(), _ip(path))
+    if score != score:
+        raise RuntimeError("decode_crf failed: %s" % last_error())
+    pos = np.zeros(nblock + 1, dtype=np.int32)
+    call = _take_string(lib().crfpath_to_basecall(_ip(path), nblock, _ip(pos)))
+    return call, score, pos
+
+
+def decode_post(post, model='rgrgr_r94', **kwargs):
+    if not isinstance(post, ScrappyMatrix):
+        raise TypeError('`post` should be a ScrappyMatrix.')
+    if model not in MODELS:
+        raise KeyError("Model type '{}' not recognised.".format(model))
+    return _decode_post_crf(post, **kwargs) if model == 'rnnrf_r94' else _decode_post(post, **kwargs)
+
+
+def decode_path(post, model='rgrgr_r94', stay_pen=0.0, skip_pen=0.0, local_pen=2.0, use_slip=False):
+    """Viterbi path (nblock + 1 ints) and score straight from the C decoders."""
+    nblock, _ = post.shape
+    path = np.zeros(nblock + 1, dtype=np.int32)
+    if model == 'rnnrf_r94':
+        score = lib().decode_crf(post.data(), _ip(path))
+    else:
+        score = lib().decode_transducer(post.data(), stay_pen, skip_pen, local_pen, _ip(path), use_slip)
+    return float(score), path
+
+
+def get_model_stride(model):
+    stride = lib().get_raw_model_stride_from_string(model.encode())
+    if stride == -1:
+        raise ValueError("Invalid scrappie model '{}'.".format(model))
+    return stride
+
+
+def basecall_raw(data, model='rgrgr_r94', **kwargs):
+    """Trim, normalise, run the network and decode one read
+    (python/scrappy/__init__.py:403-430).  Returns (call, score, pos, start, end)."""
+    raw = RawTable(data)
+    raw.trim().scale()
+    post = calc_post(raw, model, log=True)
+    seq, score, pos = decode_post(post, model, **kwargs)
+    return seq, score, pos, raw.start, raw.end
+
+
+# ---------------------------------------------------------------------------
+# batch API
+# ---------------------------------------------------------------------------
+
+class Engine(object):
+    """One CUDA device with resident model weights (sb2_engine)."""
+
+    def __init__(self, device=0, weights_dir=None):
+        wd = (weights_dir or WEIGHTS_DIR).encode()
+        self._h = lib().sb2_engine_create(device, wd)
+        if not self._h:
+            raise RuntimeError("sb2_engine_create failed: %s" % last_error())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().sb2_engine_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def load_blob(self, model, blob):
+        blob = np.ascontiguousarray(blob, dtype=np.uint8)
+        rc = lib().sb2_engine_load_blob(self._h, _MODEL_ENUM[model], blob.ctypes.data, blob.size)
+        if rc:
+            raise RuntimeError("load_blob failed: %s" % last_error())
+
+    @property
+    def launches(self):
+        return int(lib().sb2_engine_launch_count(self._h))
+
+    def batch(self, model, nsample):
+        return Batch(self, model, nsample)
+
+    def basecall_batch(self, model, signals, params=None):
+        """signals: list of trimmed + normalised float32 arrays.  Returns list of
+        (bases, score, nblock)."""
+        params = params or default_params()
+        sigs = [np.ascontiguousarray(s, dtype=np.float32) for s in signals]
+        n = len(sigs)
+        ptrs = (_f32p * n)(*[_fp(s) for s in sigs])
+        lens = (C.c_size_t * n)(*[s.size for s in sigs])
+        out = (_Call * n)()
+        rc = lib().sb2_basecall_batch(self._h, _MODEL_ENUM[model], ptrs, lens, n, C.byref(params), out)
+        if rc < 0:
+            raise RuntimeError("sb2_basecall_batch failed: %s" % last_error())
+        return [(_take_string(o.bases), float(o.score), int(o.nblock)) for o in out]
+
+
+class Batch(object):
+    """Device workspace for a batch of reads (sb2_batch)."""
+
+    def __init__(self, engine, model, nsample):
+        self.engine = engine
+        self.model = model
+        self.nread = len(nsample)
+        lens = (C.c_size_t * self.nread)(*[int(x) for x in nsample])
+        self._h = lib().sb2_batch_create(engine._h, _MODEL_ENUM[model], lens, self.nread)
+        if not self._h:
+            raise RuntimeError("sb2_batch_create failed: %s" % last_error())
+        L = lib()
+        self.nblock = [int(L.sb2_batch_nblock(self._h, r)) for r in range(self.nread)]
+        self.total_blocks = int(L.sb2_batch_total_blocks(self._h))
+        self.nstate = int(L.sb2_batch_nstate(self._h))
+        self.ostride = 4 * ((self.nstate + 3) // 4)
+        self.sample_offset = [int(L.sb2_batch_sample_offset(self._h, r)) for r in range(self.nread)]
+        self.total_samples_padded = int(L.sb2_batch_total_samples_padded(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().sb2_batch_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _check(self, rc, what):
+        if rc:
+            raise RuntimeError("%s failed: %s" % (what, last_error()))
+
+    def upload(self, signals):
+        sigs = [np.ascontiguousarray(s, dtype=np.float32) for s in signals]
+        ptrs = (_f32p * self.nread)(*[_fp(s) for s in sigs])
+        self._check(lib().sb2_batch_upload(self._h, ptrs), "upload")
+
+    def upload_concat(self, ptr, pinned_async=True):
+        self._check(lib().sb2_batch_upload_concat(self._h, ptr, int(pinned_async)), "upload_concat")
+
+    def keep_layers(self, keep=True):
+        self._check(lib().sb2_batch_keep_layers(self._h, int(keep)), "keep_layers")
+
+    def forward(self, params=None, return_log=True):
+        params = params or default_params()
+        self._check(lib().sb2_batch_forward(self._h, C.byref(params), return_log), "forward")
+
+    def decode(self, params=None):
+        params = params or default_params()
+        self._check(lib().sb2_batch_decode(self._h, C.byref(params)), "decode")
+
+    def sync(self):
+        self._check(lib().sb2_batch_sync(self._h), "sync")
+
+    def posterior(self, read):
+        out = np.zeros((self.nblock[read], self.ostride), dtype=np.float32)
+        self._check(lib().sb2_batch_download_posterior(self._h, read, _fp(out), self.ostride), "download_posterior")
+        return out
+
+    def layer(self, layer, read, H):
+        out = np.zeros((self.nblock[read], H), dtype=np.float32)
+        self._check(lib().sb2_batch_download_layer(self._h, layer, read, _fp(out)), "download_layer")
+        return out
+
+    def paths(self, out_paths=None, out_scores=None):
+        """Returns (list of per-read path arrays, scores)."""
+        paths = np.zeros(self.total_blocks + self.nread, dtype=np.int32) if out_paths is None else out_paths
+        scores = np.zeros(self.nread, dtype=np.float32) if out_scores is None else out_scores
+        self._check(lib().sb2_batch_download_paths(self._h, paths.ctypes.data, scores.ctypes.data), "download_paths")
+        per_read, off = [], 0
+        for r in range(self.nread):
+            per_read.append(paths[off:off + self.nblock[r] + 1])
+            off += self.nblock[r] + 1
+        return per_read, scores
+
+    def time(self, params=None, nrep=1, flush_l2=True):
+        """CUDA-event timing of forward+decode on the batch's stream: (total, forward, decode) ms arrays."""
+        params = params or default_params()
+        tot = np.zeros(nrep, dtype=np.float32)
+        fwd = np.zeros(nrep, dtype=np.float32)
+        dec = np.zeros(nrep, dtype=np.float32)
+        self._check(lib().sb2_batch_time(self._h, C.byref(params), nrep, int(flush_l2), _fp(tot), _fp(fwd), _fp(dec)), "time")
+        return tot, fwd, dec
+
+    def basecall(self, concat_ptr=None, pinned=True, params=None):
+        """Upload (optional), forward, decode, download, homopolymer, overlapper on this workspace.
+        Returns list of (bases, score, nblock)."""
+        params = params or default_params()
+        out = (_Call * self.nread)()
+        rc = lib().sb2_batch_basecall(self._h, concat_ptr, int(pinned), C.byref(params), out)
+        if rc < 0:
+            raise RuntimeError("sb2_batch_basecall failed: %s" % last_error())
+        return [(_take_string(o.bases), float(o.score), int(o.nblock)) for o in out]
+
+    STAGES = ("conv", "affine1", "scan1", "affine2", "scan2", "affine3", "scan3", "affine4", "scan4",
+              "affine5", "scan5", "head_gemm", "head_finish", "decode")
+
+    def stage_ms(self):
+        buf = np.zeros(len(self.STAGES), dtype=np.float32)
+        lib().sb2_batch_stage_ms(self._h, _fp(buf), buf.size)
+        return dict(zip(self.STAGES, [float(x) for x in buf]))
+
+
+def multi_time(batches, params=None, nrep=1, flush_l2=True):
+    """CUDA-event time (ms per repetition) of forward+decode over several concurrent batches."""
+    params = params or default_params()
+    hs = (C.c_void_p * len(batches))(*[b._h for b in batches])
+    ms = np.zeros(nrep, dtype=np.float32)
+    rc = lib().sb2_multi_time(hs, len(batches), C.byref(params), nrep, int(flush_l2), _fp(ms))
+    if rc:
+        raise RuntimeError("sb2_multi_time failed: %s" % last_error())
+    return ms
+
+
+class PinnedBuffer(object):
+    """Page-locked host float32 buffer (cudaMallocHost) exposed as a numpy array."""
+
+    def __init__(self, nfloat):
+        self.ptr = lib().sb2_host_alloc_pinned(nfloat * 4)
+        if not self.ptr:
+            raise RuntimeError("pinned allocation failed")
+        self.array = np.ctypeslib.as_array(C.cast(self.ptr, _f32p), shape=(nfloat,))
+
+    def close(self):
+        if getattr(self, "ptr", None):
+            self.array = None
+            lib().sb2_host_free_pinned(self.ptr)
+            self.ptr = None
+
+    __del__ = close
+
+
+def conv_plan(nsample, winlen, stride):
+    """Host-side convolution tail plan as {column: [(x0, tap0, ntap), ...]} plus (first_col, ncol)."""
+    buf = np.zeros(2 + 24 * (1 + 9), dtype=np.int32)
+    rc = lib().sb2_conv_plan_debug(nsample, winlen, stride, _ip(buf), buf.size)
+    if rc:
+        raise RuntimeError("conv plan failed: %s" % last_error())
+    first, ncol = int(buf[0]), int(buf[1])
+    plan = {}
+    for c in range(24):
+        base = 2 + c * 10
+        nseg = int(buf[base])
+        if first + c < ncol:
+            plan[first + c] = [tuple(int(v) for v in buf[base + 1 + 3 * s: base + 4 + 3 * s]) for s in range(nseg)]
+    return first, ncol, plan

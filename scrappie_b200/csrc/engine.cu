@@ -1,0 +1,761 @@
+// Engine, batches and the C-ABI entry points that touch the GPU.
+//
+// Host orchestration only: every stage of the network and both decoders run as CUDA
+// kernels (kernels_v1.cu, kernels_tc.cu).  There is deliberately no CPU fallback; when
+// CUDA is unusable the entry points fail with NULL / NAN / -1 and sb2_last_error().
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "kernels.h"
+#include "sb2_internal.h"
+
+using namespace sb2;
+
+#define CUDA_OK(call)                                                                         \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess) {                                                              \
+            sb2_set_error("CUDA error %s at %s:%d (%s)", cudaGetErrorString(e_), __FILE__,    \
+                          __LINE__, #call);                                                   \
+            return -1;                                                                        \
+        }                                                                                     \
+    } while (0)
+
+// ------------------------------------------------------------------------------------
+// engine
+// ------------------------------------------------------------------------------------
+
+struct DevModel {
+    bool loaded = false;
+    sb2_host_model host{};
+    float *d_all = nullptr;
+    float *conv_taps = nullptr, *conv_b = nullptr;
+    float *iW[SB2_NLAYER]{}, *b[SB2_NLAYER]{}, *sW[SB2_NLAYER]{}, *sW2[SB2_NLAYER]{};
+    float *FF_W = nullptr, *FF_b = nullptr;
+};
+
+struct sb2_engine {
+    int device = 0;
+    DevModel models[SB2_NMODEL];
+    char weights_dir[1024]{};
+    std::atomic<uint64_t> launches{0};
+    float *flush_buf = nullptr;
+    size_t flush_n = 0;
+    std::mutex mu;
+    int scan_impl = 0;      // 0 = ffma, 1 = tcgen05
+    int gemm_impl = 0;
+};
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static int upload_model(sb2_engine *eng, DevModel *dm) {
+    const sb2_host_model &h = dm->host;
+    const size_t H = h.H;
+    // compact device copies; each tensor starts on a 256-byte boundary
+    std::vector<std::pair<float **, std::vector<float>>> items;
+    auto compact = [](const sb2_tensor &t) {
+        std::vector<float> v((size_t)t.nc * t.nr);
+        for (uint32_t c = 0; c < t.nc; c++) memcpy(&v[(size_t)c * t.nr], t.data + (size_t)c * t.stride, t.nr * sizeof(float));
+        return v;
+    };
+    {   // conv taps: reference stores filter f as a column of winlen*4 floats with the tap at
+        // every 4th slot (src/layers.c:155-157); device layout is [tap][filter]
+        std::vector<float> taps((size_t)h.winlen * H);
+        for (uint32_t f = 0; f < H; f++)
+            for (uint32_t k = 0; k < h.winlen; k++) taps[(size_t)k * H + f] = h.conv_W.data[(size_t)f * h.conv_W.stride + 4 * k];
+        items.push_back({&dm->conv_taps, taps});
+        items.push_back({&dm->conv_b, compact(h.conv_b)});
+    }
+    for (int l = 0; l < SB2_NLAYER; l++) {
+        items.push_back({&dm->iW[l], compact(h.iW[l])});
+        items.push_back({&dm->b[l], compact(h.b[l])});
+        items.push_back({&dm->sW[l], compact(h.sW[l])});
+        items.push_back({&dm->sW2[l], compact(h.sW2[l])});
+    }
+    items.push_back({&dm->FF_W, compact(h.FF_W)});
+    items.push_back({&dm->FF_b, compact(h.FF_b)});
+    size_t total = 0;
+    for (auto &it : items) total += align_up(it.second.size() * sizeof(float), 256);
+    CUDA_OK(cudaSetDevice(eng->device));
+    CUDA_OK(cudaMalloc(&dm->d_all, total));
+    size_t off = 0;
+    for (auto &it : items) {
+        float *dst = reinterpret_cast<float *>(reinterpret_cast<char *>(dm->d_all) + off);
+        CUDA_OK(cudaMemcpy(dst, it.second.data(), it.second.size() * sizeof(float), cudaMemcpyHostToDevice));
+        *it.first = dst;
+        off += align_up(it.second.size() * sizeof(float), 256);
+    }
+    dm->loaded = true;
+    return 0;
+}
+
+extern "C" int sb2_engine_load_blob(sb2_engine *eng, enum raw_model_type model, const void *blob, size_t nbytes) {
+    if (nullptr == eng || model < 0 || model >= SCRAPPIE_MODEL_INVALID) return -1;
+    std::lock_guard<std::mutex> lock(eng->mu);
+    DevModel *dm = &eng->models[model];
+    if (dm->loaded) return 0;
+    if (0 != sb2_host_model_parse(blob, nbytes, &dm->host)) return -1;
+    if (dm->host.H != 96 && dm->host.H != 112) {
+        sb2_set_error("unsupported GRU width %u", dm->host.H);
+        return -1;
+    }
+    return upload_model(eng, dm);
+}
+
+static DevModel *get_model(sb2_engine *eng, enum raw_model_type model) {
+    if (nullptr == eng || model < 0 || model >= SCRAPPIE_MODEL_INVALID) return nullptr;
+    DevModel *dm = &eng->models[model];
+    if (dm->loaded) return dm;
+    if (model == SCRAPPIE_MODEL_RAW) {
+        sb2_set_error("model raw_r94 is not implemented by this engine (see DESIGN.md, scope)");
+        return nullptr;
+    }
+    char path[1200];
+    snprintf(path, sizeof(path), "%s/%s.bin", eng->weights_dir, sb2_model_file_stem(model));
+    void *blob = nullptr;
+    size_t nbytes = 0;
+    if (0 != sb2_read_file(path, &blob, &nbytes)) return nullptr;
+    const int rc = sb2_engine_load_blob(eng, model, blob, nbytes);
+    free(blob);
+    return (0 == rc) ? dm : nullptr;
+}
+
+extern "C" sb2_engine *sb2_engine_create(int device, const char *weights_dir) {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        sb2_set_error("no usable CUDA device (%s); libscrappie_b200 has no CPU fallback",
+                      e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        fprintf(stderr, "scrappie_b200: %s\n", sb2_last_error());
+        return nullptr;
+    }
+    if (device < 0 || device >= ndev) {
+        sb2_set_error("device %d out of range (%d visible)", device, ndev);
+        return nullptr;
+    }
+    sb2_engine *eng = new sb2_engine();
+    eng->device = device;
+    if (nullptr != weights_dir) snprintf(eng->weights_dir, sizeof(eng->weights_dir), "%s", weights_dir);
+    else if (0 != sb2_default_weights_dir(eng->weights_dir, sizeof(eng->weights_dir))) eng->weights_dir[0] = '\0';
+    const char *scan = getenv("SCRAPPIE_B200_SCAN");
+    const char *gemm = getenv("SCRAPPIE_B200_GEMM");
+    eng->scan_impl = (scan && 0 == strcmp(scan, "tc")) ? 1 : 0;
+    eng->gemm_impl = (gemm && 0 == strcmp(gemm, "tc")) ? 1 : 0;
+    if (cudaSetDevice(device) != cudaSuccess) { delete eng; return nullptr; }
+    return eng;
+}
+
+extern "C" void sb2_engine_destroy(sb2_engine *eng) {
+    if (nullptr == eng) return;
+    cudaSetDevice(eng->device);
+    for (auto &dm : eng->models) {
+        if (dm.d_all) cudaFree(dm.d_all);
+        sb2_host_model_free(&dm.host);
+    }
+    if (eng->flush_buf) cudaFree(eng->flush_buf);
+    delete eng;
+}
+
+extern "C" uint64_t sb2_engine_launch_count(const sb2_engine *eng) { return eng ? eng->launches.load() : 0; }
+
+extern "C" sb2_params sb2_default_params(void) {
+    sb2_params p;
+    p.min_prob = 1e-5f; p.tempW = 1.0f; p.tempb = 1.0f;
+    p.stay_pen = 0.0f; p.skip_pen = 0.0f; p.local_pen = 2.0f;
+    p.allow_slip = 0;
+    p.homopolymer = HOMOPOLYMER_MEAN;
+    return p;
+}
+
+extern "C" void *sb2_host_alloc_pinned(size_t nbytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, nbytes) != cudaSuccess) return nullptr;
+    return p;
+}
+extern "C" void sb2_host_free_pinned(void *p) { if (p) cudaFreeHost(p); }
+
+// ------------------------------------------------------------------------------------
+// batch
+// ------------------------------------------------------------------------------------
+
+// stage order of one pass: conv, (affine_l, scan_l) x 5, head GEMM, head finish, decode
+enum { ST_CONV = 0, ST_HEAD = 11, ST_FINISH = 12, ST_DECODE = 13, ST_COUNT = 14 };
+static inline int ST_AFFINE(int l) { return 1 + 2 * l; }
+static inline int ST_SCAN(int l) { return 2 + 2 * l; }
+
+struct sb2_batch {
+    sb2_engine *eng = nullptr;
+    enum raw_model_type model_type = SCRAPPIE_MODEL_INVALID;
+    DevModel *m = nullptr;
+    int nread = 0, total_cols = 0, max_cols = 0;
+    int64_t total_samples = 0;
+    std::vector<int> nsample, nblock, col_off;
+    std::vector<int64_t> samp_off;
+    // device
+    float *d_raw = nullptr, *d_X[2]{}, *d_Xin = nullptr, *d_post = nullptr, *d_score = nullptr, *d_layers = nullptr;
+    int *d_nsample = nullptr, *d_nblock = nullptr, *d_coloff = nullptr, *d_tbE = nullptr, *d_path = nullptr;
+    int64_t *d_sampoff = nullptr;
+    uint8_t *d_tb = nullptr;
+    sb2_conv_tail *d_tails = nullptr;
+    int final_x = 0;
+    bool keep_layers = false;
+    bool timing = false;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[ST_COUNT + 1]{};
+    float stage_ms[ST_COUNT]{};
+    BatchDims dims{};
+};
+
+template <typename T>
+static int dev_alloc(T **p, size_t n) {
+    CUDA_OK(cudaMalloc(reinterpret_cast<void **>(p), (n ? n : 1) * sizeof(T)));
+    return 0;
+}
+
+extern "C" void sb2_batch_destroy(sb2_batch *b) {
+    if (nullptr == b) return;
+    cudaSetDevice(b->eng->device);
+    if (b->stream) cudaStreamSynchronize(b->stream);
+    void *ptrs[] = {b->d_raw, b->d_X[0], b->d_X[1], b->d_Xin, b->d_post, b->d_score, b->d_layers, b->d_nsample,
+                    b->d_nblock, b->d_coloff, b->d_tbE, b->d_path, b->d_sampoff, b->d_tb, b->d_tails};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    for (auto &e : b->ev) if (e) cudaEventDestroy(e);
+    if (b->stream) cudaStreamDestroy(b->stream);
+    delete b;
+}
+
+static int batch_init(sb2_batch *b, const size_t *nsample, size_t nread) {
+    const sb2_host_model &h = b->m->host;
+    const size_t H = h.H;
+    b->nread = (int)nread;
+    b->nsample.resize(nread); b->nblock.resize(nread); b->samp_off.resize(nread); b->col_off.resize(nread + 1);
+    std::vector<sb2_conv_tail> tails(nread);
+    int64_t so = 0;
+    int64_t co = 0;
+    for (size_t r = 0; r < nread; r++) {
+        if (nsample[r] > (size_t)1 << 30) { sb2_set_error("read %zu too long", r); return -1; }
+        if (0 != sb2_conv_plan(nsample[r], h.winlen, h.conv_stride, &tails[r])) return -1;
+        b->nsample[r] = (int)nsample[r];
+        b->nblock[r] = tails[r].ncol;
+        b->samp_off[r] = so;
+        b->col_off[r] = (int)co;
+        so += (int64_t)((nsample[r] + 3) / 4 * 4);          // keep each read 16-byte aligned
+        co += tails[r].ncol;
+        b->max_cols = std::max(b->max_cols, (int)tails[r].ncol);
+        if (co > (int64_t)1 << 30) { sb2_set_error("batch too large"); return -1; }
+    }
+    b->col_off[nread] = (int)co;
+    b->total_cols = (int)co;
+    b->total_samples = so;
+
+    CUDA_OK(cudaSetDevice(b->eng->device));
+    CUDA_OK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+    for (auto &e : b->ev) CUDA_OK(cudaEventCreate(&e));
+    const size_t ncol = (size_t)b->total_cols;
+    if (dev_alloc(&b->d_raw, (size_t)so) || dev_alloc(&b->d_X[0], ncol * H) || dev_alloc(&b->d_X[1], ncol * H) ||
+        dev_alloc(&b->d_Xin, ncol * 3 * H) || dev_alloc(&b->d_post, ncol * h.ostride) ||
+        dev_alloc(&b->d_score, nread) || dev_alloc(&b->d_nsample, nread) || dev_alloc(&b->d_nblock, nread) ||
+        dev_alloc(&b->d_coloff, nread + 1) || dev_alloc(&b->d_sampoff, nread) || dev_alloc(&b->d_tails, nread) ||
+        dev_alloc(&b->d_path, ncol + nread))
+        return -1;
+    if (h.head == 0) {
+        if (dev_alloc(&b->d_tb, ncol * (h.nstate - 1)) || dev_alloc(&b->d_tbE, ncol)) return -1;
+    } else {
+        if (dev_alloc(&b->d_tb, ncol * 8)) return -1;
+    }
+    CUDA_OK(cudaMemcpy(b->d_nsample, b->nsample.data(), nread * sizeof(int), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(b->d_nblock, b->nblock.data(), nread * sizeof(int), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(b->d_coloff, b->col_off.data(), (nread + 1) * sizeof(int), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(b->d_sampoff, b->samp_off.data(), nread * sizeof(int64_t), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(b->d_tails, tails.data(), nread * sizeof(sb2_conv_tail), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemset(b->d_raw, 0, (size_t)so * sizeof(float)));
+    b->dims.nread = b->nread;
+    b->dims.total_cols = b->total_cols;
+    b->dims.max_cols = b->max_cols;
+    b->dims.nsample = b->d_nsample;
+    b->dims.nblock = b->d_nblock;
+    b->dims.samp_off = b->d_sampoff;
+    b->dims.col_off = b->d_coloff;
+    b->dims.col_read = nullptr;
+    return 0;
+}
+
+extern "C" sb2_batch *sb2_batch_create(sb2_engine *eng, enum raw_model_type model, const size_t *nsample, size_t nread) {
+    if (nullptr == eng || nullptr == nsample || 0 == nread) { sb2_set_error("batch: bad arguments"); return nullptr; }
+    DevModel *dm = get_model(eng, model);
+    if (nullptr == dm) return nullptr;
+    sb2_batch *b = new sb2_batch();
+    b->eng = eng;
+    b->model_type = model;
+    b->m = dm;
+    if (0 != batch_init(b, nsample, nread)) { sb2_batch_destroy(b); return nullptr; }
+    return b;
+}
+
+extern "C" size_t sb2_batch_nblock(const sb2_batch *b, size_t read) { return (b && read < (size_t)b->nread) ? (size_t)b->nblock[read] : 0; }
+extern "C" size_t sb2_batch_total_blocks(const sb2_batch *b) { return b ? (size_t)b->total_cols : 0; }
+extern "C" size_t sb2_batch_nstate(const sb2_batch *b) { return b ? b->m->host.nstate : 0; }
+extern "C" size_t sb2_batch_total_samples_padded(const sb2_batch *b) { return b ? (size_t)b->total_samples : 0; }
+extern "C" size_t sb2_batch_sample_offset(const sb2_batch *b, size_t read) { return (b && read < (size_t)b->nread) ? (size_t)b->samp_off[read] : 0; }
+
+extern "C" int sb2_batch_keep_layers(sb2_batch *b, int keep) {
+    if (nullptr == b) return -1;
+    CUDA_OK(cudaSetDevice(b->eng->device));
+    if (keep && nullptr == b->d_layers && dev_alloc(&b->d_layers, (size_t)6 * b->total_cols * b->m->host.H)) return -1;
+    b->keep_layers = keep != 0;
+    return 0;
+}
+
+extern "C" int sb2_batch_upload(sb2_batch *b, const float *const *signals) {
+    if (nullptr == b || nullptr == signals) return -1;
+    CUDA_OK(cudaSetDevice(b->eng->device));
+    for (int r = 0; r < b->nread; r++)
+        CUDA_OK(cudaMemcpyAsync(b->d_raw + b->samp_off[r], signals[r], (size_t)b->nsample[r] * sizeof(float),
+                                cudaMemcpyHostToDevice, b->stream));
+    CUDA_OK(cudaStreamSynchronize(b->stream));
+    return 0;
+}
+
+// `concat` uses the batch's padded layout: read r at sb2_batch_sample_offset(b, r).
+extern "C" int sb2_batch_upload_concat(sb2_batch *b, const float *concat, int pinned_async) {
+    if (nullptr == b || nullptr == concat) return -1;
+    CUDA_OK(cudaSetDevice(b->eng->device));
+    CUDA_OK(cudaMemcpyAsync(b->d_raw, concat, (size_t)b->total_samples * sizeof(float), cudaMemcpyHostToDevice, b->stream));
+    if (!pinned_async) CUDA_OK(cudaStreamSynchronize(b->stream));
+    return 0;
+}
+
+static inline void stage_mark(sb2_batch *b, int i) { if (b->timing) cudaEventRecord(b->ev[i], b->stream); }
+
+extern "C" int sb2_batch_forward(sb2_batch *b, const sb2_params *p, bool return_log) {
+    if (nullptr == b || nullptr == p) return -1;
+    const sb2_host_model &h = b->m->host;
+    const DevModel &m = *b->m;
+    if (h.head == 1 && !return_log) { sb2_set_error("rnnrf: return_log = false is unsupported (src/networks.c:569)"); return -1; }
+    if (!(p->min_prob >= 0.0f && p->min_prob <= 1.0f) || !(p->tempW > 0.0f) || !(p->tempb > 0.0f)) {
+        sb2_set_error("invalid min_prob / temperature");
+        return -1;
+    }
+    CUDA_OK(cudaSetDevice(b->eng->device));
+    const int H = (int)h.H;
+    cudaStream_t s = b->stream;
+    uint64_t nl = 0;
+
+    stage_mark(b, ST_CONV);
+    launch_conv_act(b->d_raw, b->dims, b->d_tails, m.conv_taps, m.conv_b, (int)h.winlen, H, (int)h.conv_stride,
+                    (int)h.conv_act, b->d_X[0], s);
+    nl++;
+    int cur = 0;
+    const size_t layer_bytes = (size_t)b->total_cols * H * sizeof(float);
+    if (b->keep_layers) CUDA_OK(cudaMemcpyAsync(b->d_layers, b->d_X[0], layer_bytes, cudaMemcpyDeviceToDevice, s));
+    for (int l = 0; l < SB2_NLAYER; l++) {
+        stage_mark(b, ST_AFFINE(l));
+        launch_affine(b->d_X[cur], b->total_cols, H, m.iW[l], H, m.b[l], 3 * H, b->d_Xin, 3 * H, 1.0f, 1.0f, 0, s);
+        stage_mark(b, ST_SCAN(l));
+        launch_gru_scan_ffma(b->d_Xin, m.sW[l], m.sW2[l], h.residual ? b->d_X[cur] : nullptr, b->d_X[cur ^ 1],
+                             b->dims, H, (l % 2) == 0, s);
+        nl += 2;
+        cur ^= 1;
+        if (b->keep_layers)
+            CUDA_OK(cudaMemcpyAsync(b->d_layers + (size_t)(l + 1) * b->total_cols * H, b->d_X[cur], layer_bytes,
+                                    cudaMemcpyDeviceToDevice, s));
+    }
+    b->final_x = cur;
+    stage_mark(b, ST_HEAD);
+    if (h.head == 0) {
+        launch_affine(b->d_X[cur], b->total_cols, H, m.FF_W, H, m.FF_b, (int)h.nstate, b->d_post, (int)h.ostride,
+                      p->tempW / p->tempb, p->tempb, 1, s);
+        stage_mark(b, ST_FINISH);
+        launch_softmax_finish(b->d_post, b->total_cols, (int)h.nstate, (int)h.ostride, p->min_prob, return_log ? 1 : 0, s);
+        nl += 2;
+    } else {
+        CUDA_OK(cudaMemsetAsync(b->d_post, 0, (size_t)b->total_cols * h.ostride * sizeof(float), s));
+        launch_affine(b->d_X[cur], b->total_cols, H, m.FF_W, H, m.FF_b, (int)h.nstate, b->d_post, (int)h.ostride,
+                      1.0f, 1.0f, 0, s);
+        stage_mark(b, ST_FINISH);
+        launch_globalnorm(b->d_post, b->dims, (int)h.ostride, s);
+        nl += 2;
+    }
+    stage_mark(b, ST_DECODE);
+    b->eng->launches += nl;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int sb2_batch_decode(sb2_batch *b, const sb2_params *p) {
+    if (nullptr == b || nullptr == p) return -1;
+    const sb2_host_model &h = b->m->host;
+    CUDA_OK(cudaSetDevice(b->eng->device));
+    if (h.head == 0)
+        launch_decode_transducer(b->d_post, b->dims, (int)h.nstate, (int)h.ostride, p->stay_pen, p->skip_pen,
+                                 p->local_pen, p->allow_slip, b->d_tb, b->d_tbE, b->d_path, b->d_score, b->stream);
+    else
+        launch_decode_crf(b->d_post, b->dims, (int)h.ostride, b->d_tb, b->d_path, b->d_score, b->stream);
+    b->eng->launches += 1;
+    stage_mark(b, ST_COUNT);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int sb2_batch_sync(sb2_batch *b) {
+    if (nullptr == b) return -1;
+    CUDA_OK(cudaSetDevice(b->eng->device));
+    CUDA_OK(cudaStreamSynchronize(b->stream));
+    return 0;
+}
+
+extern "C" int sb2_batch_download_posterior(sb2_batch *b, size_t read, float *dst, size_t dst_stride) {
+    if (nullptr == b || nullptr == dst || read >= (size_t)b->nread) return -1;
+    const sb2_host_model &h = b->m->host;
+    CUDA_OK(cudaSetDevice(b->eng->device));
+    CUDA_OK(cudaStreamSynchronize(b->stream));
+    const float *src = b->d_post + (size_t)b->col_off[read] * h.ostride;
+    CUDA_OK(cudaMemcpy2D(dst, dst_stride * sizeof(float), src, h.ostride * sizeof(float),
+                         std::min((size_t)h.ostride, dst_stride) * sizeof(float), (size_t)b->nblock[read],
+                         cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int sb2_batch_download_paths(sb2_batch *b, int *paths_concat, float *scores) {
+    if (nullptr == b) return -1;
+    CUDA_OK(cudaSetDevice(b->eng->device));
+    if (paths_concat)
+        CUDA_OK(cudaMemcpyAsync(paths_concat, b->d_path, ((size_t)b->total_cols + b->nread) * sizeof(int),
+                                cudaMemcpyDeviceToHost, b->stream));
+    if (scores)
+        CUDA_OK(cudaMemcpyAsync(scores, b->d_score, (size_t)b->nread * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
+    CUDA_OK(cudaStreamSynchronize(b->stream));
+    return 0;
+}
+
+extern "C" int sb2_batch_download_layer(sb2_batch *b, int layer, size_t read, float *dst) {
+    if (nullptr == b || nullptr == dst || layer < 0 || layer > 5 || read >= (size_t)b->nread || nullptr == b->d_layers) {
+        sb2_set_error("layer download: enable sb2_batch_keep_layers before forward");
+        return -1;
+    }
+    const size_t H = b->m->host.H;
+    CUDA_OK(cudaSetDevice(b->eng->device));
+    CUDA_OK(cudaStreamSynchronize(b->stream));
+    const float *src = b->d_layers + ((size_t)layer * b->total_cols + b->col_off[read]) * H;
+    CUDA_OK(cudaMemcpy(dst, src, (size_t)b->nblock[read] * H * sizeof(float), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int sb2_batch_time(sb2_batch *b, const sb2_params *p, int nrep, int flush_l2, float *ms_out,
+                              float *ms_forward_out, float *ms_decode_out) {
+    if (nullptr == b || nullptr == p || nrep <= 0) return -1;
+    sb2_engine *eng = b->eng;
+    CUDA_OK(cudaSetDevice(eng->device));
+    if (flush_l2 && nullptr == eng->flush_buf) {
+        eng->flush_n = (size_t)96 << 20;                 // 384 MB of floats > 126 MB L2
+        if (dev_alloc(&eng->flush_buf, eng->flush_n)) return -1;
+    }
+    cudaEvent_t e0, e1, e2;
+    CUDA_OK(cudaEventCreate(&e0)); CUDA_OK(cudaEventCreate(&e1)); CUDA_OK(cudaEventCreate(&e2));
+    int rc = 0;
+    for (int i = 0; i < nrep && 0 == rc; i++) {
+        if (flush_l2) launch_flush(eng->flush_buf, eng->flush_n, b->stream);
+        b->timing = (i == nrep - 1);
+        cudaEventRecord(e0, b->stream);
+        rc |= sb2_batch_forward(b, p, true);
+        cudaEventRecord(e1, b->stream);
+        rc |= sb2_batch_decode(b, p);
+        cudaEventRecord(e2, b->stream);
+        if (cudaStreamSynchronize(b->stream) != cudaSuccess) rc = -1;
+        if (rc) break;
+        float f = 0, d = 0;
+        cudaEventElapsedTime(&f, e0, e1);
+        cudaEventElapsedTime(&d, e1, e2);
+        if (ms_out) ms_out[i] = f + d;
+        if (ms_forward_out) ms_forward_out[i] = f;
+        if (ms_decode_out) ms_decode_out[i] = d;
+    }
+    if (0 == rc) {
+        for (int st = 0; st < ST_COUNT; st++) cudaEventElapsedTime(&b->stage_ms[st], b->ev[st], b->ev[st + 1]);
+    }
+    b->timing = false;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    if (rc) { cudaError_t e = cudaGetLastError(); if (e != cudaSuccess) sb2_set_error("CUDA error %s in timed run", cudaGetErrorString(e)); }
+    return rc;
+}
+
+extern "C" int sb2_batch_stage_ms(const sb2_batch *b, float *stage_ms, int nstage_max) {
+    if (nullptr == b || nullptr == stage_ms) return -1;
+    const int n = std::min(nstage_max, (int)ST_COUNT);
+    for (int i = 0; i < n; i++) stage_ms[i] = b->stage_ms[i];
+    return n;
+}
+
+// ------------------------------------------------------------------------------------
+// whole-read basecalling for a batch (calculate_post, src/scrappie_raw.c:265-315)
+// ------------------------------------------------------------------------------------
+
+static int homopolymer_fixup(sb2_batch *b, std::vector<int> &paths) {
+    // runs are found on the host from the Viterbi path; only the two posterior entries per
+    // run position (stay, repeat k-mer) are fetched from HBM (src/homopolymer.c:205-217)
+    const sb2_host_model &h = b->m->host;
+    const int klen = (int)(logf((float)h.nstate) / logf(4.0f));
+    struct Job { int read; sb2_hp_run run; size_t off; };
+    std::vector<Job> jobs;
+    std::vector<int> cols, states;
+    for (int r = 0; r < b->nread; r++) {
+        int *path = paths.data() + b->col_off[r] + r;
+        sb2_hp_run *runs = nullptr;
+        const int n = sb2_find_homopolymer_runs(path, b->nblock[r], klen, &runs);
+        if (n < 0) return -1;
+        for (int i = 0; i < n; i++) {
+            jobs.push_back({r, runs[i], cols.size()});
+            for (int j = 0; j < runs[i].length; j++) {
+                const int col = b->col_off[r] + runs[i].start + j - 1;
+                cols.push_back(col); states.push_back((int)h.nstate - 1);
+                cols.push_back(col); states.push_back(runs[i].state);
+            }
+        }
+        free(runs);
+    }
+    if (cols.empty()) return 0;
+    int *d_cols = nullptr, *d_states = nullptr;
+    float *d_vals = nullptr;
+    std::vector<float> vals(cols.size());
+    if (dev_alloc(&d_cols, cols.size()) || dev_alloc(&d_states, cols.size()) || dev_alloc(&d_vals, cols.size())) return -1;
+    int rc = 0;
+    if (cudaMemcpyAsync(d_cols, cols.data(), cols.size() * sizeof(int), cudaMemcpyHostToDevice, b->stream) != cudaSuccess) rc = -1;
+    if (cudaMemcpyAsync(d_states, states.data(), states.size() * sizeof(int), cudaMemcpyHostToDevice, b->stream) != cudaSuccess) rc = -1;
+    launch_gather(b->d_post, (int)h.ostride, d_cols, d_states, (int)cols.size(), d_vals, b->stream);
+    b->eng->launches += 1;
+    if (cudaMemcpyAsync(vals.data(), d_vals, vals.size() * sizeof(float), cudaMemcpyDeviceToHost, b->stream) != cudaSuccess) rc = -1;
+    if (cudaStreamSynchronize(b->stream) != cudaSuccess) rc = -1;
+    cudaFree(d_cols); cudaFree(d_states); cudaFree(d_vals);
+    if (rc) { sb2_set_error("homopolymer gather failed"); return -1; }
+    std::vector<float> ps, pr;
+    for (const Job &j : jobs) {
+        ps.resize(j.run.length); pr.resize(j.run.length);
+        for (int i = 0; i < j.run.length; i++) { ps[i] = vals[j.off + 2 * i]; pr[i] = vals[j.off + 2 * i + 1]; }
+        sb2_apply_homopolymer_run(paths.data() + b->col_off[j.read] + j.read, &j.run, ps.data(), pr.data());
+    }
+    return 0;
+}
+
+// Basecall on an existing batch workspace: upload (from `concat` in the padded layout if
+// given, else the signals must already be resident), forward, decode, download paths,
+// homopolymer fix-up, overlapper.
+extern "C" int sb2_batch_basecall(sb2_batch *b, const float *concat, int pinned, const sb2_params *p, sb2_call *out) {
+    if (nullptr == b || nullptr == p || nullptr == out) return -1;
+    const size_t nread = (size_t)b->nread;
+    for (size_t r = 0; r < nread; r++) out[r] = sb2_call{nullptr, NAN, 0, 0};
+    if (nullptr != concat && 0 != sb2_batch_upload_concat(b, concat, pinned)) return -1;
+    std::vector<int> paths((size_t)b->total_cols + nread);
+    std::vector<float> scores(nread);
+    if (0 != sb2_batch_forward(b, p, true) || 0 != sb2_batch_decode(b, p) ||
+        0 != sb2_batch_download_paths(b, paths.data(), scores.data()))
+        return -1;
+    const sb2_host_model &h = b->m->host;
+    if (h.head == 0 && p->homopolymer == HOMOPOLYMER_MEAN && 0 != homopolymer_fixup(b, paths)) return -1;
+    int ncalled = 0;
+    std::vector<int> pos;
+    for (size_t r = 0; r < nread; r++) {
+        const int *path = paths.data() + b->col_off[r] + r;
+        const size_t nb = (size_t)b->nblock[r];
+        pos.assign(nb + 1, 0);
+        char *bases = (h.head == 0) ? overlapper(path, nb + 1, (int)h.nstate - 1, pos.data())
+                                    : crfpath_to_basecall(path, nb, pos.data());
+        out[r].bases = bases;
+        out[r].score = scores[r];
+        out[r].nblock = nb;
+        out[r].nbase = bases ? strlen(bases) : 0;
+        if (bases) ncalled++;
+    }
+    return ncalled;
+}
+
+extern "C" int sb2_basecall_batch(sb2_engine *eng, enum raw_model_type model, const float *const *signals,
+                                  const size_t *nsample, size_t nread, const sb2_params *p, sb2_call *out) {
+    if (nullptr == eng || nullptr == signals || nullptr == nsample || nullptr == p || nullptr == out) return -1;
+    for (size_t r = 0; r < nread; r++) out[r] = sb2_call{nullptr, NAN, 0, 0};
+    sb2_batch *b = sb2_batch_create(eng, model, nsample, nread);
+    if (nullptr == b) return -1;
+    int ncalled = -1;
+    if (0 == sb2_batch_upload(b, signals)) ncalled = sb2_batch_basecall(b, nullptr, 0, p, out);
+    sb2_batch_destroy(b);
+    return ncalled;
+}
+
+// Time forward+decode of several batches running concurrently, each on its own stream
+// (the way a job larger than one batch is executed).  The timed region is bracketed by
+// events on the first batch's stream: every other stream waits for the start event and
+// the end event waits for every stream.
+extern "C" int sb2_multi_time(sb2_batch **batches, int nbatch, const sb2_params *p, int nrep, int flush_l2,
+                              float *ms_out) {
+    if (nullptr == batches || nbatch <= 0 || nullptr == p || nrep <= 0) return -1;
+    sb2_engine *eng = batches[0]->eng;
+    CUDA_OK(cudaSetDevice(eng->device));
+    if (flush_l2 && nullptr == eng->flush_buf) {
+        eng->flush_n = (size_t)96 << 20;
+        if (dev_alloc(&eng->flush_buf, eng->flush_n)) return -1;
+    }
+    cudaStream_t main_s = batches[0]->stream;
+    cudaEvent_t e0, e1;
+    std::vector<cudaEvent_t> done(nbatch);
+    CUDA_OK(cudaEventCreate(&e0)); CUDA_OK(cudaEventCreate(&e1));
+    for (auto &e : done) CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    int rc = 0;
+    for (int i = 0; i < nrep && 0 == rc; i++) {
+        for (int k = 0; k < nbatch; k++) if (cudaStreamSynchronize(batches[k]->stream) != cudaSuccess) rc = -1;
+        if (flush_l2) launch_flush(eng->flush_buf, eng->flush_n, main_s);
+        cudaEventRecord(e0, main_s);
+        for (int k = 1; k < nbatch; k++) cudaStreamWaitEvent(batches[k]->stream, e0, 0);
+        for (int k = 0; k < nbatch; k++) {
+            batches[k]->timing = (i == nrep - 1);
+            rc |= sb2_batch_forward(batches[k], p, true);
+            rc |= sb2_batch_decode(batches[k], p);
+            batches[k]->timing = false;
+            cudaEventRecord(done[k], batches[k]->stream);
+        }
+        for (int k = 1; k < nbatch; k++) cudaStreamWaitEvent(main_s, done[k], 0);
+        cudaEventRecord(e1, main_s);
+        if (cudaStreamSynchronize(main_s) != cudaSuccess) rc = -1;
+        if (rc) break;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (ms_out) ms_out[i] = ms;
+    }
+    if (0 == rc)
+        for (int k = 0; k < nbatch; k++)
+            for (int st = 0; st < ST_COUNT; st++)
+                cudaEventElapsedTime(&batches[k]->stage_ms[st], batches[k]->ev[st], batches[k]->ev[st + 1]);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    for (auto &e : done) cudaEventDestroy(e);
+    if (rc) { cudaError_t e = cudaGetLastError(); if (e != cudaSuccess) sb2_set_error("CUDA error %s in timed run", cudaGetErrorString(e)); }
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------
+// libscrappie single-read entry points (batches of one on a process-wide engine)
+// ------------------------------------------------------------------------------------
+
+static sb2_engine *default_engine() {
+    static std::mutex mu;
+    static sb2_engine *eng = nullptr;
+    static bool tried = false;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!tried) {
+        tried = true;
+        const char *dev = getenv("SCRAPPIE_B200_DEVICE");
+        eng = sb2_engine_create(dev ? atoi(dev) : 0, nullptr);
+    }
+    return eng;
+}
+
+static scrappie_matrix posterior_single(enum raw_model_type model, const raw_table signal, float min_prob,
+                                        float tempW, float tempb, bool return_log) {
+    if (0 == signal.n || nullptr == signal.raw || signal.end <= signal.start) return nullptr;
+    sb2_engine *eng = default_engine();
+    if (nullptr == eng) return nullptr;
+    const size_t n = signal.end - signal.start;
+    sb2_batch *b = sb2_batch_create(eng, model, &n, 1);
+    if (nullptr == b) return nullptr;
+    sb2_params p = sb2_default_params();
+    p.min_prob = min_prob; p.tempW = tempW; p.tempb = tempb;
+    const float *sig = signal.raw + signal.start;
+    scrappie_matrix post = nullptr;
+    if (0 == sb2_batch_upload(b, &sig) && 0 == sb2_batch_forward(b, &p, return_log)) {
+        post = make_scrappie_matrix(b->m->host.nstate, (size_t)b->nblock[0]);
+        if (post && 0 != sb2_batch_download_posterior(b, 0, post->data.f, post->stride)) post = free_scrappie_matrix(post);
+    }
+    sb2_batch_destroy(b);
+    return post;
+}
+
+extern "C" scrappie_matrix nanonet_rgrgr_r94_posterior(const raw_table signal, float min_prob, float tempW, float tempb, bool return_log) {
+    return posterior_single(SCRAPPIE_MODEL_RGRGR_R9_4, signal, min_prob, tempW, tempb, return_log);
+}
+extern "C" scrappie_matrix nanonet_rgrgr_r941_posterior(const raw_table signal, float min_prob, float tempW, float tempb, bool return_log) {
+    return posterior_single(SCRAPPIE_MODEL_RGRGR_R9_4_1, signal, min_prob, tempW, tempb, return_log);
+}
+extern "C" scrappie_matrix nanonet_rgrgr_r10_posterior(const raw_table signal, float min_prob, float tempW, float tempb, bool return_log) {
+    return posterior_single(SCRAPPIE_MODEL_RGRGR_R10, signal, min_prob, tempW, tempb, return_log);
+}
+extern "C" scrappie_matrix nanonet_rnnrf_r94_transitions(const raw_table signal, float min_prob, float tempW, float tempb, bool return_log) {
+    return posterior_single(SCRAPPIE_MODEL_RNNRF_R9_4, signal, min_prob, tempW, tempb, return_log);
+}
+
+static scrappie_matrix unsupported_raw_posterior(const raw_table, float, float, float, bool) {
+    sb2_set_error("raw_r94 is outside this engine's scope");
+    return nullptr;
+}
+
+extern "C" posterior_function_ptr get_posterior_function(const enum raw_model_type model) {
+    switch (model) {
+    case SCRAPPIE_MODEL_RAW: return unsupported_raw_posterior;
+    case SCRAPPIE_MODEL_RGRGR_R9_4: return nanonet_rgrgr_r94_posterior;
+    case SCRAPPIE_MODEL_RGRGR_R9_4_1: return nanonet_rgrgr_r941_posterior;
+    case SCRAPPIE_MODEL_RGRGR_R10: return nanonet_rgrgr_r10_posterior;
+    case SCRAPPIE_MODEL_RNNRF_R9_4: return nanonet_rnnrf_r94_transitions;
+    default:
+        fprintf(stderr, "Invalid scrappie model %s:%d\n", __FILE__, __LINE__);
+        exit(EXIT_FAILURE);
+    }
+}
+
+// Decoders on a host matrix: upload, run the kernel, download the path.
+struct DecodeScratch {
+    float *d_post = nullptr, *d_score = nullptr;
+    int *d_meta = nullptr, *d_tbE = nullptr, *d_path = nullptr;
+    uint8_t *d_tb = nullptr;
+    ~DecodeScratch() {
+        void *ptrs[] = {d_post, d_score, d_meta, d_tbE, d_path, d_tb};
+        for (void *p : ptrs) if (p) cudaFree(p);
+    }
+};
+
+static int decode_single(const_scrappie_matrix m, bool crf, float stay_pen, float skip_pen, float local_pen,
+                         bool allow_slip, int *seq, float *score_out) {
+    sb2_engine *eng = default_engine();
+    if (nullptr == eng) return -1;
+    CUDA_OK(cudaSetDevice(eng->device));
+    const size_t nb = m->nc, stride = m->stride;
+    const int nstate = (int)m->nr;
+    if (!crf && nstate != 1025 && nstate != 4097) { sb2_set_error("decode_transducer: %d states unsupported", nstate); return -1; }
+    if (crf && nstate != 25) { sb2_set_error("decode_crf: expected 25 transition rows"); return -1; }
+    DecodeScratch w;
+    const size_t tb_bytes = crf ? nb * 8 : nb * (size_t)(nstate - 1);
+    if (dev_alloc(&w.d_post, nb * stride) || dev_alloc(&w.d_score, 1) || dev_alloc(&w.d_meta, 4) ||
+        dev_alloc(&w.d_tbE, nb) || dev_alloc(&w.d_path, nb + 1) || dev_alloc(&w.d_tb, tb_bytes))
+        return -1;
+    const int meta[4] = {(int)nb, 0, (int)nb, 0};        // nblock[0]; col_off[0..1]
+    CUDA_OK(cudaMemcpy(w.d_meta, meta, sizeof(meta), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(w.d_post, m->data.f, nb * stride * sizeof(float), cudaMemcpyHostToDevice));
+    BatchDims d{};
+    d.nread = 1; d.total_cols = (int)nb; d.max_cols = (int)nb;
+    d.nblock = w.d_meta; d.col_off = w.d_meta + 1;
+    if (crf) launch_decode_crf(w.d_post, d, (int)stride, w.d_tb, w.d_path, w.d_score, 0);
+    else launch_decode_transducer(w.d_post, d, nstate, (int)stride, stay_pen, skip_pen, local_pen, allow_slip ? 1 : 0,
+                                  w.d_tb, w.d_tbE, w.d_path, w.d_score, 0);
+    eng->launches += 1;
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaMemcpy(seq, w.d_path, (nb + 1) * sizeof(int), cudaMemcpyDeviceToHost));
+    CUDA_OK(cudaMemcpy(score_out, w.d_score, sizeof(float), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" float decode_transducer(const_scrappie_matrix logpost, float stay_pen, float skip_pen, float local_pen,
+                                   int *seq, bool allow_slip) {
+    if (nullptr == logpost || nullptr == seq) return NAN;
+    float score = NAN;
+    if (0 != decode_single(logpost, false, stay_pen, skip_pen, local_pen, allow_slip, seq, &score)) return NAN;
+    return score;
+}
+
+extern "C" float decode_crf(const_scrappie_matrix trans, int *path) {
+    if (nullptr == trans || nullptr == path) return NAN;
+    float score = NAN;
+    if (0 != decode_single(trans, true, 0.f, 0.f, 0.f, false, path, &score)) return NAN;
+    return score;
+}

@@ -1,0 +1,66 @@
+// Launchers of the CUDA kernels (C++ linkage, internal to the library).
+//
+// Device layout of a batch: reads are concatenated.  Read r owns samples
+// [samp_off[r], samp_off[r] + nsample[r]) of `raw` and columns ("blocks")
+// [col_off[r], col_off[r] + nblock[r]) of every activation matrix.  Activations are
+// column-major like the reference's scrappie_matrix: one column = one time step, the
+// features of a column are contiguous ([total_cols][nfeature], no padding lanes except
+// in the posterior, which keeps the reference's stride = 4 * ceil(nstate / 4)).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "sb2_internal.h"
+
+namespace sb2 {
+
+struct BatchDims {
+    int nread;
+    int total_cols;
+    int max_cols;                   // longest read of the batch, in columns
+    const int *nsample;             // device [nread]
+    const int *nblock;              // device [nread]
+    const int64_t *samp_off;        // device [nread]
+    const int *col_off;             // device [nread + 1]
+    const int *col_read;            // device [total_cols]: owning read of each column (may be null)
+};
+
+// conv + activation (src/layers.c:159-246 + :60-68 / :15-24)
+void launch_conv_act(const float *raw, const BatchDims &d, const sb2_conv_tail *tails,
+                     const float *taps /*[winlen][nf]*/, const float *bias, int winlen, int nf,
+                     int stride, int act, float *out, cudaStream_t s);
+
+// C[col][m] = f((b[m] + sum_k W[m][k] * (X[col][k] / xdiv)) / cdiv), f = identity or exp
+// (affine_map src/scrappie_matrix.c:323-351; softmax_with_temperature src/layers.c:340-357)
+void launch_affine(const float *X, int ncol, int K, const float *W, int ldw, const float *b, int M,
+                   float *C, int ldc, float xdiv, float cdiv, int do_exp, cudaStream_t s);
+
+// row_normalise_inplace + robustlog_activation_inplace (src/scrappie_matrix.c:385-407,
+// src/layers.c:79-94) over the exp'd head output, padding lanes included
+void launch_softmax_finish(float *post, int ncol, int nstate, int ostride, float min_prob,
+                           int return_log, cudaStream_t s);
+
+// gru_forward / gru_backward (src/layers.c:373-527), fp32 FFMA path
+void launch_gru_scan_ffma(const float *Xin, const float *sW, const float *sW2, const float *resid,
+                          float *out, const BatchDims &d, int H, int backward, cudaStream_t s);
+
+// globalnorm (src/layers.c:835-889): trans -= logZ / T per read
+void launch_globalnorm(float *trans, const BatchDims &d, int ostride, cudaStream_t s);
+
+// decode_transducer + viterbi_local_backtrace (src/decode.c:58-98, :123-365)
+void launch_decode_transducer(const float *post, const BatchDims &d, int nstate, int ostride,
+                              float stay_pen, float skip_pen, float local_pen, int allow_slip,
+                              uint8_t *tb, int *tb_end, int *path, float *score, cudaStream_t s);
+
+// decode_crf (src/decode.c:836-893)
+void launch_decode_crf(const float *trans, const BatchDims &d, int ostride, uint8_t *tb, int *path,
+                       float *score, cudaStream_t s);
+
+// gather post[col][state] pairs (homopolymer fix-up needs a few posterior entries)
+void launch_gather(const float *post, int ostride, const int *cols, const int *states, int n,
+                   float *out, cudaStream_t s);
+
+// overwrite a buffer larger than L2 (benchmark hygiene)
+void launch_flush(float *buf, size_t nfloat, cudaStream_t s);
+
+}  // namespace sb2

@@ -1,0 +1,628 @@
+// First-generation CUDA kernels of the raw basecalling path (fp32 CUDA-core arithmetic).
+// They are the correctness baseline for the tcgen05 kernels in kernels_tc.cu and stay
+// selectable at run time (SCRAPPIE_B200_SCAN=ffma, SCRAPPIE_B200_GEMM=ffma).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "device_math.cuh"
+#include "kernels.h"
+
+namespace sb2 {
+
+// ---------------------------------------------------------------------------------
+// convolution + activation
+// ---------------------------------------------------------------------------------
+// One CTA = CONV_CPB consecutive output columns of one read.  Taps are staged in shared
+// memory transposed to [tap][filter] so that a warp reads consecutive filters; the
+// samples a CTA needs are staged once.  Columns in the read's tail follow the explicit
+// plan (see sb2_conv_plan), everything else is a zero padded same-convolution window.
+constexpr int CONV_CPB = 64;
+
+__global__ void __launch_bounds__(256)
+conv_act_kernel(const float *__restrict__ raw, BatchDims d, const sb2_conv_tail *__restrict__ tails,
+                const float *__restrict__ taps, const float *__restrict__ bias, int winlen, int nf,
+                int nfp, int stride, int act, float *__restrict__ out) {
+    extern __shared__ float smem[];
+    const int r = blockIdx.y;
+    const int ncol = d.nblock[r];
+    const int c0 = blockIdx.x * CONV_CPB;
+    if (c0 >= ncol) return;
+    const int n = d.nsample[r];
+    const float *x = raw + d.samp_off[r];
+    const sb2_conv_tail *tail = tails + r;
+    const int padL = (winlen - 1) / 2;
+
+    float *s_taps = smem;                               // [winlen][nf]
+    float *s_x = smem + winlen * nf;                    // samples [xlo, xlo + nx)
+    const int nx = (CONV_CPB - 1) * stride + winlen;
+    const int xlo = c0 * stride - padL;
+    for (int i = threadIdx.x; i < winlen * nf; i += blockDim.x) s_taps[i] = taps[i];
+    for (int i = threadIdx.x; i < nx; i += blockDim.x) {
+        const int xi = xlo + i;
+        s_x[i] = (xi >= 0 && xi < n) ? x[xi] : 0.0f;
+    }
+    __syncthreads();
+
+    const int f = threadIdx.x % nfp;
+    const int lane = threadIdx.x / nfp;
+    const int nlane = blockDim.x / nfp;
+    if (f >= nf || lane >= nlane) return;
+    const float bf = bias[f];
+    const int first_tail = tail->first_col;
+    for (int cc = lane; cc < CONV_CPB; cc += nlane) {
+        const int c = c0 + cc;
+        if (c >= ncol) break;
+        float acc = 0.0f;
+        if (c < first_tail) {
+            int x0 = c * stride - padL, tap0 = 0;
+            if (x0 < 0) { tap0 = -x0; x0 = 0; }
+            for (int k = tap0; k < winlen; k++) acc = fmaf(s_taps[k * nf + f], s_x[x0 - xlo + (k - tap0)], acc);
+        } else {
+            const int tc = c - first_tail;
+            const int nseg = tail->nseg[tc];
+            for (int sg = 0; sg < nseg; sg++) {
+                const int x0 = tail->seg[tc][sg][0], tap0 = tail->seg[tc][sg][1], ntap = tail->seg[tc][sg][2];
+                float part = 0.0f;
+                for (int k = 0; k < ntap; k++) part = fmaf(s_taps[(tap0 + k) * nf + f], x[x0 + k], part);
+                acc += part;
+            }
+        }
+        float v = bf + acc;
+        v = (act == 0) ? elu_cephes(v) : tanh_cephes(v);
+        out[(size_t)(d.col_off[r] + c) * nf + f] = v;
+    }
+}
+
+void launch_conv_act(const float *raw, const BatchDims &d, const sb2_conv_tail *tails, const float *taps,
+                     const float *bias, int winlen, int nf, int stride, int act, float *out,
+                     cudaStream_t s) {
+    const int nfp = (nf + 31) / 32 * 32;
+    dim3 grid((d.max_cols + CONV_CPB - 1) / CONV_CPB, d.nread);
+    const size_t smem = (size_t)(winlen * nf + (CONV_CPB - 1) * stride + winlen) * sizeof(float);
+    conv_act_kernel<<<grid, 256, smem, s>>>(raw, d, tails, taps, bias, winlen, nf, nfp, stride, act, out);
+}
+
+// ---------------------------------------------------------------------------------
+// affine map  C = f((b + W^T X) / cdiv)   (fp32 register-tiled GEMM)
+// ---------------------------------------------------------------------------------
+constexpr int AF_BM = 96;       // output rows per CTA
+constexpr int AF_BN = 128;      // columns per CTA
+constexpr int AF_KC = 32;       // K chunk
+constexpr int AF_XS = AF_BN + 4;
+
+__global__ void __launch_bounds__(256)
+affine_kernel(const float *__restrict__ X, int ncol, int K, const float *__restrict__ W, int ldw,
+              const float *__restrict__ b, int M, float *__restrict__ C, int ldc, float xdiv,
+              float cdiv, int do_exp) {
+    __shared__ __align__(16) float Ws[AF_KC][AF_BM];
+    __shared__ __align__(16) float Xs[AF_KC][AF_XS];
+    const int m_base = blockIdx.y * AF_BM;
+    const int n_base = blockIdx.x * AF_BN;
+    const int tm = threadIdx.x % 16, tn = threadIdx.x / 16;
+    const int m0 = tm * 6, n0 = tn * 8;
+    float acc[6][8];
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[i][j] = 0.0f;
+
+    for (int k0 = 0; k0 < K; k0 += AF_KC) {
+        // W chunk -> Ws[k][m]   (consecutive threads take consecutive rows: conflict-free stores)
+        for (int idx = threadIdx.x; idx < AF_BM * (AF_KC / 4); idx += 256) {
+            const int m = idx % AF_BM, k4 = idx / AF_BM;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m_base + m < M && k0 + 4 * k4 < K)
+                v = *reinterpret_cast<const float4 *>(W + (size_t)(m_base + m) * ldw + k0 + 4 * k4);
+            Ws[4 * k4 + 0][m] = v.x; Ws[4 * k4 + 1][m] = v.y; Ws[4 * k4 + 2][m] = v.z; Ws[4 * k4 + 3][m] = v.w;
+        }
+        for (int idx = threadIdx.x; idx < AF_BN * (AF_KC / 4); idx += 256) {
+            const int c = idx % AF_BN, k4 = idx / AF_BN;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n_base + c < ncol && k0 + 4 * k4 < K)
+                v = *reinterpret_cast<const float4 *>(X + (size_t)(n_base + c) * K + k0 + 4 * k4);
+            Xs[4 * k4 + 0][c] = v.x / xdiv; Xs[4 * k4 + 1][c] = v.y / xdiv;
+            Xs[4 * k4 + 2][c] = v.z / xdiv; Xs[4 * k4 + 3][c] = v.w / xdiv;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int k = 0; k < AF_KC; k++) {
+            float a[6], bb[8];
+            const float2 a0 = *reinterpret_cast<const float2 *>(&Ws[k][m0]);
+            const float2 a1 = *reinterpret_cast<const float2 *>(&Ws[k][m0 + 2]);
+            const float2 a2 = *reinterpret_cast<const float2 *>(&Ws[k][m0 + 4]);
+            a[0] = a0.x; a[1] = a0.y; a[2] = a1.x; a[3] = a1.y; a[4] = a2.x; a[5] = a2.y;
+            const float4 b0 = *reinterpret_cast<const float4 *>(&Xs[k][n0]);
+            const float4 b1 = *reinterpret_cast<const float4 *>(&Xs[k][n0 + 4]);
+            bb[0] = b0.x; bb[1] = b0.y; bb[2] = b0.z; bb[3] = b0.w;
+            bb[4] = b1.x; bb[5] = b1.y; bb[6] = b1.z; bb[7] = b1.w;
+#pragma unroll
+            for (int i = 0; i < 6; i++)
+#pragma unroll
+                for (int j = 0; j < 8; j++) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const int c = n_base + n0 + j;
+        if (c >= ncol) continue;
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+            const int m = m_base + m0 + i;
+            if (m >= M) continue;
+            float v = (b[m] + acc[i][j]) / cdiv;
+            if (do_exp) v = exp_cephes(v);
+            C[(size_t)c * ldc + m] = v;
+        }
+    }
+}
+
+void launch_affine(const float *X, int ncol, int K, const float *W, int ldw, const float *b, int M,
+                   float *C, int ldc, float xdiv, float cdiv, int do_exp, cudaStream_t s) {
+    dim3 grid((ncol + AF_BN - 1) / AF_BN, (M + AF_BM - 1) / AF_BM);
+    affine_kernel<<<grid, 256, 0, s>>>(X, ncol, K, W, ldw, b, M, C, ldc, xdiv, cdiv, do_exp);
+}
+
+// ---------------------------------------------------------------------------------
+// softmax normalisation + robust log, one warp per column
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+softmax_finish_kernel(float *__restrict__ post, int ncol, int nstate, int ostride, float min_prob,
+                      int return_log) {
+    const int col = blockIdx.x * 8 + threadIdx.x / 32;
+    const int lane = threadIdx.x % 32;
+    if (col >= ncol) return;
+    float *p = post + (size_t)col * ostride;
+    float sum = 0.0f;
+    for (int k = lane; k < nstate; k += 32) sum += p[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float recip = __fdiv_rn(1.0f, sum);
+    const float keep = __fsub_rn(1.0f, min_prob);
+    for (int k = lane; k < ostride; k += 32) {
+        // padding lanes hold exp(0) = 1 in the reference and are scaled like the rest
+        float v = __fmul_rn((k < nstate) ? p[k] : 1.0f, recip);
+        if (return_log) v = log_cephes(__fadd_rn(min_prob, __fmul_rn(keep, v)));
+        p[k] = v;
+    }
+}
+
+void launch_softmax_finish(float *post, int ncol, int nstate, int ostride, float min_prob,
+                           int return_log, cudaStream_t s) {
+    softmax_finish_kernel<<<(ncol + 7) / 8, 256, 0, s>>>(post, ncol, nstate, ostride, min_prob, return_log);
+}
+
+// ---------------------------------------------------------------------------------
+// GRU scan, fp32 CUDA cores: weights live in registers for the whole layer
+// ---------------------------------------------------------------------------------
+// One CTA = GRU_R reads stepping together; 3H threads.  Thread k < 2H owns row k of sW
+// (update / reset gates), thread 2H + j owns row j of sW2 (candidate).  Per step:
+//   phase 1  g = sigma(x[0:2H] + sW^T h);  z -> smem, r*h -> smem
+//   phase 2  c = tanh(x[2H:3H] + sW2^T (r*h));  h' = z*h + (1-z)*c
+// The hidden state is double buffered in shared memory as [H][GRU_R] so that a thread
+// fetches the state of all reads for one input index with two 16-byte broadcasts.
+constexpr int GRU_R = 8;
+
+template <int H>
+__global__ void __launch_bounds__(3 * H, 1)
+gru_scan_ffma_kernel(const float *__restrict__ Xin, const float *__restrict__ sW,
+                     const float *__restrict__ sW2, const float *__restrict__ resid,
+                     float *__restrict__ out, BatchDims d, int backward) {
+    __shared__ __align__(16) float hs[2][H][GRU_R];
+    __shared__ __align__(16) float rhs[H][GRU_R];
+    __shared__ __align__(16) float zs[H][GRU_R];
+    __shared__ int s_T[GRU_R], s_col[GRU_R];
+
+    const int k = threadIdx.x;
+    const int r0 = blockIdx.x * GRU_R;
+    if (k < GRU_R) {
+        const int r = r0 + k;
+        s_T[k] = (r < d.nread) ? d.nblock[r] : 0;
+        s_col[k] = (r < d.nread) ? d.col_off[r] : 0;
+    }
+    for (int i = k; i < 2 * H * GRU_R; i += 3 * H) (&hs[0][0][0])[i] = 0.0f;
+
+    float w[H];
+    {
+        const float *row = (k < 2 * H) ? (sW + (size_t)k * H) : (sW2 + (size_t)(k - 2 * H) * H);
+#pragma unroll
+        for (int i = 0; i < H; i += 4) {
+            const float4 v = *reinterpret_cast<const float4 *>(row + i);
+            w[i] = v.x; w[i + 1] = v.y; w[i + 2] = v.z; w[i + 3] = v.w;
+        }
+    }
+    __syncthreads();
+    int T[GRU_R], col[GRU_R], Tmax = 0;
+#pragma unroll
+    for (int r = 0; r < GRU_R; r++) { T[r] = s_T[r]; col[r] = s_col[r]; Tmax = max(Tmax, T[r]); }
+
+    float xn[GRU_R];
+#pragma unroll
+    for (int r = 0; r < GRU_R; r++) {
+        const int t = backward ? (T[r] - 1) : 0;
+        xn[r] = (T[r] > 0) ? Xin[(size_t)(col[r] + t) * (3 * H) + k] : 0.0f;
+    }
+
+    for (int s = 0; s < Tmax; s++) {
+        const int cur = s & 1;
+        float x[GRU_R];
+#pragma unroll
+        for (int r = 0; r < GRU_R; r++) x[r] = xn[r];
+        if (s + 1 < Tmax) {
+#pragma unroll
+            for (int r = 0; r < GRU_R; r++) {
+                const int t = backward ? (T[r] - 2 - s) : (s + 1);
+                xn[r] = (s + 1 < T[r]) ? Xin[(size_t)(col[r] + t) * (3 * H) + k] : 0.0f;
+            }
+        }
+        float acc[GRU_R];
+#pragma unroll
+        for (int r = 0; r < GRU_R; r++) acc[r] = 0.0f;
+
+        if (k < 2 * H) {
+#pragma unroll
+            for (int i = 0; i < H; i++) {
+                const float4 ha = *reinterpret_cast<const float4 *>(&hs[cur][i][0]);
+                const float4 hb = *reinterpret_cast<const float4 *>(&hs[cur][i][4]);
+                acc[0] = fmaf(w[i], ha.x, acc[0]); acc[1] = fmaf(w[i], ha.y, acc[1]);
+                acc[2] = fmaf(w[i], ha.z, acc[2]); acc[3] = fmaf(w[i], ha.w, acc[3]);
+                acc[4] = fmaf(w[i], hb.x, acc[4]); acc[5] = fmaf(w[i], hb.y, acc[5]);
+                acc[6] = fmaf(w[i], hb.z, acc[6]); acc[7] = fmaf(w[i], hb.w, acc[7]);
+            }
+            if (k < H) {
+#pragma unroll
+                for (int r = 0; r < GRU_R; r++) zs[k][r] = logistic_cephes(x[r] + acc[r]);
+            } else {
+#pragma unroll
+                for (int r = 0; r < GRU_R; r++) rhs[k - H][r] = logistic_cephes(x[r] + acc[r]) * hs[cur][k - H][r];
+            }
+        }
+        __syncthreads();
+        if (k >= 2 * H) {
+            const int j = k - 2 * H;
+#pragma unroll
+            for (int i = 0; i < H; i++) {
+                const float4 ha = *reinterpret_cast<const float4 *>(&rhs[i][0]);
+                const float4 hb = *reinterpret_cast<const float4 *>(&rhs[i][4]);
+                acc[0] = fmaf(w[i], ha.x, acc[0]); acc[1] = fmaf(w[i], ha.y, acc[1]);
+                acc[2] = fmaf(w[i], ha.z, acc[2]); acc[3] = fmaf(w[i], ha.w, acc[3]);
+                acc[4] = fmaf(w[i], hb.x, acc[4]); acc[5] = fmaf(w[i], hb.y, acc[5]);
+                acc[6] = fmaf(w[i], hb.z, acc[6]); acc[7] = fmaf(w[i], hb.w, acc[7]);
+            }
+#pragma unroll
+            for (int r = 0; r < GRU_R; r++) {
+                const float cand = tanh_cephes(x[r] + acc[r]);
+                const float z = zs[j][r];
+                const float hn = z * hs[cur][j][r] + (1.0f - z) * cand;
+                hs[cur ^ 1][j][r] = hn;
+                if (s < T[r]) {
+                    const int t = backward ? (T[r] - 1 - s) : s;
+                    const size_t o = (size_t)(col[r] + t) * H + j;
+                    out[o] = (resid != nullptr) ? hn + resid[o] : hn;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+void launch_gru_scan_ffma(const float *Xin, const float *sW, const float *sW2, const float *resid,
+                          float *out, const BatchDims &d, int H, int backward, cudaStream_t s) {
+    const int grid = (d.nread + GRU_R - 1) / GRU_R;
+    if (H == 96)
+        gru_scan_ffma_kernel<96><<<grid, 288, 0, s>>>(Xin, sW, sW2, resid, out, d, backward);
+    else if (H == 112)
+        gru_scan_ffma_kernel<112><<<grid, 336, 0, s>>>(Xin, sW, sW2, resid, out, d, backward);
+}
+
+// ---------------------------------------------------------------------------------
+// CRF: global normalisation and Viterbi, one warp per read
+// ---------------------------------------------------------------------------------
+// Lane l < 25 owns transition (to = l / 5, from = l % 5).  The 5-vector of forward
+// scores is replicated in every lane.
+__device__ __forceinline__ float pick5(const float (&v)[5], int i) {
+    float r = v[0];
+    r = (i == 1) ? v[1] : r; r = (i == 2) ? v[2] : r; r = (i == 3) ? v[3] : r; r = (i == 4) ? v[4] : r;
+    return r;
+}
+
+__global__ void __launch_bounds__(128)
+globalnorm_kernel(float *__restrict__ trans, BatchDims d, int ostride) {
+    const int r = blockIdx.x * 4 + threadIdx.x / 32;
+    const int lane = threadIdx.x % 32;
+    if (r >= d.nread) return;
+    const int T = d.nblock[r];
+    float *tr = trans + (size_t)d.col_off[r] * ostride;
+    const int l = (lane < 25) ? lane : 24;
+    const int to = l / 5, from = l % 5;
+    float prev[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    float nxt = (T > 0) ? tr[l] : 0.0f;
+    for (int t = 0; t < T; t++) {
+        const float e = nxt;
+        if (t + 1 < T) nxt = tr[(size_t)(t + 1) * ostride + l];
+        const float a = e + pick5(prev, from);
+        float v = __shfl_sync(0xffffffffu, a, to * 5);
+#pragma unroll
+        for (int f = 1; f < 5; f++) v = logsumexp2(v, __shfl_sync(0xffffffffu, a, to * 5 + f));
+#pragma unroll
+        for (int q = 0; q < 5; q++) prev[q] = __shfl_sync(0xffffffffu, v, q * 5);
+    }
+    float logZ = prev[0];
+#pragma unroll
+    for (int q = 1; q < 5; q++) logZ = logsumexp2(logZ, prev[q]);
+    logZ = logZ / (float)T;
+    for (int t = 0; t < T; t++)
+        if (lane < 25) tr[(size_t)t * ostride + lane] -= logZ;
+}
+
+void launch_globalnorm(float *trans, const BatchDims &d, int ostride, cudaStream_t s) {
+    globalnorm_kernel<<<(d.nread + 3) / 4, 128, 0, s>>>(trans, d, ostride);
+}
+
+__global__ void __launch_bounds__(128)
+decode_crf_kernel(const float *__restrict__ trans, BatchDims d, int ostride, uint8_t *__restrict__ tb,
+                  int *__restrict__ path, float *__restrict__ score) {
+    const int r = blockIdx.x * 4 + threadIdx.x / 32;
+    const int lane = threadIdx.x % 32;
+    if (r >= d.nread) return;
+    const int T = d.nblock[r];
+    const float *tr = trans + (size_t)d.col_off[r] * ostride;
+    uint8_t *tbr = tb + (size_t)d.col_off[r] * 8;
+    const int l = (lane < 25) ? lane : 24;
+    const int to = l / 5, from = l % 5;
+    float prev[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    float nxt = (T > 0) ? tr[l] : 0.0f;
+    for (int t = 0; t < T; t++) {
+        const float e = nxt;
+        if (t + 1 < T) nxt = tr[(size_t)(t + 1) * ostride + l];
+        const float a = e + pick5(prev, from);
+        float best = __shfl_sync(0xffffffffu, a, to * 5);
+        int arg = 0;
+#pragma unroll
+        for (int f = 1; f < 5; f++) {
+            const float c = __shfl_sync(0xffffffffu, a, to * 5 + f);
+            if (c > best) { best = c; arg = f; }           // strict: lowest `from` wins ties
+        }
+        if (lane < 25 && from == 0) tbr[(size_t)t * 8 + to] = (uint8_t)arg;
+#pragma unroll
+        for (int q = 0; q < 5; q++) prev[q] = __shfl_sync(0xffffffffu, best, q * 5);
+    }
+    __syncwarp();
+    if (lane == 0) {
+        int last = 0;
+        for (int q = 1; q < 5; q++) if (prev[q] > prev[last]) last = q;
+        score[r] = pick5(prev, last);
+        int *p = path + d.col_off[r] + r;
+        p[T] = last;
+        for (int t = T; t > 0; t--) {
+            last = tbr[(size_t)(t - 1) * 8 + last];
+            p[t - 1] = last;
+        }
+    }
+}
+
+void launch_decode_crf(const float *trans, const BatchDims &d, int ostride, uint8_t *tb, int *path,
+                       float *score, cudaStream_t s) {
+    decode_crf_kernel<<<(d.nread + 3) / 4, 128, 0, s>>>(trans, d, ostride, tb, path, score);
+}
+
+// ---------------------------------------------------------------------------------
+// transducer Viterbi: one CTA per read, NH / 4 threads, 4 consecutive states per thread
+// ---------------------------------------------------------------------------------
+// Traceback is one byte per (block, state): 0 stay, 1+r step from r*NH/4 + i/4,
+// 5+r skip from r*NH/16 + i/16, 21+r slip from r*NH/64 + i/64, 85 from the start state.
+// The end state's predecessor is a separate int per block.  All comparisons are the
+// strict ones of the reference, evaluated in its order (stay, step, skip, slip, start),
+// and every maximum keeps the lowest index, so the result is bit-identical.
+constexpr float DEC_BIG = 1.e30f;
+enum { TB_STAY = 0, TB_STEP = 1, TB_SKIP = 5, TB_SLIP = 21, TB_START = 85 };
+
+template <int NH>
+__global__ void __launch_bounds__(NH / 4)
+decode_transducer_kernel(const float *__restrict__ post, BatchDims d, int ostride, float stay_pen,
+                         float skip_pen, float local_pen, int allow_slip, uint8_t *__restrict__ tb,
+                         int *__restrict__ tb_end, int *__restrict__ path, float *__restrict__ score) {
+    constexpr int NT = NH / 4;
+    constexpr int NW = NT / 32;
+    __shared__ __align__(16) float sc[2][NH];
+    __shared__ float w_val[2][NW];
+    __shared__ int w_idx[2][NW];
+    __shared__ float fin_val[NW];
+    __shared__ int fin_idx[NW];
+
+    const int r = blockIdx.x;
+    const int t = threadIdx.x;
+    const int lane = t % 32, warp = t / 32;
+    const int T = d.nblock[r];
+    const float *lp = post + (size_t)d.col_off[r] * ostride;
+    uint8_t *tbr = tb + (size_t)d.col_off[r] * NH;
+    int *tbe = tb_end + d.col_off[r];
+    const float slip_pen = (float)(2.0 * (double)skip_pen);
+
+    float cur[4] = {-DEC_BIG, -DEC_BIG, -DEC_BIG, -DEC_BIG};
+    float curS = 0.0f, curE = -DEC_BIG;         // replicated in every thread
+    float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
+    float nxt_stay = 0.0f;
+    if (T > 0) {
+        nxt = *reinterpret_cast<const float4 *>(lp + 4 * t);
+        nxt_stay = lp[NH];
+    }
+    for (int blk = 0; blk < T; blk++) {
+        const int buf = blk & 1;
+        const float4 l4 = nxt;
+        const float lstay = nxt_stay;
+        if (blk + 1 < T) {
+            nxt = *reinterpret_cast<const float4 *>(lp + (size_t)(blk + 1) * ostride + 4 * t);
+            nxt_stay = lp[(size_t)(blk + 1) * ostride + NH];
+        }
+        // publish the previous scores; find this warp's best "enter end" candidate
+        *reinterpret_cast<float4 *>(&sc[buf][4 * t]) = make_float4(cur[0], cur[1], cur[2], cur[3]);
+        {
+            float bv = cur[0] - local_pen;
+            int bi = 4 * t;
+#pragma unroll
+            for (int j = 1; j < 4; j++) {
+                const float v = cur[j] - local_pen;
+                if (v > bv) { bv = v; bi = 4 * t + j; }
+            }
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            }
+            if (lane == 0) { w_val[buf][warp] = bv; w_idx[buf][warp] = bi; }
+        }
+        __syncthreads();
+
+        // end state: stay in it, or enter it from the best-scoring state (lowest index on ties)
+        {
+            float bv = w_val[buf][0];
+            int bi = w_idx[buf][0];
+#pragma unroll
+            for (int w = 1; w < NW; w++) {
+                const float v = w_val[buf][w];
+                const int i = w_idx[buf][w];
+                if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+            }
+            const float hold = fmaxf(-local_pen, lstay - stay_pen);
+            float e = curE + hold;
+            int from = NH + 1;
+            if (bv > e) { e = bv; from = bi; }
+            if (t == 0) tbe[blk] = from;
+            curE = e;
+        }
+
+        const float *prev = sc[buf];
+        // step: best over the 4 states sharing suffix t
+        float b4 = prev[t];
+        int r4 = 0;
+#pragma unroll
+        for (int q = 1; q < 4; q++) {
+            const float v = prev[q * (NH / 4) + t];
+            if (b4 < v) { b4 = v; r4 = q; }
+        }
+        // skip: best over 16 states sharing suffix t / 4
+        float b16 = prev[t / 4];
+        int r16 = 0;
+#pragma unroll
+        for (int q = 1; q < 16; q++) {
+            const float v = prev[q * (NH / 16) + t / 4];
+            if (b16 < v) { b16 = v; r16 = q; }
+        }
+        float b64 = 0.0f;
+        int r64 = 0;
+        if (allow_slip) {
+            b64 = prev[t / 16];
+            for (int q = 1; q < 64; q++) {
+                const float v = prev[q * (NH / 64) + t / 16];
+                if (b64 < v) { b64 = v; r64 = q; }
+            }
+        }
+        const float stay = lstay - stay_pen;
+        const float lpj[4] = {l4.x, l4.y, l4.z, l4.w};
+        uint32_t codes = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            float s = cur[j] + stay;
+            uint32_t code = TB_STAY;
+            const float st = lpj[j] + b4;
+            if (s < st) { s = st; code = TB_STEP + r4; }
+            const float sk = (lpj[j] + b16) - skip_pen;
+            if (s < sk) { s = sk; code = TB_SKIP + r16; }
+            if (allow_slip) {
+                const float sl = (lpj[j] + b64) - slip_pen;
+                if (s < sl) { s = sl; code = TB_SLIP + r64; }
+            }
+            const float ss = curS + lpj[j];
+            if (ss > s) { s = ss; code = TB_START; }
+            cur[j] = s;
+            codes |= code << (8 * j);
+        }
+        *reinterpret_cast<uint32_t *>(tbr + (size_t)blk * NH + 4 * t) = codes;
+        curS = curS + fmaxf(-local_pen, lstay - stay_pen);
+    }
+
+    // final argmax over (states..., start, end): first maximum wins
+    {
+        float bv = cur[0];
+        int bi = 4 * t;
+#pragma unroll
+        for (int j = 1; j < 4; j++) if (cur[j] > bv) { bv = cur[j]; bi = 4 * t + j; }
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) { fin_val[warp] = bv; fin_idx[warp] = bi; }
+    }
+    __syncthreads();
+    if (t == 0) {
+        float bv = fin_val[0];
+        int last = fin_idx[0];
+        for (int w = 1; w < NW; w++)
+            if (fin_val[w] > bv || (fin_val[w] == bv && fin_idx[w] < last)) { bv = fin_val[w]; last = fin_idx[w]; }
+        if (curS > bv) { bv = curS; last = NH; }
+        if (curE > bv) { bv = curE; last = NH + 1; }
+        score[r] = bv;
+        int *seq = path + d.col_off[r] + r;
+        for (int blk = T - 1; blk >= 0; blk--) {
+            int out = -1;
+            if (last == NH) {
+                out = NH;                                   // start stays in start
+            } else if (last == NH + 1) {
+                out = NH + 1;
+                last = tbe[blk];
+            } else {
+                const int code = tbr[(size_t)blk * NH + last];
+                if (code != TB_STAY) {
+                    out = last;
+                    if (code >= TB_START) last = NH;
+                    else if (code >= TB_SLIP) last = (code - TB_SLIP) * (NH / 64) + last / 64;
+                    else if (code >= TB_SKIP) last = (code - TB_SKIP) * (NH / 16) + last / 16;
+                    else last = (code - TB_STEP) * (NH / 4) + last / 4;
+                }
+            }
+            seq[blk + 1] = out;
+        }
+        seq[0] = last;
+        for (int i = 0; i < T; i++) { if (seq[i] == NH) seq[i] = -1; else break; }
+        for (int i = T; i >= 0; i--) { if (seq[i] == NH + 1) seq[i] = -1; else break; }
+    }
+}
+
+void launch_decode_transducer(const float *post, const BatchDims &d, int nstate, int ostride,
+                              float stay_pen, float skip_pen, float local_pen, int allow_slip,
+                              uint8_t *tb, int *tb_end, int *path, float *score, cudaStream_t s) {
+    const int nh = nstate - 1;
+    if (nh == 1024)
+        decode_transducer_kernel<1024><<<d.nread, 256, 0, s>>>(post, d, ostride, stay_pen, skip_pen, local_pen,
+                                                              allow_slip, tb, tb_end, path, score);
+    else if (nh == 4096)
+        decode_transducer_kernel<4096><<<d.nread, 1024, 0, s>>>(post, d, ostride, stay_pen, skip_pen, local_pen,
+                                                               allow_slip, tb, tb_end, path, score);
+}
+
+// ---------------------------------------------------------------------------------
+// small utilities
+// ---------------------------------------------------------------------------------
+__global__ void gather_kernel(const float *__restrict__ post, int ostride, const int *__restrict__ cols,
+                              const int *__restrict__ states, int n, float *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = post[(size_t)cols[i] * ostride + states[i]];
+}
+
+void launch_gather(const float *post, int ostride, const int *cols, const int *states, int n, float *out,
+                   cudaStream_t s) {
+    if (n > 0) gather_kernel<<<(n + 255) / 256, 256, 0, s>>>(post, ostride, cols, states, n, out);
+}
+
+__global__ void flush_kernel(float *buf, size_t n) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) buf[i] = 1.0f;
+}
+
+void launch_flush(float *buf, size_t nfloat, cudaStream_t s) { flush_kernel<<<148 * 8, 256, 0, s>>>(buf, nfloat); }
+
+}  // namespace sb2

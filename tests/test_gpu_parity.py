@@ -1,0 +1,295 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI, against the CPU oracle on the
+same seeded inputs, against the committed reference fixtures, and -- at the benchmark's full
+size -- through size-independent properties.
+
+Tolerances (SURVEY.md section 0.5 / BASELINE north star): decoders bit-exact (integer path and
+fp32 score given the same posterior); posterior max-abs-err <= 1e-4 in log space, <= 1e-5 in
+probability space; base sequences identical to the reference's."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from conftest import bundled_signal
+from oracle.oracle import synthetic_read
+
+pytestmark = pytest.mark.gpu
+
+LOG_TOL = 1e-4
+PROB_TOL = 1e-5
+
+
+def robustlog(p, min_prob):
+    return np.log(np.float32(min_prob) + (np.float32(1) - np.float32(min_prob)) * p).astype(np.float32)
+
+
+# ----------------------------------------------------------------------------- network
+
+@pytest.mark.parametrize("model,n", [("rgrgr_r94", 1000), ("rgrgr_r94", 1003), ("rgrgr_r94", 997), ("rgrgr_r94", 500),
+                                     ("rgrgr_r94", 96), ("rnnrf_r94", 500), ("rnnrf_r94", 1003), ("rgrgr_r941", 1000),
+                                     ("rgrgr_r10", 600)])
+def test_posterior_vs_oracle_single_read_api(sb, oracle, model, n):
+    """nanonet_*_posterior through the libscrappie-compatible symbol."""
+    x = synthetic_read(1000 + n, n)
+    post = sb.calc_post(sb.RawTable(x), model, min_prob=1e-5)
+    got = post.padded()
+    want = oracle.posterior(model, x)
+    ns = oracle.nstate(model)
+    assert got.shape == want.shape and post.shape == (want.shape[0], ns)
+    assert np.abs(got[:, :ns] - want[:, :ns]).max() < LOG_TOL
+    if got.shape[1] > ns and model != "rnnrf_r94":       # padding lanes follow the reference too
+        assert np.abs(got[:, ns:] - want[:, ns:]).max() < LOG_TOL
+
+
+def test_posterior_probability_space(sb, oracle):
+    x = synthetic_read(4242, 1200)
+    got = sb.calc_post(sb.RawTable(x), "rgrgr_r94", min_prob=1e-5, log=False).padded()
+    want = oracle.posterior("rgrgr_r94", x, return_log=False)
+    assert np.abs(got[:, :1025] - want[:, :1025]).max() < PROB_TOL
+    np.testing.assert_allclose(got[:, :1025].sum(1), 1.0, atol=1e-5)
+
+
+def test_temperature_and_min_prob(sb, oracle):
+    x = synthetic_read(99, 800)
+    got = sb.calc_post(sb.RawTable(x), "rgrgr_r94", min_prob=1e-3, tempW=1.5, tempb=0.7).padded()
+    want = oracle.posterior("rgrgr_r94", x, min_prob=1e-3, tempW=1.5, tempb=0.7)
+    assert np.abs(got[:, :1025] - want[:, :1025]).max() < LOG_TOL
+
+
+def test_rnnrf_rejects_non_log(sb):
+    with pytest.raises(ValueError):
+        sb.calc_post(sb.RawTable(synthetic_read(1, 300)), "rnnrf_r94", log=False)
+
+
+@pytest.mark.parametrize("model", ["rgrgr_r94", "rnnrf_r94"])
+def test_layerwise_parity(sb, engine, oracle, model):
+    """conv+activation and each GRU layer against the oracle's per-layer dumps (ragged batch)."""
+    lens = [1000, 1003, 431, 97] if model == "rgrgr_r94" else [400, 403, 97]
+    sigs = [synthetic_read(300 + i, n) for i, n in enumerate(lens)]
+    b = engine.batch(model, lens)
+    b.keep_layers()
+    b.upload(sigs)
+    b.forward()
+    H = 96 if model == "rgrgr_r94" else 112
+    for i, s in enumerate(sigs):
+        _, layers = oracle.posterior(model, s, layers=True)
+        for l in range(6):
+            got = b.layer(l, i, H)
+            err = np.abs(got - layers[l]).max()
+            assert err < (2e-6 if l == 0 else 5e-5), (model, i, l, err)
+    b.close()
+
+
+def test_posterior_vs_reference_fixtures(sb, engine, golden):
+    g = golden.ref_synthetic
+    for key in ("rgrgr_r94_1000", "rgrgr_r94_1003", "rgrgr_r94_997", "rgrgr_r94_500", "rgrgr_r94_503", "rnnrf_r94_1003"):
+        model, n = key.rsplit("_", 1)
+        x = synthetic_read(1000 + int(n), int(n))
+        b = engine.batch(model, [len(x)])
+        b.upload([x])
+        b.forward()
+        b.decode()
+        ns = b.nstate
+        assert np.abs(b.posterior(0)[:, :ns] - g[key + "_post"][:, :ns]).max() < LOG_TOL
+        b.close()
+        (bases, score, nblock), = engine.basecall_batch(model, [x])
+        assert bases == str(g[key + "_bases"])
+        assert abs(score - float(g[key + "_score"])) < 5e-3
+
+
+# ----------------------------------------------------------------------------- decoders
+
+def test_upstream_decoder_known_answer_on_gpu(sb, golden):
+    """src/test/test_scrappie_decoding.c:69-98 through the CUDA decode_transducer."""
+    g = golden.upstream_decode
+    logpost = np.zeros((1000, 1028), dtype=np.float32)
+    logpost[:, :1025] = robustlog(g["posterior"], 1e-5)
+    m = sb.ScrappyMatrix.from_numpy(logpost, 1025)
+    score, path = sb.decode_path(m, "rgrgr_r94", 0.0, 0.0, 100.0)
+    assert abs(score - float(g["score_expected"])) < 1e-4
+    assert np.array_equal(path[1:], g["path"])
+
+
+@pytest.mark.parametrize("pens", [(0, 0, 2, False), (2, 0, 2, False), (0, 2, 2, False), (0.5, 1.0, 2, True),
+                                  (0, 0, 100, False), (0, 0, 0.5, True)])
+def test_transducer_decode_bit_exact(sb, oracle, golden, pens):
+    """Same posterior in -> identical path and identical fp32 score (test_decode_equivalent
+    of the reference, src/test/test_scrappie_decoding.c:33-67, plus slip)."""
+    g = golden.upstream_decode
+    logpost = np.zeros((1000, 1028), dtype=np.float32)
+    logpost[:, :1025] = robustlog(g["posterior"], 1e-5)
+    for post in (logpost, golden.ref_synthetic["rgrgr_r94_1003_post"]):
+        m = sb.ScrappyMatrix.from_numpy(post, 1025)
+        score, path = sb.decode_path(m, "rgrgr_r94", *pens)
+        oscore, opath = oracle.decode_transducer(post, 1025, *pens)
+        assert np.array_equal(path, opath)
+        assert score == oscore
+
+
+def test_decode_fixture_sweeps(sb, golden):
+    g = golden.ref_decode
+    post = golden.ref_synthetic[str(g["post_key"])]
+    m = sb.ScrappyMatrix.from_numpy(post, 1025)
+    for i in range(6):
+        stay, skip, local, slip = [float(v) for v in g["pens%d" % i]]
+        score, path = sb.decode_path(m, "rgrgr_r94", stay, skip, local, bool(slip))
+        assert score == float(g["score%d" % i]) and np.array_equal(path, g["path%d" % i])
+
+
+def test_transducer_decode_ties_and_extremes(sb, oracle):
+    """Tie-breaking: constant posteriors (every comparison ties), single block, all-stay."""
+    rng = np.random.default_rng(5)
+    cases = []
+    cases.append(np.full((50, 1028), np.float32(np.log(1.0 / 1025)), dtype=np.float32))
+    q = np.round(rng.normal(size=(200, 1028)) * 2).astype(np.float32) - 8       # heavy ties
+    cases.append(q)
+    cases.append(rng.normal(size=(1, 1028)).astype(np.float32) - 7)
+    stay = np.full((64, 1028), -12.0, dtype=np.float32)
+    stay[:, 1024] = -0.01
+    cases.append(stay)
+    for post in cases:
+        for pens in ((0, 0, 2, False), (0, 0, 2, True), (1, 1, 0.25, False)):
+            m = sb.ScrappyMatrix.from_numpy(post, 1025)
+            score, path = sb.decode_path(m, "rgrgr_r94", *pens)
+            oscore, opath = oracle.decode_transducer(post, 1025, *pens)
+            assert np.array_equal(path, opath) and score == oscore
+
+
+def test_transducer_decode_4096_states(sb, oracle):
+    rng = np.random.default_rng(9)
+    p = rng.dirichlet(np.ones(4097) * 0.02, size=120).astype(np.float32)
+    post = np.zeros((120, 4100), dtype=np.float32)
+    post[:, :4097] = robustlog(p, 1e-5)
+    m = sb.ScrappyMatrix.from_numpy(post, 4097)
+    for pens in ((0, 0, 2, False), (0, 1, 2, True)):
+        score, path = sb.decode_path(m, "rgrgr_r10", *pens)
+        oscore, opath = oracle.decode_transducer(post, 4097, *pens)
+        assert np.array_equal(path, opath) and score == oscore
+
+
+def test_crf_decode_bit_exact(sb, oracle, golden):
+    syn = golden.ref_synthetic
+    rng = np.random.default_rng(2)
+    ties = np.round(rng.normal(size=(300, 28)) * 2).astype(np.float32)
+    for trans in (syn["rnnrf_r94_1003_post"], syn["rnnrf_r94_500_post"], ties, ties[:1]):
+        m = sb.ScrappyMatrix.from_numpy(trans, 25)
+        score, path = sb.decode_path(m, "rnnrf_r94")
+        oscore, opath = oracle.decode_crf(trans)
+        assert np.array_equal(path, opath) and score == oscore
+    call, score, pos = sb.decode_post(sb.ScrappyMatrix.from_numpy(syn["rnnrf_r94_1003_post"], 25), "rnnrf_r94")
+    assert call == str(syn["rnnrf_r94_1003_bases"])
+
+
+# ----------------------------------------------------------------------------- whole reads
+
+@pytest.mark.parametrize("model", ["rgrgr_r94", "rnnrf_r94"])
+def test_bundled_reads_bit_identical_bases(sb, engine, golden, model):
+    """BASELINE config 1: the three bundled reads with CLI defaults -> identical base sequences
+    (md5s as in SURVEY.md section 8c), score within 0.02 of the reference's."""
+    g = golden.ref_reads
+    sigs = []
+    for i in range(3):
+        rt = sb.RawTable(bundled_signal(golden, i)).trim().scale()
+        assert [rt.start, rt.end] == list(g["r%d_trim" % i])
+        sigs.append(rt.data(as_numpy=True).copy())
+    calls = engine.basecall_batch(model, sigs)
+    for i, (bases, score, nblock) in enumerate(calls):
+        k = "r%d_%s" % (i, model)
+        assert hashlib.md5((bases + "\n").encode()).hexdigest() == str(g[k + "_md5"])
+        assert bases == str(g[k + "_bases"])
+        assert abs(score - float(g[k + "_score"])) < 0.02
+    # posterior spot check on the subsampled columns + Viterbi path equality
+    b = engine.batch(model, [len(s) for s in sigs])
+    b.upload(sigs)
+    b.forward()
+    b.decode()
+    paths, _ = b.paths()
+    for i in range(3):
+        k = "r%d_%s" % (i, model)
+        post = b.posterior(i)
+        ns = b.nstate
+        assert np.abs(post[g[k + "_post_cols"]][:, :ns] - g[k + "_post_sub"][:, :ns]).max() < LOG_TOL
+        want = g[k + "_path_nohp"] if model == "rgrgr_r94" else g[k + "_path"]
+        assert np.array_equal(paths[i], want)
+    b.close()
+
+
+def test_scrappy_style_basecall_raw(sb, golden):
+    """basecall_raw (python/test/test_scrappy.py:72-75 compares it with the CLI)."""
+    raw = bundled_signal(golden, 2)
+    seq, score, pos, start, end = sb.basecall_raw(raw, "rgrgr_r94")
+    rt = sb.RawTable(raw).trim().scale()
+    post = sb.calc_post(rt, "rgrgr_r94", min_prob=1e-6)
+    assert post.shape == (len(pos) - 1, 1025)
+    assert (end - start + 4) // 5 == post.shape[0]          # stride 5 (python/test/test_scrappy.py:46-48)
+    assert len(seq) == pos[-1] + 5
+
+
+def test_ragged_batch_equals_single_reads(sb, engine, oracle):
+    """Dynamic batching must not change results: a mixed-length batch vs each read alone."""
+    lens = [4000, 1000, 2503, 96, 777, 4001, 19, 3999, 1500, 20]
+    sigs = [synthetic_read(50 + i, n) for i, n in enumerate(lens)]
+    b = engine.batch("rgrgr_r94", lens)
+    b.upload(sigs)
+    b.forward()
+    b.decode()
+    paths, scores = b.paths()
+    for i in (0, 3, 6, 7, 9):
+        solo = engine.batch("rgrgr_r94", [lens[i]])
+        solo.upload([sigs[i]])
+        solo.forward()
+        solo.decode()
+        p1, s1 = solo.paths()
+        assert np.array_equal(b.posterior(i), solo.posterior(0))
+        assert np.array_equal(paths[i], p1[0]) and scores[i] == s1[0]
+        solo.close()
+    want = oracle.posterior("rgrgr_r94", sigs[6])
+    assert np.abs(b.posterior(6)[:, :1025] - want[:, :1025]).max() < LOG_TOL
+    b.close()
+
+
+def test_full_size_properties(sb, engine, oracle):
+    """BASELINE config 2 shape (256 reads x 4000 samples): determinism, batch-composition
+    invariance, path validity, decode == oracle decode on the GPU's own posterior."""
+    n, B = 4000, 256
+    sigs = [synthetic_read(1000 + i, n) for i in range(B)]
+    b = engine.batch("rgrgr_r94", [n] * B)
+    b.upload(sigs)
+    b.forward()
+    b.decode()
+    paths, scores = b.paths()
+    post17 = b.posterior(17)
+    b.forward()
+    b.decode()
+    paths2, scores2 = b.paths()
+    assert all(np.array_equal(a, c) for a, c in zip(paths, paths2)) and np.array_equal(scores, scores2)
+    assert np.array_equal(post17, b.posterior(17))
+    for p in paths:
+        assert p.shape == (801,) and p.min() >= -1 and p.max() < 1024
+    for i in (0, 17, 255):
+        post = b.posterior(i)
+        np.testing.assert_allclose(np.exp(post[:, :1025].astype(np.float64)).sum(1), 1.0 + 1025e-5 - 1e-5, atol=2e-4)
+        oscore, opath = oracle.decode_transducer(post, 1025)
+        assert np.array_equal(opath, paths[i]) and oscore == scores[i]
+    want = oracle.posterior("rgrgr_r94", sigs[255])
+    assert np.abs(b.posterior(255)[:, :1025] - want[:, :1025]).max() < LOG_TOL
+    b.close()
+    sub = engine.batch("rgrgr_r94", [n] * 3)
+    sub.upload([sigs[17], sigs[200], sigs[5]])
+    sub.forward()
+    sub.decode()
+    psub, ssub = sub.paths()
+    assert np.array_equal(sub.posterior(0), post17)
+    assert np.array_equal(psub[1], paths[200]) and ssub[2] == scores[5]
+    sub.close()
+
+
+def test_error_paths(sb, engine):
+    with pytest.raises(RuntimeError):
+        engine.batch("rgrgr_r94", [10])                  # shorter than the convolution window
+    with pytest.raises(RuntimeError):
+        engine.batch("raw_r94", [1000])                  # outside this engine's scope
+    rt = sb.RawTable(np.zeros(0, dtype=np.float32))
+    with pytest.raises(RuntimeError):
+        sb.calc_post(rt, "rgrgr_r94")
+    assert engine.launches > 0
