@@ -39,6 +39,8 @@ struct DevModel {
     float *conv_taps = nullptr, *conv_b = nullptr;
     float *iW[SB2_NLAYER]{}, *b[SB2_NLAYER]{}, *sW[SB2_NLAYER]{}, *sW2[SB2_NLAYER]{};
     float *FF_W = nullptr, *FF_b = nullptr;
+    uint8_t *scan_img[SB2_NLAYER]{};     // tensor-core scan: per-layer weight image
+    uint8_t *d_img_all = nullptr;
 };
 
 struct sb2_engine {
@@ -91,6 +93,19 @@ static int upload_model(sb2_engine *eng, DevModel *dm) {
         CUDA_OK(cudaMemcpy(dst, it.second.data(), it.second.size() * sizeof(float), cudaMemcpyHostToDevice));
         *it.first = dst;
         off += align_up(it.second.size() * sizeof(float), 256);
+    }
+    {   // tensor-core scan images
+        const size_t nb = align_up(scan_image_bytes((int)H), 256);
+        std::vector<uint8_t> img(nb * SB2_NLAYER, 0);
+        std::vector<float> sw, sw2;
+        for (int l = 0; l < SB2_NLAYER; l++) {
+            sw = compact(h.sW[l]);
+            sw2 = compact(h.sW2[l]);
+            build_scan_image(sw.data(), sw2.data(), (int)H, img.data() + nb * l);
+        }
+        CUDA_OK(cudaMalloc(&dm->d_img_all, img.size()));
+        CUDA_OK(cudaMemcpy(dm->d_img_all, img.data(), img.size(), cudaMemcpyHostToDevice));
+        for (int l = 0; l < SB2_NLAYER; l++) dm->scan_img[l] = dm->d_img_all + nb * l;
     }
     dm->loaded = true;
     return 0;
@@ -146,7 +161,9 @@ extern "C" sb2_engine *sb2_engine_create(int device, const char *weights_dir) {
     else if (0 != sb2_default_weights_dir(eng->weights_dir, sizeof(eng->weights_dir))) eng->weights_dir[0] = '\0';
     const char *scan = getenv("SCRAPPIE_B200_SCAN");
     const char *gemm = getenv("SCRAPPIE_B200_GEMM");
-    eng->scan_impl = (scan && 0 == strcmp(scan, "tc")) ? 1 : 0;
+    eng->scan_impl = 0;                                  // 0 ffma, 1 tcgen05 (cephes gates), 2 tcgen05 (SFU gates)
+    if (scan && 0 == strcmp(scan, "tc")) eng->scan_impl = 1;
+    if (scan && 0 == strcmp(scan, "tc_fast")) eng->scan_impl = 2;
     eng->gemm_impl = (gemm && 0 == strcmp(gemm, "tc")) ? 1 : 0;
     if (cudaSetDevice(device) != cudaSuccess) { delete eng; return nullptr; }
     return eng;
@@ -157,6 +174,7 @@ extern "C" void sb2_engine_destroy(sb2_engine *eng) {
     cudaSetDevice(eng->device);
     for (auto &dm : eng->models) {
         if (dm.d_all) cudaFree(dm.d_all);
+        if (dm.d_img_all) cudaFree(dm.d_img_all);
         sb2_host_model_free(&dm.host);
     }
     if (eng->flush_buf) cudaFree(eng->flush_buf);
@@ -359,8 +377,14 @@ extern "C" int sb2_batch_forward(sb2_batch *b, const sb2_params *p, bool return_
         stage_mark(b, ST_AFFINE(l));
         launch_affine(b->d_X[cur], b->total_cols, H, m.iW[l], H, m.b[l], 3 * H, b->d_Xin, 3 * H, 1.0f, 1.0f, 0, s);
         stage_mark(b, ST_SCAN(l));
-        launch_gru_scan_ffma(b->d_Xin, m.sW[l], m.sW2[l], h.residual ? b->d_X[cur] : nullptr, b->d_X[cur ^ 1],
-                             b->dims, H, (l % 2) == 0, s);
+        if (b->eng->scan_impl == 0) {
+            launch_gru_scan_ffma(b->d_Xin, m.sW[l], m.sW2[l], h.residual ? b->d_X[cur] : nullptr, b->d_X[cur ^ 1],
+                                 b->dims, H, (l % 2) == 0, s);
+        } else if (0 != launch_gru_scan_tc(b->d_Xin, m.scan_img[l], h.residual ? b->d_X[cur] : nullptr, b->d_X[cur ^ 1],
+                                           b->dims, H, (l % 2) == 0, b->eng->scan_impl == 2, s)) {
+            sb2_set_error("tensor-core scan kernel could not be configured");
+            return -1;
+        }
         nl += 2;
         cur ^= 1;
         if (b->keep_layers)
@@ -758,4 +782,41 @@ extern "C" float decode_crf(const_scrappie_matrix trans, int *path) {
     float score = NAN;
     if (0 != decode_single(trans, true, 0.f, 0.f, 0.f, false, path, &score)) return NAN;
     return score;
+}
+
+// ------------------------------------------------------------------------------------
+// tensor-core self test (descriptor / layout validation and latency probe)
+// ------------------------------------------------------------------------------------
+extern "C" int sb2_tc_selftest(int K, int N, int reps, float *max_abs_err, long long *cycles3) {
+    sb2_engine *eng = default_engine();
+    if (nullptr == eng) return -1;
+    CUDA_OK(cudaSetDevice(eng->device));
+    std::vector<float> A((size_t)128 * K), B((size_t)N * K), D((size_t)128 * N);
+    uint32_t seed = 12345u;
+    auto rnd = [&]() { seed = seed * 1664525u + 1013904223u; return ((seed >> 8) & 0xFFFF) / 32768.0f - 1.0f; };
+    for (auto &v : A) v = rnd() * 2.0f;
+    for (auto &v : B) v = rnd();
+    float *dA = nullptr, *dB = nullptr, *dD = nullptr;
+    long long *dC = nullptr;
+    if (dev_alloc(&dA, A.size()) || dev_alloc(&dB, B.size()) || dev_alloc(&dD, D.size()) || dev_alloc(&dC, 4)) return -1;
+    CUDA_OK(cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemset(dD, 0, D.size() * 4));
+    CUDA_OK(cudaMemset(dC, 0, 4 * sizeof(long long)));
+    if (0 != launch_tc_selftest(dA, dB, dD, K, N, reps, dC, 0)) { sb2_set_error("selftest: cannot configure kernel"); return -1; }
+    CUDA_OK(cudaDeviceSynchronize());
+    CUDA_OK(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
+    long long cyc[4];
+    CUDA_OK(cudaMemcpy(cyc, dC, sizeof(cyc), cudaMemcpyDeviceToHost));
+    double worst = 0.0;
+    for (int m = 0; m < 128; m++)
+        for (int n = 0; n < N; n++) {
+            double acc = 0.0;
+            for (int k = 0; k < K; k++) acc += (double)A[(size_t)m * K + k] * (double)B[(size_t)n * K + k];
+            worst = std::max(worst, std::fabs(acc - (double)D[(size_t)m * N + n]));
+        }
+    if (max_abs_err) *max_abs_err = (float)worst;
+    if (cycles3) { cycles3[0] = cyc[0]; cycles3[1] = cyc[1]; cycles3[2] = cyc[2]; }
+    cudaFree(dA); cudaFree(dB); cudaFree(dD); cudaFree(dC);
+    return 0;
 }

@@ -60,6 +60,17 @@ void launch_decode_crf(const float *trans, const BatchDims &d, int ostride, uint
 void launch_gather(const float *post, int ostride, const int *cols, const int *states, int n,
                    float *out, cudaStream_t s);
 
+// ---- tensor-core path (kernels_tc.cu) ----
+// shared-memory image of one layer's recurrent weights (split fp16, canonical UMMA layout)
+size_t scan_image_bytes(int H);
+void build_scan_image(const float *sW, const float *sW2, int H, uint8_t *img);
+// gru_forward / gru_backward on tcgen05; returns -1 if the kernel could not be configured
+int launch_gru_scan_tc(const float *Xin, const uint8_t *wimg, const float *resid, float *out, const BatchDims &d,
+                       int H, int backward, int fast_math, cudaStream_t s);
+// D[128][N] = A[128][K] B[N][K]^T through the scan's operand path (validation / latency probe)
+int launch_tc_selftest(const float *A, const float *B, float *D, int K, int N, int reps, long long *cycles,
+                       cudaStream_t s);
+
 // overwrite a buffer larger than L2 (benchmark hygiene)
 void launch_flush(float *buf, size_t nfloat, cudaStream_t s);
 

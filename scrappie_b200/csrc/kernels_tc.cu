@@ -1,0 +1,386 @@
+// Tensor-core (tcgen05 / TMEM) kernels for sm_100a.
+//
+//   gru_scan_tc_kernel   the recurrent part of a GRU layer (src/layers.c:373-527 in the
+//                        reference): per time step two dependent products
+//                        sW^T h (2H x N) and sW2^T (r*h) (H x N) as UMMA tiles with the
+//                        gate math fused between them; weights stay resident in shared
+//                        memory for the whole layer, accumulators live in TMEM.
+//   tc_selftest_kernel   one UMMA tile product checked against the host (descriptor /
+//                        layout validation and latency probe).
+//
+// Numerics: split-fp16 operands, three passes, fp32 accumulation (tc_common.cuh).
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "device_math.cuh"
+#include "kernels.h"
+#include "tc_common.cuh"
+
+namespace sb2 {
+
+using namespace tc;
+
+// ---------------------------------------------------------------------------------
+// self test: D[128][N] = A[128][K] * B[N][K]^T through the same operand path as the scan
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(160, 1)
+tc_selftest_kernel(const float *__restrict__ A, const float *__restrict__ B, float *__restrict__ D, int K, int N,
+                   int reps, long long *__restrict__ cycles) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t lboA = 128, sboA = (uint32_t)(K / 8) * 128;
+    const uint32_t sboB = 128, lboB = 16u * N + 16u;
+    const uint32_t tileA = 128u * K * 2u, tileB = (uint32_t)(K / 8) * lboB;
+    uint8_t *a_hi = smem, *a_lo = smem + tileA, *b_hi = smem + 2 * tileA, *b_lo = b_hi + tileB;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(b_lo + tileB + 16);
+    bars = reinterpret_cast<uint64_t *>((reinterpret_cast<uintptr_t>(bars) + 15) & ~(uintptr_t)15);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2);
+
+    const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+    for (int i = tid; i < 128 * K; i += blockDim.x) {
+        const int m = i / K, k = i % K;
+        __half hi, lo;
+        split_fp16(A[i], hi, lo);
+        const uint32_t off = canon_off(m, k, lboA, sboA);
+        *reinterpret_cast<__half *>(a_hi + off) = hi;
+        *reinterpret_cast<__half *>(a_lo + off) = lo;
+    }
+    for (int i = tid; i < N * K; i += blockDim.x) {
+        const int n = i / K, k = i % K;
+        __half hi, lo;
+        split_fp16(B[i], hi, lo);
+        const uint32_t off = canon_off(n, k, lboB, sboB);
+        *reinterpret_cast<__half *>(b_hi + off) = hi;
+        *reinterpret_cast<__half *>(b_lo + off) = lo;
+    }
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_fence_init();
+    }
+    const uint32_t ncols = (N <= 32) ? 32 : 64;
+    if (warp == 0) tmem_alloc(tmem_slot, ncols);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_f16(128, N);
+            const uint64_t dA_hi = umma_desc(smem_u32(a_hi), lboA, sboA), dA_lo = umma_desc(smem_u32(a_lo), lboA, sboA);
+            const uint64_t dB_hi = umma_desc(smem_u32(b_hi), lboB, sboB), dB_lo = umma_desc(smem_u32(b_lo), lboB, sboB);
+            const int nk = K / 16;
+            const long long t0 = clock64();
+            long long t_issue = 0;
+            for (int rep = 0; rep < reps; rep++) {
+                const long long ta = clock64();
+                uint32_t acc = 0;
+                for (int ks = 0; ks < nk; ks++) { umma_f16(tmem, dA_hi + (uint64_t)(ks * 2 * lboA >> 4), dB_hi + (uint64_t)(ks * 2 * lboB >> 4), idesc, acc); acc = 1; }
+                for (int ks = 0; ks < nk; ks++) umma_f16(tmem, dA_lo + (uint64_t)(ks * 2 * lboA >> 4), dB_hi + (uint64_t)(ks * 2 * lboB >> 4), idesc, 1);
+                for (int ks = 0; ks < nk; ks++) umma_f16(tmem, dA_hi + (uint64_t)(ks * 2 * lboA >> 4), dB_lo + (uint64_t)(ks * 2 * lboB >> 4), idesc, 1);
+                umma_commit(&bars[0]);
+                t_issue += clock64() - ta;
+                mbar_wait(&bars[0], rep & 1);
+            }
+            const long long t1 = clock64();
+            cycles[0] = t1 - t0;
+            cycles[1] = t_issue;
+            umma_commit(&bars[1]);
+        }
+        __syncwarp();
+    } else {
+        mbar_wait(&bars[1], 0);
+        tc_fence_after();
+        const long long ta = clock64();
+        for (int c0 = 0; c0 < N; c0 += 8) {
+            float v[8];
+            tmem_ld8(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 8; j++) D[(size_t)tid * N + c0 + j] = v[j] * RESULT_SCALE;
+        }
+        if (tid == 0) cycles[2] = clock64() - ta;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, ncols);
+}
+
+int launch_tc_selftest(const float *A, const float *B, float *D, int K, int N, int reps, long long *cycles,
+                       cudaStream_t s) {
+    const size_t smem = 2 * (size_t)128 * K * 2 + 2 * (size_t)(K / 8) * (16 * N + 16) + 256;
+    cudaError_t e = cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return -1;
+    tc_selftest_kernel<<<1, 160, smem, s>>>(A, B, D, K, N, reps, cycles);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// GRU scan on tcgen05
+// ---------------------------------------------------------------------------------
+// One CTA = one tile of NR reads stepping together.  Warps 0..3 ("gate warps") own the
+// accumulator rows (TMEM lane = hidden unit), warp 4 lane 0 issues the UMMAs.
+//
+// Shared memory: [weights image 6 tiles][B operands: h_hi h_lo rh_hi rh_lo][slack][barriers]
+// The weights image is prepared once on the host (build_scan_image): per gate (z, r, c)
+// a hi and a lo fp16 tile of H rows x H (K) in canonical layout, LBO 128, SBO (H/8)*128.
+// UMMA uses M = 128, so rows H..127 of every tile read whatever follows it in shared
+// memory; those accumulator lanes are never read back.
+//
+// Per step s (t = s forward, t = T-1-s backward):
+//   UMMA  Dz, Dr  = Wz h, Wr h                  (3 passes x H/16 each)   -> commit g1
+//   gates z = sig(xz + Dz), r = sig(xr + Dr); write (r*h) operand        -> arrive rh_ready
+//   UMMA  Dc      = Wc (r*h)                                             -> commit g2
+//   gates c = tanh(xc + Dc); h = z h + (1-z) c; store h; write h operand -> arrive h_ready
+template <int H>
+struct ScanLayout {
+    static constexpr uint32_t LBO_A = 128;
+    static constexpr uint32_t SBO_A = (H / 8) * 128;
+    static constexpr uint32_t TILE_A = H * H * 2;
+    static constexpr uint32_t WEIGHTS = 6 * TILE_A;
+};
+
+size_t scan_image_bytes(int H) { return (size_t)6 * H * H * 2; }
+
+// Host: build the shared-memory image of a layer's recurrent weights.
+// sW: [2H][H] (row = output unit: z rows then r rows), sW2: [H][H].
+void build_scan_image(const float *sW, const float *sW2, int H, uint8_t *img) {
+    const uint32_t lbo = 128, sbo = (uint32_t)(H / 8) * 128, tile = (uint32_t)H * H * 2;
+    for (int g = 0; g < 3; g++) {
+        uint8_t *hi_t = img + (size_t)(2 * g) * tile, *lo_t = hi_t + tile;
+        for (int m = 0; m < H; m++) {
+            const float *row = (g < 2) ? (sW + (size_t)(g * H + m) * H) : (sW2 + (size_t)m * H);
+            for (int k = 0; k < H; k++) {
+                const float xs = row[k] * OPERAND_SCALE;
+                const __half hi = __float2half_rn(xs);
+                const __half lo = __float2half_rn(xs - __half2float(hi));
+                const uint32_t off = canon_off(m, k, lbo, sbo);
+                *reinterpret_cast<__half *>(hi_t + off) = hi;
+                *reinterpret_cast<__half *>(lo_t + off) = lo;
+            }
+        }
+    }
+}
+
+template <int H, int NR, bool FAST>
+__global__ void __launch_bounds__(160, 1)
+gru_scan_tc_kernel(const float *__restrict__ Xin, const uint8_t *__restrict__ wimg, const float *__restrict__ resid,
+                   float *__restrict__ out, BatchDims d, int backward) {
+    using L = ScanLayout<H>;
+    constexpr int NM = (NR < 16) ? 16 : NR;            // UMMA N (M = 128 requires N % 16 == 0)
+    constexpr uint32_t LBO_B = 16u * NM + 16u, SBO_B = 128u;
+    constexpr uint32_t TILE_B = (H / 8) * LBO_B;
+    constexpr uint32_t SLACK = ((128 - H) / 8) * L::SBO_A;
+    constexpr int NKS = H / 16;
+    constexpr int NGW = (H + 31) / 32;                  // gate warps that own valid rows
+    constexpr uint32_t TCOLS = (3 * NM <= 32) ? 32 : (3 * NM <= 64 ? 64 : (3 * NM <= 128 ? 128 : 256));
+
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t *w_img = smem;
+    uint8_t *b_h_hi = smem + L::WEIGHTS, *b_h_lo = b_h_hi + TILE_B, *b_rh_hi = b_h_lo + TILE_B, *b_rh_lo = b_rh_hi + TILE_B;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(b_rh_lo + TILE_B + SLACK);    // 16-byte aligned by construction
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4);
+    uint64_t *bar_g1 = &bars[0], *bar_g2 = &bars[1], *bar_rh = &bars[2], *bar_h = &bars[3];
+
+    const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+    const int r0 = blockIdx.x * NR;
+
+    // ---- one-time setup ---------------------------------------------------------
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(wimg);
+        uint4 *dst = reinterpret_cast<uint4 *>(w_img);
+        for (uint32_t i = tid; i < L::WEIGHTS / 16; i += blockDim.x) dst[i] = src[i];
+        uint4 *zb = reinterpret_cast<uint4 *>(b_h_hi);
+        for (uint32_t i = tid; i < (4 * TILE_B + SLACK) / 16; i += blockDim.x) zb[i] = make_uint4(0, 0, 0, 0);
+    }
+    if (tid == 0) {
+        mbar_init(bar_g1, 1);
+        mbar_init(bar_g2, 1);
+        mbar_init(bar_rh, NGW);
+        mbar_init(bar_h, NGW);
+        mbar_fence_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, TCOLS);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    int T[NR], col[NR], Tmax = 0;
+#pragma unroll
+    for (int n = 0; n < NR; n++) {
+        const int r = r0 + n;
+        T[n] = (r < d.nread) ? d.nblock[r] : 0;
+        col[n] = (r < d.nread) ? d.col_off[r] : 0;
+        Tmax = max(Tmax, T[n]);
+    }
+
+    if (warp == 4) {
+        // ---- UMMA issuer ----------------------------------------------------------
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_f16(128, NM);
+            uint64_t dW[6];
+#pragma unroll
+            for (int i = 0; i < 6; i++) dW[i] = umma_desc(smem_u32(w_img + i * L::TILE_A), L::LBO_A, L::SBO_A);
+            const uint64_t dHhi = umma_desc(smem_u32(b_h_hi), LBO_B, SBO_B), dHlo = umma_desc(smem_u32(b_h_lo), LBO_B, SBO_B);
+            const uint64_t dRhi = umma_desc(smem_u32(b_rh_hi), LBO_B, SBO_B), dRlo = umma_desc(smem_u32(b_rh_lo), LBO_B, SBO_B);
+            constexpr uint64_t KA = (2 * L::LBO_A) >> 4, KB = (2 * LBO_B) >> 4;
+            for (int s = 0; s < Tmax; s++) {
+                if (s > 0) mbar_wait(bar_h, (s - 1) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int g = 0; g < 2; g++) {
+                    const uint32_t dcol = tmem + g * NM;
+#pragma unroll
+                    for (int ks = 0; ks < NKS; ks++) umma_f16(dcol, dW[2 * g] + ks * KA, dHhi + ks * KB, idesc, ks > 0);
+#pragma unroll
+                    for (int ks = 0; ks < NKS; ks++) umma_f16(dcol, dW[2 * g + 1] + ks * KA, dHhi + ks * KB, idesc, 1);
+#pragma unroll
+                    for (int ks = 0; ks < NKS; ks++) umma_f16(dcol, dW[2 * g] + ks * KA, dHlo + ks * KB, idesc, 1);
+                }
+                umma_commit(bar_g1);
+                mbar_wait(bar_rh, s & 1);
+                tc_fence_after();
+                {
+                    const uint32_t dcol = tmem + 2 * NM;
+#pragma unroll
+                    for (int ks = 0; ks < NKS; ks++) umma_f16(dcol, dW[4] + ks * KA, dRhi + ks * KB, idesc, ks > 0);
+#pragma unroll
+                    for (int ks = 0; ks < NKS; ks++) umma_f16(dcol, dW[5] + ks * KA, dRhi + ks * KB, idesc, 1);
+#pragma unroll
+                    for (int ks = 0; ks < NKS; ks++) umma_f16(dcol, dW[4] + ks * KA, dRlo + ks * KB, idesc, 1);
+                }
+                umma_commit(bar_g2);
+            }
+        }
+        __syncwarp();
+    } else if (warp < NGW) {
+        // ---- gate warps -------------------------------------------------------------
+        const int j = tid;                              // hidden unit = accumulator row = TMEM lane
+        const bool valid = j < H;
+        const int jj = valid ? j : 0;
+        const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+        float h[NR], xz[NR], xr[NR], xc[NR], rs[NR];
+#pragma unroll
+        for (int n = 0; n < NR; n++) { h[n] = 0.0f; rs[n] = 0.0f; }
+        auto load_x = [&](int s) {
+#pragma unroll
+            for (int n = 0; n < NR; n++) {
+                if (s < T[n]) {
+                    const int t = backward ? (T[n] - 1 - s) : s;
+                    const float *x = Xin + (size_t)(col[n] + t) * (3 * H) + jj;
+                    xz[n] = x[0]; xr[n] = x[H]; xc[n] = x[2 * H];
+                    if (resid != nullptr) rs[n] = resid[(size_t)(col[n] + t) * H + jj];
+                } else {
+                    xz[n] = 0.0f; xr[n] = 0.0f; xc[n] = 0.0f;
+                }
+            }
+        };
+        load_x(0);
+        for (int s = 0; s < Tmax; s++) {
+            float cz[NR], cr[NR], cc[NR], crs[NR];
+#pragma unroll
+            for (int n = 0; n < NR; n++) { cz[n] = xz[n]; cr[n] = xr[n]; cc[n] = xc[n]; crs[n] = rs[n]; }
+            if (s + 1 < Tmax) load_x(s + 1);            // prefetch next step's inputs
+
+            mbar_wait(bar_g1, s & 1);
+            tc_fence_after();
+            float gz[NR];
+#pragma unroll
+            for (int c0 = 0; c0 < NR; c0 += 8) {
+                float vz[8], vr[8];
+                tmem_ld8(lane_base + c0, vz);
+                tmem_ld8(lane_base + NM + c0, vr);
+                tmem_ld_wait();
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    const int n = c0 + q;
+                    const float az = cz[n] + vz[q] * RESULT_SCALE, ar = cr[n] + vr[q] * RESULT_SCALE;
+                    gz[n] = FAST ? logistic_fast(az) : logistic_cephes(az);
+                    const float gr = FAST ? logistic_fast(ar) : logistic_cephes(ar);
+                    __half hi, lo;
+                    split_fp16(gr * h[n], hi, lo);
+                    if (valid) {
+                        const uint32_t off = canon_off(n, j, LBO_B, SBO_B);
+                        *reinterpret_cast<__half *>(b_rh_hi + off) = hi;
+                        *reinterpret_cast<__half *>(b_rh_lo + off) = lo;
+                    }
+                }
+            }
+            fence_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_rh);
+
+            mbar_wait(bar_g2, s & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int c0 = 0; c0 < NR; c0 += 8) {
+                float vc[8];
+                tmem_ld8(lane_base + 2 * NM + c0, vc);
+                tmem_ld_wait();
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    const int n = c0 + q;
+                    const float ac = cc[n] + vc[q] * RESULT_SCALE;
+                    const float cand = FAST ? tanh_fast(ac) : tanh_cephes(ac);
+                    const float hn = gz[n] * h[n] + (1.0f - gz[n]) * cand;
+                    h[n] = hn;
+                    __half hi, lo;
+                    split_fp16(hn, hi, lo);
+                    if (valid) {
+                        const uint32_t off = canon_off(n, j, LBO_B, SBO_B);
+                        *reinterpret_cast<__half *>(b_h_hi + off) = hi;
+                        *reinterpret_cast<__half *>(b_h_lo + off) = lo;
+                        if (s < T[n]) {
+                            const int t = backward ? (T[n] - 1 - s) : s;
+                            out[(size_t)(col[n] + t) * H + j] = (resid != nullptr) ? hn + crs[n] : hn;
+                        }
+                    }
+                }
+            }
+            fence_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_h);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, TCOLS);
+}
+
+template <int H, int NR>
+static size_t scan_smem_bytes() {
+    constexpr int NM = (NR < 16) ? 16 : NR;
+    return (size_t)ScanLayout<H>::WEIGHTS + 4 * (size_t)(H / 8) * (16 * NM + 16) + (size_t)((128 - H) / 8) * ScanLayout<H>::SBO_A + 64;
+}
+
+template <int H, int NR, bool FAST>
+static int launch_scan(const float *Xin, const uint8_t *wimg, const float *resid, float *out, const BatchDims &d,
+                       int backward, cudaStream_t s) {
+    const size_t smem = scan_smem_bytes<H, NR>();
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(gru_scan_tc_kernel<H, NR, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return -1;
+        configured = true;
+    }
+    const int grid = (d.nread + NR - 1) / NR;
+    gru_scan_tc_kernel<H, NR, FAST><<<grid, 160, smem, s>>>(Xin, wimg, resid, out, d, backward);
+    return 0;
+}
+
+int launch_gru_scan_tc(const float *Xin, const uint8_t *wimg, const float *resid, float *out, const BatchDims &d,
+                       int H, int backward, int fast_math, cudaStream_t s) {
+    if (H == 96) return fast_math ? launch_scan<96, 8, true>(Xin, wimg, resid, out, d, backward, s)
+                                  : launch_scan<96, 8, false>(Xin, wimg, resid, out, d, backward, s);
+    if (H == 112) return fast_math ? launch_scan<112, 8, true>(Xin, wimg, resid, out, d, backward, s)
+                                   : launch_scan<112, 8, false>(Xin, wimg, resid, out, d, backward, s);
+    return -1;
+}
+
+}  // namespace sb2
