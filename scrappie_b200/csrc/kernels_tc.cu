@@ -67,24 +67,27 @@ tc_selftest_kernel(const float *__restrict__ A, const float *__restrict__ B, flo
     const uint32_t tmem = *tmem_slot;
 
     if (warp == 4) {
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_f16(128, N);
-            const uint64_t dA_hi = umma_desc(smem_u32(a_hi), lboA, sboA), dA_lo = umma_desc(smem_u32(a_lo), lboA, sboA);
-            const uint64_t dB_hi = umma_desc(smem_u32(b_hi), lboB, sboB), dB_lo = umma_desc(smem_u32(b_lo), lboB, sboB);
-            const int nk = K / 16;
-            const long long t0 = clock64();
-            long long t_issue = 0;
-            for (int rep = 0; rep < reps; rep++) {
-                const long long ta = clock64();
-                uint32_t acc = 0;
-                for (int ks = 0; ks < nk; ks++) { umma_f16(tmem, dA_hi + (uint64_t)(ks * 2 * lboA >> 4), dB_hi + (uint64_t)(ks * 2 * lboB >> 4), idesc, acc); acc = 1; }
-                for (int ks = 0; ks < nk; ks++) umma_f16(tmem, dA_lo + (uint64_t)(ks * 2 * lboA >> 4), dB_hi + (uint64_t)(ks * 2 * lboB >> 4), idesc, 1);
-                for (int ks = 0; ks < nk; ks++) umma_f16(tmem, dA_hi + (uint64_t)(ks * 2 * lboA >> 4), dB_lo + (uint64_t)(ks * 2 * lboB >> 4), idesc, 1);
+        const uint32_t idesc = umma_idesc_f16(128, N);
+        const uint64_t dA_hi = umma_desc(smem_u32(a_hi), lboA, sboA), dA_lo = umma_desc(smem_u32(a_lo), lboA, sboA);
+        const uint64_t dB_hi = umma_desc(smem_u32(b_hi), lboB, sboB), dB_lo = umma_desc(smem_u32(b_lo), lboB, sboB);
+        const int nk = K / 16;
+        const uint64_t ka = (2 * lboA) >> 4, kb = (2 * lboB) >> 4;
+        const long long t0 = clock64();
+        long long t_issue = 0;
+        for (int rep = 0; rep < reps; rep++) {
+            const long long ta = clock64();
+            if (elect_one()) {
+                for (int ks = 0; ks < nk; ks++) umma_f16(tmem, dA_hi + ks * ka, dB_hi + ks * kb, idesc, ks > 0);
+                for (int ks = 0; ks < nk; ks++) umma_f16(tmem, dA_lo + ks * ka, dB_hi + ks * kb, idesc, 1);
+                for (int ks = 0; ks < nk; ks++) umma_f16(tmem, dA_hi + ks * ka, dB_lo + ks * kb, idesc, 1);
                 umma_commit(&bars[0]);
-                t_issue += clock64() - ta;
-                mbar_wait(&bars[0], rep & 1);
             }
-            const long long t1 = clock64();
+            __syncwarp();
+            t_issue += clock64() - ta;
+            mbar_wait(&bars[0], rep & 1);
+        }
+        const long long t1 = clock64();
+        if (elect_one()) {
             cycles[0] = t1 - t0;
             cycles[1] = t_issue;
             umma_commit(&bars[1]);
@@ -219,44 +222,45 @@ gru_scan_tc_kernel(const float *__restrict__ Xin, const uint8_t *__restrict__ wi
     }
 
     if (warp == 4) {
-        // ---- UMMA issuer ----------------------------------------------------------
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_f16(128, NM);
-            uint64_t dW[6];
-#pragma unroll
-            for (int i = 0; i < 6; i++) dW[i] = umma_desc(smem_u32(w_img + i * L::TILE_A), L::LBO_A, L::SBO_A);
-            const uint64_t dHhi = umma_desc(smem_u32(b_h_hi), LBO_B, SBO_B), dHlo = umma_desc(smem_u32(b_h_lo), LBO_B, SBO_B);
-            const uint64_t dRhi = umma_desc(smem_u32(b_rh_hi), LBO_B, SBO_B), dRlo = umma_desc(smem_u32(b_rh_lo), LBO_B, SBO_B);
-            constexpr uint64_t KA = (2 * L::LBO_A) >> 4, KB = (2 * LBO_B) >> 4;
-            for (int s = 0; s < Tmax; s++) {
-                if (s > 0) mbar_wait(bar_h, (s - 1) & 1);
-                tc_fence_after();
+        // ---- UMMA issuer: the whole warp runs the loop, one elected lane issues --------
+        const uint32_t idesc = umma_idesc_f16(128, NM);
+        const uint64_t dW = umma_desc(smem_u32(w_img), L::LBO_A, L::SBO_A);          // tile i at + i * TA
+        const uint64_t dB = umma_desc(smem_u32(b_h_hi), LBO_B, SBO_B);               // h_hi, h_lo, rh_hi, rh_lo at + i * TB
+        constexpr uint64_t TA = L::TILE_A >> 4, TB = TILE_B >> 4;
+        constexpr uint64_t KA = (2 * L::LBO_A) >> 4, KB = (2 * LBO_B) >> 4;
+        for (int s = 0; s < Tmax; s++) {
+            if (s > 0) mbar_wait(bar_h, (s - 1) & 1);
+            tc_fence_after();
+            if (elect_one()) {
 #pragma unroll
                 for (int g = 0; g < 2; g++) {
                     const uint32_t dcol = tmem + g * NM;
+                    const uint64_t w_hi = dW + (2 * g) * TA, w_lo = dW + (2 * g + 1) * TA;
 #pragma unroll
-                    for (int ks = 0; ks < NKS; ks++) umma_f16(dcol, dW[2 * g] + ks * KA, dHhi + ks * KB, idesc, ks > 0);
+                    for (int ks = 0; ks < NKS; ks++) umma_f16(dcol, w_hi + ks * KA, dB + ks * KB, idesc, ks > 0);
 #pragma unroll
-                    for (int ks = 0; ks < NKS; ks++) umma_f16(dcol, dW[2 * g + 1] + ks * KA, dHhi + ks * KB, idesc, 1);
+                    for (int ks = 0; ks < NKS; ks++) umma_f16(dcol, w_lo + ks * KA, dB + ks * KB, idesc, 1);
 #pragma unroll
-                    for (int ks = 0; ks < NKS; ks++) umma_f16(dcol, dW[2 * g] + ks * KA, dHlo + ks * KB, idesc, 1);
+                    for (int ks = 0; ks < NKS; ks++) umma_f16(dcol, w_hi + ks * KA, dB + TB + ks * KB, idesc, 1);
                 }
                 umma_commit(bar_g1);
-                mbar_wait(bar_rh, s & 1);
-                tc_fence_after();
-                {
-                    const uint32_t dcol = tmem + 2 * NM;
+            }
+            __syncwarp();
+            mbar_wait(bar_rh, s & 1);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t dcol = tmem + 2 * NM;
+                const uint64_t w_hi = dW + 4 * TA, w_lo = dW + 5 * TA;
 #pragma unroll
-                    for (int ks = 0; ks < NKS; ks++) umma_f16(dcol, dW[4] + ks * KA, dRhi + ks * KB, idesc, ks > 0);
+                for (int ks = 0; ks < NKS; ks++) umma_f16(dcol, w_hi + ks * KA, dB + 2 * TB + ks * KB, idesc, ks > 0);
 #pragma unroll
-                    for (int ks = 0; ks < NKS; ks++) umma_f16(dcol, dW[5] + ks * KA, dRhi + ks * KB, idesc, 1);
+                for (int ks = 0; ks < NKS; ks++) umma_f16(dcol, w_lo + ks * KA, dB + 2 * TB + ks * KB, idesc, 1);
 #pragma unroll
-                    for (int ks = 0; ks < NKS; ks++) umma_f16(dcol, dW[4] + ks * KA, dRlo + ks * KB, idesc, 1);
-                }
+                for (int ks = 0; ks < NKS; ks++) umma_f16(dcol, w_hi + ks * KA, dB + 3 * TB + ks * KB, idesc, 1);
                 umma_commit(bar_g2);
             }
+            __syncwarp();
         }
-        __syncwarp();
     } else if (warp < NGW) {
         // ---- gate warps -------------------------------------------------------------
         const int j = tid;                              // hidden unit = accumulator row = TMEM lane
