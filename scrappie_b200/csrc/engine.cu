@@ -161,9 +161,13 @@ extern "C" sb2_engine *sb2_engine_create(int device, const char *weights_dir) {
     else if (0 != sb2_default_weights_dir(eng->weights_dir, sizeof(eng->weights_dir))) eng->weights_dir[0] = '\0';
     const char *scan = getenv("SCRAPPIE_B200_SCAN");
     const char *gemm = getenv("SCRAPPIE_B200_GEMM");
-    eng->scan_impl = 0;                                  // 0 ffma, 1 tcgen05 (cephes gates), 2 tcgen05 (SFU gates)
+    // 0 ffma; tcgen05 with weights in TMEM: 1 cephes gates, 2 SFU gates, 3 polynomial gates;
+    // 4 tcgen05 with weights in shared memory (SFU gates)
+    eng->scan_impl = 0;
     if (scan && 0 == strcmp(scan, "tc")) eng->scan_impl = 1;
     if (scan && 0 == strcmp(scan, "tc_fast")) eng->scan_impl = 2;
+    if (scan && 0 == strcmp(scan, "tc_poly")) eng->scan_impl = 3;
+    if (scan && 0 == strcmp(scan, "tc_smem")) eng->scan_impl = 4;
     eng->gemm_impl = (gemm && 0 == strcmp(gemm, "tc")) ? 1 : 0;
     if (cudaSetDevice(device) != cudaSuccess) { delete eng; return nullptr; }
     return eng;
@@ -380,9 +384,15 @@ extern "C" int sb2_batch_forward(sb2_batch *b, const sb2_params *p, bool return_
         if (b->eng->scan_impl == 0) {
             launch_gru_scan_ffma(b->d_Xin, m.sW[l], m.sW2[l], h.residual ? b->d_X[cur] : nullptr, b->d_X[cur ^ 1],
                                  b->dims, H, (l % 2) == 0, s);
-        } else if (0 != launch_gru_scan_tc(b->d_Xin, m.scan_img[l], h.residual ? b->d_X[cur] : nullptr, b->d_X[cur ^ 1],
-                                           b->dims, H, (l % 2) == 0, b->eng->scan_impl == 2, s)) {
-            sb2_set_error("tensor-core scan kernel could not be configured");
+        } else if (b->eng->scan_impl == 4) {
+            if (0 != launch_gru_scan_tc(b->d_Xin, m.scan_img[l], h.residual ? b->d_X[cur] : nullptr, b->d_X[cur ^ 1],
+                                        b->dims, H, (l % 2) == 0, 1, s)) {
+                sb2_set_error("tensor-core scan kernel could not be configured");
+                return -1;
+            }
+        } else if (0 != launch_gru_scan_tmem(b->d_Xin, m.sW[l], m.sW2[l], h.residual ? b->d_X[cur] : nullptr,
+                                             b->d_X[cur ^ 1], b->dims, H, (l % 2) == 0, b->eng->scan_impl - 1, s)) {
+            sb2_set_error("tensor-core scan: unsupported configuration");
             return -1;
         }
         nl += 2;

@@ -67,6 +67,9 @@ void build_scan_image(const float *sW, const float *sW2, int H, uint8_t *img);
 // gru_forward / gru_backward on tcgen05; returns -1 if the kernel could not be configured
 int launch_gru_scan_tc(const float *Xin, const uint8_t *wimg, const float *resid, float *out, const BatchDims &d,
                        int H, int backward, int fast_math, cudaStream_t s);
+// same with the weights resident in TMEM (A operand from tensor memory); math: 0 cephes, 1 SFU, 2 polynomial
+int launch_gru_scan_tmem(const float *Xin, const float *sW, const float *sW2, const float *resid, float *out,
+                         const BatchDims &d, int H, int backward, int math, cudaStream_t s);
 // D[128][N] = A[128][K] B[N][K]^T through the scan's operand path (validation / latency probe)
 int launch_tc_selftest(const float *A, const float *B, float *D, int K, int N, int reps, long long *cycles,
                        cudaStream_t s);

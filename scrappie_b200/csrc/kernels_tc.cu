@@ -357,6 +357,287 @@ gru_scan_tc_kernel(const float *__restrict__ Xin, const uint8_t *__restrict__ wi
     if (warp == 0) tmem_dealloc(tmem, TCOLS);
 }
 
+
+// ---------------------------------------------------------------------------------
+// GRU scan, weights resident in TMEM (A operand from tensor memory)
+// ---------------------------------------------------------------------------------
+// Reading the 128 x 16 fp16 A tile from shared memory costs ~32 cycles per UMMA (4 KB at
+// 128 B/clk), which dominated the shared-memory-A variant above (54 UMMAs per step).  Here
+// the six weight tiles (z, r, c) x (hi, lo) are written once into TMEM with tcgen05.st
+// (lane = hidden unit, one 32-bit column = two consecutive K elements; H/2 columns per
+// tile) and every UMMA takes A from TMEM; shared memory only holds the small B operands
+// (state h and r*h, split fp16).  Pass order per product: lo*hi, hi*lo, then hi*hi -- the
+// tensor core accumulates with truncation, so the small cross terms go in while the
+// accumulator is still small.
+//
+// MATH: 0 = cephes-identical gates, 1 = SFU ex2/rcp, 2 = polynomial exp2 + refined rcp.
+template <int MATH>
+__device__ __forceinline__ float gate_sigmoid(float x) {
+    if (MATH == 0) return logistic_cephes(x);
+    if (MATH == 1) return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x));
+    // 2^t, t = -x log2(e) clamped; n = rint(t) by the magic-number trick; degree-6 minimax on [-1/2, 1/2]
+    const float t = fmaxf(fminf(x * -1.4426950408889634f, 126.0f), -126.0f);
+    const float r = t + 12582912.0f;
+    const float f = t - (r - 12582912.0f);
+    float p = 0.00015337577497120947f;
+    p = fmaf(p, f, 0.0013399859890341759f);
+    p = fmaf(p, f, 0.009618519805371761f);
+    p = fmaf(p, f, 0.05550329014658928f);
+    p = fmaf(p, f, 0.24022646248340607f);
+    p = fmaf(p, f, 0.6931471824645996f);
+    p = fmaf(p, f, 1.0f);
+    const float e = __int_as_float(__float_as_int(p) + ((__float_as_int(r) - 0x4B400000) << 23));
+    const float dd = 1.0f + e;
+    const float q = rcp_approx(dd);
+    return fmaf(q, fmaf(-dd, q, 1.0f), q);              // one Newton step
+}
+template <int MATH>
+__device__ __forceinline__ float gate_tanh(float x) {
+    if (MATH == 0) return tanh_cephes(x);
+    const float y = gate_sigmoid<MATH>(x + x);
+    return (y + y) - 1.0f;
+}
+
+__device__ __forceinline__ uint32_t pack_half2(__half lo16, __half hi16) {
+    return (uint32_t)__half_as_ushort(lo16) | ((uint32_t)__half_as_ushort(hi16) << 16);
+}
+
+template <int H, int NR, int MATH>
+__global__ void __launch_bounds__(160, 1)
+gru_scan_tmem_kernel(const float *__restrict__ Xin, const float *__restrict__ sW, const float *__restrict__ sW2,
+                     const float *__restrict__ resid, float *__restrict__ out, BatchDims d, int backward) {
+    constexpr int NM = (NR < 16) ? 16 : NR;             // UMMA N
+    constexpr uint32_t LBO_B = 16u * NM + 16u, SBO_B = 128u;
+    constexpr uint32_t TILE_B = (H / 8) * LBO_B;
+    constexpr int NKS = H / 16;
+    constexpr int NGW = (H + 31) / 32;
+    constexpr uint32_t KH = H / 2;                      // TMEM columns per weight tile
+    constexpr uint32_t ACC0 = 6 * KH;                   // accumulators: z, r, c
+    constexpr uint32_t TCOLS = 512;
+    static_assert(ACC0 + 3 * NM <= TCOLS, "TMEM budget");
+
+    __shared__ __align__(128) uint8_t b_ops[4 * TILE_B];        // h_hi, h_lo, rh_hi, rh_lo
+    __shared__ __align__(8) uint64_t bars[4];
+    __shared__ uint32_t tmem_slot;
+    uint8_t *b_h_hi = b_ops, *b_h_lo = b_ops + TILE_B, *b_rh_hi = b_ops + 2 * TILE_B, *b_rh_lo = b_ops + 3 * TILE_B;
+    uint64_t *bar_g1 = &bars[0], *bar_g2 = &bars[1], *bar_rh = &bars[2], *bar_h = &bars[3];
+
+    const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+    const int r0 = blockIdx.x * NR;
+
+    for (uint32_t i = tid; i < 4 * TILE_B / 16; i += blockDim.x) reinterpret_cast<uint4 *>(b_ops)[i] = make_uint4(0, 0, 0, 0);
+    if (tid == 0) {
+        mbar_init(bar_g1, 1);
+        mbar_init(bar_g2, 1);
+        mbar_init(bar_rh, NGW);
+        mbar_init(bar_h, NGW);
+        mbar_fence_init();
+    }
+    if (warp == 0) tmem_alloc(&tmem_slot, TCOLS);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+
+    // ---- weights -> TMEM (once per layer) -------------------------------------------
+    if (warp < 4) {
+        const int m = tid;
+        const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+        for (int g = 0; g < 3; g++) {
+            const float *row = (g < 2) ? (sW + (size_t)(g * H + (m < H ? m : 0)) * H) : (sW2 + (size_t)(m < H ? m : 0) * H);
+#pragma unroll 1
+            for (int kc = 0; kc < NKS; kc++) {
+                uint32_t whi[8], wlo[8];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    float4 v = *reinterpret_cast<const float4 *>(row + kc * 16 + q * 4);
+                    if (m >= H) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    __half h0, l0, h1, l1, h2, l2, h3, l3;
+                    split_fp16(v.x, h0, l0); split_fp16(v.y, h1, l1); split_fp16(v.z, h2, l2); split_fp16(v.w, h3, l3);
+                    whi[2 * q] = pack_half2(h0, h1); whi[2 * q + 1] = pack_half2(h2, h3);
+                    wlo[2 * q] = pack_half2(l0, l1); wlo[2 * q + 1] = pack_half2(l2, l3);
+                }
+                tmem_st8(lane_base + (2 * g) * KH + kc * 8, whi);
+                tmem_st8(lane_base + (2 * g + 1) * KH + kc * 8, wlo);
+            }
+        }
+        tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    int T[NR], col[NR], Tmax = 0;
+#pragma unroll
+    for (int n = 0; n < NR; n++) {
+        const int r = r0 + n;
+        T[n] = (r < d.nread) ? d.nblock[r] : 0;
+        col[n] = (r < d.nread) ? d.col_off[r] : 0;
+        Tmax = max(Tmax, T[n]);
+    }
+
+    if (warp == 4) {
+        // ---- UMMA issuer ----------------------------------------------------------------
+        const uint32_t idesc = umma_idesc_f16(128, NM);
+        const uint64_t dB = umma_desc(smem_u32(b_ops), LBO_B, SBO_B);       // h_hi, h_lo, rh_hi, rh_lo at + i * TB
+        constexpr uint64_t TB = TILE_B >> 4, KB = (2 * LBO_B) >> 4;
+        for (int s = 0; s < Tmax; s++) {
+            if (s > 0) mbar_wait(bar_h, (s - 1) & 1);
+            tc_fence_after();
+            if (elect_one()) {
+#pragma unroll
+                for (int g = 0; g < 2; g++) {
+                    const uint32_t dcol = tmem + ACC0 + g * NM;
+                    const uint32_t w_hi = tmem + (2 * g) * KH, w_lo = tmem + (2 * g + 1) * KH;
+#pragma unroll
+                    for (int ks = 0; ks < NKS; ks++) umma_f16_ts(dcol, w_lo + ks * 8, dB + ks * KB, idesc, ks > 0);
+#pragma unroll
+                    for (int ks = 0; ks < NKS; ks++) umma_f16_ts(dcol, w_hi + ks * 8, dB + TB + ks * KB, idesc, 1);
+#pragma unroll
+                    for (int ks = 0; ks < NKS; ks++) umma_f16_ts(dcol, w_hi + ks * 8, dB + ks * KB, idesc, 1);
+                }
+                umma_commit(bar_g1);
+            }
+            __syncwarp();
+            mbar_wait(bar_rh, s & 1);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t dcol = tmem + ACC0 + 2 * NM;
+                const uint32_t w_hi = tmem + 4 * KH, w_lo = tmem + 5 * KH;
+#pragma unroll
+                for (int ks = 0; ks < NKS; ks++) umma_f16_ts(dcol, w_lo + ks * 8, dB + 2 * TB + ks * KB, idesc, ks > 0);
+#pragma unroll
+                for (int ks = 0; ks < NKS; ks++) umma_f16_ts(dcol, w_hi + ks * 8, dB + 3 * TB + ks * KB, idesc, 1);
+#pragma unroll
+                for (int ks = 0; ks < NKS; ks++) umma_f16_ts(dcol, w_hi + ks * 8, dB + 2 * TB + ks * KB, idesc, 1);
+                umma_commit(bar_g2);
+            }
+            __syncwarp();
+        }
+    } else if (warp < NGW) {
+        // ---- gate warps -----------------------------------------------------------------
+        const int j = tid;
+        const bool valid = j < H;
+        const int jj = valid ? j : 0;
+        const uint32_t acc_base = tmem + ((uint32_t)(warp * 32) << 16) + ACC0;
+        float h[NR], xz[NR], xr[NR], xc[NR], rs[NR];
+#pragma unroll
+        for (int n = 0; n < NR; n++) { h[n] = 0.0f; rs[n] = 0.0f; }
+        auto load_x = [&](int s) {
+#pragma unroll
+            for (int n = 0; n < NR; n++) {
+                if (s < T[n]) {
+                    const int t = backward ? (T[n] - 1 - s) : s;
+                    const float *x = Xin + (size_t)(col[n] + t) * (3 * H) + jj;
+                    xz[n] = x[0]; xr[n] = x[H]; xc[n] = x[2 * H];
+                    if (resid != nullptr) rs[n] = resid[(size_t)(col[n] + t) * H + jj];
+                } else {
+                    xz[n] = 0.0f; xr[n] = 0.0f; xc[n] = 0.0f;
+                }
+            }
+        };
+        load_x(0);
+        for (int s = 0; s < Tmax; s++) {
+            float cz[NR], cr[NR], cc[NR], crs[NR];
+#pragma unroll
+            for (int n = 0; n < NR; n++) { cz[n] = xz[n]; cr[n] = xr[n]; cc[n] = xc[n]; crs[n] = rs[n]; }
+            if (s + 1 < Tmax) load_x(s + 1);
+
+            mbar_wait(bar_g1, s & 1);
+            tc_fence_after();
+            float gz[NR];
+#pragma unroll
+            for (int c0 = 0; c0 < NR; c0 += 8) {
+                float vz[8], vr[8];
+                tmem_ld8(acc_base + c0, vz);
+                tmem_ld8(acc_base + NM + c0, vr);
+                tmem_ld_wait();
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    const int n = c0 + q;
+                    gz[n] = gate_sigmoid<MATH>(fmaf(vz[q], RESULT_SCALE, cz[n]));
+                    const float gr = gate_sigmoid<MATH>(fmaf(vr[q], RESULT_SCALE, cr[n]));
+                    __half hi, lo;
+                    split_fp16(gr * h[n], hi, lo);
+                    if (valid) {
+                        const uint32_t off = canon_off(n, j, LBO_B, SBO_B);
+                        *reinterpret_cast<__half *>(b_rh_hi + off) = hi;
+                        *reinterpret_cast<__half *>(b_rh_lo + off) = lo;
+                    }
+                }
+            }
+            fence_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_rh);
+
+            mbar_wait(bar_g2, s & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int c0 = 0; c0 < NR; c0 += 8) {
+                float vc[8];
+                tmem_ld8(acc_base + 2 * NM + c0, vc);
+                tmem_ld_wait();
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    const int n = c0 + q;
+                    const float cand = gate_tanh<MATH>(fmaf(vc[q], RESULT_SCALE, cc[n]));
+                    const float hn = gz[n] * h[n] + (1.0f - gz[n]) * cand;
+                    h[n] = hn;
+                    __half hi, lo;
+                    split_fp16(hn, hi, lo);
+                    if (valid) {
+                        const uint32_t off = canon_off(n, j, LBO_B, SBO_B);
+                        *reinterpret_cast<__half *>(b_h_hi + off) = hi;
+                        *reinterpret_cast<__half *>(b_h_lo + off) = lo;
+                        if (s < T[n]) {
+                            const int t = backward ? (T[n] - 1 - s) : s;
+                            out[(size_t)(col[n] + t) * H + j] = (resid != nullptr) ? hn + crs[n] : hn;
+                        }
+                    }
+                }
+            }
+            fence_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_h);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, TCOLS);
+}
+
+template <int H, int NR, int MATH>
+static int launch_scan_tmem(const float *Xin, const float *sW, const float *sW2, const float *resid, float *out,
+                            const BatchDims &d, int backward, cudaStream_t s) {
+    // The kernel allocates all 512 TMEM columns, so two CTAs must never share an SM (the second
+    // would block in tcgen05.alloc until the first retires).  Requesting more than half of
+    // the SM's shared memory as (unused) dynamic shared memory guarantees one CTA per SM.
+    constexpr int EXCLUSIVE_SMEM = 120 * 1024;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(gru_scan_tmem_kernel<H, NR, MATH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 EXCLUSIVE_SMEM) != cudaSuccess)
+            return -1;
+        configured = true;
+    }
+    const int grid = (d.nread + NR - 1) / NR;
+    gru_scan_tmem_kernel<H, NR, MATH><<<grid, 160, EXCLUSIVE_SMEM, s>>>(Xin, sW, sW2, resid, out, d, backward);
+    return 0;
+}
+
+int launch_gru_scan_tmem(const float *Xin, const float *sW, const float *sW2, const float *resid, float *out,
+                         const BatchDims &d, int H, int backward, int math, cudaStream_t s) {
+#define SB2_CASE(HH, MM) if (H == HH && math == MM) return launch_scan_tmem<HH, 8, MM>(Xin, sW, sW2, resid, out, d, backward, s)
+    SB2_CASE(96, 0); SB2_CASE(96, 1); SB2_CASE(96, 2);
+    SB2_CASE(112, 0); SB2_CASE(112, 1); SB2_CASE(112, 2);
+#undef SB2_CASE
+    return -1;
+}
+
 template <int H, int NR>
 static size_t scan_smem_bytes() {
     constexpr int NM = (NR < 16) ? 16 : NR;
