@@ -161,9 +161,10 @@ extern "C" sb2_engine *sb2_engine_create(int device, const char *weights_dir) {
     else if (0 != sb2_default_weights_dir(eng->weights_dir, sizeof(eng->weights_dir))) eng->weights_dir[0] = '\0';
     const char *scan = getenv("SCRAPPIE_B200_SCAN");
     const char *gemm = getenv("SCRAPPIE_B200_GEMM");
-    // 0 ffma; tcgen05 with weights in TMEM: 1 cephes gates, 2 SFU gates, 3 polynomial gates;
-    // 4 tcgen05 with weights in shared memory (SFU gates)
-    eng->scan_impl = 0;
+    // tcgen05 with weights in TMEM: 1 cephes gates, 2 SFU gates, 3 polynomial gates (default);
+    // 4 tcgen05 with weights in shared memory (SFU gates); 0 fp32 CUDA cores (debug cross-check)
+    eng->scan_impl = 3;
+    if (scan && 0 == strcmp(scan, "ffma")) eng->scan_impl = 0;
     if (scan && 0 == strcmp(scan, "tc")) eng->scan_impl = 1;
     if (scan && 0 == strcmp(scan, "tc_fast")) eng->scan_impl = 2;
     if (scan && 0 == strcmp(scan, "tc_poly")) eng->scan_impl = 3;

@@ -76,7 +76,10 @@ def test_layerwise_parity(sb, engine, oracle, model):
         for l in range(6):
             got = b.layer(l, i, H)
             err = np.abs(got - layers[l]).max()
-            assert err < (2e-6 if l == 0 else 5e-5), (model, i, l, err)
+            # GRU outputs are in [-1, 1]; rnnrf's residual sums grow past that, so its bound is
+            # relative to the layer's magnitude (the reference and the oracle differ by as much)
+            tol = 2e-6 if l == 0 else 5e-5 * max(1.0, float(np.abs(layers[l]).max()))
+            assert err < tol, (model, i, l, err)
     b.close()
 
 
@@ -197,7 +200,10 @@ def test_bundled_reads_bit_identical_bases(sb, engine, golden, model):
         k = "r%d_%s" % (i, model)
         assert hashlib.md5((bases + "\n").encode()).hexdigest() == str(g[k + "_md5"])
         assert bases == str(g[k + "_bases"])
-        assert abs(score - float(g[k + "_score"])) < 0.02
+        # rgrgr: score is a sum of ~1e4 log-probabilities.  rnnrf: the CRF score is the path score
+        # minus logZ, both ~4e5 in fp32 (ulp 0.03) -- two OpenBLAS builds of the reference itself
+        # differ by 7e-3 here, so the bound is a few ulp of the partition sum.
+        assert abs(score - float(g[k + "_score"])) < (0.02 if model == "rgrgr_r94" else 0.25)
     # posterior spot check on the subsampled columns + Viterbi path equality
     b = engine.batch(model, [len(s) for s in sigs])
     b.upload(sigs)
