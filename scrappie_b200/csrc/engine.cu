@@ -41,6 +41,9 @@ struct DevModel {
     float *FF_W = nullptr, *FF_b = nullptr;
     uint8_t *scan_img[SB2_NLAYER]{};     // tensor-core scan: per-layer weight image
     uint8_t *d_img_all = nullptr;
+    uint8_t *iw_img[SB2_NLAYER]{};       // tensor-core affine: per-layer input-transform image
+    uint8_t *d_gemm_img_all = nullptr;
+    uint8_t *head_img = nullptr;         // fused output head (1025-state models, K = 96)
 };
 
 struct sb2_engine {
@@ -53,6 +56,7 @@ struct sb2_engine {
     std::mutex mu;
     int scan_impl = 0;      // 0 = ffma, 1 = tcgen05
     int gemm_impl = 0;
+    int head_exact = 0;     // 1: cephes exp / log in the fused head (bit-level mirror of the reference's maths)
 };
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -106,6 +110,24 @@ static int upload_model(sb2_engine *eng, DevModel *dm) {
         CUDA_OK(cudaMalloc(&dm->d_img_all, img.size()));
         CUDA_OK(cudaMemcpy(dm->d_img_all, img.data(), img.size(), cudaMemcpyHostToDevice));
         for (int l = 0; l < SB2_NLAYER; l++) dm->scan_img[l] = dm->d_img_all + nb * l;
+    }
+    {   // tensor-core affine images (input transforms)
+        const size_t nb = align_up(gemm_image_bytes(3, (int)H, (int)H), 256);
+        std::vector<uint8_t> img(nb * SB2_NLAYER, 0);
+        for (int l = 0; l < SB2_NLAYER; l++) {
+            const std::vector<float> iw = compact(h.iW[l]);
+            build_gemm_image(iw.data(), (int)H, 3 * (int)H, (int)H, (int)H, 3, img.data() + nb * l);
+        }
+        CUDA_OK(cudaMalloc(&dm->d_gemm_img_all, img.size()));
+        CUDA_OK(cudaMemcpy(dm->d_gemm_img_all, img.data(), img.size(), cudaMemcpyHostToDevice));
+        for (int l = 0; l < SB2_NLAYER; l++) dm->iw_img[l] = dm->d_gemm_img_all + nb * l;
+    }
+    if (h.head == 0 && h.nstate == 1025 && H == 96) {
+        std::vector<uint8_t> img(head_image_bytes((int)H), 0);
+        const std::vector<float> ff = compact(h.FF_W);
+        build_gemm_image(ff.data(), (int)H, 1024, (int)H, 128, 8, img.data());
+        CUDA_OK(cudaMalloc(&dm->head_img, img.size()));
+        CUDA_OK(cudaMemcpy(dm->head_img, img.data(), img.size(), cudaMemcpyHostToDevice));
     }
     dm->loaded = true;
     return 0;
@@ -169,7 +191,9 @@ extern "C" sb2_engine *sb2_engine_create(int device, const char *weights_dir) {
     if (scan && 0 == strcmp(scan, "tc_fast")) eng->scan_impl = 2;
     if (scan && 0 == strcmp(scan, "tc_poly")) eng->scan_impl = 3;
     if (scan && 0 == strcmp(scan, "tc_smem")) eng->scan_impl = 4;
-    eng->gemm_impl = (gemm && 0 == strcmp(gemm, "tc")) ? 1 : 0;
+    eng->gemm_impl = (gemm && 0 == strcmp(gemm, "ffma")) ? 0 : 1;    // 1 = tcgen05 (default), 0 = fp32 CUDA cores
+    const char *headm = getenv("SCRAPPIE_B200_HEAD");
+    eng->head_exact = (headm && 0 == strcmp(headm, "exact")) ? 1 : 0;
     if (cudaSetDevice(device) != cudaSuccess) { delete eng; return nullptr; }
     return eng;
 }
@@ -180,6 +204,8 @@ extern "C" void sb2_engine_destroy(sb2_engine *eng) {
     for (auto &dm : eng->models) {
         if (dm.d_all) cudaFree(dm.d_all);
         if (dm.d_img_all) cudaFree(dm.d_img_all);
+        if (dm.d_gemm_img_all) cudaFree(dm.d_gemm_img_all);
+        if (dm.head_img) cudaFree(dm.head_img);
         sb2_host_model_free(&dm.host);
     }
     if (eng->flush_buf) cudaFree(eng->flush_buf);
@@ -380,7 +406,12 @@ extern "C" int sb2_batch_forward(sb2_batch *b, const sb2_params *p, bool return_
     if (b->keep_layers) CUDA_OK(cudaMemcpyAsync(b->d_layers, b->d_X[0], layer_bytes, cudaMemcpyDeviceToDevice, s));
     for (int l = 0; l < SB2_NLAYER; l++) {
         stage_mark(b, ST_AFFINE(l));
-        launch_affine(b->d_X[cur], b->total_cols, H, m.iW[l], H, m.b[l], 3 * H, b->d_Xin, 3 * H, 1.0f, 1.0f, 0, s);
+        if (b->eng->gemm_impl == 0) {
+            launch_affine(b->d_X[cur], b->total_cols, H, m.iW[l], H, m.b[l], 3 * H, b->d_Xin, 3 * H, 1.0f, 1.0f, 0, s);
+        } else if (0 != launch_affine_tc(b->d_X[cur], b->total_cols, H, m.iw_img[l], m.b[l], b->d_Xin, s)) {
+            sb2_set_error("tensor-core affine kernel could not be configured");
+            return -1;
+        }
         stage_mark(b, ST_SCAN(l));
         if (b->eng->scan_impl == 0) {
             launch_gru_scan_ffma(b->d_Xin, m.sW[l], m.sW2[l], h.residual ? b->d_X[cur] : nullptr, b->d_X[cur ^ 1],
@@ -404,7 +435,16 @@ extern "C" int sb2_batch_forward(sb2_batch *b, const sb2_params *p, bool return_
     }
     b->final_x = cur;
     stage_mark(b, ST_HEAD);
-    if (h.head == 0) {
+    if (h.head == 0 && b->eng->gemm_impl != 0 && nullptr != m.head_img) {
+        if (0 != launch_head_softmax_tc(b->d_X[cur], b->total_cols, H, m.head_img, m.FF_W + (size_t)1024 * H, m.FF_b,
+                                        b->d_post, (int)h.ostride, p->tempW / p->tempb, p->tempb, p->min_prob,
+                                        return_log ? 1 : 0, b->eng->head_exact, s)) {
+            sb2_set_error("tensor-core head kernel could not be configured");
+            return -1;
+        }
+        stage_mark(b, ST_FINISH);
+        nl += 1;
+    } else if (h.head == 0) {
         launch_affine(b->d_X[cur], b->total_cols, H, m.FF_W, H, m.FF_b, (int)h.nstate, b->d_post, (int)h.ostride,
                       p->tempW / p->tempb, p->tempb, 1, s);
         stage_mark(b, ST_FINISH);

@@ -74,6 +74,20 @@ int launch_gru_scan_tmem(const float *Xin, const float *sW, const float *sW2, co
 int launch_tc_selftest(const float *A, const float *B, float *D, int K, int N, int reps, long long *cycles,
                        cudaStream_t s);
 
+// ---- tensor-core affine maps (kernels_gemm.cu) ----
+// weight image: ntile tiles of `rows` output units, hi + lo fp16, canonical UMMA layout
+size_t gemm_image_bytes(int ntile, int rows, int K);
+void build_gemm_image(const float *W, int ldw, int M, int K, int rows, int ntile, uint8_t *img);
+// feedforward_linear for a GRU layer: C[col][0:3H] = b + iW^T X[col]  (src/layers.c:248-252)
+int launch_affine_tc(const float *X, int ncol, int H, const uint8_t *wimg, const float *bias, float *C, cudaStream_t s);
+
+// fused output head for 1025-state models: FF GEMM -> softmax with temperature -> robust log
+// (src/layers.c:340-357, :79-94); wimg = build_gemm_image(FF_W, K, 1024, K, 128, 8, .), w_stay = FF_W row 1024
+size_t head_image_bytes(int K);
+int launch_head_softmax_tc(const float *X, int ncol, int K, const uint8_t *wimg, const float *w_stay, const float *bias,
+                           float *post, int ostride, float xdiv, float cdiv, float min_prob, int return_log,
+                           int exact_math, cudaStream_t s);
+
 // overwrite a buffer larger than L2 (benchmark hygiene)
 void launch_flush(float *buf, size_t nfloat, cudaStream_t s);
 

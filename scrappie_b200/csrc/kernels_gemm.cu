@@ -1,0 +1,554 @@
+// Time-batched affine maps on the 5th-generation tensor cores (tcgen05 / TMEM).
+//
+//   affine_tc_kernel   C[col][m] = b[m] + sum_k W[m][k] X[col][k]       (feedforward_linear ->
+//                      affine_map, src/layers.c:248-252, src/scrappie_matrix.c:323-351): the input
+//                      transform of every GRU layer for ALL time steps of ALL reads of a batch.
+//
+// Roles inside a CTA (persistent, one CTA per SM, 288 threads):
+//   warps 5-8  producers  load a chunk of NT activation columns (fp32, coalesced), split each value
+//                         into fp16 hi + lo and store it as the canonical K-major UMMA B operand
+//   warp  4    issuer     one elected lane issues tcgen05.mma: A = weight tile (shared memory,
+//                         resident for the whole kernel, fetched once by a TMA bulk copy),
+//                         B = activation chunk, D = fp32 accumulator in TMEM (double buffered)
+//   warps 0-3  epilogue   tcgen05.ld the accumulator (TMEM lane = output unit), add the bias and
+//                         store: for a fixed column the 32 lanes of a warp write 128 contiguous bytes
+//
+// Numerics: split-fp16, three passes (lo*hi, hi*lo, hi*hi), fp32 accumulation -- see tc_common.cuh.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "device_math.cuh"
+#include "kernels.h"
+#include "tc_common.cuh"
+
+namespace sb2 {
+
+using namespace tc;
+
+// ---------------------------------------------------------------------------------
+// host: weight images
+// ---------------------------------------------------------------------------------
+// `ntile` tiles of `rows` output units each; per tile a hi and a lo fp16 matrix of rows x K in the
+// canonical K-major layout (core matrix = 8 rows x 16 bytes; LBO 128, SBO (K/8)*128).  The UMMA
+// reads 128 rows per tile: with rows < 128 it runs into the next tile / the zeroed slack at the end,
+// and those accumulator lanes are never read back.
+size_t gemm_image_bytes(int ntile, int rows, int K) {
+    const size_t tile = (size_t)rows * K * 2;
+    const size_t slack = (size_t)((128 - rows) / 8) * (size_t)(K / 8) * 128;
+    return 2 * (size_t)ntile * tile + slack;
+}
+
+void build_gemm_image(const float *W, int ldw, int M, int K, int rows, int ntile, uint8_t *img) {
+    const uint32_t lbo = 128, sbo = (uint32_t)(K / 8) * 128;
+    const size_t tile = (size_t)rows * K * 2;
+    memset(img, 0, gemm_image_bytes(ntile, rows, K));
+    for (int t = 0; t < ntile; t++) {
+        uint8_t *hi_t = img + (size_t)(2 * t) * tile, *lo_t = hi_t + tile;
+        for (int r = 0; r < rows; r++) {
+            const int m = t * rows + r;
+            if (m >= M) break;
+            for (int k = 0; k < K; k++) {
+                const float xs = W[(size_t)m * ldw + k] * OPERAND_SCALE;
+                const __half hi = __float2half_rn(xs);
+                const __half lo = __float2half_rn(xs - __half2float(hi));
+                const uint32_t off = canon_off((uint32_t)r, (uint32_t)k, lbo, sbo);
+                *reinterpret_cast<__half *>(hi_t + off) = hi;
+                *reinterpret_cast<__half *>(lo_t + off) = lo;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// device
+// ---------------------------------------------------------------------------------
+template <int K, int ROWS, int NTILE, int NT>
+struct GemmCfg {
+    static constexpr uint32_t LBO_A = 128, SBO_A = (K / 8) * 128;
+    static constexpr uint32_t TILE_A = ROWS * K * 2;
+    static constexpr uint32_t SLACK = ((128 - ROWS) / 8) * SBO_A;
+    static constexpr uint32_t WBYTES = 2 * NTILE * TILE_A + SLACK;
+    static constexpr uint32_t LBO_B = 16 * NT + 16, SBO_B = 128;
+    static constexpr uint32_t TILE_B = (K / 8) * LBO_B;
+    static constexpr uint32_t STAGE_B = 2 * TILE_B;            // hi, lo
+    static constexpr uint32_t SMEM = WBYTES + 2 * STAGE_B + 128;
+    static constexpr int NKS = K / 16;
+    static constexpr uint32_t TCOLS = (2 * NT <= 32) ? 32 : (2 * NT <= 64 ? 64 : (2 * NT <= 128 ? 128 : (2 * NT <= 256 ? 256 : 512)));
+    static_assert(K % 16 == 0 && ROWS % 8 == 0 && ROWS <= 128 && NT % 16 == 0 && NT <= 256, "tile shape");
+    static_assert(WBYTES % 16 == 0 && STAGE_B % 16 == 0, "alignment");
+    static_assert(SMEM <= 227 * 1024, "shared memory budget");
+};
+
+// split 8 consecutive K values into the hi / lo 16-byte rows of a core matrix
+__device__ __forceinline__ void split8(const float4 &a, const float4 &b, float scale, uint4 &hi, uint4 &lo) {
+    const float x[8] = {a.x * scale, a.y * scale, a.z * scale, a.w * scale, b.x * scale, b.y * scale, b.z * scale, b.w * scale};
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const __half h0 = __float2half_rn(x[2 * i]), h1 = __float2half_rn(x[2 * i + 1]);
+        const __half l0 = __float2half_rn(x[2 * i] - __half2float(h0)), l1 = __float2half_rn(x[2 * i + 1] - __half2float(h1));
+        h[i] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+        l[i] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+template <int K, int ROWS, int NTILE, int NT>
+__global__ void __launch_bounds__(288, 1)
+affine_tc_kernel(const float *__restrict__ X, int ncol, const uint8_t *__restrict__ wimg, const float *__restrict__ bias,
+                 int M, float *__restrict__ C, int ldc) {
+    using G = GemmCfg<K, ROWS, NTILE, NT>;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t *w_img = smem;
+    uint8_t *b_ring = smem + G::WBYTES;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(b_ring + 2 * G::STAGE_B);
+    uint64_t *full = bars, *empty = bars + 2, *accf = bars + 4, *acce = bars + 6, *wbar = bars + 8;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 9);
+
+    const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+    const int nchunk = (ncol + NT - 1) / NT;
+
+    if (tid == 0) {
+        mbar_init(&full[0], 4); mbar_init(&full[1], 4);
+        mbar_init(&empty[0], 1); mbar_init(&empty[1], 1);
+        mbar_init(&accf[0], 1); mbar_init(&accf[1], 1);
+        mbar_init(&acce[0], 4); mbar_init(&acce[1], 4);
+        mbar_init(wbar, 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, G::TCOLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 4) {
+        // ---- weights: one TMA bulk copy stream, then the UMMA issue loop ----------------
+        if (lane == 0) {
+            mbar_arrive_expect_tx(wbar, G::WBYTES);
+            constexpr uint32_t PIECE = 32768;
+            for (uint32_t off = 0; off < G::WBYTES; off += PIECE)
+                bulk_g2s(w_img + off, wimg + off, (G::WBYTES - off < PIECE) ? (G::WBYTES - off) : PIECE, wbar);
+        }
+        __syncwarp();
+        mbar_wait(wbar, 0);
+        const uint32_t idesc = umma_idesc_f16(128, NT);
+        const uint64_t dW = umma_desc(smem_u32(w_img), G::LBO_A, G::SBO_A);
+        constexpr uint64_t TA = G::TILE_A >> 4, KA = (2 * G::LBO_A) >> 4, KB = (2 * G::LBO_B) >> 4, TB = G::TILE_B >> 4;
+        uint32_t it = 0, acc_it = 0;
+        for (int c = blockIdx.x; c < nchunk; c += gridDim.x, it++) {
+            const uint32_t s = it & 1;
+            mbar_wait(&full[s], (it >> 1) & 1);
+            const uint64_t dB = umma_desc(smem_u32(b_ring + s * G::STAGE_B), G::LBO_B, G::SBO_B);   // hi; lo at + TB
+#pragma unroll 1
+            for (int g = 0; g < NTILE; g++, acc_it++) {
+                const uint32_t a = acc_it & 1;
+                mbar_wait(&acce[a], ((acc_it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t dcol = tmem + a * NT;
+                    const uint64_t w_hi = dW + (uint64_t)(2 * g) * TA, w_lo = w_hi + TA;
+#pragma unroll
+                    for (int ks = 0; ks < G::NKS; ks++) umma_f16(dcol, w_lo + ks * KA, dB + ks * KB, idesc, ks > 0);
+#pragma unroll
+                    for (int ks = 0; ks < G::NKS; ks++) umma_f16(dcol, w_hi + ks * KA, dB + TB + ks * KB, idesc, 1);
+#pragma unroll
+                    for (int ks = 0; ks < G::NKS; ks++) umma_f16(dcol, w_hi + ks * KA, dB + ks * KB, idesc, 1);
+                    umma_commit(&accf[a]);
+                }
+                __syncwarp();
+            }
+            if (elect_one()) umma_commit(&empty[s]);
+            __syncwarp();
+        }
+    } else if (warp >= 5) {
+        // ---- producers: fp32 activations -> split fp16 canonical B operand ---------------
+        const int pt = tid - 160;                       // 0..127
+        constexpr int K8 = K / 8;
+        constexpr int UNITS = NT * K8;
+        uint32_t it = 0;
+        for (int c = blockIdx.x; c < nchunk; c += gridDim.x, it++) {
+            const uint32_t s = it & 1;
+            mbar_wait(&empty[s], ((it >> 1) & 1) ^ 1);
+            uint8_t *b_hi = b_ring + s * G::STAGE_B, *b_lo = b_hi + G::TILE_B;
+            const int col0 = c * NT;
+            const float *src = X + (size_t)col0 * K;
+            const int nvalid = min(NT, ncol - col0) * K8;
+#pragma unroll 4
+            for (int u = pt; u < UNITS; u += 128) {
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+                if (u < nvalid) {
+                    a = *reinterpret_cast<const float4 *>(src + (size_t)u * 8);
+                    b = *reinterpret_cast<const float4 *>(src + (size_t)u * 8 + 4);
+                }
+                const int n = u / K8, k8 = u % K8;
+                uint4 hi, lo;
+                split8(a, b, OPERAND_SCALE, hi, lo);
+                const uint32_t off = (uint32_t)(n >> 3) * G::SBO_B + (uint32_t)k8 * G::LBO_B + (uint32_t)(n & 7) * 16;
+                *reinterpret_cast<uint4 *>(b_hi + off) = hi;
+                *reinterpret_cast<uint4 *>(b_lo + off) = lo;
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[s]);
+        }
+    } else {
+        // ---- epilogue: accumulator + bias -> global ---------------------------------------
+        const int m = tid;                              // TMEM lane = row inside the tile
+        const bool warp_valid = (warp * 32) < ROWS;
+        const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+        float bg[NTILE];
+        bool ok[NTILE];
+#pragma unroll
+        for (int g = 0; g < NTILE; g++) {
+            ok[g] = (m < ROWS) && (g * ROWS + m < M);
+            bg[g] = ok[g] ? bias[g * ROWS + m] : 0.0f;
+        }
+        uint32_t acc_it = 0;
+        for (int c = blockIdx.x; c < nchunk; c += gridDim.x) {
+            const int col0 = c * NT;
+#pragma unroll
+            for (int g = 0; g < NTILE; g++, acc_it++) {
+                const uint32_t a = acc_it & 1;
+                mbar_wait(&accf[a], (acc_it >> 1) & 1);
+                tc_fence_after();
+                if (warp_valid) {
+                    float *dst = C + (size_t)col0 * ldc + g * ROWS + m;
+#pragma unroll 1
+                    for (int n0 = 0; n0 < NT; n0 += 32) {
+                        float v[32];
+                        tmem_ld32(lane_base + a * NT + n0, v);
+                        tmem_ld_wait();
+                        if (ok[g]) {
+#pragma unroll
+                            for (int j = 0; j < 32; j++)
+                                if (col0 + n0 + j < ncol) dst[(size_t)(n0 + j) * ldc] = fmaf(v[j], RESULT_SCALE, bg[g]);
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acce[a]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, G::TCOLS);
+}
+
+template <int K, int ROWS, int NTILE, int NT>
+static int launch_affine_cfg(const float *X, int ncol, const uint8_t *wimg, const float *bias, int M, float *C, int ldc,
+                             cudaStream_t s) {
+    using G = GemmCfg<K, ROWS, NTILE, NT>;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(affine_tc_kernel<K, ROWS, NTILE, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)G::SMEM) != cudaSuccess)
+            return -1;
+        configured = true;
+    }
+    const int nchunk = (ncol + NT - 1) / NT;
+    const int grid = nchunk < 148 ? nchunk : 148;
+    affine_tc_kernel<K, ROWS, NTILE, NT><<<grid, 288, G::SMEM, s>>>(X, ncol, wimg, bias, M, C, ldc);
+    return 0;
+}
+
+// GRU input transform: M = 3H rows as three tiles (z, r, candidate) of H rows, K = H.
+int launch_affine_tc(const float *X, int ncol, int H, const uint8_t *wimg, const float *bias, float *C, cudaStream_t s) {
+    if (ncol <= 0) return 0;
+    if (H == 96) return launch_affine_cfg<96, 96, 3, 128>(X, ncol, wimg, bias, 3 * H, C, 3 * H, s);
+    if (H == 112) return launch_affine_cfg<112, 112, 3, 64>(X, ncol, wimg, bias, 3 * H, C, 3 * H, s);
+    return -1;
+}
+
+
+// ---------------------------------------------------------------------------------
+// output head: FF -> softmax (with temperature) -> robust log, one kernel
+// ---------------------------------------------------------------------------------
+// softmax_with_temperature + robustlog_activation_inplace (src/layers.c:340-357, :79-94) for the
+// 4^k + 1 state transducer models with 1025 states:
+//     p[m] = exp((b[m] + W[m] . (x / xdiv)) / cdiv) / sum_m' (...),   out = log(min_prob + (1 - min_prob) p)
+// A chunk of NT = 64 columns keeps ALL 1024 k-mer logits in TMEM (8 tiles x 64 columns = the
+// SM's 512 TMEM columns), so the column sum is local and the posterior is written to HBM exactly
+// once, already normalised.  The 393 KB of split-fp16 weights do not fit in shared memory: a TMA
+// bulk-copy ring streams the 8 tile images from L2 once per chunk.  The stay state (row 1024) is a
+// 96-term dot product per column on the CUDA cores.
+//
+// warps 0-7  epilogue   (TMEM lane quarter q = warp % 4, column half ch = warp / 4)
+//            pass A: e = exp(logit) written back to TMEM, column sums; pass B: normalise, log, store
+// warp  8    UMMA issuer        warp 9  TMA weight streamer       warps 10-13  activation producers
+template <int K>
+struct HeadCfg {
+    static constexpr int NT = 64, NTILE = 8, WSTAGES = 3;
+    static constexpr uint32_t LBO_A = 128, SBO_A = (K / 8) * 128;
+    static constexpr uint32_t TILE_A = 128 * K * 2, WTILE = 2 * TILE_A;
+    static constexpr uint32_t LBO_B = 16 * NT + 16, SBO_B = 128;
+    static constexpr uint32_t TILE_B = (K / 8) * LBO_B, STAGE_B = 2 * TILE_B;
+    static constexpr uint32_t PART = 2 * 2 * 4 * 32 * 4;                        // [buf][ch][q][lane] floats, x2 arrays
+    static constexpr uint32_t OFF_B = WSTAGES * WTILE, OFF_PART = OFF_B + 2 * STAGE_B, OFF_BAR = OFF_PART + 2 * PART;
+    static constexpr uint32_t SMEM = OFF_BAR + 32 * 8 + 16;
+    static constexpr int NKS = K / 16;
+    static_assert(SMEM <= 227 * 1024, "shared memory budget");
+};
+
+template <bool FAST>
+__device__ __forceinline__ float head_exp(float x) {
+    if (!FAST) return exp_cephes(x);
+    x = fminf(fmaxf(x, -88.3762626647949f), 88.3762626647949f);         // the reference's clamp
+    return ex2_approx(x * 1.4426950408889634f);
+}
+template <bool FAST>
+__device__ __forceinline__ float head_log(float x) {
+    if (!FAST) return log_cephes(x);
+    return lg2_approx(x) * 0.6931471805599453f;
+}
+
+template <int K, bool FAST>
+__global__ void __launch_bounds__(448, 1)
+head_softmax_tc_kernel(const float *__restrict__ X, int ncol, const uint8_t *__restrict__ wimg,
+                       const float *__restrict__ w_stay, const float *__restrict__ bias, float *__restrict__ post,
+                       int ostride, float xdiv, float cdiv, float min_prob, int return_log) {
+    using G = HeadCfg<K>;
+    constexpr int NT = G::NT, NTILE = G::NTILE;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t *w_ring = smem;
+    uint8_t *b_ring = smem + G::OFF_B;
+    float *part_sum = reinterpret_cast<float *>(smem + G::OFF_PART);            // [2][2][4][32]
+    float *part_stay = part_sum + 2 * 2 * 4 * 32;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + G::OFF_BAR);
+    uint64_t *full_b = bars, *empty_b = bars + 2, *wfull = bars + 4, *wempty = bars + 7, *tile_full = bars + 10,
+             *tile_free = bars + 18;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 26);
+
+    const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+    const int nchunk = (ncol + NT - 1) / NT;
+
+    if (tid == 0) {
+        for (int i = 0; i < 2; i++) { mbar_init(&full_b[i], 4); mbar_init(&empty_b[i], 1); }
+        for (int i = 0; i < G::WSTAGES; i++) { mbar_init(&wfull[i], 1); mbar_init(&wempty[i], 1); }
+        for (int i = 0; i < NTILE; i++) { mbar_init(&tile_full[i], 1); mbar_init(&tile_free[i], 8); }
+        mbar_fence_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 8) {
+        // ---- UMMA issuer ------------------------------------------------------------------
+        const uint32_t idesc = umma_idesc_f16(128, NT);
+        constexpr uint64_t TA = G::TILE_A >> 4, KA = (2 * G::LBO_A) >> 4, KB = (2 * G::LBO_B) >> 4, TB = G::TILE_B >> 4;
+        uint32_t it = 0, wslot = 0, wphase = 0;
+        for (int c = blockIdx.x; c < nchunk; c += gridDim.x, it++) {
+            const uint32_t s = it & 1;
+            mbar_wait(&full_b[s], (it >> 1) & 1);
+            const uint64_t dB = umma_desc(smem_u32(b_ring + s * G::STAGE_B), G::LBO_B, G::SBO_B);
+#pragma unroll 1
+            for (int t = 0; t < NTILE; t++) {
+                mbar_wait(&wfull[wslot], wphase);
+                mbar_wait(&tile_free[t], (it & 1) ^ 1);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t dcol = tmem + t * NT;
+                    const uint64_t w_hi = umma_desc(smem_u32(w_ring + wslot * G::WTILE), G::LBO_A, G::SBO_A), w_lo = w_hi + TA;
+#pragma unroll
+                    for (int ks = 0; ks < G::NKS; ks++) umma_f16(dcol, w_lo + ks * KA, dB + ks * KB, idesc, ks > 0);
+#pragma unroll
+                    for (int ks = 0; ks < G::NKS; ks++) umma_f16(dcol, w_hi + ks * KA, dB + TB + ks * KB, idesc, 1);
+#pragma unroll
+                    for (int ks = 0; ks < G::NKS; ks++) umma_f16(dcol, w_hi + ks * KA, dB + ks * KB, idesc, 1);
+                    umma_commit(&wempty[wslot]);
+                    umma_commit(&tile_full[t]);
+                }
+                __syncwarp();
+                if (++wslot == G::WSTAGES) { wslot = 0; wphase ^= 1; }
+            }
+            if (elect_one()) umma_commit(&empty_b[s]);
+            __syncwarp();
+        }
+    } else if (warp == 9) {
+        // ---- weight streamer: 8 tile images per chunk through a 3-deep TMA ring ------------
+        uint32_t wslot = 0, wphase = 0;
+        for (int c = blockIdx.x; c < nchunk; c += gridDim.x) {
+#pragma unroll 1
+            for (int t = 0; t < NTILE; t++) {
+                mbar_wait(&wempty[wslot], wphase ^ 1);
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(&wfull[wslot], G::WTILE);
+                    uint8_t *dst = w_ring + wslot * G::WTILE;
+                    const uint8_t *src = wimg + (size_t)t * G::WTILE;
+                    bulk_g2s(dst, src, G::TILE_A, &wfull[wslot]);
+                    bulk_g2s(dst + G::TILE_A, src + G::TILE_A, G::TILE_A, &wfull[wslot]);
+                }
+                __syncwarp();
+                if (++wslot == G::WSTAGES) { wslot = 0; wphase ^= 1; }
+            }
+        }
+    } else if (warp >= 10) {
+        // ---- producers ------------------------------------------------------------------------
+        const int pt = tid - 320;
+        constexpr int K8 = K / 8;
+        constexpr int UNITS = NT * K8;
+        const float scale = OPERAND_SCALE;
+        uint32_t it = 0;
+        for (int c = blockIdx.x; c < nchunk; c += gridDim.x, it++) {
+            const uint32_t s = it & 1;
+            mbar_wait(&empty_b[s], ((it >> 1) & 1) ^ 1);
+            uint8_t *b_hi = b_ring + s * G::STAGE_B, *b_lo = b_hi + G::TILE_B;
+            const int col0 = c * NT;
+            const float *src = X + (size_t)col0 * K;
+            const int nvalid = min(NT, ncol - col0) * K8;
+#pragma unroll 2
+            for (int u = pt; u < UNITS; u += 128) {
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+                if (u < nvalid) {
+                    a = *reinterpret_cast<const float4 *>(src + (size_t)u * 8);
+                    b = *reinterpret_cast<const float4 *>(src + (size_t)u * 8 + 4);
+                    if (xdiv != 1.0f) {
+                        a.x /= xdiv; a.y /= xdiv; a.z /= xdiv; a.w /= xdiv;
+                        b.x /= xdiv; b.y /= xdiv; b.z /= xdiv; b.w /= xdiv;
+                    }
+                }
+                const int n = u / K8, k8 = u % K8;
+                uint4 hi, lo;
+                split8(a, b, scale, hi, lo);
+                const uint32_t off = (uint32_t)(n >> 3) * G::SBO_B + (uint32_t)k8 * G::LBO_B + (uint32_t)(n & 7) * 16;
+                *reinterpret_cast<uint4 *>(b_hi + off) = hi;
+                *reinterpret_cast<uint4 *>(b_lo + off) = lo;
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full_b[s]);
+        }
+    } else {
+        // ---- epilogue ---------------------------------------------------------------------------
+        const int q = warp & 3, ch = warp >> 2;
+        const int m = q * 32 + lane;
+        const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + ch * 32;
+        constexpr int KQ = K / 4;                         // the stay dot product is split over the 4 q-warps
+        const float b_stay = bias[NTILE * 128];
+        float ws[KQ];
+#pragma unroll
+        for (int i = 0; i < KQ; i++) ws[i] = w_stay[q * KQ + i];
+        const float keep = 1.0f - min_prob;
+        uint32_t it = 0;
+        for (int c = blockIdx.x; c < nchunk; c += gridDim.x, it++) {
+            const int col0 = c * NT + ch * 32;            // first column of this warp's half
+            const int mycol = col0 + lane;
+            // stay logit, partial over k in [q*KQ, (q+1)*KQ) for column `mycol`
+            float sp = 0.0f;
+            if (mycol < ncol) {
+                const float4 *xp = reinterpret_cast<const float4 *>(X + (size_t)mycol * K + q * KQ);
+#pragma unroll
+                for (int i = 0; i < KQ / 4; i++) {
+                    float4 x4 = xp[i];
+                    if (xdiv != 1.0f) { x4.x /= xdiv; x4.y /= xdiv; x4.z /= xdiv; x4.w /= xdiv; }
+                    sp = fmaf(ws[4 * i], x4.x, sp); sp = fmaf(ws[4 * i + 1], x4.y, sp);
+                    sp = fmaf(ws[4 * i + 2], x4.z, sp); sp = fmaf(ws[4 * i + 3], x4.w, sp);
+                }
+            }
+            // pass A: e = exp(logit), column sums over this thread's 8 rows
+            float cs[32];
+#pragma unroll
+            for (int j = 0; j < 32; j++) cs[j] = 0.0f;
+#pragma unroll 1
+            for (int t = 0; t < NTILE; t++) {
+                mbar_wait(&tile_full[t], it & 1);
+                tc_fence_after();
+                float v[32];
+                tmem_ld32(tbase + t * NT, v);
+                tmem_ld_wait();
+                const float bt = __ldg(bias + t * 128 + m);
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    const float e = head_exp<FAST>((fmaf(v[j], RESULT_SCALE, bt)) / cdiv);
+                    cs[j] += e;
+                    v[j] = e;
+                }
+                tmem_st32(tbase + t * NT, v);
+            }
+            tmem_st_wait();
+            // column sums: over the lanes of the warp, then over the 4 q-warps of this half
+            float mine = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                float x = cs[j];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+                if (lane == j) mine = x;
+            }
+            const int pb = ((it & 1) * 2 + ch) * 4 * 32;
+            part_sum[pb + q * 32 + lane] = mine;
+            part_stay[pb + q * 32 + lane] = sp;
+            named_bar_sync(1 + ch, 128);
+            float tot = 0.0f, sl = 0.0f;
+#pragma unroll
+            for (int qq = 0; qq < 4; qq++) { tot += part_sum[pb + qq * 32 + lane]; sl += part_stay[pb + qq * 32 + lane]; }
+            const float e_stay = head_exp<FAST>((b_stay + sl) / cdiv);
+            const float recip = __fdiv_rn(1.0f, tot + e_stay);
+            if (q == 0 && mycol < ncol) {
+                // stay state and the three padding lanes (exp(0) = 1 in the reference, normalised like the rest)
+                float ps = e_stay * recip, pp = recip;
+                if (return_log) { ps = head_log<FAST>(min_prob + keep * ps); pp = head_log<FAST>(min_prob + keep * pp); }
+                float *o = post + (size_t)mycol * ostride + NTILE * 128;
+                o[0] = ps;
+                for (int i = NTILE * 128 + 1; i < ostride; i++) o[i - NTILE * 128] = pp;
+            }
+            float rc[32];
+#pragma unroll
+            for (int j = 0; j < 32; j++) rc[j] = __shfl_sync(0xffffffffu, recip, j);
+            // pass B: normalise, robust log, store
+            const int nok = min(32, ncol - col0);
+#pragma unroll 1
+            for (int t = 0; t < NTILE; t++) {
+                float v[32];
+                tmem_ld32(tbase + t * NT, v);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tile_free[t]);
+                float *dst = post + (size_t)col0 * ostride + t * 128 + m;
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    float p = v[j] * rc[j];
+                    if (return_log) p = head_log<FAST>(fmaf(keep, p, min_prob));
+                    if (j < nok) dst[(size_t)j * ostride] = p;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+size_t head_image_bytes(int K) { return gemm_image_bytes(8, 128, K); }
+
+int launch_head_softmax_tc(const float *X, int ncol, int K, const uint8_t *wimg, const float *w_stay, const float *bias,
+                           float *post, int ostride, float xdiv, float cdiv, float min_prob, int return_log,
+                           int exact_math, cudaStream_t s) {
+    if (ncol <= 0) return 0;
+    if (K != 96) return -1;
+    using G = HeadCfg<96>;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(head_softmax_tc_kernel<96, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM) != cudaSuccess ||
+            cudaFuncSetAttribute(head_softmax_tc_kernel<96, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM) != cudaSuccess)
+            return -1;
+        configured = true;
+    }
+    const int nchunk = (ncol + G::NT - 1) / G::NT;
+    const int grid = nchunk < 148 ? nchunk : 148;
+    if (exact_math)
+        head_softmax_tc_kernel<96, false><<<grid, 448, G::SMEM, s>>>(X, ncol, wimg, w_stay, bias, post, ostride, xdiv, cdiv, min_prob, return_log);
+    else
+        head_softmax_tc_kernel<96, true><<<grid, 448, G::SMEM, s>>>(X, ncol, wimg, w_stay, bias, post, ostride, xdiv, cdiv, min_prob, return_log);
+    return 0;
+}
+
+}  // namespace sb2

@@ -17,6 +17,10 @@ pytestmark = pytest.mark.gpu
 
 LOG_TOL = 1e-4
 PROB_TOL = 1e-5
+# rnnrf_r94 emits unnormalised CRF transition scores (|x| up to ~14), not log-probabilities: the
+# bound is the same ~2e-5 relative.  On the 80k-sample bundled reads the scalar oracle and the
+# reference's OpenBLAS build differ from each other by 4e-5 (tools/parity_report.py).
+CRF_TOL = 2.5e-4
 
 
 def robustlog(p, min_prob):
@@ -214,7 +218,7 @@ def test_bundled_reads_bit_identical_bases(sb, engine, golden, model):
         k = "r%d_%s" % (i, model)
         post = b.posterior(i)
         ns = b.nstate
-        assert np.abs(post[g[k + "_post_cols"]][:, :ns] - g[k + "_post_sub"][:, :ns]).max() < LOG_TOL
+        assert np.abs(post[g[k + "_post_cols"]][:, :ns] - g[k + "_post_sub"][:, :ns]).max() < (LOG_TOL if model == "rgrgr_r94" else CRF_TOL)
         want = g[k + "_path_nohp"] if model == "rgrgr_r94" else g[k + "_path"]
         assert np.array_equal(paths[i], want)
     b.close()
