@@ -207,6 +207,10 @@ int sb2_batch_basecall(sb2_batch *b, const float *concat, int pinned, const sb2_
  * job larger than one batch executes); CUDA events on the launching stream. */
 int sb2_multi_time(sb2_batch **batches, int nbatch, const sb2_params *p, int nrep, int flush_l2, float *ms_out);
 
+/* Diagnostic hook (SCRAPPIE_B200_TRACE=1 at engine creation): clock64() stamps recorded by CTA 0 of
+ * the second GRU layer's scan at its hand-over points, steps 100..103, 16 slots per step. */
+int sb2_engine_read_trace(sb2_engine *eng, long long *out, int n);
+
 /* Test hook: flat dump of the host-side convolution tail plan, which reproduces the
  * right-edge behaviour of the reference's strided convolution (src/layers.c:218-241).
  * out = {first_col, ncol, then 24 x {nseg, (x0, tap0, ntap) x 3}}. */

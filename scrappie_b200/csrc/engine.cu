@@ -56,6 +56,7 @@ struct sb2_engine {
     std::mutex mu;
     int scan_impl = 0;      // 0 = ffma, 1 = tcgen05
     int gemm_impl = 0;
+    long long *d_trace = nullptr;   // diagnostic: hand-over timestamps of the scan kernel (SCRAPPIE_B200_TRACE=1)
     int head_exact = 0;     // 1: cephes exp / log in the fused head (bit-level mirror of the reference's maths)
 };
 
@@ -185,8 +186,15 @@ extern "C" sb2_engine *sb2_engine_create(int device, const char *weights_dir) {
     const char *gemm = getenv("SCRAPPIE_B200_GEMM");
     // tcgen05 with weights in TMEM: 1 cephes gates, 2 SFU gates, 3 polynomial gates (default);
     // 4 tcgen05 with weights in shared memory (SFU gates); 0 fp32 CUDA cores (debug cross-check)
-    eng->scan_impl = 3;
+    // 5..7: v3 kernel (two-pass, reset gate first) with cephes / SFU / polynomial gates
+    // 8..10: v4 kernel (v3 + two read groups per CTA) with cephes / SFU / polynomial gates (10 = default)
+    eng->scan_impl = 10;
+    if (scan && 0 == strcmp(scan, "v3")) eng->scan_impl = 7;
+    if (scan && 0 == strcmp(scan, "v4_cephes")) eng->scan_impl = 8;
+    if (scan && 0 == strcmp(scan, "v4_fast")) eng->scan_impl = 9;
     if (scan && 0 == strcmp(scan, "ffma")) eng->scan_impl = 0;
+    if (scan && 0 == strcmp(scan, "v3_cephes")) eng->scan_impl = 5;
+    if (scan && 0 == strcmp(scan, "v3_fast")) eng->scan_impl = 6;
     if (scan && 0 == strcmp(scan, "tc")) eng->scan_impl = 1;
     if (scan && 0 == strcmp(scan, "tc_fast")) eng->scan_impl = 2;
     if (scan && 0 == strcmp(scan, "tc_poly")) eng->scan_impl = 3;
@@ -195,6 +203,8 @@ extern "C" sb2_engine *sb2_engine_create(int device, const char *weights_dir) {
     const char *headm = getenv("SCRAPPIE_B200_HEAD");
     eng->head_exact = (headm && 0 == strcmp(headm, "exact")) ? 1 : 0;
     if (cudaSetDevice(device) != cudaSuccess) { delete eng; return nullptr; }
+    if (getenv("SCRAPPIE_B200_TRACE") && cudaMalloc(&eng->d_trace, 64 * sizeof(long long)) == cudaSuccess)
+        cudaMemset(eng->d_trace, 0, 64 * sizeof(long long));
     return eng;
 }
 
@@ -209,7 +219,17 @@ extern "C" void sb2_engine_destroy(sb2_engine *eng) {
         sb2_host_model_free(&dm.host);
     }
     if (eng->flush_buf) cudaFree(eng->flush_buf);
+    if (eng->d_trace) cudaFree(eng->d_trace);
     delete eng;
+}
+
+// Diagnostic: clock64() stamps recorded by CTA 0 of the layer-2 scan (steps 100..103, 16 slots each).
+extern "C" int sb2_engine_read_trace(sb2_engine *eng, long long *out, int n) {
+    if (nullptr == eng || nullptr == eng->d_trace || nullptr == out) return -1;
+    CUDA_OK(cudaSetDevice(eng->device));
+    CUDA_OK(cudaDeviceSynchronize());
+    CUDA_OK(cudaMemcpy(out, eng->d_trace, sizeof(long long) * (size_t)std::min(n, 64), cudaMemcpyDeviceToHost));
+    return 0;
 }
 
 extern "C" uint64_t sb2_engine_launch_count(const sb2_engine *eng) { return eng ? eng->launches.load() : 0; }
@@ -420,6 +440,18 @@ extern "C" int sb2_batch_forward(sb2_batch *b, const sb2_params *p, bool return_
             if (0 != launch_gru_scan_tc(b->d_Xin, m.scan_img[l], h.residual ? b->d_X[cur] : nullptr, b->d_X[cur ^ 1],
                                         b->dims, H, (l % 2) == 0, 1, s)) {
                 sb2_set_error("tensor-core scan kernel could not be configured");
+                return -1;
+            }
+        } else if (b->eng->scan_impl >= 8) {
+            if (0 != launch_gru_scan_v4(b->d_Xin, m.sW[l], m.sW2[l], h.residual ? b->d_X[cur] : nullptr, b->d_X[cur ^ 1],
+                                        b->dims, H, (l % 2) == 0, b->eng->scan_impl - 8, (l == 1) ? b->eng->d_trace : nullptr, s)) {
+                sb2_set_error("tensor-core scan v4: unsupported configuration");
+                return -1;
+            }
+        } else if (b->eng->scan_impl >= 5) {
+            if (0 != launch_gru_scan_v3(b->d_Xin, m.sW[l], m.sW2[l], h.residual ? b->d_X[cur] : nullptr, b->d_X[cur ^ 1],
+                                        b->dims, H, (l % 2) == 0, b->eng->scan_impl - 5, (l == 1) ? b->eng->d_trace : nullptr, s)) {
+                sb2_set_error("tensor-core scan v3: unsupported configuration");
                 return -1;
             }
         } else if (0 != launch_gru_scan_tmem(b->d_Xin, m.sW[l], m.sW2[l], h.residual ? b->d_X[cur] : nullptr,

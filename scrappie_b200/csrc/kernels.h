@@ -70,6 +70,12 @@ int launch_gru_scan_tc(const float *Xin, const uint8_t *wimg, const float *resid
 // same with the weights resident in TMEM (A operand from tensor memory); math: 0 cephes, 1 SFU, 2 polynomial
 int launch_gru_scan_tmem(const float *Xin, const float *sW, const float *sW2, const float *resid, float *out,
                          const BatchDims &d, int H, int backward, int math, cudaStream_t s);
+// v3: hi|lo of the state packed in the UMMA N dimension (two passes), reset gate first, 8 gate warps
+int launch_gru_scan_v3(const float *Xin, const float *sW, const float *sW2, const float *resid, float *out,
+                       const BatchDims &d, int H, int backward, int math, long long *trace, cudaStream_t s);
+// v4: v3 + two independent groups of 4 reads per CTA (own operands / accumulators / issuer warp), ILP-friendly gates
+int launch_gru_scan_v4(const float *Xin, const float *sW, const float *sW2, const float *resid, float *out,
+                       const BatchDims &d, int H, int backward, int math, long long *trace, cudaStream_t s);
 // D[128][N] = A[128][K] B[N][K]^T through the scan's operand path (validation / latency probe)
 int launch_tc_selftest(const float *A, const float *B, float *D, int K, int N, int reps, long long *cycles,
                        cudaStream_t s);

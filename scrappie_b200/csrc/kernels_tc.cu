@@ -12,6 +12,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "device_math.cuh"
 #include "kernels.h"
@@ -632,6 +633,685 @@ static int launch_scan_tmem(const float *Xin, const float *sW, const float *sW2,
 int launch_gru_scan_tmem(const float *Xin, const float *sW, const float *sW2, const float *resid, float *out,
                          const BatchDims &d, int H, int backward, int math, cudaStream_t s) {
 #define SB2_CASE(HH, MM) if (H == HH && math == MM) return launch_scan_tmem<HH, 8, MM>(Xin, sW, sW2, resid, out, d, backward, s)
+    SB2_CASE(96, 0); SB2_CASE(96, 1); SB2_CASE(96, 2);
+    SB2_CASE(112, 0); SB2_CASE(112, 1); SB2_CASE(112, 2);
+#undef SB2_CASE
+    return -1;
+}
+
+
+// ---------------------------------------------------------------------------------
+// GRU scan v3: two-pass split arithmetic, reset gate first, eight gate warps
+// ---------------------------------------------------------------------------------
+// Same data flow as gru_scan_tmem_kernel (weights resident in TMEM, TS-mode UMMA) with the
+// per-step dependency chain shortened:
+//  * The B operand holds the hi AND the lo half of the state side by side in the UMMA N
+//    dimension: rows 0..7 = fp16 hi of the 8 reads, rows 8..15 = fp16 lo.  One product is then
+//    two passes (A = W_lo, A = W_hi) instead of three, D[:, n] + D[:, 8 + n] is the result, and
+//    the N = 16 the instruction needs anyway is fully used.  (W_lo * h_lo comes for free.)
+//  * The reset gate is issued and committed first; the update gate's UMMAs run on the tensor
+//    pipe while the gate warps turn r into the (r * h) operand, and sigma(z) is evaluated while
+//    the candidate's UMMAs run.
+//  * Eight gate warps: TMEM lane quarter q = warp % 4 (hidden units 32q..32q+31), read group
+//    cg = warp / 4 (reads 4cg..4cg+3), so a thread evaluates 4 reads instead of 8.
+// At N = 16 a UMMA costs ~38 cycles whatever it computes (profiles/r5_summary.md), so the step
+// time is (36 UMMAs) x 38 cycles plus the two hand-overs; see DESIGN.md.
+template <int H, int MATH>
+__global__ void __launch_bounds__(288, 1)
+gru_scan_v3_kernel(const float *__restrict__ Xin, const float *__restrict__ sW, const float *__restrict__ sW2,
+                   const float *__restrict__ resid, float *__restrict__ out, BatchDims d, int backward,
+                   long long *__restrict__ trace, int dbg) {
+    // diagnostic variants (timing only, wrong results): 1 no global IO, 2 no gate math, 4 no loads, 8 no stores
+    const bool dbg_no_math = (trace != nullptr) && (dbg & 2);
+    const bool dbg_no_ld = (trace != nullptr) && (dbg & 5);
+    const bool dbg_no_st = (trace != nullptr) && (dbg & 9);
+    // trace (diagnostic, normally null): CTA 0 records clock64() at the hand-over points of steps 100..103;
+    // slots 0..3 issuer, 4..12 gate warp 0 (see tools/scan_trace.py)
+#define SB2_TRACE(slot) do { if (trace != nullptr && blockIdx.x == 0 && lane == 0 && s >= 100 && s < 104) trace[(s - 100) * 16 + (slot)] = clock64(); } while (0)
+    constexpr int NR = 8, NM = 16, RPT = 4;             // reads per CTA, UMMA N, reads per gate thread
+    constexpr uint32_t LBO_B = 16u * NM + 16u, SBO_B = 128u;
+    constexpr uint32_t TILE_B = (H / 8) * LBO_B;
+    constexpr int NKS = H / 16;
+    constexpr int NQ = (H + 31) / 32;                   // lane quarters that own hidden units
+    constexpr int NGW = 2 * NQ;                         // active gate warps
+    constexpr uint32_t KH = H / 2;                      // TMEM columns per weight tile
+    constexpr uint32_t ACC0 = 6 * KH;                   // accumulators: r, z, c (16 columns each)
+    constexpr uint32_t TCOLS = 512;
+    static_assert(ACC0 + 3 * NM <= TCOLS, "TMEM budget");
+
+    __shared__ __align__(128) uint8_t b_ops[2 * TILE_B];        // h [hi|lo], r*h [hi|lo]
+    __shared__ __align__(8) uint64_t bars[5];
+    __shared__ uint32_t tmem_slot;
+    uint8_t *b_h = b_ops, *b_rh = b_ops + TILE_B;
+    uint64_t *bar_r = &bars[0], *bar_z = &bars[1], *bar_c = &bars[2], *bar_rh = &bars[3], *bar_h = &bars[4];
+
+    const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+    const int r0 = blockIdx.x * NR;
+
+    for (uint32_t i = tid; i < 2 * TILE_B / 16; i += blockDim.x) reinterpret_cast<uint4 *>(b_ops)[i] = make_uint4(0, 0, 0, 0);
+    if (tid == 0) {
+        mbar_init(bar_r, 1);
+        mbar_init(bar_z, 1);
+        mbar_init(bar_c, 1);
+        mbar_init(bar_rh, NGW);
+        mbar_init(bar_h, NGW);
+        mbar_fence_init();
+    }
+    if (warp == 0) tmem_alloc(&tmem_slot, TCOLS);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+
+    // ---- weights -> TMEM (once per layer): tiles r_hi r_lo z_hi z_lo c_hi c_lo -------------
+    if (warp < 4) {
+        const int m = tid;
+        const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+        for (int g = 0; g < 3; g++) {
+            // tile order r, z, c; the reference stores z rows first, then r (src/layers.c:511-526)
+            const int mm = (m < H) ? m : 0;
+            const float *row = (g == 0) ? (sW + (size_t)(H + mm) * H) : ((g == 1) ? (sW + (size_t)mm * H) : (sW2 + (size_t)mm * H));
+#pragma unroll 1
+            for (int kc = 0; kc < NKS; kc++) {
+                uint32_t whi[8], wlo[8];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    float4 v = *reinterpret_cast<const float4 *>(row + kc * 16 + q * 4);
+                    if (m >= H) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    __half h0, l0, h1, l1, h2, l2, h3, l3;
+                    split_fp16(v.x, h0, l0); split_fp16(v.y, h1, l1); split_fp16(v.z, h2, l2); split_fp16(v.w, h3, l3);
+                    whi[2 * q] = pack_half2(h0, h1); whi[2 * q + 1] = pack_half2(h2, h3);
+                    wlo[2 * q] = pack_half2(l0, l1); wlo[2 * q + 1] = pack_half2(l2, l3);
+                }
+                tmem_st8(lane_base + (2 * g) * KH + kc * 8, whi);
+                tmem_st8(lane_base + (2 * g + 1) * KH + kc * 8, wlo);
+            }
+        }
+        tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    if (warp == 8) {
+        // ---- UMMA issuer --------------------------------------------------------------------
+        int Tmax = 0;
+        for (int n = 0; n < NR; n++) {
+            const int r = r0 + n;
+            if (r < d.nread) Tmax = max(Tmax, d.nblock[r]);
+        }
+        const uint32_t idesc = umma_idesc_f16(128, NM);
+        const uint64_t dBh = umma_desc(smem_u32(b_h), LBO_B, SBO_B), dBrh = umma_desc(smem_u32(b_rh), LBO_B, SBO_B);
+        constexpr uint64_t KB = (2 * LBO_B) >> 4;
+        for (int s = 0; s < Tmax; s++) {
+            if (s > 0) mbar_wait(bar_h, (s - 1) & 1);
+            tc_fence_after();
+            SB2_TRACE(0);
+            if (elect_one()) {
+#pragma unroll
+                for (int g = 0; g < 2; g++) {
+                    const uint32_t dcol = tmem + ACC0 + g * NM;
+                    const uint32_t w_hi = tmem + (2 * g) * KH, w_lo = w_hi + KH;
+#pragma unroll
+                    for (int ks = 0; ks < NKS; ks++) umma_f16_ts(dcol, w_lo + ks * 8, dBh + ks * KB, idesc, ks > 0);
+#pragma unroll
+                    for (int ks = 0; ks < NKS; ks++) umma_f16_ts(dcol, w_hi + ks * 8, dBh + ks * KB, idesc, 1);
+                    umma_commit(g == 0 ? bar_r : bar_z);
+                }
+            }
+            __syncwarp();
+            SB2_TRACE(1);
+            mbar_wait(bar_rh, s & 1);
+            tc_fence_after();
+            SB2_TRACE(2);
+            if (elect_one()) {
+                const uint32_t dcol = tmem + ACC0 + 2 * NM;
+                const uint32_t w_hi = tmem + 4 * KH, w_lo = w_hi + KH;
+#pragma unroll
+                for (int ks = 0; ks < NKS; ks++) umma_f16_ts(dcol, w_lo + ks * 8, dBrh + ks * KB, idesc, ks > 0);
+#pragma unroll
+                for (int ks = 0; ks < NKS; ks++) umma_f16_ts(dcol, w_hi + ks * 8, dBrh + ks * KB, idesc, 1);
+                umma_commit(bar_c);
+            }
+            __syncwarp();
+            SB2_TRACE(3);
+        }
+    } else if ((warp & 3) < NQ) {
+        // ---- gate warps -----------------------------------------------------------------------
+        const int q = warp & 3, cg = warp >> 2;
+        const int j = q * 32 + lane;                    // hidden unit = accumulator row = TMEM lane
+        const bool valid = j < H;
+        const int jj = valid ? j : 0;
+        const uint32_t acc_base = tmem + ((uint32_t)(q * 32) << 16) + ACC0 + cg * RPT;
+        int T[RPT], col[RPT], Tmax = 0;
+        for (int n = 0; n < NR; n++) {
+            const int r = r0 + n;
+            if (r < d.nread) Tmax = max(Tmax, d.nblock[r]);
+        }
+#pragma unroll
+        for (int i = 0; i < RPT; i++) {
+            const int r = r0 + cg * RPT + i;
+            T[i] = (r < d.nread) ? d.nblock[r] : 0;
+            col[i] = (r < d.nread) ? d.col_off[r] : 0;
+        }
+        // byte offsets of this thread's operand elements: row n = cg*4 + i (hi), + SBO_B (lo)
+        const uint32_t op_off = (uint32_t)(j >> 3) * LBO_B + (uint32_t)(cg * RPT) * 16 + (uint32_t)(j & 7) * 2;
+        float h[RPT], xz[RPT], xr[RPT], xc[RPT], rs[RPT];
+#pragma unroll
+        for (int i = 0; i < RPT; i++) { h[i] = 0.0f; rs[i] = 0.0f; }
+        auto load_x = [&](int s) {
+#pragma unroll
+            for (int i = 0; i < RPT; i++) {
+                if (s < T[i]) {
+                    const int t = backward ? (T[i] - 1 - s) : s;
+                    const float *x = Xin + (size_t)(col[i] + t) * (3 * H) + jj;
+                    xz[i] = x[0]; xr[i] = x[H]; xc[i] = x[2 * H];
+                    if (resid != nullptr) rs[i] = resid[(size_t)(col[i] + t) * H + jj];
+                } else {
+                    xz[i] = 0.0f; xr[i] = 0.0f; xc[i] = 0.0f;
+                }
+            }
+        };
+        load_x(0);
+        for (int s = 0; s < Tmax; s++) {
+            float cz[RPT], cr[RPT], cc[RPT], crs[RPT];
+#pragma unroll
+            for (int i = 0; i < RPT; i++) { cz[i] = xz[i]; cr[i] = xr[i]; cc[i] = xc[i]; crs[i] = rs[i]; }
+            if (s + 1 < Tmax && !dbg_no_ld) load_x(s + 1);            // prefetch the next step's inputs
+
+            // reset gate -> (r * h) operand
+            mbar_wait(bar_r, s & 1);
+            tc_fence_after();
+            if (warp == 0) SB2_TRACE(4);
+            {
+                float a[4], b[4];
+                tmem_ld4(acc_base, a);
+                tmem_ld4(acc_base + NR, b);
+                tmem_ld_wait();
+                if (warp == 0) SB2_TRACE(5);
+#pragma unroll
+                for (int i = 0; i < RPT; i++) {
+                    const float gr = dbg_no_math ? (a[i] + b[i]) : gate_sigmoid<MATH>(fmaf(a[i] + b[i], RESULT_SCALE, cr[i]));
+                    __half hi, lo;
+                    split_fp16(gr * h[i], hi, lo);
+                    if (valid) {
+                        *reinterpret_cast<__half *>(b_rh + op_off + i * 16) = hi;
+                        *reinterpret_cast<__half *>(b_rh + op_off + i * 16 + SBO_B) = lo;
+                    }
+                }
+            }
+            if (warp == 0) SB2_TRACE(6);
+            fence_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_rh);
+            if (warp == 0) SB2_TRACE(7);
+
+            // update gate (its UMMAs ran while the reset gate was being evaluated)
+            float gz[RPT];
+            mbar_wait(bar_z, s & 1);
+            tc_fence_after();
+            if (warp == 0) SB2_TRACE(8);
+            {
+                float a[4], b[4];
+                tmem_ld4(acc_base + NM, a);
+                tmem_ld4(acc_base + NM + NR, b);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < RPT; i++) gz[i] = dbg_no_math ? a[i] : gate_sigmoid<MATH>(fmaf(a[i] + b[i], RESULT_SCALE, cz[i]));
+            }
+
+            // candidate, state update, next step's operand
+            if (warp == 0) SB2_TRACE(9);
+            mbar_wait(bar_c, s & 1);
+            tc_fence_after();
+            if (warp == 0) SB2_TRACE(10);
+            float hn[RPT];
+            {
+                float a[4], b[4];
+                tmem_ld4(acc_base + 2 * NM, a);
+                tmem_ld4(acc_base + 2 * NM + NR, b);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < RPT; i++) {
+                    const float cand = dbg_no_math ? b[i] : gate_tanh<MATH>(fmaf(a[i] + b[i], RESULT_SCALE, cc[i]));
+                    hn[i] = gz[i] * h[i] + (1.0f - gz[i]) * cand;
+                    h[i] = hn[i];
+                    __half hi, lo;
+                    split_fp16(hn[i], hi, lo);
+                    if (valid) {
+                        *reinterpret_cast<__half *>(b_h + op_off + i * 16) = hi;
+                        *reinterpret_cast<__half *>(b_h + op_off + i * 16 + SBO_B) = lo;
+                    }
+                }
+            }
+            if (warp == 0) SB2_TRACE(11);
+            fence_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_h);
+            if (warp == 0) SB2_TRACE(12);
+            // results to HBM, off the critical path
+            if (valid && !dbg_no_st) {
+#pragma unroll
+                for (int i = 0; i < RPT; i++) {
+                    if (s < T[i]) {
+                        const int t = backward ? (T[i] - 1 - s) : s;
+                        out[(size_t)(col[i] + t) * H + j] = (resid != nullptr) ? hn[i] + crs[i] : hn[i];
+                    }
+                }
+            }
+        }
+    }
+#undef SB2_TRACE
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, TCOLS);
+}
+
+template <int H, int MATH>
+static int launch_scan_v3(const float *Xin, const float *sW, const float *sW2, const float *resid, float *out,
+                          const BatchDims &d, int backward, long long *trace, int dbg, cudaStream_t s) {
+    // all 512 TMEM columns are allocated: keep a second scan CTA off the SM (see launch_scan_tmem)
+    constexpr int EXCLUSIVE_SMEM = 120 * 1024;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(gru_scan_v3_kernel<H, MATH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 EXCLUSIVE_SMEM) != cudaSuccess)
+            return -1;
+        configured = true;
+    }
+    const int grid = (d.nread + 7) / 8;
+    gru_scan_v3_kernel<H, MATH><<<grid, 288, EXCLUSIVE_SMEM, s>>>(Xin, sW, sW2, resid, out, d, backward, trace, dbg);
+    return 0;
+}
+
+int launch_gru_scan_v3(const float *Xin, const float *sW, const float *sW2, const float *resid, float *out,
+                       const BatchDims &d, int H, int backward, int math, long long *trace, cudaStream_t s) {
+    static int dbg = -1;
+    if (dbg < 0) { const char *e = getenv("SCRAPPIE_B200_SCAN_DBG"); dbg = e ? atoi(e) : 0; }
+#define SB2_CASE(HH, MM) if (H == HH && math == MM) return launch_scan_v3<HH, MM>(Xin, sW, sW2, resid, out, d, backward, trace, dbg, s)
+    SB2_CASE(96, 0); SB2_CASE(96, 1); SB2_CASE(96, 2);
+    SB2_CASE(112, 0); SB2_CASE(112, 1); SB2_CASE(112, 2);
+#undef SB2_CASE
+    return -1;
+}
+
+
+// ---------------------------------------------------------------------------------
+// GRU scan v4: two independent read groups per CTA, gate math written for ILP
+// ---------------------------------------------------------------------------------
+// Measured on v3 (tools/scan_trace.py, profiles/): the UMMAs of a step are cheap (~10-14 cycles
+// each to issue, ~300 cycles from first issue to the commit being seen); the step time is set by
+// the CUDA-core side -- the gate polynomials are a long dependent chain, and a TMEM lane quarter
+// can only be read by the warps of ONE scheduler (warp % 4), so all the math of 32 hidden units
+// lands on one SMSP.  v4 therefore
+//  * splits the 8 reads of a CTA into two groups of 4 with their own operands, accumulators,
+//    barriers and issuer warp, so one group's gate math fills the other group's UMMA / hand-over
+//    waits on the same schedulers;
+//  * evaluates the 4 reads of a thread stage by stage (sigmoid4 / tanh4) so the four dependent
+//    chains interleave;
+//  * keeps hi and lo of a read in the same 8-row core-matrix group (rows i and 4 + i), so one
+//    tcgen05.ld.x8 fetches both partial sums.
+template <int MATH>
+__device__ __forceinline__ void sigmoid4(const float (&x)[4], float (&y)[4]) {
+    if (MATH == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) y[i] = logistic_cephes(x[i]);
+    } else if (MATH == 1) {
+        float e[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) e[i] = ex2_approx(-1.4426950408889634f * x[i]);
+#pragma unroll
+        for (int i = 0; i < 4; i++) y[i] = rcp_approx(1.0f + e[i]);
+    } else {
+        float t[4], r[4], f[4], p[4], dd[4], q[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) t[i] = fmaxf(fminf(x[i] * -1.4426950408889634f, 126.0f), -126.0f);
+#pragma unroll
+        for (int i = 0; i < 4; i++) r[i] = t[i] + 12582912.0f;
+#pragma unroll
+        for (int i = 0; i < 4; i++) f[i] = t[i] - (r[i] - 12582912.0f);
+#pragma unroll
+        for (int i = 0; i < 4; i++) p[i] = fmaf(0.00015337577497120947f, f[i], 0.0013399859890341759f);
+#pragma unroll
+        for (int i = 0; i < 4; i++) p[i] = fmaf(p[i], f[i], 0.009618519805371761f);
+#pragma unroll
+        for (int i = 0; i < 4; i++) p[i] = fmaf(p[i], f[i], 0.05550329014658928f);
+#pragma unroll
+        for (int i = 0; i < 4; i++) p[i] = fmaf(p[i], f[i], 0.24022646248340607f);
+#pragma unroll
+        for (int i = 0; i < 4; i++) p[i] = fmaf(p[i], f[i], 0.6931471824645996f);
+#pragma unroll
+        for (int i = 0; i < 4; i++) p[i] = fmaf(p[i], f[i], 1.0f);
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            dd[i] = 1.0f + __int_as_float(__float_as_int(p[i]) + ((__float_as_int(r[i]) - 0x4B400000) << 23));
+#pragma unroll
+        for (int i = 0; i < 4; i++) q[i] = rcp_approx(dd[i]);
+#pragma unroll
+        for (int i = 0; i < 4; i++) y[i] = fmaf(q[i], fmaf(-dd[i], q[i], 1.0f), q[i]);
+    }
+}
+template <int MATH>
+__device__ __forceinline__ void tanh4(const float (&x)[4], float (&y)[4]) {
+    if (MATH == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) y[i] = tanh_cephes(x[i]);
+    } else {
+        float x2[4], s[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) x2[i] = x[i] + x[i];
+        sigmoid4<MATH>(x2, s);
+#pragma unroll
+        for (int i = 0; i < 4; i++) y[i] = (s[i] + s[i]) - 1.0f;
+    }
+}
+
+template <int H, int MATH>
+__global__ void __launch_bounds__(512, 1)
+gru_scan_v4_kernel(const float *__restrict__ Xin, const float *__restrict__ sW, const float *__restrict__ sW2,
+                   const float *__restrict__ resid, float *__restrict__ out, BatchDims d, int backward,
+                   long long *__restrict__ trace) {
+#define SB2_TRACE(slot) do { if (trace != nullptr && blockIdx.x == 0 && grp == 0 && lane == 0 && s >= 100 && s < 104) trace[(s - 100) * 16 + (slot)] = clock64(); } while (0)
+    constexpr int NG = 2, RPG = 4, NM = 16;             // groups per CTA, reads per group, UMMA N
+    constexpr uint32_t LBO_B = 16u * NM + 16u, SBO_B = 128u;
+    constexpr uint32_t TILE_B = (H / 8) * LBO_B;
+    constexpr int NKS = H / 16;
+    constexpr int NQ = (H + 31) / 32;                   // lane quarters that own hidden units
+    constexpr uint32_t KH = H / 2;                      // TMEM columns per weight tile
+    constexpr uint32_t ACC0 = 6 * KH;                   // accumulators: per group r, z, c (16 columns each)
+    constexpr uint32_t TCOLS = 512;
+    static_assert(ACC0 + NG * 3 * NM <= TCOLS, "TMEM budget");
+
+    __shared__ __align__(128) uint8_t b_ops[NG * 2 * TILE_B];   // per group: h [hi|lo], r*h [hi|lo]
+    __shared__ __align__(8) uint64_t bars[NG * 5];
+    __shared__ uint32_t tmem_slot;
+
+    const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+    const int r0 = blockIdx.x * (NG * RPG);
+
+    for (uint32_t i = tid; i < NG * 2 * TILE_B / 16; i += blockDim.x) reinterpret_cast<uint4 *>(b_ops)[i] = make_uint4(0, 0, 0, 0);
+    if (tid == 0) {
+        for (int g = 0; g < NG; g++) {
+            mbar_init(&bars[g * 5 + 0], 1);             // r committed
+            mbar_init(&bars[g * 5 + 1], 1);             // z committed
+            mbar_init(&bars[g * 5 + 2], 1);             // c committed
+            mbar_init(&bars[g * 5 + 3], NQ);            // r*h operand written
+            mbar_init(&bars[g * 5 + 4], NQ);            // h operand written
+        }
+        mbar_fence_init();
+    }
+    if (warp == 0) tmem_alloc(&tmem_slot, TCOLS);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+
+    // ---- weights -> TMEM (once per layer): tiles r_hi r_lo z_hi z_lo c_hi c_lo -------------
+    if (warp < 4) {
+        const int m = tid;
+        const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+        for (int g = 0; g < 3; g++) {
+            // tile order r, z, c; the reference stores z rows first, then r (src/layers.c:511-526)
+            const int mm = (m < H) ? m : 0;
+            const float *row = (g == 0) ? (sW + (size_t)(H + mm) * H) : ((g == 1) ? (sW + (size_t)mm * H) : (sW2 + (size_t)mm * H));
+#pragma unroll 1
+            for (int kc = 0; kc < NKS; kc++) {
+                uint32_t whi[8], wlo[8];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    float4 v = *reinterpret_cast<const float4 *>(row + kc * 16 + q * 4);
+                    if (m >= H) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    __half h0, l0, h1, l1, h2, l2, h3, l3;
+                    split_fp16(v.x, h0, l0); split_fp16(v.y, h1, l1); split_fp16(v.z, h2, l2); split_fp16(v.w, h3, l3);
+                    whi[2 * q] = pack_half2(h0, h1); whi[2 * q + 1] = pack_half2(h2, h3);
+                    wlo[2 * q] = pack_half2(l0, l1); wlo[2 * q + 1] = pack_half2(l2, l3);
+                }
+                tmem_st8(lane_base + (2 * g) * KH + kc * 8, whi);
+                tmem_st8(lane_base + (2 * g + 1) * KH + kc * 8, wlo);
+            }
+        }
+        tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    const bool is_issuer = (warp == 11 || warp == 15);  // scheduler 3: free of gate math when H <= 96
+    const bool is_gate = (warp < 8) && ((warp & 3) < NQ);
+    const int grp = is_issuer ? (warp == 15) : (warp >> 2);
+    uint8_t *b_h = b_ops + grp * 2 * TILE_B, *b_rh = b_h + TILE_B;
+    uint64_t *bar_r = &bars[grp * 5 + 0], *bar_z = &bars[grp * 5 + 1], *bar_c = &bars[grp * 5 + 2],
+             *bar_rh = &bars[grp * 5 + 3], *bar_h = &bars[grp * 5 + 4];
+    const uint32_t acc0 = tmem + ACC0 + grp * 3 * NM;
+    int Tmax = 0;
+    for (int i = 0; i < RPG; i++) {
+        const int r = r0 + grp * RPG + i;
+        if (r < d.nread) Tmax = max(Tmax, d.nblock[r]);
+    }
+
+    if (is_issuer) {
+        // ---- UMMA issuer of one group -----------------------------------------------------------
+        if (grp == 1) {                                  // start the second group half a step late
+            const long long t0 = clock64();
+            while (clock64() - t0 < 700) { }
+        }
+        const uint32_t idesc = umma_idesc_f16(128, NM);
+        const uint64_t dBh = umma_desc(smem_u32(b_h), LBO_B, SBO_B), dBrh = umma_desc(smem_u32(b_rh), LBO_B, SBO_B);
+        constexpr uint64_t KB = (2 * LBO_B) >> 4;
+        for (int s = 0; s < Tmax; s++) {
+            if (s > 0) mbar_wait(bar_h, (s - 1) & 1);
+            tc_fence_after();
+            SB2_TRACE(0);
+            if (elect_one()) {
+#pragma unroll
+                for (int g = 0; g < 2; g++) {
+                    const uint32_t dcol = acc0 + g * NM;
+                    const uint32_t w_hi = tmem + (2 * g) * KH, w_lo = w_hi + KH;
+#pragma unroll
+                    for (int ks = 0; ks < NKS; ks++) umma_f16_ts(dcol, w_lo + ks * 8, dBh + ks * KB, idesc, ks > 0);
+#pragma unroll
+                    for (int ks = 0; ks < NKS; ks++) umma_f16_ts(dcol, w_hi + ks * 8, dBh + ks * KB, idesc, 1);
+                    umma_commit(g == 0 ? bar_r : bar_z);
+                }
+            }
+            __syncwarp();
+            SB2_TRACE(1);
+            mbar_wait(bar_rh, s & 1);
+            tc_fence_after();
+            SB2_TRACE(2);
+            if (elect_one()) {
+                const uint32_t dcol = acc0 + 2 * NM;
+                const uint32_t w_hi = tmem + 4 * KH, w_lo = w_hi + KH;
+#pragma unroll
+                for (int ks = 0; ks < NKS; ks++) umma_f16_ts(dcol, w_lo + ks * 8, dBrh + ks * KB, idesc, ks > 0);
+#pragma unroll
+                for (int ks = 0; ks < NKS; ks++) umma_f16_ts(dcol, w_hi + ks * 8, dBrh + ks * KB, idesc, 1);
+                umma_commit(bar_c);
+            }
+            __syncwarp();
+            SB2_TRACE(3);
+        }
+    } else if (is_gate) {
+        // ---- gate warps ---------------------------------------------------------------------------
+        const int q = warp & 3;
+        const int j = q * 32 + lane;                    // hidden unit = accumulator row = TMEM lane
+        const bool valid = j < H;
+        const int jj = valid ? j : 0;
+        const uint32_t acc_base = acc0 + ((uint32_t)(q * 32) << 16);
+        int T[RPG];
+        const float *xp[RPG];                           // this thread's element of the current input column
+        const float *rp[RPG];
+        float *op[RPG];
+#pragma unroll
+        for (int i = 0; i < RPG; i++) {
+            const int r = r0 + grp * RPG + i;
+            T[i] = (r < d.nread) ? d.nblock[r] : 0;
+            const int col = (r < d.nread) ? d.col_off[r] : 0;
+            const int t0 = backward ? max(T[i] - 1, 0) : 0;
+            xp[i] = Xin + (size_t)(col + t0) * (3 * H) + jj;
+            rp[i] = (resid != nullptr) ? resid + (size_t)(col + t0) * H + jj : nullptr;
+            op[i] = out + (size_t)(col + t0) * H + jj;
+        }
+        const int xstep = backward ? -3 * H : 3 * H, ostep = backward ? -H : H;
+        // operand element of (read i, unit j): row i (hi) / row 4 + i (lo) of k-group j / 8
+        const uint32_t op_off = (uint32_t)(j >> 3) * LBO_B + (uint32_t)(j & 7) * 2;
+        float h[RPG], xz[RPG], xr[RPG], xc[RPG], rs[RPG];
+#pragma unroll
+        for (int i = 0; i < RPG; i++) { h[i] = 0.0f; rs[i] = 0.0f; }
+        auto load_x = [&](int s) {
+#pragma unroll
+            for (int i = 0; i < RPG; i++) {
+                if (s < T[i]) {
+                    xz[i] = xp[i][0]; xr[i] = xp[i][H]; xc[i] = xp[i][2 * H];
+                    if (resid != nullptr) rs[i] = rp[i][0];
+                } else {
+                    xz[i] = 0.0f; xr[i] = 0.0f; xc[i] = 0.0f;
+                }
+            }
+        };
+        load_x(0);
+        for (int s = 0; s < Tmax; s++) {
+            float cz[RPG], cr[RPG], cc[RPG], crs[RPG];
+#pragma unroll
+            for (int i = 0; i < RPG; i++) { cz[i] = xz[i]; cr[i] = xr[i]; cc[i] = xc[i]; crs[i] = rs[i]; }
+            float *ocur[RPG];
+#pragma unroll
+            for (int i = 0; i < RPG; i++) {
+                ocur[i] = op[i];
+                xp[i] += xstep; op[i] += ostep;
+                if (resid != nullptr) rp[i] += ostep;
+            }
+            if (s + 1 < Tmax) load_x(s + 1);            // prefetch the next step's inputs
+
+            // reset gate -> (r * h) operand
+            mbar_wait(bar_r, s & 1);
+            tc_fence_after();
+            SB2_TRACE(4);
+            {
+                float a[8], pre[RPG], gr[RPG];
+                tmem_ld8(acc_base, a);
+                tmem_ld_wait();
+                SB2_TRACE(5);
+#pragma unroll
+                for (int i = 0; i < RPG; i++) pre[i] = fmaf(a[i] + a[4 + i], RESULT_SCALE, cr[i]);
+                sigmoid4<MATH>(pre, gr);
+                float xs[RPG], fh[RPG];
+                __half hi[RPG], lo[RPG];
+#pragma unroll
+                for (int i = 0; i < RPG; i++) xs[i] = gr[i] * h[i] * OPERAND_SCALE;
+#pragma unroll
+                for (int i = 0; i < RPG; i++) hi[i] = __float2half_rn(xs[i]);
+#pragma unroll
+                for (int i = 0; i < RPG; i++) fh[i] = __half2float(hi[i]);
+#pragma unroll
+                for (int i = 0; i < RPG; i++) lo[i] = __float2half_rn(xs[i] - fh[i]);
+                if (valid) {
+#pragma unroll
+                    for (int i = 0; i < RPG; i++) {
+                        *reinterpret_cast<__half *>(b_rh + op_off + i * 16) = hi[i];
+                        *reinterpret_cast<__half *>(b_rh + op_off + (4 + i) * 16) = lo[i];
+                    }
+                }
+            }
+            SB2_TRACE(6);
+            fence_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_rh);
+            SB2_TRACE(7);
+
+            // update gate (its UMMAs ran while the reset gate was being evaluated)
+            float gz[RPG];
+            mbar_wait(bar_z, s & 1);
+            tc_fence_after();
+            SB2_TRACE(8);
+            {
+                float a[8], pre[RPG];
+                tmem_ld8(acc_base + NM, a);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < RPG; i++) pre[i] = fmaf(a[i] + a[4 + i], RESULT_SCALE, cz[i]);
+                sigmoid4<MATH>(pre, gz);
+            }
+            SB2_TRACE(9);
+
+            // candidate, state update, next step's operand
+            mbar_wait(bar_c, s & 1);
+            tc_fence_after();
+            SB2_TRACE(10);
+            float hn[RPG];
+            {
+                float a[8], pre[RPG], cand[RPG];
+                tmem_ld8(acc_base + 2 * NM, a);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < RPG; i++) pre[i] = fmaf(a[i] + a[4 + i], RESULT_SCALE, cc[i]);
+                tanh4<MATH>(pre, cand);
+#pragma unroll
+                for (int i = 0; i < RPG; i++) hn[i] = gz[i] * h[i] + (1.0f - gz[i]) * cand[i];
+                float xs[RPG], fh[RPG];
+                __half hi[RPG], lo[RPG];
+#pragma unroll
+                for (int i = 0; i < RPG; i++) { h[i] = hn[i]; xs[i] = hn[i] * OPERAND_SCALE; }
+#pragma unroll
+                for (int i = 0; i < RPG; i++) hi[i] = __float2half_rn(xs[i]);
+#pragma unroll
+                for (int i = 0; i < RPG; i++) fh[i] = __half2float(hi[i]);
+#pragma unroll
+                for (int i = 0; i < RPG; i++) lo[i] = __float2half_rn(xs[i] - fh[i]);
+                if (valid) {
+#pragma unroll
+                    for (int i = 0; i < RPG; i++) {
+                        *reinterpret_cast<__half *>(b_h + op_off + i * 16) = hi[i];
+                        *reinterpret_cast<__half *>(b_h + op_off + (4 + i) * 16) = lo[i];
+                    }
+                }
+            }
+            SB2_TRACE(11);
+            fence_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_h);
+            SB2_TRACE(12);
+            // results to HBM, off the critical path
+            if (valid) {
+#pragma unroll
+                for (int i = 0; i < RPG; i++)
+                    if (s < T[i]) *ocur[i] = (resid != nullptr) ? hn[i] + crs[i] : hn[i];
+            }
+        }
+    }
+#undef SB2_TRACE
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, TCOLS);
+}
+
+template <int H, int MATH>
+static int launch_scan_v4(const float *Xin, const float *sW, const float *sW2, const float *resid, float *out,
+                          const BatchDims &d, int backward, long long *trace, cudaStream_t s) {
+    constexpr int EXCLUSIVE_SMEM = 120 * 1024;          // all 512 TMEM columns are allocated: one CTA per SM
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(gru_scan_v4_kernel<H, MATH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 EXCLUSIVE_SMEM) != cudaSuccess)
+            return -1;
+        configured = true;
+    }
+    const int grid = (d.nread + 7) / 8;
+    gru_scan_v4_kernel<H, MATH><<<grid, 512, EXCLUSIVE_SMEM, s>>>(Xin, sW, sW2, resid, out, d, backward, trace);
+    return 0;
+}
+
+int launch_gru_scan_v4(const float *Xin, const float *sW, const float *sW2, const float *resid, float *out,
+                       const BatchDims &d, int H, int backward, int math, long long *trace, cudaStream_t s) {
+#define SB2_CASE(HH, MM) if (H == HH && math == MM) return launch_scan_v4<HH, MM>(Xin, sW, sW2, resid, out, d, backward, trace, s)
     SB2_CASE(96, 0); SB2_CASE(96, 1); SB2_CASE(96, 2);
     SB2_CASE(112, 0); SB2_CASE(112, 1); SB2_CASE(112, 2);
 #undef SB2_CASE
