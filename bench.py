@@ -44,7 +44,7 @@ def parse_args():
     ap.add_argument("--reads", type=int, default=1024)
     ap.add_argument("--samples", type=int, default=4000)
     ap.add_argument("--batch", type=int, default=256)
-    ap.add_argument("--cpu-sample-reads", type=int, default=512)
+    ap.add_argument("--cpu-sample-reads", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -140,7 +140,7 @@ def run_oracle_port(model, sigs):
 
 
 def cpu_baseline(model, sigs, nreads_sample):
-    sample = sigs[:nreads_sample]
+    sample = (sigs * ((nreads_sample + len(sigs) - 1) // len(sigs)))[:nreads_sample]   # the workload's reads, repeated
     res = run_reference(model, sample)
     kind = "reference"
     if res is None:
@@ -158,7 +158,8 @@ def cpu_baseline(model, sigs, nreads_sample):
 def main_reference(args, rank, world):
     if rank != 0:
         return
-    sigs = make_workload(args.cpu_sample_reads, args.samples, 1000)
+    base = make_workload(min(args.cpu_sample_reads, args.reads), args.samples, 1000)
+    sigs = (base * ((args.cpu_sample_reads + len(base) - 1) // len(base)))[:args.cpu_sample_reads]
     for _ in range(max(1, min(args.warmup, 1))):
         run_reference(args.model, sigs[:32]) if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_bench.so")) else None
     times, kind, threads, nbases = [], "reference", 1, 0
@@ -202,20 +203,9 @@ def main_b200(args, rank, world, local_rank):
 
     eng = sb.Engine(local_rank)
     # weights: rank 0 reads the blob, every other rank receives it over NCCL (init only)
+    from scrappie_b200.sharding import broadcast_blob, max_over_ranks
     blob_path = os.path.join(sb.WEIGHTS_DIR, args.model + ".bin")
-    if world > 1:
-        if rank == 0:
-            blob = torch.from_numpy(np.fromfile(blob_path, dtype=np.uint8)).cuda()
-            size = torch.tensor([blob.numel()], device="cuda")
-        else:
-            size = torch.zeros(1, dtype=torch.int64, device="cuda")
-        dist.broadcast(size, 0)
-        if rank != 0:
-            blob = torch.empty(int(size.item()), dtype=torch.uint8, device="cuda")
-        dist.broadcast(blob, 0)
-        eng.load_blob(args.model, blob.cpu().numpy())
-    else:
-        eng.load_blob(args.model, np.fromfile(blob_path, dtype=np.uint8))
+    eng.load_blob(args.model, broadcast_blob(blob_path, rank, dist, device="cuda" if world > 1 else "cpu"))
 
     sigs = make_workload(args.reads, args.samples, 1000 + rank * args.reads)
     nbatch = (args.reads + args.batch - 1) // args.batch
@@ -275,10 +265,7 @@ def main_b200(args, rank, world, local_rank):
     d2h = sum((b.total_blocks + b.nread) * 4 + b.nread * 4 for b in batches)
 
     # ---- reduce over ranks (max time) ------------------------------------------------------
-    if dist is not None:
-        t = torch.tensor([step_ms, e2e_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        step_ms, e2e_s = float(t[0]), float(t[1])
+    step_ms, e2e_s = max_over_ranks([step_ms, e2e_s], dist, device="cuda" if world > 1 else "cpu")
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
