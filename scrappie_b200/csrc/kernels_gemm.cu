@@ -96,10 +96,10 @@ __device__ __forceinline__ void split8(const float4 &a, const float4 &b, float s
     lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-template <int K, int ROWS, int NTILE, int NT>
+template <int K, int ROWS, int NTILE, int NT, int LDC>
 __global__ void __launch_bounds__(288, 1)
 affine_tc_kernel(const float *__restrict__ X, int ncol, const uint8_t *__restrict__ wimg, const float *__restrict__ bias,
-                 int M, float *__restrict__ C, int ldc) {
+                 int M, float *__restrict__ C) {
     using G = GemmCfg<K, ROWS, NTILE, NT>;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t *w_img = smem;
@@ -216,16 +216,24 @@ affine_tc_kernel(const float *__restrict__ X, int ncol, const uint8_t *__restric
                 mbar_wait(&accf[a], (acc_it >> 1) & 1);
                 tc_fence_after();
                 if (warp_valid) {
-                    float *dst = C + (size_t)col0 * ldc + g * ROWS + m;
+                    // ldc is a compile-time constant: every store address is base + immediate
+                    float *dst = C + (size_t)col0 * LDC + g * ROWS + m;
+                    const bool full = (col0 + NT <= ncol);
 #pragma unroll 1
                     for (int n0 = 0; n0 < NT; n0 += 32) {
                         float v[32];
                         tmem_ld32(lane_base + a * NT + n0, v);
                         tmem_ld_wait();
                         if (ok[g]) {
+                            float *d0 = dst + (size_t)n0 * LDC;
+                            if (full) {
 #pragma unroll
-                            for (int j = 0; j < 32; j++)
-                                if (col0 + n0 + j < ncol) dst[(size_t)(n0 + j) * ldc] = fmaf(v[j], RESULT_SCALE, bg[g]);
+                                for (int j = 0; j < 32; j++) d0[j * LDC] = fmaf(v[j], RESULT_SCALE, bg[g]);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 32; j++)
+                                    if (col0 + n0 + j < ncol) d0[j * LDC] = fmaf(v[j], RESULT_SCALE, bg[g]);
+                            }
                         }
                     }
                 }
@@ -240,28 +248,28 @@ affine_tc_kernel(const float *__restrict__ X, int ncol, const uint8_t *__restric
     if (warp == 0) tmem_dealloc(tmem, G::TCOLS);
 }
 
-template <int K, int ROWS, int NTILE, int NT>
-static int launch_affine_cfg(const float *X, int ncol, const uint8_t *wimg, const float *bias, int M, float *C, int ldc,
+template <int K, int ROWS, int NTILE, int NT, int LDC>
+static int launch_affine_cfg(const float *X, int ncol, const uint8_t *wimg, const float *bias, int M, float *C,
                              cudaStream_t s) {
     using G = GemmCfg<K, ROWS, NTILE, NT>;
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(affine_tc_kernel<K, ROWS, NTILE, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        if (cudaFuncSetAttribute(affine_tc_kernel<K, ROWS, NTILE, NT, LDC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)G::SMEM) != cudaSuccess)
             return -1;
         configured = true;
     }
     const int nchunk = (ncol + NT - 1) / NT;
     const int grid = nchunk < 148 ? nchunk : 148;
-    affine_tc_kernel<K, ROWS, NTILE, NT><<<grid, 288, G::SMEM, s>>>(X, ncol, wimg, bias, M, C, ldc);
+    affine_tc_kernel<K, ROWS, NTILE, NT, LDC><<<grid, 288, G::SMEM, s>>>(X, ncol, wimg, bias, M, C);
     return 0;
 }
 
 // GRU input transform: M = 3H rows as three tiles (z, r, candidate) of H rows, K = H.
 int launch_affine_tc(const float *X, int ncol, int H, const uint8_t *wimg, const float *bias, float *C, cudaStream_t s) {
     if (ncol <= 0) return 0;
-    if (H == 96) return launch_affine_cfg<96, 96, 3, 128>(X, ncol, wimg, bias, 3 * H, C, 3 * H, s);
-    if (H == 112) return launch_affine_cfg<112, 112, 3, 64>(X, ncol, wimg, bias, 3 * H, C, 3 * H, s);
+    if (H == 96) return launch_affine_cfg<96, 96, 3, 128, 288>(X, ncol, wimg, bias, 3 * H, C, s);
+    if (H == 112) return launch_affine_cfg<112, 112, 3, 64, 336>(X, ncol, wimg, bias, 3 * H, C, s);
     return -1;
 }
 
@@ -314,6 +322,7 @@ head_softmax_tc_kernel(const float *__restrict__ X, int ncol, const uint8_t *__r
                        int ostride, float xdiv, float cdiv, float min_prob, int return_log) {
     using G = HeadCfg<K>;
     constexpr int NT = G::NT, NTILE = G::NTILE;
+    constexpr int OSTRIDE = NTILE * 128 + 4;            // 1028 = 4 * ceil(1025 / 4), the reference's column stride
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t *w_ring = smem;
     uint8_t *b_ring = smem + G::OFF_B;
@@ -436,6 +445,9 @@ head_softmax_tc_kernel(const float *__restrict__ X, int ncol, const uint8_t *__r
 #pragma unroll
         for (int i = 0; i < KQ; i++) ws[i] = w_stay[q * KQ + i];
         const float keep = 1.0f - min_prob;
+        // FAST: exp((acc * 2^-16 + b) / cdiv) = 2^(acc * sc + b * bsc), one FFMA in front of ex2.approx
+        const float inv_cdiv = 1.0f / cdiv;
+        const float sc = RESULT_SCALE * inv_cdiv * 1.4426950408889634f, bsc = inv_cdiv * 1.4426950408889634f;
         uint32_t it = 0;
         for (int c = blockIdx.x; c < nchunk; c += gridDim.x, it++) {
             const int col0 = c * NT + ch * 32;            // first column of this warp's half
@@ -464,45 +476,60 @@ head_softmax_tc_kernel(const float *__restrict__ X, int ncol, const uint8_t *__r
                 tmem_ld32(tbase + t * NT, v);
                 tmem_ld_wait();
                 const float bt = __ldg(bias + t * 128 + m);
+                if (FAST) {
+                    const float bt2 = bt * bsc;
 #pragma unroll
-                for (int j = 0; j < 32; j++) {
-                    const float e = head_exp<FAST>((fmaf(v[j], RESULT_SCALE, bt)) / cdiv);
-                    cs[j] += e;
-                    v[j] = e;
+                    for (int j = 0; j < 32; j++) {
+                        // clamp = the reference's exp_ps input clamp (+-88.376) expressed in base 2
+                        const float e = ex2_approx(fminf(fmaxf(fmaf(v[j], sc, bt2), -127.5f), 127.5f));
+                        cs[j] += e;
+                        v[j] = e;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        const float e = exp_cephes((fmaf(v[j], RESULT_SCALE, bt)) / cdiv);
+                        cs[j] += e;
+                        v[j] = e;
+                    }
                 }
                 tmem_st32(tbase + t * NT, v);
             }
             tmem_st_wait();
-            // column sums: over the lanes of the warp, then over the 4 q-warps of this half
-            float mine = 0.0f;
+            // column sums over the 32 lanes: halving butterfly (31 shuffles); lane L ends with column L
 #pragma unroll
-            for (int j = 0; j < 32; j++) {
-                float x = cs[j];
+            for (int w = 16; w > 0; w >>= 1) {
+                const bool up = (lane & w) != 0;
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-                if (lane == j) mine = x;
+                for (int j = 0; j < w; j++) {
+                    const float lo_v = cs[j], hi_v = cs[j + w];
+                    const float send = up ? lo_v : hi_v;
+                    const float mine_v = up ? hi_v : lo_v;
+                    cs[j] = mine_v + __shfl_xor_sync(0xffffffffu, send, w);
+                }
             }
             const int pb = ((it & 1) * 2 + ch) * 4 * 32;
-            part_sum[pb + q * 32 + lane] = mine;
+            part_sum[pb + q * 32 + lane] = cs[0];
             part_stay[pb + q * 32 + lane] = sp;
             named_bar_sync(1 + ch, 128);
             float tot = 0.0f, sl = 0.0f;
 #pragma unroll
             for (int qq = 0; qq < 4; qq++) { tot += part_sum[pb + qq * 32 + lane]; sl += part_stay[pb + qq * 32 + lane]; }
-            const float e_stay = head_exp<FAST>((b_stay + sl) / cdiv);
+            const float e_stay = FAST ? ex2_approx(fminf(fmaxf((b_stay + sl) * bsc, -127.5f), 127.5f))
+                                      : exp_cephes((b_stay + sl) / cdiv);
             const float recip = __fdiv_rn(1.0f, tot + e_stay);
             if (q == 0 && mycol < ncol) {
                 // stay state and the three padding lanes (exp(0) = 1 in the reference, normalised like the rest)
                 float ps = e_stay * recip, pp = recip;
                 if (return_log) { ps = head_log<FAST>(min_prob + keep * ps); pp = head_log<FAST>(min_prob + keep * pp); }
-                float *o = post + (size_t)mycol * ostride + NTILE * 128;
-                o[0] = ps;
-                for (int i = NTILE * 128 + 1; i < ostride; i++) o[i - NTILE * 128] = pp;
+                float *o = post + (size_t)mycol * OSTRIDE + NTILE * 128;
+                o[0] = ps; o[1] = pp; o[2] = pp; o[3] = pp;
             }
+            // pass B: normalise, robust log, store.  out = log(min_prob + keep * e * recip)
+            const float krc_mine = return_log ? keep * recip : recip;
             float rc[32];
 #pragma unroll
-            for (int j = 0; j < 32; j++) rc[j] = __shfl_sync(0xffffffffu, recip, j);
-            // pass B: normalise, robust log, store
+            for (int j = 0; j < 32; j++) rc[j] = __shfl_sync(0xffffffffu, krc_mine, j);
             const int nok = min(32, ncol - col0);
 #pragma unroll 1
             for (int t = 0; t < NTILE; t++) {
@@ -512,12 +539,21 @@ head_softmax_tc_kernel(const float *__restrict__ X, int ncol, const uint8_t *__r
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tile_free[t]);
-                float *dst = post + (size_t)col0 * ostride + t * 128 + m;
+                float *dst = post + (size_t)col0 * OSTRIDE + t * 128 + m;
+                if (return_log) {
 #pragma unroll
-                for (int j = 0; j < 32; j++) {
-                    float p = v[j] * rc[j];
-                    if (return_log) p = head_log<FAST>(fmaf(keep, p, min_prob));
-                    if (j < nok) dst[(size_t)j * ostride] = p;
+                    for (int j = 0; j < 32; j++) v[j] = head_log<FAST>(fmaf(v[j], rc[j], min_prob));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) v[j] = v[j] * rc[j];
+                }
+                if (nok == 32) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) dst[j * OSTRIDE] = v[j];
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; j++)
+                        if (j < nok) dst[j * OSTRIDE] = v[j];
                 }
             }
         }
@@ -533,7 +569,7 @@ int launch_head_softmax_tc(const float *X, int ncol, int K, const uint8_t *wimg,
                            float *post, int ostride, float xdiv, float cdiv, float min_prob, int return_log,
                            int exact_math, cudaStream_t s) {
     if (ncol <= 0) return 0;
-    if (K != 96) return -1;
+    if (K != 96 || ostride != 1028) return -1;
     using G = HeadCfg<96>;
     static bool configured = false;
     if (!configured) {

@@ -3,6 +3,8 @@
 // selectable at run time (SCRAPPIE_B200_SCAN=ffma, SCRAPPIE_B200_GEMM=ffma).
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "device_math.cuh"
 #include "kernels.h"
@@ -592,16 +594,244 @@ decode_transducer_kernel(const float *__restrict__ post, BatchDims d, int ostrid
     }
 }
 
+// ---------------------------------------------------------------------------------
+// transducer Viterbi, second generation (same results, ~40 % fewer instructions per block)
+// ---------------------------------------------------------------------------------
+// Same thread <-> state mapping and traceback format as decode_transducer_kernel.  Differences:
+//  * step / skip maxima are hierarchical: thread t computes m4[t] = max_r prev[r*NH/4 + t] once and
+//    publishes (value, argmax); the 16-way skip maximum is then the max over four m4 entries.
+//    argmax ties resolve to the lowest predecessor index exactly as the reference's ascending
+//    scans do (r16 = 4a + b: the smallest r16 among the maximal entries).
+//  * warp maxima use redux.sync (CREDUX.MAX.F32 / REDUX.MIN on sm_100a) instead of shuffle trees.
+//  * only warp 0 tracks the end state.
+//  * the backtrace stages 16 KB of traceback rows per chunk in shared memory with coalesced loads
+//    from all threads, instead of one dependent HBM load per block from a single thread.
+__device__ __forceinline__ float redux_max_f32(float v) {
+    float m;
+    asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(m) : "f"(v));
+    return m;
+}
+__device__ __forceinline__ int redux_min_s32(int v) {
+    int m;
+    asm volatile("redux.sync.min.s32 %0, %1, 0xffffffff;" : "=r"(m) : "r"(v));
+    return m;
+}
+
+template <int NH>
+__global__ void __launch_bounds__(NH / 4)
+decode_transducer_v2_kernel(const float *__restrict__ post, BatchDims d, int ostride, float stay_pen,
+                            float skip_pen, float local_pen, int allow_slip, uint8_t *__restrict__ tb,
+                            int *__restrict__ tb_end, int *__restrict__ path, float *__restrict__ score) {
+    constexpr int NT = NH / 4;
+    constexpr int NW = NT / 32;
+    constexpr int BT_ROWS = 16384 / NH;                 // traceback rows staged per backtrace chunk (16 KB)
+    constexpr int BIG_IDX = 0x7fffffff;
+    constexpr int SC_BYTES = 2 * NH * 4, BT_BYTES = BT_ROWS * NH;
+    // the score exchange buffers and the backtrace staging area are never live at the same time
+    __shared__ __align__(16) uint8_t sc_or_bt[SC_BYTES > BT_BYTES ? SC_BYTES : BT_BYTES];
+    __shared__ __align__(16) float2 m4s[NT];            // (max over the 4 step predecessors, its r) per suffix
+    __shared__ float w_val[NW];
+    __shared__ int w_idx[NW];
+    __shared__ int s_last;
+    float (*sc)[NH] = reinterpret_cast<float (*)[NH]>(sc_or_bt);
+    uint8_t *bt_rows = sc_or_bt;
+
+    const int r = blockIdx.x;
+    const int t = threadIdx.x;
+    const int lane = t % 32, warp = t / 32;
+    const int T = d.nblock[r];
+    const float *lp = post + (size_t)d.col_off[r] * ostride;
+    uint8_t *tbr = tb + (size_t)d.col_off[r] * NH;
+    int *tbe = tb_end + d.col_off[r];
+    const float slip_pen = (float)(2.0 * (double)skip_pen);
+
+    float cur[4] = {-DEC_BIG, -DEC_BIG, -DEC_BIG, -DEC_BIG};
+    float curS = 0.0f, curE = -DEC_BIG;         // curS replicated in every thread, curE tracked by warp 0
+    float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
+    float nxt_stay = 0.0f;
+    if (T > 0) {
+        nxt = *reinterpret_cast<const float4 *>(lp + 4 * t);
+        nxt_stay = lp[NH];
+    }
+    for (int blk = 0; blk < T; blk++) {
+        const int buf = blk & 1;
+        const float4 l4 = nxt;
+        const float lstay = nxt_stay;
+        if (blk + 1 < T) {
+            nxt = *reinterpret_cast<const float4 *>(lp + (size_t)(blk + 1) * ostride + 4 * t);
+            nxt_stay = lp[(size_t)(blk + 1) * ostride + NH];
+        }
+        // ---- phase A: publish the previous scores; this warp's best "enter end" candidate
+        *reinterpret_cast<float4 *>(&sc[buf][4 * t]) = make_float4(cur[0], cur[1], cur[2], cur[3]);
+        {
+            const float v0 = cur[0] - local_pen, v1 = cur[1] - local_pen, v2 = cur[2] - local_pen, v3 = cur[3] - local_pen;
+            const float wv = redux_max_f32(fmaxf(fmaxf(v0, v1), fmaxf(v2, v3)));
+            int cand = BIG_IDX;
+            cand = (v3 == wv) ? 4 * t + 3 : cand;
+            cand = (v2 == wv) ? 4 * t + 2 : cand;
+            cand = (v1 == wv) ? 4 * t + 1 : cand;
+            cand = (v0 == wv) ? 4 * t : cand;
+            const int wi = redux_min_s32(cand);          // lowest state index among the maximal ones
+            if (lane == 0) { w_val[warp] = wv; w_idx[warp] = wi; }
+        }
+        __syncthreads();
+
+        // ---- phase B: step maxima (one per thread); warp 0 also advances the end state
+        const float *prev = sc[buf];
+        float b4 = prev[t];
+        int r4 = 0;
+#pragma unroll
+        for (int q = 1; q < 4; q++) {
+            const float v = prev[q * (NH / 4) + t];
+            if (b4 < v) { b4 = v; r4 = q; }
+        }
+        m4s[t] = make_float2(b4, __int_as_float(r4));
+        if (warp == 0) {
+            const float v = (lane < NW) ? w_val[lane] : -INFINITY;
+            const int i = (lane < NW) ? w_idx[lane] : BIG_IDX;
+            const float bv = redux_max_f32(v);
+            const int bi = redux_min_s32((v == bv) ? i : BIG_IDX);
+            float e = curE + fmaxf(-local_pen, lstay - stay_pen);
+            int from = NH + 1;
+            if (bv > e) { e = bv; from = bi; }
+            if (lane == 0) tbe[blk] = from;
+            curE = e;
+        }
+        __syncthreads();
+
+        // ---- phase C: skip maximum from four step maxima, then the state updates
+        float b16;
+        int r16;
+        {
+            const float2 e0 = m4s[t / 4], e1 = m4s[(NH / 16) + t / 4], e2 = m4s[2 * (NH / 16) + t / 4], e3 = m4s[3 * (NH / 16) + t / 4];
+            b16 = fmaxf(fmaxf(e0.x, e1.x), fmaxf(e2.x, e3.x));
+            // predecessor block index r16 = 4 * a + b (a = e_b's own argmax): lowest among the maximal entries
+            const int c0 = (e0.x == b16) ? 4 * __float_as_int(e0.y) : 99;
+            const int c1 = (e1.x == b16) ? 4 * __float_as_int(e1.y) + 1 : 99;
+            const int c2 = (e2.x == b16) ? 4 * __float_as_int(e2.y) + 2 : 99;
+            const int c3 = (e3.x == b16) ? 4 * __float_as_int(e3.y) + 3 : 99;
+            r16 = min(min(c0, c1), min(c2, c3));
+        }
+        float b64 = 0.0f;
+        int r64 = 0;
+        if (allow_slip) {
+            b64 = prev[t / 16];
+            for (int q = 1; q < 64; q++) {
+                const float v = prev[q * (NH / 64) + t / 16];
+                if (b64 < v) { b64 = v; r64 = q; }
+            }
+        }
+        const float stay = lstay - stay_pen;
+        const float lpj[4] = {l4.x, l4.y, l4.z, l4.w};
+        uint32_t codes = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            float s = cur[j] + stay;
+            uint32_t code = TB_STAY;
+            const float st = lpj[j] + b4;
+            if (s < st) { s = st; code = TB_STEP + r4; }
+            const float sk = (lpj[j] + b16) - skip_pen;
+            if (s < sk) { s = sk; code = TB_SKIP + r16; }
+            if (allow_slip) {
+                const float sl = (lpj[j] + b64) - slip_pen;
+                if (s < sl) { s = sl; code = TB_SLIP + r64; }
+            }
+            const float ss = curS + lpj[j];
+            if (ss > s) { s = ss; code = TB_START; }
+            cur[j] = s;
+            codes |= code << (8 * j);
+        }
+        *reinterpret_cast<uint32_t *>(tbr + (size_t)blk * NH + 4 * t) = codes;
+        curS = curS + fmaxf(-local_pen, lstay - stay_pen);
+    }
+
+    // ---- final argmax over (states..., start, end): first maximum wins
+    {
+        const float wv = redux_max_f32(fmaxf(fmaxf(cur[0], cur[1]), fmaxf(cur[2], cur[3])));
+        int cand = BIG_IDX;
+        cand = (cur[3] == wv) ? 4 * t + 3 : cand;
+        cand = (cur[2] == wv) ? 4 * t + 2 : cand;
+        cand = (cur[1] == wv) ? 4 * t + 1 : cand;
+        cand = (cur[0] == wv) ? 4 * t : cand;
+        const int wi = redux_min_s32(cand);
+        __syncthreads();
+        if (lane == 0) { w_val[warp] = wv; w_idx[warp] = wi; }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        const float v = (lane < NW) ? w_val[lane] : -INFINITY;
+        const int i = (lane < NW) ? w_idx[lane] : BIG_IDX;
+        float bv = redux_max_f32(v);
+        int last = redux_min_s32((v == bv) ? i : BIG_IDX);
+        if (curS > bv) { bv = curS; last = NH; }
+        if (curE > bv) { bv = curE; last = NH + 1; }
+        if (lane == 0) { score[r] = bv; s_last = last; }
+    }
+    __syncthreads();
+
+    // ---- backtrace: chunks of BT_ROWS traceback rows staged in shared memory
+    int *seq = path + d.col_off[r] + r;
+    int last = s_last;
+    for (int hi_blk = T; hi_blk > 0; hi_blk -= BT_ROWS) {
+        const int lo_blk = max(hi_blk - BT_ROWS, 0);
+        const int nrow = hi_blk - lo_blk;
+        {
+            const uint4 *src = reinterpret_cast<const uint4 *>(tbr + (size_t)lo_blk * NH);
+            uint4 *dst = reinterpret_cast<uint4 *>(bt_rows);
+            for (int i = t; i < nrow * (NH / 16); i += NT) dst[i] = src[i];
+        }
+        __syncthreads();
+        if (t == 0) {
+            for (int blk = hi_blk - 1; blk >= lo_blk; blk--) {
+                int out = -1;
+                if (last == NH) {
+                    out = NH;                                   // start stays in start
+                } else if (last == NH + 1) {
+                    out = NH + 1;
+                    last = tbe[blk];
+                } else {
+                    const int code = bt_rows[(blk - lo_blk) * NH + last];
+                    if (code != TB_STAY) {
+                        out = last;
+                        if (code >= TB_START) last = NH;
+                        else if (code >= TB_SLIP) last = (code - TB_SLIP) * (NH / 64) + last / 64;
+                        else if (code >= TB_SKIP) last = (code - TB_SKIP) * (NH / 16) + last / 16;
+                        else last = (code - TB_STEP) * (NH / 4) + last / 4;
+                    }
+                }
+                seq[blk + 1] = out;
+            }
+        }
+        __syncthreads();
+    }
+    if (t == 0) {
+        seq[0] = last;
+        for (int i = 0; i < T; i++) { if (seq[i] == NH) seq[i] = -1; else break; }
+        for (int i = T; i >= 0; i--) { if (seq[i] == NH + 1) seq[i] = -1; else break; }
+    }
+}
+
 void launch_decode_transducer(const float *post, const BatchDims &d, int nstate, int ostride,
                               float stay_pen, float skip_pen, float local_pen, int allow_slip,
                               uint8_t *tb, int *tb_end, int *path, float *score, cudaStream_t s) {
+    static int gen = -1;
+    if (gen < 0) { const char *e = getenv("SCRAPPIE_B200_DECODE"); gen = (e && 0 == strcmp(e, "v1")) ? 1 : 2; }
     const int nh = nstate - 1;
+    if (gen == 1) {
+        if (nh == 1024)
+            decode_transducer_kernel<1024><<<d.nread, 256, 0, s>>>(post, d, ostride, stay_pen, skip_pen, local_pen,
+                                                                  allow_slip, tb, tb_end, path, score);
+        else if (nh == 4096)
+            decode_transducer_kernel<4096><<<d.nread, 1024, 0, s>>>(post, d, ostride, stay_pen, skip_pen, local_pen,
+                                                                   allow_slip, tb, tb_end, path, score);
+        return;
+    }
     if (nh == 1024)
-        decode_transducer_kernel<1024><<<d.nread, 256, 0, s>>>(post, d, ostride, stay_pen, skip_pen, local_pen,
-                                                              allow_slip, tb, tb_end, path, score);
+        decode_transducer_v2_kernel<1024><<<d.nread, 256, 0, s>>>(post, d, ostride, stay_pen, skip_pen, local_pen,
+                                                                 allow_slip, tb, tb_end, path, score);
     else if (nh == 4096)
-        decode_transducer_kernel<4096><<<d.nread, 1024, 0, s>>>(post, d, ostride, stay_pen, skip_pen, local_pen,
-                                                               allow_slip, tb, tb_end, path, score);
+        decode_transducer_v2_kernel<4096><<<d.nread, 1024, 0, s>>>(post, d, ostride, stay_pen, skip_pen, local_pen,
+                                                                  allow_slip, tb, tb_end, path, score);
 }
 
 // ---------------------------------------------------------------------------------
