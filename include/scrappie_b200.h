@@ -199,6 +199,7 @@ typedef struct {
 } sb2_call;
 int sb2_basecall_batch(sb2_engine *eng, enum raw_model_type model, const float *const *signals,
                        const size_t *nsample, size_t nread, const sb2_params *p, sb2_call *out);
+void sb2_calls_free(sb2_call *calls, size_t n);     /* free() every calls[i].bases */
 /* Same on an existing batch workspace (no device allocation per call).  concat: signals in
  * the batch's padded layout (pinned != 0 if it came from sb2_host_alloc_pinned), or NULL
  * when the signals are already resident. */

@@ -115,6 +115,7 @@ def lib():
         "sb2_basecall_batch": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(_f32p), C.POINTER(C.c_size_t), C.c_size_t,
                                          C.POINTER(Params), C.POINTER(_Call)]),
         "sb2_batch_basecall": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(Params), C.POINTER(_Call)]),
+        "sb2_calls_free": (None, [C.POINTER(_Call), C.c_size_t]),
         "sb2_multi_time": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(Params), C.c_int, C.c_int, _f32p]),
         "sb2_conv_plan_debug": (C.c_int, [C.c_size_t, C.c_size_t, C.c_size_t, _i32p, C.c_int]),
     }
@@ -454,15 +455,17 @@ class Batch(object):
         self._check(lib().sb2_batch_time(self._h, C.byref(params), nrep, int(flush_l2), _fp(tot), _fp(fwd), _fp(dec)), "time")
         return tot, fwd, dec
 
-    def basecall(self, concat_ptr=None, pinned=True, params=None):
+    def basecall(self, concat_ptr=None, pinned=True, params=None, lazy=False):
         """Upload (optional), forward, decode, download, homopolymer, overlapper on this workspace.
-        Returns list of (bases, score, nblock)."""
+        Returns list of (bases, score, nblock); with lazy=True a CallSet that leaves the base strings
+        in C memory until they are asked for (no per-read Python work inside the call)."""
         params = params or default_params()
         out = (_Call * self.nread)()
         rc = lib().sb2_batch_basecall(self._h, concat_ptr, int(pinned), C.byref(params), out)
         if rc < 0:
             raise RuntimeError("sb2_batch_basecall failed: %s" % last_error())
-        return [(_take_string(o.bases), float(o.score), int(o.nblock)) for o in out]
+        cs = CallSet(out, self.nread)
+        return cs if lazy else cs.tolist()
 
     STAGES = ("conv", "affine1", "scan1", "affine2", "scan2", "affine3", "scan3", "affine4", "scan4",
               "affine5", "scan5", "head_gemm", "head_finish", "decode")
@@ -471,6 +474,53 @@ class Batch(object):
         buf = np.zeros(len(self.STAGES), dtype=np.float32)
         lib().sb2_batch_stage_ms(self._h, _fp(buf), buf.size)
         return dict(zip(self.STAGES, [float(x) for x in buf]))
+
+
+class CallSet(object):
+    """The sb2_call records of one batch.  Scores / lengths are numpy views of the C array; base strings
+    are converted on access and freed with the set."""
+    _DT = np.dtype({"names": ["bases", "score", "nblock", "nbase"], "formats": ["u8", "f4", "u8", "u8"],
+                    "offsets": [0, 8, 16, 24], "itemsize": 32})
+
+    def __init__(self, calls, n):
+        assert C.sizeof(_Call) == 32
+        self._calls, self._n = calls, n
+        self._view = np.frombuffer(calls, dtype=self._DT, count=n)
+
+    def __len__(self):
+        return self._n
+
+    @property
+    def scores(self):
+        return self._view["score"]
+
+    @property
+    def nbase(self):
+        return self._view["nbase"]
+
+    @property
+    def nblock(self):
+        return self._view["nblock"]
+
+    def bases(self, i):
+        p = self._calls[i].bases
+        return C.string_at(p).decode() if p else None
+
+    def __getitem__(self, i):
+        return self.bases(i), float(self._view["score"][i]), int(self._view["nblock"][i])
+
+    def tolist(self):
+        out = [self[i] for i in range(self._n)]
+        self.close()
+        return out
+
+    def close(self):
+        if getattr(self, "_calls", None) is not None:
+            self._view = None
+            lib().sb2_calls_free(self._calls, self._n)
+            self._calls = None
+
+    __del__ = close
 
 
 def multi_time(batches, params=None, nrep=1, flush_l2=True):

@@ -5,6 +5,8 @@
 // CUDA is unusable the entry points fail with NULL / NAN / -1 and sb2_last_error().
 #include <cuda_runtime.h>
 
+#include <time.h>
+
 #include <atomic>
 #include <cmath>
 #include <cstdio>
@@ -276,6 +278,14 @@ struct sb2_batch {
     int final_x = 0;
     bool keep_layers = false;
     bool timing = false;
+    // persistent buffers of the basecall path (allocated on first use, never in the hot loop)
+    int *h_paths = nullptr;          // pinned: total_cols + nread ints
+    float *h_scores = nullptr;       // pinned: nread
+    int *h_gidx = nullptr;           // pinned: 2 ints (column, state) per gathered posterior entry
+    float *h_gval = nullptr;         // pinned
+    int *d_gidx = nullptr;
+    float *d_gval = nullptr;
+    size_t gcap = 0;                 // capacity in entries
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[ST_COUNT + 1]{};
     float stage_ms[ST_COUNT]{};
@@ -295,6 +305,10 @@ extern "C" void sb2_batch_destroy(sb2_batch *b) {
     void *ptrs[] = {b->d_raw, b->d_X[0], b->d_X[1], b->d_Xin, b->d_post, b->d_score, b->d_layers, b->d_nsample,
                     b->d_nblock, b->d_coloff, b->d_tbE, b->d_path, b->d_sampoff, b->d_tb, b->d_tails};
     for (void *p : ptrs) if (p) cudaFree(p);
+    if (b->d_gidx) cudaFree(b->d_gidx);
+    if (b->d_gval) cudaFree(b->d_gval);
+    void *hptrs[] = {b->h_paths, b->h_scores, b->h_gidx, b->h_gval};
+    for (void *p : hptrs) if (p) cudaFreeHost(p);
     for (auto &e : b->ev) if (e) cudaEventDestroy(e);
     if (b->stream) cudaStreamDestroy(b->stream);
     delete b;
@@ -604,50 +618,93 @@ extern "C" int sb2_batch_stage_ms(const sb2_batch *b, float *stage_ms, int nstag
 // whole-read basecalling for a batch (calculate_post, src/scrappie_raw.c:265-315)
 // ------------------------------------------------------------------------------------
 
-static int homopolymer_fixup(sb2_batch *b, std::vector<int> &paths) {
-    // runs are found on the host from the Viterbi path; only the two posterior entries per
-    // run position (stay, repeat k-mer) are fetched from HBM (src/homopolymer.c:205-217)
+static double now_ms() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
+// Number of host threads for the per-read post-processing of one batch (SCRAPPIE_B200_HOST_THREADS, default 4).
+static int host_threads() {
+    static int n = 0;
+    if (n == 0) {
+        const char *e = getenv("SCRAPPIE_B200_HOST_THREADS");
+        n = e ? atoi(e) : 4;
+        if (n < 1) n = 1;
+    }
+    return n;
+}
+
+static int basecall_buffers(sb2_batch *b) {
+    if (nullptr != b->h_paths) return 0;
+    const size_t np = (size_t)b->total_cols + b->nread;
+    // every run position needs (stay, repeat k-mer) of one column; runs can overlap, so leave head room
+    b->gcap = 4 * (size_t)b->total_cols + 64;
+    CUDA_OK(cudaMallocHost(reinterpret_cast<void **>(&b->h_paths), np * sizeof(int)));
+    CUDA_OK(cudaMallocHost(reinterpret_cast<void **>(&b->h_scores), (size_t)b->nread * sizeof(float)));
+    CUDA_OK(cudaMallocHost(reinterpret_cast<void **>(&b->h_gidx), b->gcap * 2 * sizeof(int)));
+    CUDA_OK(cudaMallocHost(reinterpret_cast<void **>(&b->h_gval), b->gcap * sizeof(float)));
+    if (dev_alloc(&b->d_gidx, b->gcap * 2) || dev_alloc(&b->d_gval, b->gcap)) return -1;
+    return 0;
+}
+
+struct HpJob { int read; sb2_hp_run run; size_t off; };
+
+// Homopolymer fix-up: runs are found on the host from the Viterbi path; only the two posterior
+// entries per run position (stay, repeat k-mer) are fetched from HBM (src/homopolymer.c:205-217).
+static int homopolymer_fixup(sb2_batch *b, int *paths) {
     const sb2_host_model &h = b->m->host;
     const int klen = (int)(logf((float)h.nstate) / logf(4.0f));
-    struct Job { int read; sb2_hp_run run; size_t off; };
-    std::vector<Job> jobs;
-    std::vector<int> cols, states;
-    for (int r = 0; r < b->nread; r++) {
-        int *path = paths.data() + b->col_off[r] + r;
-        sb2_hp_run *runs = nullptr;
-        const int n = sb2_find_homopolymer_runs(path, b->nblock[r], klen, &runs);
-        if (n < 0) return -1;
-        for (int i = 0; i < n; i++) {
-            jobs.push_back({r, runs[i], cols.size()});
-            for (int j = 0; j < runs[i].length; j++) {
-                const int col = b->col_off[r] + runs[i].start + j - 1;
-                cols.push_back(col); states.push_back((int)h.nstate - 1);
-                cols.push_back(col); states.push_back(runs[i].state);
+    const int nread = b->nread;
+    std::vector<sb2_hp_run *> runs(nread, nullptr);
+    std::vector<int> nrun(nread, 0);
+    std::vector<size_t> need(nread + 1, 0);
+    int bad = 0;
+#pragma omp parallel for schedule(static) num_threads(host_threads()) reduction(| : bad)
+    for (int r = 0; r < nread; r++) {
+        nrun[r] = sb2_find_homopolymer_runs(paths + b->col_off[r] + r, b->nblock[r], klen, &runs[r]);
+        if (nrun[r] < 0) { bad |= 1; nrun[r] = 0; }
+        size_t n = 0;
+        for (int i = 0; i < nrun[r]; i++) n += (size_t)runs[r][i].length;
+        need[r + 1] = n;
+    }
+    for (int r = 0; r < nread; r++) need[r + 1] += need[r];
+    const size_t nent = 2 * need[nread];
+    int rc = bad ? -1 : 0;
+    if (0 == rc && nent > b->gcap) { sb2_set_error("homopolymer gather buffer too small"); rc = -1; }
+    if (0 == rc && nent > 0) {
+#pragma omp parallel for schedule(static) num_threads(host_threads())
+        for (int r = 0; r < nread; r++) {
+            size_t k = 2 * need[r];
+            for (int i = 0; i < nrun[r]; i++)
+                for (int j = 0; j < runs[r][i].length; j++) {
+                    const int col = b->col_off[r] + runs[r][i].start + j - 1;
+                    b->h_gidx[2 * k] = col; b->h_gidx[2 * k + 1] = (int)h.nstate - 1; k++;
+                    b->h_gidx[2 * k] = col; b->h_gidx[2 * k + 1] = runs[r][i].state; k++;
+                }
+        }
+        if (cudaMemcpyAsync(b->d_gidx, b->h_gidx, nent * 2 * sizeof(int), cudaMemcpyHostToDevice, b->stream) != cudaSuccess) rc = -1;
+        launch_gather(b->d_post, (int)h.ostride, b->d_gidx, (int)nent, b->d_gval, b->stream);
+        b->eng->launches += 1;
+        if (cudaMemcpyAsync(b->h_gval, b->d_gval, nent * sizeof(float), cudaMemcpyDeviceToHost, b->stream) != cudaSuccess) rc = -1;
+        if (cudaStreamSynchronize(b->stream) != cudaSuccess) rc = -1;
+        if (rc) sb2_set_error("homopolymer gather failed");
+    }
+    if (0 == rc && nent > 0) {
+#pragma omp parallel for schedule(static) num_threads(host_threads())
+        for (int r = 0; r < nread; r++) {
+            std::vector<float> ps, pr;
+            size_t k = 2 * need[r];
+            for (int i = 0; i < nrun[r]; i++) {
+                const int len = runs[r][i].length;
+                ps.resize(len); pr.resize(len);
+                for (int j = 0; j < len; j++) { ps[j] = b->h_gval[k++]; pr[j] = b->h_gval[k++]; }
+                sb2_apply_homopolymer_run(paths + b->col_off[r] + r, &runs[r][i], ps.data(), pr.data());
             }
         }
-        free(runs);
     }
-    if (cols.empty()) return 0;
-    int *d_cols = nullptr, *d_states = nullptr;
-    float *d_vals = nullptr;
-    std::vector<float> vals(cols.size());
-    if (dev_alloc(&d_cols, cols.size()) || dev_alloc(&d_states, cols.size()) || dev_alloc(&d_vals, cols.size())) return -1;
-    int rc = 0;
-    if (cudaMemcpyAsync(d_cols, cols.data(), cols.size() * sizeof(int), cudaMemcpyHostToDevice, b->stream) != cudaSuccess) rc = -1;
-    if (cudaMemcpyAsync(d_states, states.data(), states.size() * sizeof(int), cudaMemcpyHostToDevice, b->stream) != cudaSuccess) rc = -1;
-    launch_gather(b->d_post, (int)h.ostride, d_cols, d_states, (int)cols.size(), d_vals, b->stream);
-    b->eng->launches += 1;
-    if (cudaMemcpyAsync(vals.data(), d_vals, vals.size() * sizeof(float), cudaMemcpyDeviceToHost, b->stream) != cudaSuccess) rc = -1;
-    if (cudaStreamSynchronize(b->stream) != cudaSuccess) rc = -1;
-    cudaFree(d_cols); cudaFree(d_states); cudaFree(d_vals);
-    if (rc) { sb2_set_error("homopolymer gather failed"); return -1; }
-    std::vector<float> ps, pr;
-    for (const Job &j : jobs) {
-        ps.resize(j.run.length); pr.resize(j.run.length);
-        for (int i = 0; i < j.run.length; i++) { ps[i] = vals[j.off + 2 * i]; pr[i] = vals[j.off + 2 * i + 1]; }
-        sb2_apply_homopolymer_run(paths.data() + b->col_off[j.read] + j.read, &j.run, ps.data(), pr.data());
-    }
-    return 0;
+    for (int r = 0; r < nread; r++) free(runs[r]);
+    return rc;
 }
 
 // Basecall on an existing batch workspace: upload (from `concat` in the padded layout if
@@ -655,31 +712,45 @@ static int homopolymer_fixup(sb2_batch *b, std::vector<int> &paths) {
 // homopolymer fix-up, overlapper.
 extern "C" int sb2_batch_basecall(sb2_batch *b, const float *concat, int pinned, const sb2_params *p, sb2_call *out) {
     if (nullptr == b || nullptr == p || nullptr == out) return -1;
-    const size_t nread = (size_t)b->nread;
-    for (size_t r = 0; r < nread; r++) out[r] = sb2_call{nullptr, NAN, 0, 0};
+    const int nread = b->nread;
+    for (int r = 0; r < nread; r++) out[r] = sb2_call{nullptr, NAN, 0, 0};
+    static const bool timing = getenv("SCRAPPIE_B200_TIMING") != nullptr;
+    const double t0 = now_ms();
+    CUDA_OK(cudaSetDevice(b->eng->device));
+    if (0 != basecall_buffers(b)) return -1;
     if (nullptr != concat && 0 != sb2_batch_upload_concat(b, concat, pinned)) return -1;
-    std::vector<int> paths((size_t)b->total_cols + nread);
-    std::vector<float> scores(nread);
     if (0 != sb2_batch_forward(b, p, true) || 0 != sb2_batch_decode(b, p) ||
-        0 != sb2_batch_download_paths(b, paths.data(), scores.data()))
+        0 != sb2_batch_download_paths(b, b->h_paths, b->h_scores))
         return -1;
+    const double t1 = now_ms();
     const sb2_host_model &h = b->m->host;
+    int *paths = b->h_paths;
     if (h.head == 0 && p->homopolymer == HOMOPOLYMER_MEAN && 0 != homopolymer_fixup(b, paths)) return -1;
+    const double t2 = now_ms();
     int ncalled = 0;
-    std::vector<int> pos;
-    for (size_t r = 0; r < nread; r++) {
-        const int *path = paths.data() + b->col_off[r] + r;
+#pragma omp parallel for schedule(static) num_threads(host_threads()) reduction(+ : ncalled)
+    for (int r = 0; r < nread; r++) {
+        const int *path = paths + b->col_off[r] + r;
         const size_t nb = (size_t)b->nblock[r];
-        pos.assign(nb + 1, 0);
+        std::vector<int> pos(nb + 1, 0);
         char *bases = (h.head == 0) ? overlapper(path, nb + 1, (int)h.nstate - 1, pos.data())
                                     : crfpath_to_basecall(path, nb, pos.data());
         out[r].bases = bases;
-        out[r].score = scores[r];
+        out[r].score = b->h_scores[r];
         out[r].nblock = nb;
         out[r].nbase = bases ? strlen(bases) : 0;
         if (bases) ncalled++;
     }
+    if (timing)
+        fprintf(stderr, "scrappie_b200: basecall %d reads: gpu+copies %.2f ms, homopolymer %.2f ms, bases %.2f ms\n", nread,
+                t1 - t0, t2 - t1, now_ms() - t2);
     return ncalled;
+}
+
+// Release the base strings of an array of calls (bases are calloc'd, as in the reference).
+extern "C" void sb2_calls_free(sb2_call *calls, size_t n) {
+    if (nullptr == calls) return;
+    for (size_t i = 0; i < n; i++) { free(calls[i].bases); calls[i].bases = nullptr; }
 }
 
 extern "C" int sb2_basecall_batch(sb2_engine *eng, enum raw_model_type model, const float *const *signals,

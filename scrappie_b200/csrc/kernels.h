@@ -57,8 +57,7 @@ void launch_decode_crf(const float *trans, const BatchDims &d, int ostride, uint
                        float *score, cudaStream_t s);
 
 // gather post[col][state] pairs (homopolymer fix-up needs a few posterior entries)
-void launch_gather(const float *post, int ostride, const int *cols, const int *states, int n,
-                   float *out, cudaStream_t s);
+void launch_gather(const float *post, int ostride, const int *col_state_pairs, int n, float *out, cudaStream_t s);
 
 // ---- tensor-core path (kernels_tc.cu) ----
 // shared-memory image of one layer's recurrent weights (split fp16, canonical UMMA layout)

@@ -837,15 +837,18 @@ void launch_decode_transducer(const float *post, const BatchDims &d, int nstate,
 // ---------------------------------------------------------------------------------
 // small utilities
 // ---------------------------------------------------------------------------------
-__global__ void gather_kernel(const float *__restrict__ post, int ostride, const int *__restrict__ cols,
-                              const int *__restrict__ states, int n, float *__restrict__ out) {
+__global__ void gather_kernel(const float *__restrict__ post, int ostride, const int2 *__restrict__ idx, int n,
+                              float *__restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = post[(size_t)cols[i] * ostride + states[i]];
+    if (i < n) {
+        const int2 cs = idx[i];                          // (column, state)
+        out[i] = post[(size_t)cs.x * ostride + cs.y];
+    }
 }
 
-void launch_gather(const float *post, int ostride, const int *cols, const int *states, int n, float *out,
-                   cudaStream_t s) {
-    if (n > 0) gather_kernel<<<(n + 255) / 256, 256, 0, s>>>(post, ostride, cols, states, n, out);
+void launch_gather(const float *post, int ostride, const int *col_state_pairs, int n, float *out, cudaStream_t s) {
+    if (n > 0)
+        gather_kernel<<<(n + 255) / 256, 256, 0, s>>>(post, ostride, reinterpret_cast<const int2 *>(col_state_pairs), n, out);
 }
 
 __global__ void flush_kernel(float *buf, size_t n) {
