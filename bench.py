@@ -272,12 +272,38 @@ def main_b200(args, rank, world, local_rank):
         return
 
     pk, pk_src = peaks()
-    scan_ms = [st["scan%d" % l] for st in stage for l in range(1, 6)]
-    scan_avg_ms = float(np.mean(scan_ms))
-    blocks_per_batch = batches[0].total_blocks
-    flop_per_launch = FLOP_PER_READ_STEP_RECURRENT[args.model] * blocks_per_batch
+    # Per-kernel figures from ONE batch timed alone (CUDA events on its stream, L2 flushed), after the timed region:
+    # in the concurrent step the stage intervals of different batches overlap, so they are not launch durations.
+    _, _, _ = batches[0].time(params, nrep=3, flush_l2=True)
+    solo = batches[0].stage_ms()
+    H = 112 if args.model == "rnnrf_r94" else 96
+    nstate_stride = batches[0].ostride
+    cols = batches[0].total_blocks
+    nsamp0 = batches[0].total_samples_padded
+    scan_avg_ms = float(np.mean([solo["scan%d" % l] for l in range(1, 6)]))
+    flop_per_launch = FLOP_PER_READ_STEP_RECURRENT[args.model] * cols
     achieved = flop_per_launch / (scan_avg_ms * 1e-3) / 1e12
-    peak = pk["bf16_tflops_sustained"]
+    peak = pk["bf16_tflops"]
+    hbm = pk["hbm_gbs"]
+    traffic = None
+    tfiles = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_traffic.json")) \
+        if os.path.isdir(os.path.join(ROOT, "profiles")) else []
+    measured = json.load(open(os.path.join(ROOT, "profiles", tfiles[-1]))) if tfiles else {}
+    for k, v in measured.items():
+        if k.startswith("gru_scan") and args.model != "rnnrf_r94":
+            traffic = v["dram_read_bytes"] + v["dram_write_bytes"]
+
+    def hbm_kernel(name, ms, nbytes):
+        return {"kernel": name, "bound": "hbm", "avg_launch_ms": ms, "bytes_per_launch": nbytes,
+                "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s", "frac": nbytes / (ms * 1e-3) / 1e9 / hbm}
+    aff_ms = float(np.mean([solo["affine%d" % l] for l in range(1, 6)]))
+    tb_bytes = (nstate_stride - 4 + 4) if args.model != "rnnrf_r94" else 8
+    kernels = [
+        hbm_kernel("conv_act", solo["conv"], nsamp0 * 4 + cols * H * 4),
+        hbm_kernel("affine_tc (GRU input transform)", aff_ms, cols * (H + 3 * H) * 4),
+        hbm_kernel("head (FF + softmax + robust log)", solo["head_gemm"] + solo["head_finish"], cols * (H + nstate_stride) * 4),
+        hbm_kernel("decode (Viterbi + traceback)", solo["decode"], cols * (nstate_stride * 4 + tb_bytes + 4)),
+    ]
     stage_sum = {k: float(np.mean([st[k] for st in stage])) for k in stage[0]}
     line = {
         "metric": "raw samples/sec (%s)" % args.model, "value": world * total_samples / (step_ms * 1e-3),
@@ -295,12 +321,15 @@ def main_b200(args, rank, world, local_rank):
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"kernel": "gru_scan (recurrent sW/sW2 products + gates), 5 launches per batch",
+        "roofline": {"kernel": "gru_scan (recurrent sW/sW2 products + gates): 5 of the 13 launches per batch, "
+                               "the largest share of the step (profiles/*_summary.md)",
                      "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                     "frac": achieved / peak, "traffic": None,
-                     "peak_source": "%s bf16 dense sustained (MEASURED_PEAKS.json); tf32 nominal is half of bf16" % pk_src,
+                     "frac": achieved / peak, "traffic": traffic,
+                     "peak_source": "%s bf16 dense burst (MEASURED_PEAKS.json), kernel timed alone; the scan is a chain of "
+                                    "dependent 12-instruction UMMA groups, latency- not throughput-bound (DESIGN.md section 4)" % pk_src,
                      "flop_per_launch": flop_per_launch, "avg_launch_ms": scan_avg_ms,
-                     "stage_ms_per_batch": stage_sum},
+                     "stage_ms_solo_batch": solo, "stage_ms_per_batch_concurrent": stage_sum,
+                     "other_kernels": kernels},
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.model, sigs, args.cpu_sample_reads)

@@ -16,7 +16,7 @@ import json
 try:
     b=json.loads(open("$OUT/${TAG}_bench.json").read().strip().splitlines()[-1])
     print("value %.4g e2e %.4g ms/step %.3f"%(b["value"],b["e2e"]["value"],b["ms_per_step"]))
-    print({k:round(v,3) for k,v in b["roofline"]["stage_ms_per_batch"].items()})
+    print({k:round(v,3) for k,v in (b["roofline"].get("stage_ms_solo_batch") or b["roofline"]["stage_ms_per_batch"]).items()})
 except Exception as e:
     print("no bench line", e)
 PY

@@ -31,9 +31,9 @@ def launches(path):
 
 def main():
     tag = sys.argv[1]
-    rep = None
+    reps = []
     if "--rep" in sys.argv:
-        rep = sys.argv[sys.argv.index("--rep") + 1]
+        reps = sys.argv[sys.argv.index("--rep") + 1:]
     out = ["# ncu summary `%s`" % tag, ""]
     bj = os.path.join(ROOT, "gpurun_out", tag + "_bench.json")
     if os.path.exists(bj) and os.path.getsize(bj):
@@ -41,7 +41,7 @@ def main():
         out += ["Bench line of the same build (not under ncu): value %.4g %s, e2e %.4g, %.3f ms/step, launches %s" %
                 (b["value"], b["unit"], b["e2e"]["value"], b["ms_per_step"], b.get("gpu_launches")), ""]
         out += ["stage ms per batch (CUDA events, concurrent batches): " +
-                ", ".join("%s %.3f" % kv for kv in b["roofline"].get("stage_ms_per_batch", {}).items()), ""]
+                ", ".join("%s %.3f" % kv for kv in (b["roofline"].get("stage_ms_per_batch_concurrent") or b["roofline"].get("stage_ms_per_batch", {})).items()), ""]
     lp = os.path.join(ROOT, "gpurun_out", tag + "_launches.csv")
     if os.path.exists(lp):
         rows = launches(lp)
@@ -58,7 +58,9 @@ def main():
         for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             out.append("| `%s` | %d | %.3f | %.4f | %.1f%% | %s | %s |" % (k, v[0], v[1], v[1] / v[0], 100 * v[1] / tot, v[2], v[3]))
         out.append("")
-    if rep and os.path.exists(rep):
+    for rep in reps:
+        if not os.path.exists(rep):
+            continue
         txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(txt.splitlines()))
         hdr, units = rows[0], rows[1]
