@@ -98,6 +98,9 @@ posterior_function_ptr get_posterior_function(const enum raw_model_type model);
 
 /* -- network forward (GPU): src/networks.c:250-394, :567-615.
  *    Returns a new matrix [nstate x nblock] owned by the caller, or NULL. -- */
+/* raw_r94 (interface/scrappie.h:49-51, src/networks.c:196-247): two bidirectional GRU pairs */
+scrappie_matrix nanonet_raw_posterior(const raw_table signal, float min_prob,
+                                      float tempW, float tempb, bool return_log);
 scrappie_matrix nanonet_rgrgr_r94_posterior(const raw_table signal, float min_prob,
                                             float tempW, float tempb, bool return_log);
 scrappie_matrix nanonet_rgrgr_r941_posterior(const raw_table signal, float min_prob,

@@ -42,8 +42,9 @@ class _Tensor(C.Structure):
 
 class _Model(C.Structure):
     _fields_ = [("conv_stride", C.c_uint32), ("conv_act", C.c_uint32), ("head", C.c_uint32),
-                ("residual", C.c_uint32), ("conv_W", _Tensor), ("conv_b", _Tensor),
+                ("residual", C.c_uint32), ("arch", C.c_uint32), ("conv_W", _Tensor), ("conv_b", _Tensor),
                 ("iW", _Tensor * 5), ("b", _Tensor * 5), ("sW", _Tensor * 5), ("sW2", _Tensor * 5),
+                ("comb_Wf", _Tensor * 2), ("comb_Wb", _Tensor * 2), ("comb_b", _Tensor * 2),
                 ("FF_W", _Tensor), ("FF_b", _Tensor)]
 
 
@@ -108,6 +109,7 @@ class Oracle:
         stride = 4 * ((ns + 3) // 4)
         out = np.zeros((ncol, stride), dtype=np.float32)
         H = m.conv_W.nc
+        assert not (layers and m.arch != 0), "per-layer dumps exist only for the rgrgr / rnnrf stack"
         lay = [np.zeros((ncol, H), dtype=np.float32) for _ in range(6)] if layers else None
         lp = (c_float_p * 6)(*[_fp(a) for a in lay]) if layers else None
         n = self.lib.sb2o_posterior(C.byref(m), _fp(raw), raw.size, min_prob, tempW, tempb,
@@ -216,7 +218,7 @@ def reference_available():
 class Reference:
     """The reference's own C code (oracle/_ref/libscrappie_ref.so), 1 BLAS thread."""
 
-    POSTERIOR = {"rgrgr_r94": "nanonet_rgrgr_r94_posterior", "rgrgr_r941": "nanonet_rgrgr_r941_posterior",
+    POSTERIOR = {"raw_r94": "nanonet_raw_posterior", "rgrgr_r94": "nanonet_rgrgr_r94_posterior", "rgrgr_r941": "nanonet_rgrgr_r941_posterior",
                  "rgrgr_r10": "nanonet_rgrgr_r10_posterior", "rnnrf_r94": "nanonet_rnnrf_r94_transitions"}
 
     def __init__(self):

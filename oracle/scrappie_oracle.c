@@ -116,13 +116,21 @@ int sb2o_model_from_blob(const void *blob, size_t nbytes, sb2o_model *m) {
     uint32_t hdr[8];
     memcpy(hdr, p + 8, sizeof(hdr));
     const uint32_t nt = hdr[0];
-    m->conv_stride = hdr[1]; m->conv_act = hdr[2]; m->head = hdr[3]; m->residual = hdr[4];
+    m->conv_stride = hdr[1]; m->conv_act = hdr[2]; m->head = hdr[3]; m->residual = hdr[4]; m->arch = hdr[5];
     const blob_entry *tab = (const blob_entry *)(p + 40);
     const float *data = (const float *)(p + 40 + (size_t)nt * sizeof(blob_entry));
     int rc = 0;
     rc |= find_tensor(tab, nt, data, "conv_W", &m->conv_W);
     rc |= find_tensor(tab, nt, data, "conv_b", &m->conv_b);
-    for (int l = 0; l < 5; l++) {
+    if (m->arch == 1) {
+        const char *cn[2][3] = {{"comb1_Wf", "comb1_Wb", "comb1_b"}, {"comb2_Wf", "comb2_Wb", "comb2_b"}};
+        for (int i = 0; i < 2; i++) {
+            rc |= find_tensor(tab, nt, data, cn[i][0], &m->comb_Wf[i]);
+            rc |= find_tensor(tab, nt, data, cn[i][1], &m->comb_Wb[i]);
+            rc |= find_tensor(tab, nt, data, cn[i][2], &m->comb_b[i]);
+        }
+    }
+    for (int l = 0; l < (m->arch == 1 ? 4 : 5); l++) {
         char nm[24];
         const char *parts[4] = {"iW", "b", "sW", "sW2"};
         sb2o_tensor *dst[4] = {&m->iW[l], &m->b[l], &m->sW[l], &m->sW2[l]};
@@ -314,10 +322,51 @@ static void head_globalnorm(const float *X, size_t ncol, const sb2o_tensor *W, c
     free(tmp);
 }
 
+/* feedforward2_tanh -> affine_map2 (src/layers.c:359-371, src/scrappie_matrix.c:353-383):
+ * out[c][k] = tanh((b[k] + sum Wf[k][i] Xf[c][i]) + sum Wb[k][i] Xb[c][i]) */
+static void affine2_tanh(const float *Xf, const float *Xb, size_t ncol, const sb2o_tensor *Wf,
+                         const sb2o_tensor *Wb, const sb2o_tensor *b, float *out) {
+    const size_t nin = Wf->nr, nout = Wf->nc;
+    for (size_t c = 0; c < ncol; c++)
+        for (size_t k = 0; k < nout; k++) {
+            const float *wf = Wf->data + k * Wf->stride, *wb = Wb->data + k * Wb->stride;
+            float af = 0.0f, ab = 0.0f;
+            for (size_t i = 0; i < nin; i++) af += wf[i] * Xf[c * nin + i];
+            for (size_t i = 0; i < nin; i++) ab += wb[i] * Xb[c * nin + i];
+            out[c * nout + k] = sb2o_tanhf((b->data[k] + af) + ab);
+        }
+}
+
+/* nanonet_raw_posterior, src/networks.c:196-247 */
+static size_t posterior_raw_r94(const sb2o_model *m, const float *raw, size_t n, float min_prob,
+                                float tempW, float tempb, int return_log, float *out) {
+    const size_t NF = m->conv_W.nc, H = m->sW2[0].nc, FW = m->comb_b[0].nr;
+    const size_t ncol = sb2o_conv_ncol(n, m->conv_stride);
+    const size_t wide = (FW > NF) ? FW : NF;
+    float *ff = malloc(ncol * wide * sizeof(float));
+    float *ff2 = malloc(ncol * wide * sizeof(float));
+    float *xin = malloc(ncol * 3 * H * sizeof(float));
+    float *gf = malloc(ncol * H * sizeof(float)), *gb = malloc(ncol * H * sizeof(float));
+    sb2o_convolution(raw, n, &m->conv_W, &m->conv_b, m->conv_stride, ff);
+    for (size_t i = 0; i < ncol * NF; i++) ff[i] = m->conv_act ? sb2o_tanhf(ff[i]) : sb2o_eluf(ff[i]);
+    for (int pair = 0; pair < 2; pair++) {
+        sb2o_affine(ff, ncol, &m->iW[2 * pair], &m->b[2 * pair], xin);
+        sb2o_gru(xin, ncol, &m->sW[2 * pair], &m->sW2[2 * pair], 0, gf);
+        sb2o_affine(ff, ncol, &m->iW[2 * pair + 1], &m->b[2 * pair + 1], xin);
+        sb2o_gru(xin, ncol, &m->sW[2 * pair + 1], &m->sW2[2 * pair + 1], 1, gb);
+        affine2_tanh(gf, gb, ncol, &m->comb_Wf[pair], &m->comb_Wb[pair], &m->comb_b[pair], ff2);
+        float *t = ff; ff = ff2; ff2 = t;
+    }
+    head_softmax(ff, ncol, &m->FF_W, &m->FF_b, min_prob, tempW, tempb, return_log, out);
+    free(gb); free(gf); free(xin); free(ff2); free(ff);
+    return ncol;
+}
+
 /* nanonet_rgrgr_*_posterior (src/networks.c:250-296) / nanonet_rnnrf_r94_transitions (:567-615) */
 size_t sb2o_posterior(const sb2o_model *m, const float *raw, size_t n, float min_prob,
                       float tempW, float tempb, int return_log, float *out, float **layer_out) {
     if (NULL == m || NULL == raw || 0 == n || NULL == out) return 0;
+    if (m->arch == 1) return posterior_raw_r94(m, raw, n, min_prob, tempW, tempb, return_log, out);
     const size_t H = m->conv_W.nc;
     const size_t ncol = sb2o_conv_ncol(n, m->conv_stride);
     float *cur = malloc(ncol * H * sizeof(float));

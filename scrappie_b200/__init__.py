@@ -20,7 +20,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libscrappie_b200.so")
 WEIGHTS_DIR = os.path.join(_HERE, "weights")
 
-MODELS = ("rgrgr_r94", "rgrgr_r941", "rgrgr_r10", "rnnrf_r94")
+MODELS = ("raw_r94", "rgrgr_r94", "rgrgr_r941", "rgrgr_r10", "rnnrf_r94")
 _MODEL_ENUM = {"raw_r94": 0, "rgrgr_r94": 1, "rgrgr_r941": 2, "rgrgr_r10": 3, "rnnrf_r94": 4}
 
 _f32p = C.POINTER(C.c_float)
@@ -46,6 +46,13 @@ class Params(C.Structure):
 
 class _Call(C.Structure):
     _fields_ = [("bases", C.c_void_p), ("score", C.c_float), ("nblock", C.c_size_t), ("nbase", C.c_size_t)]
+
+
+def _posterior_symbol(model):
+    """Exported posterior function of a model (names as in src/networks.h:42-49, interface/scrappie.h:49)."""
+    if model == "raw_r94":
+        return "nanonet_raw_posterior"
+    return "nanonet_%s_%s" % (model, "transitions" if model == "rnnrf_r94" else "posterior")
 
 
 def build_library(verbose=False):
@@ -120,8 +127,7 @@ def lib():
         "sb2_conv_plan_debug": (C.c_int, [C.c_size_t, C.c_size_t, C.c_size_t, _i32p, C.c_int]),
     }
     for name in MODELS:
-        fn = "nanonet_%s_%s" % (name, "transitions" if name == "rnnrf_r94" else "posterior")
-        sig[fn] = (mp, [_RawTable, C.c_float, C.c_float, C.c_float, C.c_bool])
+        sig[_posterior_symbol(name)] = (mp, [_RawTable, C.c_float, C.c_float, C.c_float, C.c_bool])
     for name, (res, args) in sig.items():
         f = getattr(L, name)
         f.restype = res
@@ -253,7 +259,7 @@ class ScrappyMatrix(object):
 def _posterior_fn(model):
     if model not in MODELS:
         raise KeyError("Model type '{}' not recognised.".format(model))
-    return getattr(lib(), "nanonet_%s_%s" % (model, "transitions" if model == "rnnrf_r94" else "posterior"))
+    return getattr(lib(), _posterior_symbol(model))
 
 
 def calc_post(rt, model='rgrgr_r94', min_prob=1e-6, log=True, tempW=1.0, tempb=1.0):

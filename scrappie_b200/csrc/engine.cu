@@ -41,6 +41,7 @@ struct DevModel {
     float *conv_taps = nullptr, *conv_b = nullptr;
     float *iW[SB2_NLAYER]{}, *b[SB2_NLAYER]{}, *sW[SB2_NLAYER]{}, *sW2[SB2_NLAYER]{};
     float *FF_W = nullptr, *FF_b = nullptr;
+    float *comb_Wf[2]{}, *comb_Wb[2]{}, *comb_b[2]{};    // raw_r94: feedforward2_tanh layers
     uint8_t *scan_img[SB2_NLAYER]{};     // tensor-core scan: per-layer weight image
     uint8_t *d_img_all = nullptr;
     uint8_t *iw_img[SB2_NLAYER]{};       // tensor-core affine: per-layer input-transform image
@@ -76,18 +77,26 @@ static int upload_model(sb2_engine *eng, DevModel *dm) {
     };
     {   // conv taps: reference stores filter f as a column of winlen*4 floats with the tap at
         // every 4th slot (src/layers.c:155-157); device layout is [tap][filter]
-        std::vector<float> taps((size_t)h.winlen * H);
-        for (uint32_t f = 0; f < H; f++)
-            for (uint32_t k = 0; k < h.winlen; k++) taps[(size_t)k * H + f] = h.conv_W.data[(size_t)f * h.conv_W.stride + 4 * k];
+        const size_t NF = h.nfilter;
+        std::vector<float> taps((size_t)h.winlen * NF);
+        for (uint32_t f = 0; f < NF; f++)
+            for (uint32_t k = 0; k < h.winlen; k++) taps[(size_t)k * NF + f] = h.conv_W.data[(size_t)f * h.conv_W.stride + 4 * k];
         items.push_back({&dm->conv_taps, taps});
         items.push_back({&dm->conv_b, compact(h.conv_b)});
     }
-    for (int l = 0; l < SB2_NLAYER; l++) {
+    const int nlayer = (h.arch == 0) ? SB2_NLAYER : 4;
+    for (int l = 0; l < nlayer; l++) {
         items.push_back({&dm->iW[l], compact(h.iW[l])});
         items.push_back({&dm->b[l], compact(h.b[l])});
         items.push_back({&dm->sW[l], compact(h.sW[l])});
         items.push_back({&dm->sW2[l], compact(h.sW2[l])});
     }
+    if (h.arch == 1)
+        for (int i = 0; i < 2; i++) {
+            items.push_back({&dm->comb_Wf[i], compact(h.comb_Wf[i])});
+            items.push_back({&dm->comb_Wb[i], compact(h.comb_Wb[i])});
+            items.push_back({&dm->comb_b[i], compact(h.comb_b[i])});
+        }
     items.push_back({&dm->FF_W, compact(h.FF_W)});
     items.push_back({&dm->FF_b, compact(h.FF_b)});
     size_t total = 0;
@@ -100,6 +109,10 @@ static int upload_model(sb2_engine *eng, DevModel *dm) {
         CUDA_OK(cudaMemcpy(dst, it.second.data(), it.second.size() * sizeof(float), cudaMemcpyHostToDevice));
         *it.first = dst;
         off += align_up(it.second.size() * sizeof(float), 256);
+    }
+    if (h.arch == 1) {      // raw_r94: the scans read fp32 weights; its odd-shaped affine maps use the fp32 kernel
+        dm->loaded = true;
+        return 0;
     }
     {   // tensor-core scan images
         const size_t nb = align_up(scan_image_bytes((int)H), 256);
@@ -153,10 +166,6 @@ static DevModel *get_model(sb2_engine *eng, enum raw_model_type model) {
     if (nullptr == eng || model < 0 || model >= SCRAPPIE_MODEL_INVALID) return nullptr;
     DevModel *dm = &eng->models[model];
     if (dm->loaded) return dm;
-    if (model == SCRAPPIE_MODEL_RAW) {
-        sb2_set_error("model raw_r94 is not implemented by this engine (see DESIGN.md, scope)");
-        return nullptr;
-    }
     char path[1200];
     snprintf(path, sizeof(path), "%s/%s.bin", eng->weights_dir, sb2_model_file_stem(model));
     void *blob = nullptr;
@@ -271,6 +280,7 @@ struct sb2_batch {
     std::vector<int64_t> samp_off;
     // device
     float *d_raw = nullptr, *d_X[2]{}, *d_Xin = nullptr, *d_post = nullptr, *d_score = nullptr, *d_layers = nullptr;
+    float *d_Xin2 = nullptr, *d_FF = nullptr;          // raw_r94 only
     int *d_nsample = nullptr, *d_nblock = nullptr, *d_coloff = nullptr, *d_tbE = nullptr, *d_path = nullptr;
     int64_t *d_sampoff = nullptr;
     uint8_t *d_tb = nullptr;
@@ -305,6 +315,8 @@ extern "C" void sb2_batch_destroy(sb2_batch *b) {
     void *ptrs[] = {b->d_raw, b->d_X[0], b->d_X[1], b->d_Xin, b->d_post, b->d_score, b->d_layers, b->d_nsample,
                     b->d_nblock, b->d_coloff, b->d_tbE, b->d_path, b->d_sampoff, b->d_tb, b->d_tails};
     for (void *p : ptrs) if (p) cudaFree(p);
+    if (b->d_Xin2) cudaFree(b->d_Xin2);
+    if (b->d_FF) cudaFree(b->d_FF);
     if (b->d_gidx) cudaFree(b->d_gidx);
     if (b->d_gval) cudaFree(b->d_gval);
     void *hptrs[] = {b->h_paths, b->h_scores, b->h_gidx, b->h_gval};
@@ -342,6 +354,8 @@ static int batch_init(sb2_batch *b, const size_t *nsample, size_t nread) {
     CUDA_OK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
     for (auto &e : b->ev) CUDA_OK(cudaEventCreate(&e));
     const size_t ncol = (size_t)b->total_cols;
+    // raw_r94 keeps both directions of a bidirectional pair alive and merges them into `ffw` features
+    if (h.arch == 1 && (dev_alloc(&b->d_Xin2, ncol * 3 * H) || dev_alloc(&b->d_FF, ncol * std::max(h.ffw, h.nfilter)))) return -1;
     if (dev_alloc(&b->d_raw, (size_t)so) || dev_alloc(&b->d_X[0], ncol * H) || dev_alloc(&b->d_X[1], ncol * H) ||
         dev_alloc(&b->d_Xin, ncol * 3 * H) || dev_alloc(&b->d_post, ncol * h.ostride) ||
         dev_alloc(&b->d_score, nread) || dev_alloc(&b->d_nsample, nread) || dev_alloc(&b->d_nblock, nread) ||
@@ -390,6 +404,7 @@ extern "C" size_t sb2_batch_sample_offset(const sb2_batch *b, size_t read) { ret
 
 extern "C" int sb2_batch_keep_layers(sb2_batch *b, int keep) {
     if (nullptr == b) return -1;
+    if (b->m->host.arch != 0) { sb2_set_error("per-layer dumps are only available for the rgrgr / rnnrf topology"); return -1; }
     CUDA_OK(cudaSetDevice(b->eng->device));
     if (keep && nullptr == b->d_layers && dev_alloc(&b->d_layers, (size_t)6 * b->total_cols * b->m->host.H)) return -1;
     b->keep_layers = keep != 0;
@@ -417,6 +432,76 @@ extern "C" int sb2_batch_upload_concat(sb2_batch *b, const float *concat, int pi
 
 static inline void stage_mark(sb2_batch *b, int i) { if (b->timing) cudaEventRecord(b->ev[i], b->stream); }
 
+// One GRU layer scan with the engine's selected kernel generation.
+static int run_scan(sb2_batch *b, const float *Xin, const DevModel &m, int l, const float *resid, float *out, int backward,
+                    long long *trace) {
+    const int H = (int)b->m->host.H;
+    cudaStream_t s = b->stream;
+    const int impl = b->eng->scan_impl;
+    if (impl == 0) {
+        launch_gru_scan_ffma(Xin, m.sW[l], m.sW2[l], resid, out, b->dims, H, backward, s);
+        return 0;
+    }
+    int rc;
+    if (impl == 4) {
+        rc = (nullptr == m.scan_img[l]) ? -1 : launch_gru_scan_tc(Xin, m.scan_img[l], resid, out, b->dims, H, backward, 1, s);
+    } else if (impl >= 8) {
+        rc = launch_gru_scan_v4(Xin, m.sW[l], m.sW2[l], resid, out, b->dims, H, backward, impl - 8, trace, s);
+    } else if (impl >= 5) {
+        rc = launch_gru_scan_v3(Xin, m.sW[l], m.sW2[l], resid, out, b->dims, H, backward, impl - 5, trace, s);
+    } else {
+        rc = launch_gru_scan_tmem(Xin, m.sW[l], m.sW2[l], resid, out, b->dims, H, backward, impl - 1, s);
+    }
+    if (0 != rc) sb2_set_error("tensor-core scan: unsupported configuration");
+    return rc;
+}
+
+// nanonet_raw_posterior (src/networks.c:196-247): conv+tanh, two bidirectional GRU pairs each merged by
+// feedforward2_tanh, softmax head.  The GRU scans run on the tensor-core kernel; the affine maps of this
+// legacy model (K = 32 / 128, M = 128) use the fp32 kernel.
+static int forward_raw_r94(sb2_batch *b, const sb2_params *p, bool return_log) {
+    const sb2_host_model &h = b->m->host;
+    const DevModel &m = *b->m;
+    const int H = (int)h.H, NF = (int)h.nfilter, FW = (int)h.ffw, ncol = b->total_cols;
+    cudaStream_t s = b->stream;
+    uint64_t nl = 0;
+    stage_mark(b, ST_CONV);
+    launch_conv_act(b->d_raw, b->dims, b->d_tails, m.conv_taps, m.conv_b, (int)h.winlen, NF, (int)h.conv_stride,
+                    (int)h.conv_act, b->d_FF, s);
+    nl++;
+    const float *in = b->d_FF;
+    int K = NF;
+    for (int pair = 0; pair < 2; pair++) {
+        const int lf = 2 * pair, lb = 2 * pair + 1;
+        stage_mark(b, ST_AFFINE(2 * pair));
+        launch_affine(in, ncol, K, m.iW[lf], K, m.b[lf], 3 * H, b->d_Xin, 3 * H, 1.0f, 1.0f, 0, 0, s);
+        launch_affine(in, ncol, K, m.iW[lb], K, m.b[lb], 3 * H, b->d_Xin2, 3 * H, 1.0f, 1.0f, 0, 0, s);
+        stage_mark(b, ST_SCAN(2 * pair));
+        if (0 != run_scan(b, b->d_Xin, m, lf, nullptr, b->d_X[0], 0, nullptr)) return -1;
+        stage_mark(b, ST_AFFINE(2 * pair + 1));
+        stage_mark(b, ST_SCAN(2 * pair + 1));
+        if (0 != run_scan(b, b->d_Xin2, m, lb, nullptr, b->d_X[1], 1, nullptr)) return -1;
+        // feedforward2_tanh: tanh(b + Wf gruF + Wb gruB)
+        launch_affine(b->d_X[0], ncol, H, m.comb_Wf[pair], H, m.comb_b[pair], FW, b->d_FF, FW, 1.0f, 1.0f, 0, 0, s);
+        launch_affine(b->d_X[1], ncol, H, m.comb_Wb[pair], H, nullptr, FW, b->d_FF, FW, 1.0f, 1.0f, 2, 1, s);
+        nl += 6;
+        in = b->d_FF;
+        K = FW;
+    }
+    stage_mark(b, ST_AFFINE(4));
+    stage_mark(b, ST_SCAN(4));
+    stage_mark(b, ST_HEAD);
+    launch_affine(b->d_FF, ncol, FW, m.FF_W, FW, m.FF_b, (int)h.nstate, b->d_post, (int)h.ostride,
+                  p->tempW / p->tempb, p->tempb, 1, 0, s);
+    stage_mark(b, ST_FINISH);
+    launch_softmax_finish(b->d_post, ncol, (int)h.nstate, (int)h.ostride, p->min_prob, return_log ? 1 : 0, s);
+    nl += 2;
+    stage_mark(b, ST_DECODE);
+    b->eng->launches += nl;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int sb2_batch_forward(sb2_batch *b, const sb2_params *p, bool return_log) {
     if (nullptr == b || nullptr == p) return -1;
     const sb2_host_model &h = b->m->host;
@@ -427,6 +512,7 @@ extern "C" int sb2_batch_forward(sb2_batch *b, const sb2_params *p, bool return_
         return -1;
     }
     CUDA_OK(cudaSetDevice(b->eng->device));
+    if (h.arch == 1) return forward_raw_r94(b, p, return_log);
     const int H = (int)h.H;
     cudaStream_t s = b->stream;
     uint64_t nl = 0;
@@ -441,38 +527,15 @@ extern "C" int sb2_batch_forward(sb2_batch *b, const sb2_params *p, bool return_
     for (int l = 0; l < SB2_NLAYER; l++) {
         stage_mark(b, ST_AFFINE(l));
         if (b->eng->gemm_impl == 0) {
-            launch_affine(b->d_X[cur], b->total_cols, H, m.iW[l], H, m.b[l], 3 * H, b->d_Xin, 3 * H, 1.0f, 1.0f, 0, s);
+            launch_affine(b->d_X[cur], b->total_cols, H, m.iW[l], H, m.b[l], 3 * H, b->d_Xin, 3 * H, 1.0f, 1.0f, 0, 0, s);
         } else if (0 != launch_affine_tc(b->d_X[cur], b->total_cols, H, m.iw_img[l], m.b[l], b->d_Xin, s)) {
             sb2_set_error("tensor-core affine kernel could not be configured");
             return -1;
         }
         stage_mark(b, ST_SCAN(l));
-        if (b->eng->scan_impl == 0) {
-            launch_gru_scan_ffma(b->d_Xin, m.sW[l], m.sW2[l], h.residual ? b->d_X[cur] : nullptr, b->d_X[cur ^ 1],
-                                 b->dims, H, (l % 2) == 0, s);
-        } else if (b->eng->scan_impl == 4) {
-            if (0 != launch_gru_scan_tc(b->d_Xin, m.scan_img[l], h.residual ? b->d_X[cur] : nullptr, b->d_X[cur ^ 1],
-                                        b->dims, H, (l % 2) == 0, 1, s)) {
-                sb2_set_error("tensor-core scan kernel could not be configured");
-                return -1;
-            }
-        } else if (b->eng->scan_impl >= 8) {
-            if (0 != launch_gru_scan_v4(b->d_Xin, m.sW[l], m.sW2[l], h.residual ? b->d_X[cur] : nullptr, b->d_X[cur ^ 1],
-                                        b->dims, H, (l % 2) == 0, b->eng->scan_impl - 8, (l == 1) ? b->eng->d_trace : nullptr, s)) {
-                sb2_set_error("tensor-core scan v4: unsupported configuration");
-                return -1;
-            }
-        } else if (b->eng->scan_impl >= 5) {
-            if (0 != launch_gru_scan_v3(b->d_Xin, m.sW[l], m.sW2[l], h.residual ? b->d_X[cur] : nullptr, b->d_X[cur ^ 1],
-                                        b->dims, H, (l % 2) == 0, b->eng->scan_impl - 5, (l == 1) ? b->eng->d_trace : nullptr, s)) {
-                sb2_set_error("tensor-core scan v3: unsupported configuration");
-                return -1;
-            }
-        } else if (0 != launch_gru_scan_tmem(b->d_Xin, m.sW[l], m.sW2[l], h.residual ? b->d_X[cur] : nullptr,
-                                             b->d_X[cur ^ 1], b->dims, H, (l % 2) == 0, b->eng->scan_impl - 1, s)) {
-            sb2_set_error("tensor-core scan: unsupported configuration");
+        if (0 != run_scan(b, b->d_Xin, m, l, h.residual ? b->d_X[cur] : nullptr, b->d_X[cur ^ 1], (l % 2) == 0,
+                          (l == 1) ? b->eng->d_trace : nullptr))
             return -1;
-        }
         nl += 2;
         cur ^= 1;
         if (b->keep_layers)
@@ -492,14 +555,14 @@ extern "C" int sb2_batch_forward(sb2_batch *b, const sb2_params *p, bool return_
         nl += 1;
     } else if (h.head == 0) {
         launch_affine(b->d_X[cur], b->total_cols, H, m.FF_W, H, m.FF_b, (int)h.nstate, b->d_post, (int)h.ostride,
-                      p->tempW / p->tempb, p->tempb, 1, s);
+                      p->tempW / p->tempb, p->tempb, 1, 0, s);
         stage_mark(b, ST_FINISH);
         launch_softmax_finish(b->d_post, b->total_cols, (int)h.nstate, (int)h.ostride, p->min_prob, return_log ? 1 : 0, s);
         nl += 2;
     } else {
         CUDA_OK(cudaMemsetAsync(b->d_post, 0, (size_t)b->total_cols * h.ostride * sizeof(float), s));
         launch_affine(b->d_X[cur], b->total_cols, H, m.FF_W, H, m.FF_b, (int)h.nstate, b->d_post, (int)h.ostride,
-                      1.0f, 1.0f, 0, s);
+                      1.0f, 1.0f, 0, 0, s);
         stage_mark(b, ST_FINISH);
         launch_globalnorm(b->d_post, b->dims, (int)h.ostride, s);
         nl += 2;
@@ -864,14 +927,14 @@ extern "C" scrappie_matrix nanonet_rnnrf_r94_transitions(const raw_table signal,
     return posterior_single(SCRAPPIE_MODEL_RNNRF_R9_4, signal, min_prob, tempW, tempb, return_log);
 }
 
-static scrappie_matrix unsupported_raw_posterior(const raw_table, float, float, float, bool) {
-    sb2_set_error("raw_r94 is outside this engine's scope");
-    return nullptr;
+// interface/scrappie.h:49-51
+extern "C" scrappie_matrix nanonet_raw_posterior(const raw_table signal, float min_prob, float tempW, float tempb, bool return_log) {
+    return posterior_single(SCRAPPIE_MODEL_RAW, signal, min_prob, tempW, tempb, return_log);
 }
 
 extern "C" posterior_function_ptr get_posterior_function(const enum raw_model_type model) {
     switch (model) {
-    case SCRAPPIE_MODEL_RAW: return unsupported_raw_posterior;
+    case SCRAPPIE_MODEL_RAW: return nanonet_raw_posterior;
     case SCRAPPIE_MODEL_RGRGR_R9_4: return nanonet_rgrgr_r94_posterior;
     case SCRAPPIE_MODEL_RGRGR_R9_4_1: return nanonet_rgrgr_r941_posterior;
     case SCRAPPIE_MODEL_RGRGR_R10: return nanonet_rgrgr_r10_posterior;

@@ -104,19 +104,29 @@ int sb2_host_model_parse(const void *blob, size_t nbytes, sb2_host_model *m) {
     const uint32_t nt = hdr[0];
     const size_t table_bytes = (size_t)nt * sizeof(blob_entry);
     if (40 + table_bytes > nbytes) { sb2_host_model_free(m); return -1; }
-    m->conv_stride = hdr[1]; m->conv_act = hdr[2]; m->head = hdr[3]; m->residual = hdr[4];
+    m->conv_stride = hdr[1]; m->conv_act = hdr[2]; m->head = hdr[3]; m->residual = hdr[4]; m->arch = hdr[5];
     const blob_entry *tab = (const blob_entry *)(p + 40);
     const float *data = (const float *)(p + 40 + table_bytes);
     const size_t nfloat = (nbytes - 40 - table_bytes) / sizeof(float);
+    if (m->arch > 1) { sb2_set_error("weight blob: unknown architecture %u", m->arch); sb2_host_model_free(m); return -1; }
+    const int nlayer = (m->arch == 0) ? SB2_NLAYER : 4;
 
     int rc = lookup(tab, nt, data, nfloat, "conv_W", &m->conv_W);
     rc |= lookup(tab, nt, data, nfloat, "conv_b", &m->conv_b);
-    for (int l = 0; l < SB2_NLAYER; l++) {
+    for (int l = 0; l < nlayer; l++) {
         char nm[24];
         snprintf(nm, sizeof(nm), "gru%d_iW", l + 1);  rc |= lookup(tab, nt, data, nfloat, nm, &m->iW[l]);
         snprintf(nm, sizeof(nm), "gru%d_b", l + 1);   rc |= lookup(tab, nt, data, nfloat, nm, &m->b[l]);
         snprintf(nm, sizeof(nm), "gru%d_sW", l + 1);  rc |= lookup(tab, nt, data, nfloat, nm, &m->sW[l]);
         snprintf(nm, sizeof(nm), "gru%d_sW2", l + 1); rc |= lookup(tab, nt, data, nfloat, nm, &m->sW2[l]);
+    }
+    if (m->arch == 1) {
+        for (int i = 0; i < 2; i++) {
+            char nm[24];
+            snprintf(nm, sizeof(nm), "comb%d_Wf", i + 1); rc |= lookup(tab, nt, data, nfloat, nm, &m->comb_Wf[i]);
+            snprintf(nm, sizeof(nm), "comb%d_Wb", i + 1); rc |= lookup(tab, nt, data, nfloat, nm, &m->comb_Wb[i]);
+            snprintf(nm, sizeof(nm), "comb%d_b", i + 1);  rc |= lookup(tab, nt, data, nfloat, nm, &m->comb_b[i]);
+        }
     }
     rc |= lookup(tab, nt, data, nfloat, "FF_W", &m->FF_W);
     rc |= lookup(tab, nt, data, nfloat, "FF_b", &m->FF_b);
@@ -126,20 +136,38 @@ int sb2_host_model_parse(const void *blob, size_t nbytes, sb2_host_model *m) {
         return -1;
     }
     m->winlen = m->conv_W.stride / 4;       /* taps sit at every 4th float of a filter column */
-    m->H = m->conv_W.nc;
+    m->nfilter = m->conv_W.nc;
+    m->H = m->sW2[0].nc;
     m->nstate = m->FF_W.nc;
     m->ostride = 4 * ((m->nstate + 3) / 4);
-    /* shape sanity: this engine assumes the rgrgr / rnnrf topology */
-    for (int l = 0; l < SB2_NLAYER; l++) {
-        if (m->iW[l].nr != m->H || m->iW[l].nc != 3 * m->H || m->sW[l].nc != 2 * m->H ||
+    /* shape sanity: GRU blocks of width H; input widths follow the topology */
+    for (int l = 0; l < nlayer; l++) {
+        uint32_t in = m->H;
+        if (m->arch == 1) in = (l < 2) ? m->nfilter : m->comb_b[0].nr;
+        if (m->iW[l].nr != in || m->iW[l].nc != 3 * m->H || m->sW[l].nc != 2 * m->H ||
             m->sW[l].nr != m->H || m->sW2[l].nc != m->H || m->sW2[l].nr != m->H ||
-            m->b[l].nr != 3 * m->H || m->iW[l].stride != m->H) {
+            m->b[l].nr != 3 * m->H || m->iW[l].stride != in) {
             sb2_set_error("weight blob: unexpected GRU shapes in layer %d", l + 1);
             sb2_host_model_free(m);
             return -1;
         }
     }
-    if (m->FF_W.nr != m->H || m->H % 4 != 0) { sb2_host_model_free(m); return -1; }
+    if (m->arch == 0) {
+        if (m->nfilter != m->H || m->FF_W.nr != m->H || m->H % 4 != 0) { sb2_host_model_free(m); return -1; }
+    } else {
+        m->ffw = m->comb_b[0].nr;
+        for (int i = 0; i < 2; i++)
+            if (m->comb_Wf[i].nr != m->H || m->comb_Wb[i].nr != m->H || m->comb_Wf[i].nc != m->ffw ||
+                m->comb_Wb[i].nc != m->ffw || m->comb_b[i].nr != m->ffw || m->comb_Wf[i].stride != m->H) {
+                sb2_set_error("weight blob: unexpected feedforward2 shapes");
+                sb2_host_model_free(m);
+                return -1;
+            }
+        if (m->FF_W.nr != m->ffw || m->FF_W.stride != m->ffw || m->H % 4 != 0 || m->ffw % 4 != 0 || m->nfilter % 4 != 0) {
+            sb2_host_model_free(m);
+            return -1;
+        }
+    }
     return 0;
 }
 

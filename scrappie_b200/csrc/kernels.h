@@ -30,10 +30,12 @@ void launch_conv_act(const float *raw, const BatchDims &d, const sb2_conv_tail *
                      const float *taps /*[winlen][nf]*/, const float *bias, int winlen, int nf,
                      int stride, int act, float *out, cudaStream_t s);
 
-// C[col][m] = f((b[m] + sum_k W[m][k] * (X[col][k] / xdiv)) / cdiv), f = identity or exp
-// (affine_map src/scrappie_matrix.c:323-351; softmax_with_temperature src/layers.c:340-357)
+// C[col][m] = f((base + sum_k W[m][k] * (X[col][k] / xdiv)) / cdiv); base = b[m], or the old C[col][m]
+// when `accumulate` (second product of affine_map2); f (act) = 0 identity, 1 exp, 2 tanh
+// (affine_map / affine_map2 src/scrappie_matrix.c:323-383; softmax_with_temperature src/layers.c:340-357;
+//  feedforward2_tanh src/layers.c:359-371)
 void launch_affine(const float *X, int ncol, int K, const float *W, int ldw, const float *b, int M,
-                   float *C, int ldc, float xdiv, float cdiv, int do_exp, cudaStream_t s);
+                   float *C, int ldc, float xdiv, float cdiv, int act, int accumulate, cudaStream_t s);
 
 // row_normalise_inplace + robustlog_activation_inplace (src/scrappie_matrix.c:385-407,
 // src/layers.c:79-94) over the exp'd head output, padding lanes included

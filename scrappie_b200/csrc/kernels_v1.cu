@@ -95,7 +95,7 @@ constexpr int AF_XS = AF_BN + 4;
 __global__ void __launch_bounds__(256)
 affine_kernel(const float *__restrict__ X, int ncol, int K, const float *__restrict__ W, int ldw,
               const float *__restrict__ b, int M, float *__restrict__ C, int ldc, float xdiv,
-              float cdiv, int do_exp) {
+              float cdiv, int act, int accumulate) {
     __shared__ __align__(16) float Ws[AF_KC][AF_BM];
     __shared__ __align__(16) float Xs[AF_KC][AF_XS];
     const int m_base = blockIdx.y * AF_BM;
@@ -152,17 +152,20 @@ affine_kernel(const float *__restrict__ X, int ncol, int K, const float *__restr
         for (int i = 0; i < 6; i++) {
             const int m = m_base + m0 + i;
             if (m >= M) continue;
-            float v = (b[m] + acc[i][j]) / cdiv;
-            if (do_exp) v = exp_cephes(v);
+            // accumulate: second half of affine_map2 (src/scrappie_matrix.c:353-383), C already holds b + W1 x1
+            const float base = accumulate ? C[(size_t)c * ldc + m] : b[m];
+            float v = (base + acc[i][j]) / cdiv;
+            if (act == 1) v = exp_cephes(v);
+            else if (act == 2) v = tanh_cephes(v);
             C[(size_t)c * ldc + m] = v;
         }
     }
 }
 
 void launch_affine(const float *X, int ncol, int K, const float *W, int ldw, const float *b, int M,
-                   float *C, int ldc, float xdiv, float cdiv, int do_exp, cudaStream_t s) {
+                   float *C, int ldc, float xdiv, float cdiv, int act, int accumulate, cudaStream_t s) {
     dim3 grid((ncol + AF_BN - 1) / AF_BN, (M + AF_BM - 1) / AF_BM);
-    affine_kernel<<<grid, 256, 0, s>>>(X, ncol, K, W, ldw, b, M, C, ldc, xdiv, cdiv, do_exp);
+    affine_kernel<<<grid, 256, 0, s>>>(X, ncol, K, W, ldw, b, M, C, ldc, xdiv, cdiv, act, accumulate);
 }
 
 // ---------------------------------------------------------------------------------

@@ -27,9 +27,14 @@ typedef struct {
     void *blob;             /* owned copy of the blob */
     size_t nbytes;
     uint32_t conv_stride, conv_act, head, residual;
+    uint32_t arch;              /* 0: conv + 5 alternating GRU layers + head; 1: raw_r94 (bidirectional pairs) */
     uint32_t winlen, H, nstate, ostride;
+    uint32_t nfilter;           /* convolution filters (= H for arch 0) */
+    uint32_t ffw;               /* arch 1: width of the feedforward2_tanh layers that merge a GRU pair */
     sb2_tensor conv_W, conv_b;
+    /* arch 0: layers 1..5;  arch 1: entries 0..3 = F1, B1, F2, B2 (src/networks.c:196-247) */
     sb2_tensor iW[SB2_NLAYER], b[SB2_NLAYER], sW[SB2_NLAYER], sW2[SB2_NLAYER];
+    sb2_tensor comb_Wf[2], comb_Wb[2], comb_b[2];       /* arch 1: FF1 / FF2 */
     sb2_tensor FF_W, FF_b;
 } sb2_host_model;
 

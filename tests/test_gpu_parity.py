@@ -60,6 +60,27 @@ def test_temperature_and_min_prob(sb, oracle):
     assert np.abs(got[:, :1025] - want[:, :1025]).max() < LOG_TOL
 
 
+@pytest.mark.parametrize("n", [500, 1000, 1003])
+def test_raw_r94_posterior_and_basecall(sb, engine, oracle, golden, n):
+    """nanonet_raw_posterior (interface/scrappie.h:49-51; bidirectional GRU pairs + feedforward2_tanh):
+    posterior vs the oracle and vs the reference fixture, base sequence identical to the reference's."""
+    g = golden.ref_raw_r94
+    key = "raw_r94_%d" % n
+    x = synthetic_read(1000 + n, n)
+    got = sb.calc_post(sb.RawTable(x), "raw_r94", min_prob=1e-5).padded()
+    want = oracle.posterior("raw_r94", x)
+    assert got.shape == want.shape
+    assert np.abs(got[:, :1025] - want[:, :1025]).max() < LOG_TOL
+    assert np.abs(got[g[key + "_post_cols"]][:, :1025] - g[key + "_post_sub"][:, :1025]).max() < LOG_TOL
+    (bases, score, nblock), = engine.basecall_batch("raw_r94", [x])
+    assert bases == str(g[key + "_bases"])
+    assert abs(score - float(g[key + "_score"])) < 5e-3
+    # ragged batch through the batch interface
+    xs = [x, synthetic_read(77, 731)]
+    calls = engine.basecall_batch("raw_r94", xs)
+    assert calls[0][0] == bases and calls[1][0] == oracle.basecall_raw("raw_r94", xs[1])[2]
+
+
 def test_rnnrf_rejects_non_log(sb):
     with pytest.raises(ValueError):
         sb.calc_post(sb.RawTable(synthetic_read(1, 300)), "rnnrf_r94", log=False)
@@ -297,8 +318,6 @@ def test_full_size_properties(sb, engine, oracle):
 def test_error_paths(sb, engine):
     with pytest.raises(RuntimeError):
         engine.batch("rgrgr_r94", [10])                  # shorter than the convolution window
-    with pytest.raises(RuntimeError):
-        engine.batch("raw_r94", [1000])                  # outside this engine's scope
     rt = sb.RawTable(np.zeros(0, dtype=np.float32))
     with pytest.raises(RuntimeError):
         sb.calc_post(rt, "rgrgr_r94")

@@ -98,6 +98,18 @@ def test_rgrgr_r10_subsampled(oracle, golden):
     assert bases == str(g["rgrgr_r10_600_bases"])
 
 
+@pytest.mark.parametrize("n", [500, 1000, 1003])
+def test_raw_r94_against_reference_fixture(oracle, golden, n):
+    """Pins the restatement of nanonet_raw_posterior (src/networks.c:196-247)."""
+    g = golden.ref_raw_r94
+    key = "raw_r94_%d" % n
+    x = synthetic_read(1000 + n, n)
+    score, path, bases, post = oracle.basecall_raw("raw_r94", x)
+    assert np.abs(post[g[key + "_post_cols"]][:, :1025] - g[key + "_post_sub"][:, :1025]).max() < 1e-4
+    assert bases == str(g[key + "_bases"])
+    assert np.array_equal(path, g[key + "_path"])
+
+
 def test_decoder_sweeps_exact(oracle, golden):
     g, syn = golden.ref_decode, golden.ref_synthetic
     post = syn[str(g["post_key"])]

@@ -16,7 +16,10 @@ Blob layout (all little-endian):
     uint32   conv_act      0 = ELU, 1 = tanh       (src/networks.c:260 / :358)
     uint32   head          0 = softmax, 1 = globalnorm (src/networks.c:287 / :609)
     uint32   residual      1 = GRU layers wrapped in residual (src/networks.c:583)
-    uint32   reserved[3]
+    uint32   arch          0 = conv + 5 alternating unidirectional GRU layers + head (rgrgr / rnnrf),
+                           1 = raw_r94: conv + 2 x (bidirectional GRU pair + feedforward2_tanh) + head
+                               (src/networks.c:196-247); tensors gru1..4 = F1, B1, F2, B2, comb1/2 = FF1/FF2
+    uint32   reserved[2]
     n_tensor x { char name[24]; uint32 nr, nc, stride, offset }   offset in floats
     float    data[]      each tensor exactly as the reference stores it:
                          column-major, nc columns of `stride` floats
@@ -56,19 +59,23 @@ def read_mat(lib, sym):
     return int(m.nr), int(m.nc), int(m.stride), arr
 
 
-def extract(lib, model, outdir):
-    conv_act, head, residual = MODELS[model]
-    tensors = []
-    tensors.append(("conv_W",) + read_mat(lib, "_conv_%s_W" % model))
-    tensors.append(("conv_b",) + read_mat(lib, "_conv_%s_b" % model))
-    for i, lay in enumerate(LAYERS, 1):
+def extract_raw_r94(lib, outdir):
+    """nanonet_raw_posterior's weights (src/networks.c:196-247, src/models/raw_r94.h)."""
+    tensors = [("conv_W",) + read_mat(lib, "_conv_raw_W"), ("conv_b",) + read_mat(lib, "_conv_raw_b")]
+    for i, lay in enumerate(["gruF1", "gruB1", "gruF2", "gruB2"], 1):
         for part in ("iW", "b", "sW", "sW2"):
-            tensors.append(("gru%d_%s" % (i, part),) + read_mat(lib, "_%s_%s_%s" % (lay, model, part)))
-    tensors.append(("FF_W",) + read_mat(lib, "_FF_%s_W" % model))
-    tensors.append(("FF_b",) + read_mat(lib, "_FF_%s_b" % model))
-    stride = ctypes.c_int.in_dll(lib, "conv_%s_stride" % model).value
+            tensors.append(("gru%d_%s" % (i, part),) + read_mat(lib, "_%s_raw_%s" % (lay, part)))
+    for i in (1, 2):
+        for part in ("Wf", "Wb", "b"):
+            tensors.append(("comb%d_%s" % (i, part),) + read_mat(lib, "_FF%d_raw_%s" % (i, part)))
+    tensors.append(("FF_W",) + read_mat(lib, "_FF3_raw_W"))
+    tensors.append(("FF_b",) + read_mat(lib, "_FF3_raw_b"))
+    stride = ctypes.c_int.in_dll(lib, "conv_raw_stride").value
+    write_blob("raw_r94", tensors, stride, 1, 0, 0, 1, outdir)
 
-    hdr = b"SB2WTS01" + struct.pack("<8I", len(tensors), stride, conv_act, head, residual, 0, 0, 0)
+
+def write_blob(model, tensors, stride, conv_act, head, residual, arch, outdir):
+    hdr = b"SB2WTS01" + struct.pack("<8I", len(tensors), stride, conv_act, head, residual, arch, 0, 0)
     table = b""
     off = 0
     for name, nr, nc, st, arr in tensors:
@@ -83,6 +90,21 @@ def extract(lib, model, outdir):
     print("%s: %d tensors, %d floats, conv stride %d -> %s" % (model, len(tensors), off, stride, path))
 
 
+def extract(lib, model, outdir):
+    conv_act, head, residual = MODELS[model]
+    tensors = []
+    tensors.append(("conv_W",) + read_mat(lib, "_conv_%s_W" % model))
+    tensors.append(("conv_b",) + read_mat(lib, "_conv_%s_b" % model))
+    for i, lay in enumerate(LAYERS, 1):
+        for part in ("iW", "b", "sW", "sW2"):
+            tensors.append(("gru%d_%s" % (i, part),) + read_mat(lib, "_%s_%s_%s" % (lay, model, part)))
+    tensors.append(("FF_W",) + read_mat(lib, "_FF_%s_W" % model))
+    tensors.append(("FF_b",) + read_mat(lib, "_FF_%s_b" % model))
+    stride = ctypes.c_int.in_dll(lib, "conv_%s_stride" % model).value
+
+    write_blob(model, tensors, stride, conv_act, head, residual, 0, outdir)
+
+
 def main():
     so = os.path.join(ROOT, "oracle", "_ref", "libscrappie_ref.so")
     if not os.path.exists(so):
@@ -92,6 +114,7 @@ def main():
     os.makedirs(outdir, exist_ok=True)
     for model in MODELS:
         extract(lib, model, outdir)
+    extract_raw_r94(lib, outdir)
 
 
 if __name__ == "__main__":

@@ -140,8 +140,28 @@ def reference_outputs():
     np.savez_compressed(os.path.join(OUT, "ref_reads.npz"), **out)
 
 
+def raw_r94_outputs():
+    """nanonet_raw_posterior (interface/scrappie.h:49-51) fixtures: kept in their own file so that adding them
+    did not disturb the other fixtures."""
+    ref = Reference()
+    d = {}
+    for n in (500, 1000, 1003):
+        x = synthetic_read(1000 + n, n)
+        score, path, bases, post = ref.basecall_raw("raw_r94", x)
+        key = "raw_r94_%d" % n
+        d[key + "_score"] = np.float32(score)
+        d[key + "_path"] = path
+        d[key + "_bases"] = np.array(bases)
+        d[key + "_post_cols"] = np.arange(0, post.shape[0], 5)
+        d[key + "_post_sub"] = post[::5]
+    np.savez_compressed(os.path.join(OUT, "ref_raw_r94.npz"), **d)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "raw_r94":
+        raw_r94_outputs()
+        sys.exit(0)
     upstream()
     bundled_reads()
     reference_outputs()
