@@ -46,6 +46,9 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--cpu-sample-reads", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="fixed", choices=["fixed", "mixed"],
+                    help="fixed: --reads reads of --samples samples (BASELINE config 2); mixed: --reads reads with "
+                         "log-normal lengths in [1k, 200k] samples, length-bucketed dynamic batching (config 4)")
     return ap.parse_args()
 
 
@@ -207,9 +210,18 @@ def main_b200(args, rank, world, local_rank):
     blob_path = os.path.join(sb.WEIGHTS_DIR, args.model + ".bin")
     eng.load_blob(args.model, broadcast_blob(blob_path, rank, dist, device="cuda" if world > 1 else "cpu"))
 
-    sigs = make_workload(args.reads, args.samples, 1000 + rank * args.reads)
-    nbatch = (args.reads + args.batch - 1) // args.batch
-    groups = [sigs[i * args.batch:(i + 1) * args.batch] for i in range(nbatch)]
+    if args.workload == "mixed":
+        from scrappie_b200.sharding import lognormal_lengths, plan_batches
+        from scrappie_b200.synthetic import synthetic_read
+        lens = lognormal_lengths(args.reads, seed=4 + rank)
+        sigs = [synthetic_read(1000 + rank * args.reads + i, int(n)) for i, n in enumerate(lens)]
+        plan = plan_batches(lens, max_reads=args.batch, max_samples=args.batch * 4096)
+        groups = [[sigs[i] for i in idx] for idx in plan]
+        nbatch = len(groups)
+    else:
+        sigs = make_workload(args.reads, args.samples, 1000 + rank * args.reads)
+        nbatch = (args.reads + args.batch - 1) // args.batch
+        groups = [sigs[i * args.batch:(i + 1) * args.batch] for i in range(nbatch)]
     batches = [eng.batch(args.model, [len(s) for s in g]) for g in groups]
     pinned = []
     for b, g in zip(batches, groups):
@@ -309,8 +321,13 @@ def main_b200(args, rank, world, local_rank):
         "metric": "raw samples/sec (%s)" % args.model, "value": world * total_samples / (step_ms * 1e-3),
         "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%s raw, %d synthetic %d-sample reads per GPU, batch=%d (%d concurrent batches), "
-                               "forward + Viterbi decode" % (args.model, args.reads, args.samples, args.batch, nbatch),
+        "config": {"workload": ("%s raw, %d synthetic %d-sample reads per GPU, batch=%d (%d concurrent batches), "
+                                "forward + Viterbi decode" % (args.model, args.reads, args.samples, args.batch, nbatch))
+                               if args.workload == "fixed" else
+                               ("%s raw, %d synthetic reads per GPU with log-normal lengths (median 8000, sigma 1.0, clipped "
+                                "to [1k, 200k] samples; %d samples in total, longest %d), length-bucketed dynamic batching "
+                                "into %d concurrent batches of <= %d reads" % (args.model, args.reads, total_samples,
+                                                                              max(len(x) for x in sigs), nbatch, args.batch)),
                    "l2": "flushed between timed steps (384 MB overwrite, outside the timed region)",
                    "scan_impl": os.environ.get("SCRAPPIE_B200_SCAN", "default"),
                    "parallelism": "reads sharded, %d rank(s), NCCL weight broadcast at init only" % world},

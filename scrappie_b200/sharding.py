@@ -22,6 +22,36 @@ def shard_reads(lengths, rank, world):
     return np.flatnonzero(owner == rank)
 
 
+def plan_batches(lengths, max_reads=256, max_samples=1 << 20):
+    """Dynamic batching for mixed-length reads: returns a list of index arrays, one per batch.
+
+    Reads are sorted by length (longest first) and cut into consecutive runs of at most `max_reads` reads and
+    `max_samples` samples, so that (i) the reads that step together inside one scan CTA (groups of 4 consecutive
+    reads of a batch) have nearly the same number of blocks -- a GRU layer costs max(T) steps per group -- and
+    (ii) a batch's device workspace (about 1.5 KB per sample for rgrgr_r94) stays bounded.  A read longer than
+    `max_samples` gets a batch of its own: a read cannot be split, its recurrence is serial
+    (src/layers.c:373-470)."""
+    lengths = np.asarray(lengths, dtype=np.int64)
+    order = np.argsort(-lengths, kind="stable")
+    batches, cur, cur_samples = [], [], 0
+    for i in order:
+        n = int(lengths[i])
+        if cur and (len(cur) >= max_reads or cur_samples + n > max_samples):
+            batches.append(np.array(cur, dtype=np.int64))
+            cur, cur_samples = [], 0
+        cur.append(int(i))
+        cur_samples += n
+    if cur:
+        batches.append(np.array(cur, dtype=np.int64))
+    return batches
+
+
+def lognormal_lengths(nreads, seed=4, median=8000.0, sigma=1.0, lo=1000, hi=200000):
+    """Read lengths of BASELINE config 4: log-normal, clipped to [1k, 200k] samples, seeded."""
+    rng = np.random.default_rng(seed)
+    return np.clip(rng.lognormal(np.log(median), sigma, size=nreads), lo, hi).astype(np.int64)
+
+
 def broadcast_blob(path, rank, dist=None, device="cpu"):
     """The weight blob as a uint8 numpy array on every rank; only rank 0 touches the file system."""
     import torch

@@ -279,6 +279,29 @@ def test_ragged_batch_equals_single_reads(sb, engine, oracle):
     b.close()
 
 
+def test_long_and_mixed_length_reads(sb, engine, oracle):
+    """BASELINE config 4 shape: one batch mixing a 150k-sample read with short ones (both conv tail branches:
+    N % 5 == 0 and != 0).  Long reads exercise the chunked backtrace and the 64-bit offsets."""
+    lens = [150000, 60003, 20000, 4000, 1234]
+    sigs = [synthetic_read(900 + i, n) for i, n in enumerate(lens)]
+    b = engine.batch("rgrgr_r94", lens)
+    b.upload(sigs)
+    b.forward()
+    b.decode()
+    paths, scores = b.paths()
+    assert [len(p) for p in paths] == [30001, 12002, 4001, 801, 248]
+    for i in (0, 1, 4):                                   # decode is exact on the GPU's own posterior
+        oscore, opath = oracle.decode_transducer(b.posterior(i), 1025)
+        assert np.array_equal(opath, paths[i]) and oscore == scores[i]
+    for i in (2, 4):                                      # network vs oracle
+        want = oracle.posterior("rgrgr_r94", sigs[i])
+        assert np.abs(b.posterior(i)[:, :1025] - want[:, :1025]).max() < LOG_TOL
+    calls = engine.basecall_batch("rgrgr_r94", sigs)
+    assert calls[2][0] == oracle.basecall_raw("rgrgr_r94", sigs[2])[2]
+    assert all(c[0] for c in calls)
+    b.close()
+
+
 def test_full_size_properties(sb, engine, oracle):
     """BASELINE config 2 shape (256 reads x 4000 samples): determinism, batch-composition
     invariance, path validity, decode == oracle decode on the GPU's own posterior."""

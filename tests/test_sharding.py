@@ -24,6 +24,19 @@ def test_shards_partition_and_balance():
     assert all(len(s) == 128 for s in eq)
 
 
+def test_plan_batches_covers_and_bounds():
+    from scrappie_b200.sharding import lognormal_lengths, plan_batches
+    lens = lognormal_lengths(700)
+    assert lens.min() >= 1000 and lens.max() <= 200000 and (lens % 5 != 0).any()
+    batches = plan_batches(lens, max_reads=256, max_samples=1 << 20)
+    assert np.array_equal(np.sort(np.concatenate(batches)), np.arange(700))
+    for b in batches:
+        assert len(b) <= 256
+        assert lens[b].sum() <= (1 << 20) or len(b) == 1
+        assert (np.diff(lens[b]) <= 0).all()                 # sorted: CTA groups are homogeneous
+    assert len(plan_batches([300000, 10, 10], max_samples=1000)) == 2
+
+
 def _worker(rank, world, port, blob_path, out_dir):
     import torch.distributed as dist
     from scrappie_b200.sharding import broadcast_blob, max_over_ranks, shard_reads
