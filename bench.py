@@ -37,8 +37,8 @@ FLOP_PER_BLOCK_TOTAL = {"rgrgr_r94": 753408, "rnnrf_r94": 760704}
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--model", default="rgrgr_r94")
     ap.add_argument("--reads", type=int, default=1024)
@@ -61,7 +61,7 @@ def peaks():
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms from the warm-up to the end of the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -69,7 +69,7 @@ class ClockSampler(object):
         self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -124,7 +124,9 @@ def run_reference(model, sigs, nthreads=0):
     lens = np.array([len(s) for s in sigs], dtype=np.uint64)
     offs = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.uint64)
     nb, nk = C.c_size_t(0), C.c_size_t(0)
-    threads = nthreads or L.ref_bench_max_threads()
+    # all host threads this process may use (torchrun exports OMP_NUM_THREADS=1, which is not what the
+    # reference's own recommendation -- one read per core -- means; README.md:66-71)
+    threads = nthreads or len(os.sched_getaffinity(0))
     secs = L.ref_bench_run(model.encode(), concat.ctypes.data, offs.ctypes.data, lens.ctypes.data, len(sigs),
                            threads, C.byref(nb), C.byref(nk), None)
     return secs, nb.value, nk.value, threads
@@ -161,8 +163,9 @@ def cpu_baseline(model, sigs, nreads_sample):
 def main_reference(args, rank, world):
     if rank != 0:
         return
-    base = make_workload(min(args.cpu_sample_reads, args.reads), args.samples, 1000)
-    sigs = (base * ((args.cpu_sample_reads + len(base) - 1) // len(base)))[:args.cpu_sample_reads]
+    # one step = one pass over the same workload as the GPU arm (args.reads reads), capped so that K steps stay bounded
+    nstep_reads = min(args.reads, args.cpu_sample_reads)
+    sigs = make_workload(nstep_reads, args.samples, 1000)
     for _ in range(max(1, min(args.warmup, 1))):
         run_reference(args.model, sigs[:32]) if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_bench.so")) else None
     times, kind, threads, nbases = [], "reference", 1, 0
@@ -241,9 +244,9 @@ def main_b200(args, rank, world, local_rank):
             dist.barrier()
 
     # ---- device-resident throughput ------------------------------------------------
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     sb.multi_time(batches, params, nrep=args.warmup, flush_l2=True)
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = eng.launches
     ms = sb.multi_time(batches, params, nrep=args.steps, flush_l2=True)
     launches = eng.launches - launches0
