@@ -75,11 +75,106 @@ conv_act_kernel(const float *__restrict__ raw, BatchDims d, const sb2_conv_tail 
     }
 }
 
+// Second generation: one thread = one filter, its taps live in registers, and it produces four
+// consecutive columns from one shared-memory window (3 * STRIDE + WINLEN samples read once, broadcast
+// within the warp) -- 4 * WINLEN FMAs per window instead of two shared-memory loads per FMA.
+// Columns that touch the left edge or the planned tail take the generic per-column path.
+template <int WINLEN, int STRIDE>
+__global__ void __launch_bounds__(256)
+conv_act_v2_kernel(const float *__restrict__ raw, BatchDims d, const sb2_conv_tail *__restrict__ tails,
+                   const float *__restrict__ taps, const float *__restrict__ bias, int nf, int nfp, int act,
+                   float *__restrict__ out) {
+    constexpr int CPB = CONV_CPB;
+    constexpr int NX = (CPB - 1) * STRIDE + WINLEN;
+    constexpr int PADL = (WINLEN - 1) / 2;
+    constexpr int WIN4 = 3 * STRIDE + WINLEN;
+    __shared__ float s_x[NX];
+    const int r = blockIdx.y;
+    const int ncol = d.nblock[r];
+    const int c0 = blockIdx.x * CPB;
+    if (c0 >= ncol) return;
+    const int n = d.nsample[r];
+    const float *x = raw + d.samp_off[r];
+    const sb2_conv_tail *tail = tails + r;
+    const int xlo = c0 * STRIDE - PADL;
+    for (int i = threadIdx.x; i < NX; i += blockDim.x) {
+        const int xi = xlo + i;
+        s_x[i] = (xi >= 0 && xi < n) ? x[xi] : 0.0f;
+    }
+    const int f = threadIdx.x % nfp;
+    const int lane = threadIdx.x / nfp;
+    const int nlane = blockDim.x / nfp;
+    float w[WINLEN];
+    const bool active = (f < nf) && (lane < nlane);
+#pragma unroll
+    for (int k = 0; k < WINLEN; k++) w[k] = active ? taps[k * nf + f] : 0.0f;
+    const float bf = active ? bias[f] : 0.0f;
+    __syncthreads();
+    if (!active) return;
+    const int first_tail = tail->first_col;
+    float *orow = out + (size_t)d.col_off[r] * nf + f;
+    for (int cc = 4 * lane; cc < CPB; cc += 4 * nlane) {
+        const int c = c0 + cc;
+        if (c >= ncol) break;
+        if (c * STRIDE - PADL >= 0 && c + 3 < first_tail && c + 3 < ncol) {
+            float xs[WIN4];
+#pragma unroll
+            for (int i = 0; i < WIN4; i++) xs[i] = s_x[cc * STRIDE + i];
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int k = 0; k < WINLEN; k++) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[j] = fmaf(w[k], xs[j * STRIDE + k], acc[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                float v = bf + acc[j];
+                v = (act == 0) ? elu_cephes(v) : tanh_cephes(v);
+                orow[(size_t)(c + j) * nf] = v;
+            }
+        } else {
+            for (int j = 0; j < 4 && c + j < ncol; j++) {
+                const int cj = c + j;
+                float acc = 0.0f;
+                if (cj < first_tail) {
+                    int x0 = cj * STRIDE - PADL, tap0 = 0;
+                    if (x0 < 0) { tap0 = -x0; x0 = 0; }
+                    for (int k = tap0; k < WINLEN; k++) acc = fmaf(taps[k * nf + f], s_x[x0 - xlo + (k - tap0)], acc);
+                } else {
+                    const int tc = cj - first_tail;
+                    const int nseg = tail->nseg[tc];
+                    for (int sg = 0; sg < nseg; sg++) {
+                        const int x0 = tail->seg[tc][sg][0], tap0 = tail->seg[tc][sg][1], ntap = tail->seg[tc][sg][2];
+                        float part = 0.0f;
+                        for (int k = 0; k < ntap; k++) part = fmaf(taps[(tap0 + k) * nf + f], x[x0 + k], part);
+                        acc += part;
+                    }
+                }
+                float v = bf + acc;
+                v = (act == 0) ? elu_cephes(v) : tanh_cephes(v);
+                orow[(size_t)cj * nf] = v;
+            }
+        }
+    }
+}
+
 void launch_conv_act(const float *raw, const BatchDims &d, const sb2_conv_tail *tails, const float *taps,
                      const float *bias, int winlen, int nf, int stride, int act, float *out,
                      cudaStream_t s) {
     const int nfp = (nf + 31) / 32 * 32;
     dim3 grid((d.max_cols + CONV_CPB - 1) / CONV_CPB, d.nread);
+    if (winlen == 19 && stride == 5) {
+        conv_act_v2_kernel<19, 5><<<grid, 256, 0, s>>>(raw, d, tails, taps, bias, nf, nfp, act, out);
+        return;
+    }
+    if (winlen == 11 && stride == 1) {
+        conv_act_v2_kernel<11, 1><<<grid, 256, 0, s>>>(raw, d, tails, taps, bias, nf, nfp, act, out);
+        return;
+    }
+    if (winlen == 11 && stride == 5) {
+        conv_act_v2_kernel<11, 5><<<grid, 256, 0, s>>>(raw, d, tails, taps, bias, nf, nfp, act, out);
+        return;
+    }
     const size_t smem = (size_t)(winlen * nf + (CONV_CPB - 1) * stride + winlen) * sizeof(float);
     conv_act_kernel<<<grid, 256, smem, s>>>(raw, d, tails, taps, bias, winlen, nf, nfp, stride, act, out);
 }
@@ -621,7 +716,7 @@ __device__ __forceinline__ int redux_min_s32(int v) {
 }
 
 template <int NH>
-__global__ void __launch_bounds__(NH / 4)
+__global__ void __launch_bounds__(NH / 4, (NH == 1024) ? 6 : 1)
 decode_transducer_v2_kernel(const float *__restrict__ post, BatchDims d, int ostride, float stay_pen,
                             float skip_pen, float local_pen, int allow_slip, uint8_t *__restrict__ tb,
                             int *__restrict__ tb_end, int *__restrict__ path, float *__restrict__ score) {
@@ -656,13 +751,19 @@ decode_transducer_v2_kernel(const float *__restrict__ post, BatchDims d, int ost
         nxt = *reinterpret_cast<const float4 *>(lp + 4 * t);
         nxt_stay = lp[NH];
     }
-    for (int blk = 0; blk < T; blk++) {
+    // running pointers: one add per block instead of re-deriving every address
+    const float *lp_next = lp + ostride + 4 * t;        // this thread's 4 log-posteriors of block blk + 1
+    const float *stay_next = lp + ostride + NH;
+    uint8_t *tb_cur = tbr + 4 * t;
+    int *tbe_cur = tbe;
+    const float stay_c = -stay_pen, nlocal = -local_pen;
+    for (int blk = 0; blk < T; blk++, lp_next += ostride, stay_next += ostride, tb_cur += NH, tbe_cur++) {
         const int buf = blk & 1;
         const float4 l4 = nxt;
         const float lstay = nxt_stay;
         if (blk + 1 < T) {
-            nxt = *reinterpret_cast<const float4 *>(lp + (size_t)(blk + 1) * ostride + 4 * t);
-            nxt_stay = lp[(size_t)(blk + 1) * ostride + NH];
+            nxt = *reinterpret_cast<const float4 *>(lp_next);
+            nxt_stay = *stay_next;
         }
         // ---- phase A: publish the previous scores; this warp's best "enter end" candidate
         *reinterpret_cast<float4 *>(&sc[buf][4 * t]) = make_float4(cur[0], cur[1], cur[2], cur[3]);
@@ -697,7 +798,7 @@ decode_transducer_v2_kernel(const float *__restrict__ post, BatchDims d, int ost
             float e = curE + fmaxf(-local_pen, lstay - stay_pen);
             int from = NH + 1;
             if (bv > e) { e = bv; from = bi; }
-            if (lane == 0) tbe[blk] = from;
+            if (lane == 0) *tbe_cur = from;
             curE = e;
         }
         __syncthreads();
@@ -744,7 +845,7 @@ decode_transducer_v2_kernel(const float *__restrict__ post, BatchDims d, int ost
             cur[j] = s;
             codes |= code << (8 * j);
         }
-        *reinterpret_cast<uint32_t *>(tbr + (size_t)blk * NH + 4 * t) = codes;
+        *reinterpret_cast<uint32_t *>(tb_cur) = codes;
         curS = curS + fmaxf(-local_pen, lstay - stay_pen);
     }
 
