@@ -198,11 +198,17 @@ extern "C" sb2_engine *sb2_engine_create(int device, const char *weights_dir) {
     // tcgen05 with weights in TMEM: 1 cephes gates, 2 SFU gates, 3 polynomial gates (default);
     // 4 tcgen05 with weights in shared memory (SFU gates); 0 fp32 CUDA cores (debug cross-check)
     // 5..7: v3 kernel (two-pass, reset gate first) with cephes / SFU / polynomial gates
-    // 8..10: v4 kernel (v3 + two read groups per CTA) with cephes / SFU / polynomial gates (10 = default)
-    eng->scan_impl = 10;
+    // 8..13: v4 kernel (v3 + two read groups per CTA); gate math 0 cephes, 1 SFU ex2 + rcp, 2 polynomial exp2 +
+    //        refined rcp, 3 / 4 compensated-argument ex2 with / without the Newton step, 5 plain ex2.approx +
+    //        Newton-refined rcp (13 = default: as accurate as the polynomial, shortest dependent chain that is)
+    eng->scan_impl = 13;
+    if (scan && 0 == strcmp(scan, "v4_poly")) eng->scan_impl = 10;
     if (scan && 0 == strcmp(scan, "v3")) eng->scan_impl = 7;
     if (scan && 0 == strcmp(scan, "v4_cephes")) eng->scan_impl = 8;
     if (scan && 0 == strcmp(scan, "v4_fast")) eng->scan_impl = 9;
+    if (scan && 0 == strcmp(scan, "v4_sfu")) eng->scan_impl = 11;   // ex2.approx with compensated argument
+    if (scan && 0 == strcmp(scan, "v4_sfu2")) eng->scan_impl = 13;  // plain ex2.approx, Newton-refined reciprocal
+    if (scan && 0 == strcmp(scan, "v4_sfu1")) eng->scan_impl = 12;  // same without the Newton step on rcp.approx
     if (scan && 0 == strcmp(scan, "ffma")) eng->scan_impl = 0;
     if (scan && 0 == strcmp(scan, "v3_cephes")) eng->scan_impl = 5;
     if (scan && 0 == strcmp(scan, "v3_fast")) eng->scan_impl = 6;

@@ -966,6 +966,38 @@ __device__ __forceinline__ void sigmoid4(const float (&x)[4], float (&y)[4]) {
         for (int i = 0; i < 4; i++) e[i] = ex2_approx(-1.4426950408889634f * x[i]);
 #pragma unroll
         for (int i = 0; i < 4; i++) y[i] = rcp_approx(1.0f + e[i]);
+    } else if (MATH == 5) {
+        // ex2.approx on the plainly rounded argument, Newton-refined reciprocal
+        float e[4], d[4], q[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) e[i] = ex2_approx(fminf(x[i] * -1.4426950408889634f, 126.0f));
+#pragma unroll
+        for (int i = 0; i < 4; i++) d[i] = 1.0f + e[i];
+#pragma unroll
+        for (int i = 0; i < 4; i++) q[i] = rcp_approx(d[i]);
+#pragma unroll
+        for (int i = 0; i < 4; i++) y[i] = fmaf(q[i], fmaf(-d[i], q[i], 1.0f), q[i]);
+    } else if (MATH == 3 || MATH == 4) {
+        // SFU exponential with a compensated argument: t = -x log2(e) is formed as th + tl (tl = the rounding
+        // error of the product plus the low part of the constant), 2^t = ex2(th) * (1 + ln2 * tl).  Removes the
+        // |t| * 2^-24 argument error that dominates ex2.approx(x * log2e) for |x| > 2; ~3 ulp overall.
+        float th[4], tl[4], e[4], d[4], q[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) th[i] = x[i] * -1.4426950216293335f;
+#pragma unroll
+        for (int i = 0; i < 4; i++) tl[i] = fmaf(x[i], -1.4426950216293335f, -th[i]);
+#pragma unroll
+        for (int i = 0; i < 4; i++) tl[i] = fmaf(x[i], -1.9259629911783985e-08f, tl[i]);
+#pragma unroll
+        for (int i = 0; i < 4; i++) e[i] = ex2_approx(fminf(th[i], 126.0f));       // keep 1 + e finite
+#pragma unroll
+        for (int i = 0; i < 4; i++) tl[i] = tl[i] * 0.6931471805599453f;
+#pragma unroll
+        for (int i = 0; i < 4; i++) d[i] = 1.0f + fmaf(e[i], tl[i], e[i]);
+#pragma unroll
+        for (int i = 0; i < 4; i++) q[i] = rcp_approx(d[i]);
+#pragma unroll
+        for (int i = 0; i < 4; i++) y[i] = (MATH == 4) ? q[i] : fmaf(q[i], fmaf(-d[i], q[i], 1.0f), q[i]);   // 4: no Newton step
     } else {
         float t[4], r[4], f[4], p[4], dd[4], q[4];
 #pragma unroll
@@ -1314,6 +1346,7 @@ int launch_gru_scan_v4(const float *Xin, const float *sW, const float *sW2, cons
 #define SB2_CASE(HH, MM) if (H == HH && math == MM) return launch_scan_v4<HH, MM>(Xin, sW, sW2, resid, out, d, backward, trace, s)
     SB2_CASE(96, 0); SB2_CASE(96, 1); SB2_CASE(96, 2);
     SB2_CASE(112, 0); SB2_CASE(112, 1); SB2_CASE(112, 2);
+    SB2_CASE(96, 3); SB2_CASE(112, 3); SB2_CASE(96, 4); SB2_CASE(112, 4); SB2_CASE(96, 5); SB2_CASE(112, 5);
 #undef SB2_CASE
     return -1;
 }
