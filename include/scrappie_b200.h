@@ -176,6 +176,8 @@ int sb2_batch_keep_layers(sb2_batch *b, int keep);
 int sb2_batch_forward(sb2_batch *b, const sb2_params *p, bool return_log);
 /* Viterbi decode of the resident posterior: paths + scores stay in HBM */
 int sb2_batch_decode(sb2_batch *b, const sb2_params *p);
+/* forward (log posterior) + decode in one call; replays a captured CUDA graph from the third call on */
+int sb2_batch_run(sb2_batch *b, const sb2_params *p);
 int sb2_batch_sync(sb2_batch *b);
 /* device -> host */
 int sb2_batch_download_posterior(sb2_batch *b, size_t read, float *dst, size_t dst_stride);

@@ -113,6 +113,7 @@ def lib():
         "sb2_batch_keep_layers": (C.c_int, [C.c_void_p, C.c_int]),
         "sb2_batch_forward": (C.c_int, [C.c_void_p, C.POINTER(Params), C.c_bool]),
         "sb2_batch_decode": (C.c_int, [C.c_void_p, C.POINTER(Params)]),
+        "sb2_batch_run": (C.c_int, [C.c_void_p, C.POINTER(Params)]),
         "sb2_batch_sync": (C.c_int, [C.c_void_p]),
         "sb2_batch_download_posterior": (C.c_int, [C.c_void_p, C.c_size_t, _f32p, C.c_size_t]),
         "sb2_batch_download_paths": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -427,6 +428,11 @@ class Batch(object):
     def decode(self, params=None):
         params = params or default_params()
         self._check(lib().sb2_batch_decode(self._h, C.byref(params)), "decode")
+
+    def run(self, params=None):
+        """forward (log posterior) + decode; a captured CUDA graph is replayed from the third call on."""
+        params = params or default_params()
+        self._check(lib().sb2_batch_run(self._h, C.byref(params)), "run")
 
     def sync(self):
         self._check(lib().sb2_batch_sync(self._h), "sync")

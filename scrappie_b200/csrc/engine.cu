@@ -302,6 +302,11 @@ struct sb2_batch {
     int *d_gidx = nullptr;
     float *d_gval = nullptr;
     size_t gcap = 0;                 // capacity in entries
+    // forward + decode captured once as a CUDA graph and replayed (13 launches -> 1)
+    cudaGraphExec_t graph = nullptr;
+    sb2_params graph_params{};
+    uint64_t graph_launches = 0;
+    int eager_runs = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[ST_COUNT + 1]{};
     float stage_ms[ST_COUNT]{};
@@ -321,6 +326,7 @@ extern "C" void sb2_batch_destroy(sb2_batch *b) {
     void *ptrs[] = {b->d_raw, b->d_X[0], b->d_X[1], b->d_Xin, b->d_post, b->d_score, b->d_layers, b->d_nsample,
                     b->d_nblock, b->d_coloff, b->d_tbE, b->d_path, b->d_sampoff, b->d_tb, b->d_tails};
     for (void *p : ptrs) if (p) cudaFree(p);
+    if (b->graph) cudaGraphExecDestroy(b->graph);
     if (b->d_Xin2) cudaFree(b->d_Xin2);
     if (b->d_FF) cudaFree(b->d_FF);
     if (b->d_gidx) cudaFree(b->d_gidx);
@@ -594,6 +600,42 @@ extern "C" int sb2_batch_decode(sb2_batch *b, const sb2_params *p) {
     return 0;
 }
 
+// forward (log posterior) + decode.  After one eager run the launch sequence of a batch is captured into a CUDA
+// graph and replayed while the parameters stay the same; SCRAPPIE_B200_GRAPH=0 keeps every launch eager.
+extern "C" int sb2_batch_run(sb2_batch *b, const sb2_params *p) {
+    if (nullptr == b || nullptr == p) return -1;
+    static const bool use_graph = !(getenv("SCRAPPIE_B200_GRAPH") && 0 == strcmp(getenv("SCRAPPIE_B200_GRAPH"), "0"));
+    if (!use_graph || b->timing || b->keep_layers)
+        return (0 == sb2_batch_forward(b, p, true) && 0 == sb2_batch_decode(b, p)) ? 0 : -1;
+    CUDA_OK(cudaSetDevice(b->eng->device));
+    if (nullptr != b->graph && 0 == memcmp(&b->graph_params, p, sizeof(*p))) {
+        CUDA_OK(cudaGraphLaunch(b->graph, b->stream));
+        b->eng->launches += b->graph_launches;
+        return 0;
+    }
+    if (b->eager_runs++ == 0)       // first run eager: one-time kernel attribute set-up must not happen under capture
+        return (0 == sb2_batch_forward(b, p, true) && 0 == sb2_batch_decode(b, p)) ? 0 : -1;
+    if (b->graph) { cudaGraphExecDestroy(b->graph); b->graph = nullptr; }
+    const uint64_t l0 = b->eng->launches.load();
+    CUDA_OK(cudaStreamBeginCapture(b->stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = (0 == sb2_batch_forward(b, p, true) && 0 == sb2_batch_decode(b, p)) ? 0 : -1;
+    cudaGraph_t g = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(b->stream, &g);
+    if (0 != rc || e != cudaSuccess || nullptr == g) {
+        if (g) cudaGraphDestroy(g);
+        if (0 == rc) sb2_set_error("CUDA graph capture failed: %s", cudaGetErrorString(e));
+        return -1;
+    }
+    const cudaError_t ei = cudaGraphInstantiate(&b->graph, g, 0);
+    cudaGraphDestroy(g);
+    if (ei != cudaSuccess) { b->graph = nullptr; sb2_set_error("CUDA graph instantiation failed: %s", cudaGetErrorString(ei)); return -1; }
+    b->graph_params = *p;
+    // the launches counted while capturing were recorded, not executed: they run now, with the graph
+    b->graph_launches = b->eng->launches.load() - l0;
+    CUDA_OK(cudaGraphLaunch(b->graph, b->stream));
+    return 0;
+}
+
 extern "C" int sb2_batch_sync(sb2_batch *b) {
     if (nullptr == b) return -1;
     CUDA_OK(cudaSetDevice(b->eng->device));
@@ -788,9 +830,7 @@ extern "C" int sb2_batch_basecall(sb2_batch *b, const float *concat, int pinned,
     CUDA_OK(cudaSetDevice(b->eng->device));
     if (0 != basecall_buffers(b)) return -1;
     if (nullptr != concat && 0 != sb2_batch_upload_concat(b, concat, pinned)) return -1;
-    if (0 != sb2_batch_forward(b, p, true) || 0 != sb2_batch_decode(b, p) ||
-        0 != sb2_batch_download_paths(b, b->h_paths, b->h_scores))
-        return -1;
+    if (0 != sb2_batch_run(b, p) || 0 != sb2_batch_download_paths(b, b->h_paths, b->h_scores)) return -1;
     const double t1 = now_ms();
     const sb2_host_model &h = b->m->host;
     int *paths = b->h_paths;
@@ -860,8 +900,7 @@ extern "C" int sb2_multi_time(sb2_batch **batches, int nbatch, const sb2_params 
         for (int k = 1; k < nbatch; k++) cudaStreamWaitEvent(batches[k]->stream, e0, 0);
         for (int k = 0; k < nbatch; k++) {
             batches[k]->timing = (i == nrep - 1);
-            rc |= sb2_batch_forward(batches[k], p, true);
-            rc |= sb2_batch_decode(batches[k], p);
+            rc |= sb2_batch_run(batches[k], p);
             batches[k]->timing = false;
             cudaEventRecord(done[k], batches[k]->stream);
         }

@@ -338,6 +338,32 @@ def test_full_size_properties(sb, engine, oracle):
     sub.close()
 
 
+def test_graph_replay_equals_eager(sb, engine):
+    """sb2_batch_run: eager, captured and replayed executions give identical results; a parameter change re-captures."""
+    lens = [2000, 1503, 777]
+    sigs = [synthetic_read(640 + i, n) for i, n in enumerate(lens)]
+    b = engine.batch("rgrgr_r94", lens)
+    b.upload(sigs)
+    b.forward()
+    b.decode()
+    want_paths, want_scores = b.paths()
+    want_paths = [p.copy() for p in want_paths]
+    want_scores = want_scores.copy()
+    for _ in range(4):                                    # eager, capture, replay, replay
+        b.run()
+        paths, scores = b.paths()
+        assert all(np.array_equal(a, c) for a, c in zip(paths, want_paths)) and np.array_equal(scores, want_scores)
+    pen = sb.default_params(skip_pen=1.5, local_pen=0.5)
+    b.forward(pen)
+    b.decode(pen)
+    want2 = [p.copy() for p in b.paths()[0]]
+    for _ in range(3):
+        b.run(pen)
+        assert all(np.array_equal(a, c) for a, c in zip(b.paths()[0], want2))
+    assert any(not np.array_equal(a, c) for a, c in zip(want2, want_paths))
+    b.close()
+
+
 def test_error_paths(sb, engine):
     with pytest.raises(RuntimeError):
         engine.batch("rgrgr_r94", [10])                  # shorter than the convolution window
