@@ -302,6 +302,10 @@ struct sb2_batch {
     int *d_gidx = nullptr;
     float *d_gval = nullptr;
     size_t gcap = 0;                 // capacity in entries
+    // device-side finishing (homopolymer + overlapper on the GPU): only base strings come back
+    int *d_path2 = nullptr, *d_nbase = nullptr, *h_nbase = nullptr;
+    char *d_bases = nullptr, *h_bases = nullptr;
+    int bases_stride = 0;
     // forward + decode captured once as a CUDA graph and replayed (13 launches -> 1)
     cudaGraphExec_t graph = nullptr;
     sb2_params graph_params{};
@@ -327,6 +331,11 @@ extern "C" void sb2_batch_destroy(sb2_batch *b) {
                     b->d_nblock, b->d_coloff, b->d_tbE, b->d_path, b->d_sampoff, b->d_tb, b->d_tails};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (b->graph) cudaGraphExecDestroy(b->graph);
+    if (b->d_path2) cudaFree(b->d_path2);
+    if (b->d_nbase) cudaFree(b->d_nbase);
+    if (b->d_bases) cudaFree(b->d_bases);
+    if (b->h_nbase) cudaFreeHost(b->h_nbase);
+    if (b->h_bases) cudaFreeHost(b->h_bases);
     if (b->d_Xin2) cudaFree(b->d_Xin2);
     if (b->d_FF) cudaFree(b->d_FF);
     if (b->d_gidx) cudaFree(b->d_gidx);
@@ -759,6 +768,55 @@ static int basecall_buffers(sb2_batch *b) {
     return 0;
 }
 
+static int finish_buffers(sb2_batch *b) {
+    if (nullptr != b->d_bases) return 0;
+    const sb2_host_model &h = b->m->host;
+    const int klen = (h.head == 0) ? (int)(logf((float)h.nstate) / logf(4.0f)) : 1;
+    // worst case: every block moves by a full k-mer
+    b->bases_stride = (int)align_up((size_t)klen * ((size_t)b->max_cols + 1) + 1, 16);
+    const size_t nbytes = (size_t)b->nread * b->bases_stride;
+    if (dev_alloc(&b->d_path2, (size_t)b->total_cols + b->nread) || dev_alloc(&b->d_nbase, b->nread) ||
+        dev_alloc(&b->d_bases, nbytes))
+        return -1;
+    CUDA_OK(cudaMallocHost(reinterpret_cast<void **>(&b->h_nbase), (size_t)b->nread * sizeof(int)));
+    CUDA_OK(cudaMallocHost(reinterpret_cast<void **>(&b->h_bases), nbytes));
+    return 0;
+}
+
+// The tail of calculate_post (src/scrappie_raw.c:290-312) for a whole batch on the device.
+static int finish_on_device(sb2_batch *b, const sb2_params *p, sb2_call *out) {
+    const sb2_host_model &h = b->m->host;
+    if (0 != finish_buffers(b)) return -1;
+    const int klen = (h.head == 0) ? (int)(logf((float)h.nstate) / logf(4.0f)) : 1;
+    launch_finish_reads(b->d_post, b->dims, (int)h.nstate, (int)h.ostride, (int)h.head,
+                        (h.head == 0 && p->homopolymer == HOMOPOLYMER_MEAN) ? 1 : 0, klen, b->d_path, b->d_path2,
+                        b->d_bases, b->bases_stride, b->d_nbase, b->stream);
+    b->eng->launches += 1;
+    CUDA_OK(cudaMemcpyAsync(b->h_nbase, b->d_nbase, (size_t)b->nread * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+    CUDA_OK(cudaMemcpyAsync(b->h_scores, b->d_score, (size_t)b->nread * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
+    CUDA_OK(cudaStreamSynchronize(b->stream));
+    int maxlen = 0;
+    for (int r = 0; r < b->nread; r++) maxlen = std::max(maxlen, b->h_nbase[r]);
+    const size_t width = std::min((size_t)b->bases_stride, align_up((size_t)maxlen + 1, 16));
+    CUDA_OK(cudaMemcpy2DAsync(b->h_bases, b->bases_stride, b->d_bases, b->bases_stride, width, (size_t)b->nread,
+                              cudaMemcpyDeviceToHost, b->stream));
+    CUDA_OK(cudaStreamSynchronize(b->stream));
+    int ncalled = 0;
+    for (int r = 0; r < b->nread; r++) {
+        const int nbase = b->h_nbase[r];
+        out[r].score = b->h_scores[r];
+        out[r].nblock = (size_t)b->nblock[r];
+        if (nbase < 0) continue;                         // no k-mer in the path: NULL like the host overlapper
+        char *bases = static_cast<char *>(calloc((size_t)nbase + 1, 1));
+        if (nullptr == bases) continue;
+        memcpy(bases, b->h_bases + (size_t)r * b->bases_stride, (size_t)nbase);
+        out[r].bases = bases;
+        out[r].nbase = (size_t)nbase;
+        ncalled++;
+    }
+    return ncalled;
+}
+
 struct HpJob { int read; sb2_hp_run run; size_t off; };
 
 // Homopolymer fix-up: runs are found on the host from the Viterbi path; only the two posterior
@@ -830,6 +888,15 @@ extern "C" int sb2_batch_basecall(sb2_batch *b, const float *concat, int pinned,
     CUDA_OK(cudaSetDevice(b->eng->device));
     if (0 != basecall_buffers(b)) return -1;
     if (nullptr != concat && 0 != sb2_batch_upload_concat(b, concat, pinned)) return -1;
+    // SCRAPPIE_B200_FINISH=host keeps the homopolymer fix-up and the overlapper on the CPU (cross-check path)
+    static const bool finish_host = getenv("SCRAPPIE_B200_FINISH") && 0 == strcmp(getenv("SCRAPPIE_B200_FINISH"), "host");
+    if (!finish_host) {
+        if (0 != sb2_batch_run(b, p)) return -1;
+        const double tg = now_ms();
+        const int n = finish_on_device(b, p, out);
+        if (timing) fprintf(stderr, "scrappie_b200: basecall %d reads: launch %.2f ms, gpu + finishing + copies %.2f ms\n", nread, tg - t0, now_ms() - tg);
+        return n;
+    }
     if (0 != sb2_batch_run(b, p) || 0 != sb2_batch_download_paths(b, b->h_paths, b->h_scores)) return -1;
     const double t1 = now_ms();
     const sb2_host_model &h = b->m->host;

@@ -58,6 +58,12 @@ void launch_decode_transducer(const float *post, const BatchDims &d, int nstate,
 void launch_decode_crf(const float *trans, const BatchDims &d, int ostride, uint8_t *tb, int *path,
                        float *score, cudaStream_t s);
 
+// homopolymer_path + overlapper (or crfpath_to_basecall) per read on the device; bases[r * bases_stride ...] receives a
+// NUL-terminated string, nbase[r] its length (-1 when the path holds no k-mer)
+void launch_finish_reads(const float *post, const BatchDims &d, int nstate, int ostride, int head, int homopolymer,
+                         int klen, const int *path_in, int *path_work, char *bases, int bases_stride, int *nbase,
+                         cudaStream_t s);
+
 // gather post[col][state] pairs (homopolymer fix-up needs a few posterior entries)
 void launch_gather(const float *post, int ostride, const int *col_state_pairs, int n, float *out, cudaStream_t s);
 

@@ -1167,6 +1167,255 @@ void launch_decode_transducer(const float *post, const BatchDims &d, int nstate,
 }
 
 // ---------------------------------------------------------------------------------
+// read finishing on the device: homopolymer fix-up + overlapper / crfpath_to_basecall
+// ---------------------------------------------------------------------------------
+// One thread per read walks that read's Viterbi path exactly as homopolymer_path
+// (src/homopolymer.c:67-235: runs are detected on the ORIGINAL path, base-major, and applied in that
+// order to the working copy) and overlapper (src/decode.c:367-382, :449-509) do on the host.  Only the
+// base strings travel back over PCIe.  The host implementations (host_decode.c) remain the library's
+// single-read entry points and the cross-check of this kernel (tests/test_gpu_parity.py).
+__device__ __forceinline__ int dev_kmer_shift(int prev, int next, int nkmer) {
+    int mask = nkmer - 1;
+    int shift = 0;
+    do {
+        mask >>= 2;
+        prev &= mask;
+        next >>= 2;
+        shift++;
+    } while (prev != next);
+    return shift;
+}
+
+__device__ __forceinline__ int dev_homopolymer_kmer(int base, int len) {
+    int k = 0;
+    for (int i = 0; i < len; i++) k = 4 * k + base;
+    return k;
+}
+
+// expf as the host's libm evaluates it to within rounding: exp in double, rounded once to float
+__device__ __forceinline__ double dev_expf_as_host(float x) { return (double)(float)exp((double)x); }
+
+__device__ void dev_apply_run(const float *post, int ostride, int col0, int stay, int *pw, int start, int length, int state) {
+    int nviterbi = 0;
+    double expect = 0.0;
+    for (int i = 0; i < length; i++) {
+        const float *col = post + (size_t)(col0 + start + i - 1) * ostride;     // path[i] pairs with column i - 1
+        const double ps = dev_expf_as_host(col[stay]);
+        const double pr = dev_expf_as_host(col[state]);
+        expect += pr / (pr + ps);
+        if (pw[start + i] == state) nviterbi++;
+    }
+    const int nnew = (int)(expect + 0.5);
+    if (nnew == nviterbi) return;
+    for (int i = 0; i < length; i++) pw[start + i] = (i < nnew) ? state : -1;
+}
+
+__global__ void __launch_bounds__(32)
+finish_reads_kernel(const float *__restrict__ post, BatchDims d, int nstate, int ostride, int head, int homopolymer,
+                    int klen, const int *__restrict__ path_in, int *__restrict__ path_work, char *__restrict__ bases,
+                    int bases_stride, int *__restrict__ nbase_out) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= d.nread) return;
+    const int nb = d.nblock[r];
+    const int col0 = d.col_off[r];
+    const int *pin = path_in + col0 + r;
+    int *pw = path_work + col0 + r;
+    char *out = bases + (size_t)r * bases_stride;
+    const char base_of[4] = {'A', 'C', 'G', 'T'};
+    if (head == 1) {                                    // crfpath_to_basecall, src/decode.c:895-918
+        int n = 0;
+        for (int i = 0; i < nb; i++)
+            if (pin[i] < 4) out[n++] = base_of[pin[i]];
+        out[n] = 0;
+        nbase_out[r] = n;
+        return;
+    }
+    for (int i = 0; i <= nb; i++) pw[i] = pin[i];
+    const int nkmer = nstate - 1;
+    if (homopolymer == 1) {
+        const int pathlen = nb;                         // homopolymer_path scans post->nc entries
+        const int mod1 = 1 << (2 * (klen - 1)), mod2 = 1 << (2 * (klen - 2));
+        const int stay = nstate - 1;
+        for (int base = 0; base < 4; base++) {
+            const int full = dev_homopolymer_kmer(base, klen);
+            const int tail1 = dev_homopolymer_kmer(base, klen - 1);
+            const int tail2 = dev_homopolymer_kmer(base, klen - 2);
+            for (int i = 1; i < pathlen - 2; i++) {
+                const int before = pin[i - 1], here = pin[i];
+                const bool here_ok = (here == -1) || (here == full);
+                if (before == -1 || !here_ok) continue;
+                if ((before % mod1 == tail1) && before != full) {
+                    int e = i + 1;
+                    while (e < pathlen && (pin[e] == -1 || pin[e] == full)) e++;
+                    dev_apply_run(post, ostride, col0, stay, pw, i, e - i, full);
+                }
+                if ((before % mod2 == tail2) && (before % mod1 != tail1)) {
+                    int j = i;
+                    while (j < pathlen && pin[j] == -1) j++;
+                    if (pin[j] == full && j < pathlen - 1) {
+                        int e = j + 1;
+                        while (e < pathlen && (pin[e] == -1 || pin[e] == full)) e++;
+                        dev_apply_run(post, ostride, col0, stay, pw, j, e - j, full);
+                    }
+                }
+            }
+        }
+    }
+    // overlapper
+    const int n = nb + 1;
+    int first = 0;
+    while (first < n && pw[first] < 0) first++;
+    if (first == n) { out[0] = 0; nbase_out[r] = -1; return; }      // all stays: the host returns NULL
+    for (int j = 0, kmer = pw[first]; j < klen; j++, kmer >>= 2) out[klen - 1 - j] = base_of[kmer & 3];
+    int tail = klen - 1;
+    int prev = pw[first];
+    for (int i = first + 1; i < n; i++) {
+        const int cur = pw[i];
+        if (cur < 0) continue;
+        const int shift = dev_kmer_shift(prev, cur, nkmer);
+        int kmer = cur;
+        for (int j = 0; j < shift; j++, kmer >>= 2) out[tail + shift - j] = base_of[kmer & 3];
+        tail += shift;
+        prev = cur;
+    }
+    out[tail + 1] = 0;
+    nbase_out[r] = tail + 1;
+}
+
+// Same, one WARP per read with the path staged in shared memory: run detection is evaluated for 32
+// positions at a time (ballot), hits are processed in ascending position order -- rule "XYYYY" before
+// rule "ZXYYY" at the same position, bases outermost -- i.e. in exactly the host's order.  Used when a
+// read's path fits the staging area; longer reads take finish_reads_kernel.
+constexpr int FIN_WARPS = 4;
+
+__global__ void __launch_bounds__(32 * FIN_WARPS)
+finish_reads_warp_kernel(const float *__restrict__ post, BatchDims d, int nstate, int ostride, int head, int homopolymer,
+                         int klen, int maxb, const int *__restrict__ path_in, char *__restrict__ bases, int bases_stride,
+                         int *__restrict__ nbase_out) {
+    extern __shared__ __align__(16) uint8_t fin_smem[];
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int r = blockIdx.x * FIN_WARPS + warp;
+    if (r >= d.nread) return;
+    const int bcap = klen * (maxb + 1) + 1;
+    const size_t per_warp = (size_t)2 * (maxb + 1) * sizeof(int) + (size_t)((bcap + 15) / 16 * 16);
+    int *po = reinterpret_cast<int *>(fin_smem + warp * per_warp);      // original path
+    int *pw = po + (maxb + 1);                                           // working copy
+    char *sb = reinterpret_cast<char *>(pw + (maxb + 1));
+    const int nb = d.nblock[r];
+    const int col0 = d.col_off[r];
+    const int *pin = path_in + col0 + r;
+    char *out = bases + (size_t)r * bases_stride;
+    for (int i = lane; i <= nb; i += 32) { const int v = pin[i]; po[i] = v; pw[i] = v; }
+    __syncwarp();
+    int nbase = 0;
+    if (head == 1) {                                    // crfpath_to_basecall
+        for (int i0 = 0; i0 < nb; i0 += 32) {
+            const int i = i0 + lane;
+            const int st = (i < nb) ? po[i] : 4;
+            const unsigned m = __ballot_sync(0xffffffffu, st < 4);
+            if (st < 4) sb[nbase + __popc(m & ((1u << lane) - 1))] = "ACGT"[st];
+            nbase += __popc(m);
+        }
+    } else {
+        const int nkmer = nstate - 1;
+        if (homopolymer == 1) {
+            const int pathlen = nb;
+            const int mod1 = 1 << (2 * (klen - 1)), mod2 = 1 << (2 * (klen - 2));
+            const int stay = nstate - 1;
+            for (int base = 0; base < 4; base++) {
+                const int full = dev_homopolymer_kmer(base, klen);
+                const int tail1 = dev_homopolymer_kmer(base, klen - 1);
+                const int tail2 = dev_homopolymer_kmer(base, klen - 2);
+                for (int i0 = 1; i0 < pathlen - 2; i0 += 32) {
+                    const int i = i0 + lane;
+                    bool c1 = false, c2 = false;
+                    if (i < pathlen - 2) {
+                        const int before = po[i - 1], here = po[i];
+                        const bool ok = (before != -1) && ((here == -1) || (here == full));
+                        c1 = ok && (before % mod1 == tail1) && (before != full);
+                        c2 = ok && (before % mod2 == tail2) && (before % mod1 != tail1);
+                    }
+                    unsigned hits = __ballot_sync(0xffffffffu, c1 || c2);
+                    const unsigned m1 = __ballot_sync(0xffffffffu, c1), m2 = __ballot_sync(0xffffffffu, c2);
+                    while (hits) {                       // every lane walks the hits identically (warp-uniform)
+                        const int l = __ffs(hits) - 1;
+                        hits &= hits - 1;
+                        const int ii = i0 + l;
+                        if ((m1 >> l) & 1u) {
+                            int e = ii + 1;
+                            while (e < pathlen && (po[e] == -1 || po[e] == full)) e++;
+                            if (lane == 0) dev_apply_run(post, ostride, col0, stay, pw, ii, e - ii, full);
+                        }
+                        if ((m2 >> l) & 1u) {
+                            int j = ii;
+                            while (j < pathlen && po[j] == -1) j++;
+                            if (po[j] == full && j < pathlen - 1) {
+                                int e = j + 1;
+                                while (e < pathlen && (po[e] == -1 || po[e] == full)) e++;
+                                if (lane == 0) dev_apply_run(post, ostride, col0, stay, pw, j, e - j, full);
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        // overlapper: serial over the path (lane 0), bases staged in shared memory
+        if (lane == 0) {
+            const char base_of[4] = {'A', 'C', 'G', 'T'};
+            const int n = nb + 1;
+            int first = 0;
+            while (first < n && pw[first] < 0) first++;
+            if (first == n) {
+                nbase = -1;
+            } else {
+                for (int j = 0, kmer = pw[first]; j < klen; j++, kmer >>= 2) sb[klen - 1 - j] = base_of[kmer & 3];
+                int tail = klen - 1;
+                int prev = pw[first];
+                for (int i = first + 1; i < n; i++) {
+                    const int cur = pw[i];
+                    if (cur < 0) continue;
+                    const int shift = dev_kmer_shift(prev, cur, nkmer);
+                    int kmer = cur;
+                    for (int j = 0; j < shift; j++, kmer >>= 2) sb[tail + shift - j] = base_of[kmer & 3];
+                    tail += shift;
+                    prev = cur;
+                }
+                nbase = tail + 1;
+            }
+        }
+        nbase = __shfl_sync(0xffffffffu, nbase, 0);
+    }
+    __syncwarp();
+    const int nout = (nbase > 0) ? nbase : 0;
+    for (int i = lane; i < nout; i += 32) out[i] = sb[i];
+    if (lane == 0) { out[nout] = 0; nbase_out[r] = nbase; }
+}
+
+void launch_finish_reads(const float *post, const BatchDims &d, int nstate, int ostride, int head, int homopolymer,
+                         int klen, const int *path_in, int *path_work, char *bases, int bases_stride, int *nbase,
+                         cudaStream_t s) {
+    const int maxb = d.max_cols;
+    const size_t per_warp = (size_t)2 * (maxb + 1) * sizeof(int) + (size_t)((klen * (maxb + 1) + 1 + 15) / 16 * 16);
+    const size_t smem = per_warp * FIN_WARPS;
+    static size_t configured = 0;
+    if (smem <= 200 * 1024) {
+        if (smem > configured) {
+            if (cudaFuncSetAttribute(finish_reads_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess)
+                configured = smem;
+        }
+        if (smem <= configured || smem <= 48 * 1024) {
+            finish_reads_warp_kernel<<<(d.nread + FIN_WARPS - 1) / FIN_WARPS, 32 * FIN_WARPS, smem, s>>>(
+                post, d, nstate, ostride, head, homopolymer, klen, maxb, path_in, bases, bases_stride, nbase);
+            return;
+        }
+    }
+    finish_reads_kernel<<<(d.nread + 31) / 32, 32, 0, s>>>(post, d, nstate, ostride, head, homopolymer, klen, path_in,
+                                                        path_work, bases, bases_stride, nbase);
+}
+
+// ---------------------------------------------------------------------------------
 // small utilities
 // ---------------------------------------------------------------------------------
 __global__ void gather_kernel(const float *__restrict__ post, int ostride, const int2 *__restrict__ idx, int n,

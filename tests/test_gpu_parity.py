@@ -338,6 +338,32 @@ def test_full_size_properties(sb, engine, oracle):
     sub.close()
 
 
+def test_device_finishing_equals_host_postprocessing(sb, engine, oracle, golden):
+    """The batch basecall finishes reads on the GPU (homopolymer fix-up + overlapper / crfpath_to_basecall);
+    the result must equal the library's host functions applied to the downloaded paths and posterior."""
+    g = golden.ref_reads
+    rt = sb.RawTable(bundled_signal(golden, 2)).trim().scale()
+    sigs = [rt.data(as_numpy=True).copy()] + [synthetic_read(70 + i, n) for i, n in enumerate((4000, 1503, 300, 60))]
+    for model in ("rgrgr_r94", "rnnrf_r94"):
+        b = engine.batch(model, [len(s) for s in sigs])
+        b.upload(sigs)
+        calls = b.basecall()                              # device finishing (signals already resident)
+        paths, scores = b.paths()
+        for i, s in enumerate(sigs):
+            post = sb.ScrappyMatrix.from_numpy(b.posterior(i), b.nstate)
+            path = paths[i].copy()
+            if model == "rgrgr_r94":
+                assert sb.lib().homopolymer_path(post.data(), path.ctypes.data_as(sb._i32p), 1) == 0
+                pos = np.zeros(len(path), dtype=np.int32)
+                want = sb._take_string(sb.lib().overlapper(path.ctypes.data_as(sb._i32p), len(path), 1024, pos.ctypes.data_as(sb._i32p)))
+            else:
+                pos = np.zeros(len(path), dtype=np.int32)
+                want = sb._take_string(sb.lib().crfpath_to_basecall(path.ctypes.data_as(sb._i32p), len(path) - 1, pos.ctypes.data_as(sb._i32p)))
+            assert calls[i][0] == want and calls[i][1] == scores[i]
+        assert calls[0][0] == str(g["r2_%s_bases" % model])
+        b.close()
+
+
 def test_graph_replay_equals_eager(sb, engine):
     """sb2_batch_run: eager, captured and replayed executions give identical results; a parameter change re-captures."""
     lens = [2000, 1503, 777]
