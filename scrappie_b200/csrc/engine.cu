@@ -581,9 +581,13 @@ extern "C" int sb2_batch_forward(sb2_batch *b, const sb2_params *p, bool return_
         launch_softmax_finish(b->d_post, b->total_cols, (int)h.nstate, (int)h.ostride, p->min_prob, return_log ? 1 : 0, s);
         nl += 2;
     } else {
-        CUDA_OK(cudaMemsetAsync(b->d_post, 0, (size_t)b->total_cols * h.ostride * sizeof(float), s));
-        launch_affine(b->d_X[cur], b->total_cols, H, m.FF_W, H, m.FF_b, (int)h.nstate, b->d_post, (int)h.ostride,
-                      1.0f, 1.0f, 0, 0, s);
+        if (h.nstate <= 32 && h.ostride <= 32 && b->eng->gemm_impl != 0) {
+            launch_small_head(b->d_X[cur], b->total_cols, H, m.FF_W, m.FF_b, (int)h.nstate, b->d_post, (int)h.ostride, s);
+        } else {
+            CUDA_OK(cudaMemsetAsync(b->d_post, 0, (size_t)b->total_cols * h.ostride * sizeof(float), s));
+            launch_affine(b->d_X[cur], b->total_cols, H, m.FF_W, H, m.FF_b, (int)h.nstate, b->d_post, (int)h.ostride,
+                          1.0f, 1.0f, 0, 0, s);
+        }
         stage_mark(b, ST_FINISH);
         launch_globalnorm(b->d_post, b->dims, (int)h.ostride, s);
         nl += 2;

@@ -64,6 +64,10 @@ void launch_finish_reads(const float *post, const BatchDims &d, int nstate, int 
                          int klen, const int *path_in, int *path_work, char *bases, int bases_stride, int *nbase,
                          cudaStream_t s);
 
+// small-M affine map for the CRF head (M <= 32 rows): C[col][0:M] = b + W^T X[col], lanes M..ldc-1 zeroed
+void launch_small_head(const float *X, int ncol, int K, const float *W, const float *b, int M, float *C, int ldc,
+                       cudaStream_t s);
+
 // gather post[col][state] pairs (homopolymer fix-up needs a few posterior entries)
 void launch_gather(const float *post, int ostride, const int *col_state_pairs, int n, float *out, cudaStream_t s);
 

@@ -455,9 +455,6 @@ globalnorm_kernel(float *__restrict__ trans, BatchDims d, int ostride) {
         if (lane < 25) tr[(size_t)t * ostride + lane] -= logZ;
 }
 
-void launch_globalnorm(float *trans, const BatchDims &d, int ostride, cudaStream_t s) {
-    globalnorm_kernel<<<(d.nread + 3) / 4, 128, 0, s>>>(trans, d, ostride);
-}
 
 __global__ void __launch_bounds__(128)
 decode_crf_kernel(const float *__restrict__ trans, BatchDims d, int ostride, uint8_t *__restrict__ tb,
@@ -501,10 +498,210 @@ decode_crf_kernel(const float *__restrict__ trans, BatchDims d, int ostride, uin
     }
 }
 
+// ---------------------------------------------------------------------------------
+// CRF (rnnrf_r94), second generation: transitions staged through shared memory
+// ---------------------------------------------------------------------------------
+// One warp per read.  Lanes 0..4 each own a destination state and evaluate its five incoming
+// transitions locally, so a step costs five shuffles (broadcast of the new forward vector) instead of
+// ten plus a serial log-sum-exp chain; all 32 lanes stream the transition rows in tiles of CRF_TILE
+// steps (coalesced float4 loads, one tile ahead), which hides the HBM latency that the per-step loads of
+// the first generation exposed.  The backtrace walks traceback tiles staged the same way.
+constexpr int CRF_TILE = 32;
+constexpr int CRF_WARPS = 4;
+
+// crf_partition_function + globalnorm (src/layers.c:835-889).
+__global__ void __launch_bounds__(32 * CRF_WARPS)
+globalnorm_v2_kernel(float *__restrict__ trans, BatchDims d, int ostride) {
+    __shared__ __align__(16) float tile[CRF_WARPS][2][CRF_TILE * 28];
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int r = blockIdx.x * CRF_WARPS + warp;
+    if (r >= d.nread || ostride != 28) return;
+    const int T = d.nblock[r];
+    float *tr = trans + (size_t)d.col_off[r] * 28;
+    const int to = (lane < 5) ? lane : 0;
+    float prev[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    constexpr int F4 = CRF_TILE * 28 / 4 / 32;          // float4 per lane per tile = 7
+    float4 stage[F4];
+    auto load_tile = [&](int t0) {
+        const float4 *src = reinterpret_cast<const float4 *>(tr + (size_t)t0 * 28);
+        const int nvalid4 = min(CRF_TILE, T - t0) * 7;   // 28 floats = 7 float4 per step
+#pragma unroll
+        for (int i = 0; i < F4; i++) {
+            const int idx = i * 32 + lane;
+            stage[i] = (idx < nvalid4) ? src[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    if (T > 0) load_tile(0);
+    for (int t0 = 0, k = 0; t0 < T; t0 += CRF_TILE, k ^= 1) {
+        float4 *dst = reinterpret_cast<float4 *>(tile[warp][k]);
+#pragma unroll
+        for (int i = 0; i < F4; i++) dst[i * 32 + lane] = stage[i];
+        __syncwarp();
+        if (t0 + CRF_TILE < T) load_tile(t0 + CRF_TILE);
+        const int nt = min(CRF_TILE, T - t0);
+        for (int t = 0; t < nt; t++) {
+            const float *e = &tile[warp][k][t * 28 + to * 5];
+            // the reference's nested pairwise log-sum-exp, in its order: the forward variables grow to ~5 T, where an
+            // fp32 ulp is 0.03 for T = 80 000 -- any other summation form drifts from the reference's logZ by a
+            // random walk of those roundings (measured: 14 on the longest bundled read)
+            float v = e[0] + prev[0];
+#pragma unroll
+            for (int f = 1; f < 5; f++) v = logsumexp2(v, e[f] + prev[f]);
+#pragma unroll
+            for (int q = 0; q < 5; q++) prev[q] = __shfl_sync(0xffffffffu, v, q);
+        }
+        __syncwarp();
+    }
+    float logZ = prev[0];
+#pragma unroll
+    for (int q = 1; q < 5; q++) logZ = logsumexp2(logZ, prev[q]);
+    logZ = logZ / (float)T;
+    // second pass: subtract from the 25 real rows of every column (padding lanes stay zero)
+    const size_t n = (size_t)T * 28;
+    for (size_t i = lane; i < n; i += 32)
+        if ((i % 28) < 25) tr[i] -= logZ;
+}
+
+void launch_globalnorm(float *trans, const BatchDims &d, int ostride, cudaStream_t s) {
+    static int gen = -1;
+    if (gen < 0) { const char *e = getenv("SCRAPPIE_B200_CRF"); gen = (e && 0 == strcmp(e, "v1")) ? 1 : 2; }
+    if (gen == 2 && ostride == 28)
+        globalnorm_v2_kernel<<<(d.nread + CRF_WARPS - 1) / CRF_WARPS, 32 * CRF_WARPS, 0, s>>>(trans, d, ostride);
+    else
+        globalnorm_kernel<<<(d.nread + 3) / 4, 128, 0, s>>>(trans, d, ostride);
+}
+
+// decode_crf (src/decode.c:836-893): identical arithmetic and tie-breaking as decode_crf_kernel.
+__global__ void __launch_bounds__(32 * CRF_WARPS)
+decode_crf_v2_kernel(const float *__restrict__ trans, BatchDims d, int ostride, uint8_t *__restrict__ tb,
+                     int *__restrict__ path, float *__restrict__ score) {
+    __shared__ __align__(16) float tile[CRF_WARPS][2][CRF_TILE * 28];
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int r = blockIdx.x * CRF_WARPS + warp;
+    if (r >= d.nread || ostride != 28) return;
+    const int T = d.nblock[r];
+    const float *tr = trans + (size_t)d.col_off[r] * 28;
+    uint8_t *tbr = tb + (size_t)d.col_off[r] * 8;
+    const int to = (lane < 5) ? lane : 0;
+    float prev[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    constexpr int F4 = CRF_TILE * 28 / 4 / 32;
+    float4 stage[F4];
+    auto load_tile = [&](int t0) {
+        const float4 *src = reinterpret_cast<const float4 *>(tr + (size_t)t0 * 28);
+        const int nvalid4 = min(CRF_TILE, T - t0) * 7;
+#pragma unroll
+        for (int i = 0; i < F4; i++) {
+            const int idx = i * 32 + lane;
+            stage[i] = (idx < nvalid4) ? src[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    if (T > 0) load_tile(0);
+    for (int t0 = 0, k = 0; t0 < T; t0 += CRF_TILE, k ^= 1) {
+        float4 *dst = reinterpret_cast<float4 *>(tile[warp][k]);
+#pragma unroll
+        for (int i = 0; i < F4; i++) dst[i * 32 + lane] = stage[i];
+        __syncwarp();
+        if (t0 + CRF_TILE < T) load_tile(t0 + CRF_TILE);
+        const int nt = min(CRF_TILE, T - t0);
+        for (int t = 0; t < nt; t++) {
+            const float *e = &tile[warp][k][t * 28 + to * 5];
+            float best = e[0] + prev[0];
+            int arg = 0;
+#pragma unroll
+            for (int f = 1; f < 5; f++) {
+                const float c = e[f] + prev[f];
+                if (c > best) { best = c; arg = f; }       // strict: lowest `from` wins ties
+            }
+            if (lane < 5) tbr[(size_t)(t0 + t) * 8 + lane] = (uint8_t)arg;
+#pragma unroll
+            for (int q = 0; q < 5; q++) prev[q] = __shfl_sync(0xffffffffu, best, q);
+        }
+        __syncwarp();
+    }
+    int last = 0;
+    for (int q = 1; q < 5; q++) if (prev[q] > prev[last]) last = q;
+    int *p = path + d.col_off[r] + r;
+    if (lane == 0) { score[r] = pick5(prev, last); p[T] = last; }
+    // backtrace: traceback rows staged CRF_BT steps at a time (8 bytes per step) in the tile buffer
+    constexpr int CRF_BT = 2 * CRF_TILE * 28 * 4 / 8;   // steps that fit the warp's tile buffers
+    uint8_t *bt = reinterpret_cast<uint8_t *>(tile[warp][0]);
+    __syncwarp();
+    for (int hi = T; hi > 0; hi -= CRF_BT) {
+        const int lo = max(hi - CRF_BT, 0);
+        const int nrow = hi - lo;
+        const uint2 *src = reinterpret_cast<const uint2 *>(tbr + (size_t)lo * 8);
+        uint2 *dst2 = reinterpret_cast<uint2 *>(bt);
+        for (int i = lane; i < nrow; i += 32) dst2[i] = src[i];
+        __syncwarp();
+        if (lane == 0) {
+            for (int t = hi; t > lo; t--) {
+                last = bt[(size_t)(t - 1 - lo) * 8 + last];
+                p[t - 1] = last;
+            }
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        __syncwarp();
+    }
+}
+
 void launch_decode_crf(const float *trans, const BatchDims &d, int ostride, uint8_t *tb, int *path,
                        float *score, cudaStream_t s) {
-    decode_crf_kernel<<<(d.nread + 3) / 4, 128, 0, s>>>(trans, d, ostride, tb, path, score);
+    static int gen = -1;
+    if (gen < 0) { const char *e = getenv("SCRAPPIE_B200_CRF"); gen = (e && 0 == strcmp(e, "v1")) ? 1 : 2; }
+    if (gen == 2 && ostride == 28)
+        decode_crf_v2_kernel<<<(d.nread + CRF_WARPS - 1) / CRF_WARPS, 32 * CRF_WARPS, 0, s>>>(trans, d, ostride, tb, path, score);
+    else
+        decode_crf_kernel<<<(d.nread + 3) / 4, 128, 0, s>>>(trans, d, ostride, tb, path, score);
 }
+
+// CRF head: C[col][0:25] = b + W^T x (feedforward_linear inside globalnorm, src/layers.c:874-880), M = 25 rows.
+// One warp per column tile; lane m < M accumulates its row over k in ascending order (the same fused multiply-add
+// sequence as affine_kernel); lanes M..ostride-1 write the zero padding.
+constexpr int HEADS_COLS = 8;                          // columns per warp per iteration
+
+__global__ void __launch_bounds__(256)
+small_head_kernel(const float *__restrict__ X, int ncol, int K, const float *__restrict__ W, const float *__restrict__ b,
+                  int M, float *__restrict__ C, int ldc) {
+    extern __shared__ __align__(16) float sh[];
+    float *Ws = sh;                                    // [K][32]: Ws[k * 32 + m]
+    float *xs = sh + (size_t)K * 32;                   // per warp [HEADS_COLS][K]
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, nwarp = blockDim.x / 32;
+    for (int i = threadIdx.x; i < K * 32; i += blockDim.x) {
+        const int k = i / 32, m = i % 32;
+        Ws[i] = (m < M) ? W[(size_t)m * K + k] : 0.0f;
+    }
+    __syncthreads();
+    float *xw = xs + (size_t)warp * HEADS_COLS * K;
+    const float bm = (lane < M) ? b[lane] : 0.0f;
+    for (int c0 = (blockIdx.x * nwarp + warp) * HEADS_COLS; c0 < ncol; c0 += gridDim.x * nwarp * HEADS_COLS) {
+        const int nc = min(HEADS_COLS, ncol - c0);
+        const float *src = X + (size_t)c0 * K;
+        for (int i = lane; i < nc * K; i += 32) xw[i] = src[i];
+        __syncwarp();
+        float acc[HEADS_COLS];
+#pragma unroll
+        for (int j = 0; j < HEADS_COLS; j++) acc[j] = 0.0f;
+        for (int k = 0; k < K; k++) {
+            const float w = Ws[k * 32 + lane];
+#pragma unroll
+            for (int j = 0; j < HEADS_COLS; j++) acc[j] = fmaf(w, xw[j * K + k], acc[j]);
+        }
+        if (lane < ldc) {
+#pragma unroll
+            for (int j = 0; j < HEADS_COLS; j++)
+                if (j < nc) C[(size_t)(c0 + j) * ldc + lane] = (lane < M) ? (bm + acc[j]) : 0.0f;
+        }
+        __syncwarp();
+    }
+}
+
+void launch_small_head(const float *X, int ncol, int K, const float *W, const float *b, int M, float *C, int ldc,
+                       cudaStream_t s) {
+    const size_t smem = ((size_t)K * 32 + (size_t)8 * HEADS_COLS * K) * sizeof(float);
+    const int grid = 148 * 4;
+    small_head_kernel<<<grid, 256, smem, s>>>(X, ncol, K, W, b, M, C, ldc);
+}
+
 
 // ---------------------------------------------------------------------------------
 // transducer Viterbi: one CTA per read, NH / 4 threads, 4 consecutive states per thread
