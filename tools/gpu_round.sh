@@ -16,7 +16,7 @@ timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/${TAG}_
 timeout 600 python bench.py --model rnnrf_r94 --no-cpu-baseline > $OUT/${TAG}_bench_rnnrf.json 2>> $OUT/${TAG}_bench.err; echo "rnnrf rc=$?"; cat $OUT/${TAG}_bench_rnnrf.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches.csv \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $OUT/${TAG}_ncu_bench.log 2>&1; echo "ncu list rc=$?"
-for K in gru_scan_v4 decode_transducer_v2 head_softmax affine_tc conv_act; do
+for K in ${KERNELS:-gru_scan_v4 decode_transducer_v2 head_softmax affine_tc conv_act}; do
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:$K -s 1 -c 1 -f -o $OUT/${TAG}_${K} \
       python tools/prof_one.py > $OUT/${TAG}_ncu_${K}.log 2>&1; echo "ncu $K rc=$?"
 done
