@@ -191,6 +191,8 @@ int sb2_batch_time(sb2_batch *b, const sb2_params *p, int nrep, int flush_l2, fl
                    float *ms_forward_out, float *ms_decode_out);
 /* Per-kernel-stage times of the last sb2_batch_time repetition, ms. */
 int sb2_batch_stage_ms(const sb2_batch *b, float *stage_ms, int nstage_max);
+/* stage boundaries (n <= 15) of the last sb2_multi_time run, ms after the first batch's first launch */
+int sb2_batch_stage_offsets(const sb2_batch *b, float *at, int n_max);
 
 /* One basecall, the equivalent of calculate_post (src/scrappie_raw.c:265-315) for many
  * reads: upload, forward, decode, homopolymer fix-up, overlapper.  signals are trimmed +
@@ -212,6 +214,9 @@ int sb2_batch_basecall(sb2_batch *b, const float *concat, int pinned, const sb2_
 /* Time forward+decode of several batches running concurrently on their own streams (how a
  * job larger than one batch executes); CUDA events on the launching stream. */
 int sb2_multi_time(sb2_batch **batches, int nbatch, const sb2_params *p, int nrep, int flush_l2, float *ms_out);
+/* streaming throughput: nrep steps per batch back to back on the batches' own streams, no synchronisation
+   between steps; *ms_total = device time of all nbatch * nrep runs */
+int sb2_multi_stream_time(sb2_batch **batches, int nbatch, const sb2_params *p, int nrep, float *ms_total);
 
 /* Diagnostic hook (SCRAPPIE_B200_TRACE=1 at engine creation): clock64() stamps recorded by CTA 0 of
  * the second GRU layer's scan at its hand-over points, steps 100..103, 16 slots per step. */

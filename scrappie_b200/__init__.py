@@ -120,11 +120,13 @@ def lib():
         "sb2_batch_download_layer": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, _f32p]),
         "sb2_batch_time": (C.c_int, [C.c_void_p, C.POINTER(Params), C.c_int, C.c_int, _f32p, _f32p, _f32p]),
         "sb2_batch_stage_ms": (C.c_int, [C.c_void_p, _f32p, C.c_int]),
+        "sb2_batch_stage_offsets": (C.c_int, [C.c_void_p, _f32p, C.c_int]),
         "sb2_basecall_batch": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(_f32p), C.POINTER(C.c_size_t), C.c_size_t,
                                          C.POINTER(Params), C.POINTER(_Call)]),
         "sb2_batch_basecall": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(Params), C.POINTER(_Call)]),
         "sb2_calls_free": (None, [C.POINTER(_Call), C.c_size_t]),
         "sb2_multi_time": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(Params), C.c_int, C.c_int, _f32p]),
+        "sb2_multi_stream_time": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(Params), C.c_int, _f32p]),
         "sb2_conv_plan_debug": (C.c_int, [C.c_size_t, C.c_size_t, C.c_size_t, _i32p, C.c_int]),
     }
     for name in MODELS:
@@ -487,6 +489,12 @@ class Batch(object):
         lib().sb2_batch_stage_ms(self._h, _fp(buf), buf.size)
         return dict(zip(self.STAGES, [float(x) for x in buf]))
 
+    def stage_offsets(self):
+        """Stage boundaries of the last `multi_time` run: ms after the first batch's first launch."""
+        buf = np.zeros(len(self.STAGES) + 1, dtype=np.float32)
+        lib().sb2_batch_stage_offsets(self._h, _fp(buf), buf.size)
+        return [float(x) for x in buf]
+
 
 class CallSet(object):
     """The sb2_call records of one batch.  Scores / lengths are numpy views of the C array; base strings
@@ -544,6 +552,18 @@ def multi_time(batches, params=None, nrep=1, flush_l2=True):
     if rc:
         raise RuntimeError("sb2_multi_time failed: %s" % last_error())
     return ms
+
+
+def multi_stream_time(batches, params=None, nrep=1):
+    """Device time (ms, total) of `nrep` forward+decode steps per batch, the batches free-running on their own
+    streams with no synchronisation between steps (streaming throughput)."""
+    params = params or default_params()
+    hs = (C.c_void_p * len(batches))(*[b._h for b in batches])
+    ms = np.zeros(1, dtype=np.float32)
+    rc = lib().sb2_multi_stream_time(hs, len(batches), C.byref(params), nrep, _fp(ms))
+    if rc:
+        raise RuntimeError("sb2_multi_stream_time failed: %s" % last_error())
+    return float(ms[0])
 
 
 class PinnedBuffer(object):

@@ -314,6 +314,7 @@ struct sb2_batch {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[ST_COUNT + 1]{};
     float stage_ms[ST_COUNT]{};
+    float stage_at[ST_COUNT + 1]{};          // start of each stage relative to the first batch of a timed multi-batch run
     BatchDims dims{};
 };
 
@@ -738,6 +739,14 @@ extern "C" int sb2_batch_stage_ms(const sb2_batch *b, float *stage_ms, int nstag
     return n;
 }
 
+// stage boundaries of the last timed multi-batch run, in ms after the first batch's first launch
+extern "C" int sb2_batch_stage_offsets(const sb2_batch *b, float *at, int n_max) {
+    if (nullptr == b || nullptr == at) return -1;
+    const int n = std::min(n_max, (int)ST_COUNT + 1);
+    for (int i = 0; i < n; i++) at[i] = b->stage_at[i];
+    return n;
+}
+
 // ------------------------------------------------------------------------------------
 // whole-read basecalling for a batch (calculate_post, src/scrappie_raw.c:265-315)
 // ------------------------------------------------------------------------------------
@@ -987,6 +996,42 @@ extern "C" int sb2_multi_time(sb2_batch **batches, int nbatch, const sb2_params 
         for (int k = 0; k < nbatch; k++)
             for (int st = 0; st < ST_COUNT; st++)
                 cudaEventElapsedTime(&batches[k]->stage_ms[st], batches[k]->ev[st], batches[k]->ev[st + 1]);
+    if (0 == rc)
+        for (int k = 0; k < nbatch; k++)
+            for (int st = 0; st <= ST_COUNT; st++)
+                cudaEventElapsedTime(&batches[k]->stage_at[st], batches[0]->ev[0], batches[k]->ev[st]);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    for (auto &e : done) cudaEventDestroy(e);
+    if (rc) { cudaError_t e = cudaGetLastError(); if (e != cudaSuccess) sb2_set_error("CUDA error %s in timed run", cudaGetErrorString(e)); }
+    return rc;
+}
+
+// Streaming throughput: every batch runs `nrep` steps back to back on its own stream with no host or
+// cross-stream synchronisation between steps, so a batch's decode overlaps the other batches' next network
+// pass the way a continuously fed basecaller runs.  One event pair brackets all nbatch * nrep runs; the
+// per-step working set (GBs) is far larger than L2, so no flush is needed between steps.
+extern "C" int sb2_multi_stream_time(sb2_batch **batches, int nbatch, const sb2_params *p, int nrep, float *ms_total) {
+    if (nullptr == batches || nbatch <= 0 || nullptr == p || nrep <= 0 || nullptr == ms_total) return -1;
+    sb2_engine *eng = batches[0]->eng;
+    CUDA_OK(cudaSetDevice(eng->device));
+    cudaStream_t main_s = batches[0]->stream;
+    cudaEvent_t e0, e1;
+    std::vector<cudaEvent_t> done(nbatch);
+    CUDA_OK(cudaEventCreate(&e0)); CUDA_OK(cudaEventCreate(&e1));
+    for (auto &e : done) CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    int rc = 0;
+    for (int k = 0; k < nbatch; k++) if (cudaStreamSynchronize(batches[k]->stream) != cudaSuccess) rc = -1;
+    cudaEventRecord(e0, main_s);
+    for (int k = 1; k < nbatch; k++) cudaStreamWaitEvent(batches[k]->stream, e0, 0);
+    for (int i = 0; i < nrep && 0 == rc; i++)
+        for (int k = 0; k < nbatch; k++) rc |= sb2_batch_run(batches[k], p);
+    for (int k = 1; k < nbatch; k++) {
+        cudaEventRecord(done[k], batches[k]->stream);
+        cudaStreamWaitEvent(main_s, done[k], 0);
+    }
+    cudaEventRecord(e1, main_s);
+    if (cudaStreamSynchronize(main_s) != cudaSuccess) rc = -1;
+    if (0 == rc) cudaEventElapsedTime(ms_total, e0, e1);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     for (auto &e : done) cudaEventDestroy(e);
     if (rc) { cudaError_t e = cudaGetLastError(); if (e != cudaSuccess) sb2_set_error("CUDA error %s in timed run", cudaGetErrorString(e)); }

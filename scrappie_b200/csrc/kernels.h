@@ -54,6 +54,11 @@ void launch_decode_transducer(const float *post, const BatchDims &d, int nstate,
                               float stay_pen, float skip_pen, float local_pen, int allow_slip,
                               uint8_t *tb, int *tb_end, int *path, float *score, cudaStream_t s);
 
+// the same for 1024 histories without slip, one warp per read (kernels_decode.cu)
+void launch_decode_transducer_warp(const float *post, const BatchDims &d, int ostride, float stay_pen,
+                                   float skip_pen, float local_pen, uint8_t *tb, int *tb_end, int *path,
+                                   float *score, cudaStream_t s);
+
 // decode_crf (src/decode.c:836-893)
 void launch_decode_crf(const float *trans, const BatchDims &d, int ostride, uint8_t *tb, int *path,
                        float *score, cudaStream_t s);

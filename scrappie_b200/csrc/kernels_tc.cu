@@ -1043,7 +1043,7 @@ __device__ __forceinline__ void tanh4(const float (&x)[4], float (&y)[4]) {
 }
 
 template <int H, int MATH>
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__((H > 96) ? 512 : 256, 1)
 gru_scan_v4_kernel(const float *__restrict__ Xin, const float *__restrict__ sW, const float *__restrict__ sW2,
                    const float *__restrict__ resid, float *__restrict__ out, BatchDims d, int backward,
                    long long *__restrict__ trace) {
@@ -1114,9 +1114,12 @@ gru_scan_v4_kernel(const float *__restrict__ Xin, const float *__restrict__ sW, 
     __syncthreads();
     tc_fence_after();
 
-    const bool is_issuer = (warp == 11 || warp == 15);  // scheduler 3: free of gate math when H <= 96
+    // H <= 96: eight warps -- gate warps 0-2 / 4-6 (lane quarters 0-2 of group 0 / 1), issuers 3 / 7, i.e. on
+    // scheduler 3, which has no gate math; the small CTA leaves registers for decode / conv CTAs of other
+    // batches on the same SM.  H = 112: all eight warps 0-7 are gate warps, issuers are warps 11 / 15 (512 threads).
+    const bool is_issuer = (NQ < 4) ? (warp == 3 || warp == 7) : (warp == 11 || warp == 15);
     const bool is_gate = (warp < 8) && ((warp & 3) < NQ);
-    const int grp = is_issuer ? (warp == 15) : (warp >> 2);
+    const int grp = is_issuer ? ((NQ < 4) ? (warp == 7) : (warp == 15)) : (warp >> 2);
     uint8_t *b_h = b_ops + grp * 2 * TILE_B, *b_rh = b_h + TILE_B;
     uint64_t *bar_r = &bars[grp * 5 + 0], *bar_z = &bars[grp * 5 + 1], *bar_c = &bars[grp * 5 + 2],
              *bar_rh = &bars[grp * 5 + 3], *bar_h = &bars[grp * 5 + 4];
@@ -1337,7 +1340,7 @@ static int launch_scan_v4(const float *Xin, const float *sW, const float *sW2, c
         configured = true;
     }
     const int grid = (d.nread + 7) / 8;
-    gru_scan_v4_kernel<H, MATH><<<grid, 512, EXCLUSIVE_SMEM, s>>>(Xin, sW, sW2, resid, out, d, backward, trace);
+    gru_scan_v4_kernel<H, MATH><<<grid, (H > 96) ? 512 : 256, EXCLUSIVE_SMEM, s>>>(Xin, sW, sW2, resid, out, d, backward, trace);
     return 0;
 }
 

@@ -1334,9 +1334,16 @@ void launch_decode_transducer(const float *post, const BatchDims &d, int nstate,
         const char *e = getenv("SCRAPPIE_B200_DECODE");
         // v2 is the default: v3 (eight states per thread) executes fewer instructions but measures the same --
         // the kernel is bound by the ALU pipe (compare / select), not by issue slots (profiles/)
-        gen = (e && 0 == strcmp(e, "v1")) ? 1 : ((e && 0 == strcmp(e, "v3")) ? 3 : 2);
+        // default: one warp per read with the scores in registers (kernels_decode.cu) for the 1024-history
+        // models without slip; the CTA-per-read generations stay selectable and serve 4096 histories / slip
+        gen = (e && 0 == strcmp(e, "none")) ? 0 : (e && 0 == strcmp(e, "v1")) ? 1 : ((e && 0 == strcmp(e, "v3")) ? 3 : ((e && 0 == strcmp(e, "v2")) ? 2 : 4));
     }
     const int nh = nstate - 1;
+    if (gen == 0) return;                           // "none": timing experiments only (tools/exp_timeline.py)
+    if (gen == 4 && nh == 1024 && !allow_slip) {
+        launch_decode_transducer_warp(post, d, ostride, stay_pen, skip_pen, local_pen, tb, tb_end, path, score, s);
+        return;
+    }
     if (gen == 3) {
         if (nh == 1024)
             decode_transducer_v3_kernel<1024><<<d.nread, 128, 0, s>>>(post, d, ostride, stay_pen, skip_pen, local_pen,
