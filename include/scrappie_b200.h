@@ -115,6 +115,9 @@ scrappie_matrix nanonet_rnnrf_r94_transitions(const raw_table signal, float min_
 float decode_transducer(const_scrappie_matrix logpost, float stay_pen, float skip_pen,
                         float local_pen, int *seq, bool allow_slip);
 float decode_crf(const_scrappie_matrix trans, int *path);
+/* python/pyscrap.h:22, src/decode.h:30 (src/decode.c:928-1012): per-block state probabilities (ACGT-) of a CRF;
+   new 5 x (nblock + 1) matrix owned by the caller, NULL on failure */
+scrappie_matrix posterior_crf(const_scrappie_matrix trans);
 
 /* -- integer post-processing (host): src/decode.c:449-509, :895-918,
  *    src/homopolymer.c:175-235.  Returned strings are calloc'd; caller frees. -- */
@@ -179,6 +182,10 @@ int sb2_batch_decode(sb2_batch *b, const sb2_params *p);
 /* forward (log posterior) + decode in one call; replays a captured CUDA graph from the third call on */
 int sb2_batch_run(sb2_batch *b, const sb2_params *p);
 int sb2_batch_sync(sb2_batch *b);
+/* posterior_crf for every read of an rnnrf_r94 batch, on the device, after sb2_batch_forward / sb2_batch_run;
+   sb2_batch_download_base_probs copies one read's (nblock + 1) x 8 floats (5 used per column) */
+int sb2_batch_posterior_crf(sb2_batch *b);
+int sb2_batch_download_base_probs(sb2_batch *b, size_t read, float *dst);
 /* device -> host */
 int sb2_batch_download_posterior(sb2_batch *b, size_t read, float *dst, size_t dst_stride);
 int sb2_batch_download_paths(sb2_batch *b, int *paths_concat /* sum(nblock+1) */, float *scores /* nread */);

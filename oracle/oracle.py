@@ -72,6 +72,8 @@ class Oracle:
         L.sb2o_decode_crf.argtypes = [c_float_p, C.c_size_t, C.c_size_t, c_int_p]
         L.sb2o_overlapper.restype = C.c_void_p
         L.sb2o_overlapper.argtypes = [c_int_p, C.c_size_t, C.c_int, c_int_p]
+        L.sb2o_posterior_crf.restype = C.c_int
+        L.sb2o_posterior_crf.argtypes = [c_float_p, C.c_size_t, C.c_size_t, c_float_p, C.c_size_t]
         L.sb2o_crfpath_to_basecall.restype = C.c_void_p
         L.sb2o_crfpath_to_basecall.argtypes = [c_int_p, C.c_size_t]
         L.sb2o_homopolymer_path.argtypes = [c_float_p, C.c_size_t, C.c_size_t, C.c_size_t, c_int_p]
@@ -141,6 +143,15 @@ class Oracle:
         path = np.zeros(nblock + 1, dtype=np.int32)
         score = self.lib.sb2o_decode_crf(_fp(trans), nblock, stride, _ip(path))
         return float(score), path
+
+    def posterior_crf(self, trans):
+        """(nblock + 1, 8) state probabilities (ACGT-), the reference's matrix layout (stride 8, 5 rows used)."""
+        trans = np.ascontiguousarray(trans, dtype=np.float32)
+        nblock, stride = trans.shape
+        post = np.zeros((nblock + 1, 8), dtype=np.float32)
+        rc = self.lib.sb2o_posterior_crf(_fp(trans), nblock, stride, _fp(post), 8)
+        assert rc == 0
+        return post
 
     def _take_str(self, ptr):
         if not ptr:
@@ -241,6 +252,8 @@ class Reference:
         L.overlapper.argtypes = [c_int_p, C.c_size_t, C.c_int, c_int_p]
         L.crfpath_to_basecall.restype = C.c_void_p
         L.crfpath_to_basecall.argtypes = [c_int_p, C.c_size_t, c_int_p]
+        L.posterior_crf.restype = C.POINTER(_Mat)
+        L.posterior_crf.argtypes = [C.POINTER(_Mat)]
         L.homopolymer_path.argtypes = [C.POINTER(_Mat), c_int_p, C.c_int]
         L.medmad_normalise_array.argtypes = [c_float_p, C.c_size_t]
         L.trim_and_segment_raw.restype = _RawTable
@@ -298,6 +311,15 @@ class Reference:
         score = self.lib.decode_crf(mp, _ip(path))
         self.lib.free_scrappie_matrix(mp)
         return float(score), path
+
+    def posterior_crf(self, trans):
+        mp = self._mat(trans, 25)
+        pp = self.lib.posterior_crf(mp)
+        assert pp, "reference returned NULL"
+        out, nr = self._to_np(pp)
+        self.lib.free_scrappie_matrix(pp)
+        self.lib.free_scrappie_matrix(mp)
+        return out
 
     def _take_str(self, ptr):
         if not ptr:

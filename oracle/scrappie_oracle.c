@@ -508,6 +508,49 @@ float sb2o_decode_crf(const float *trans, size_t nblock, size_t stride, int *pat
     return score;
 }
 
+/* posterior_crf, src/decode.c:928-1012: forward-backward over the 5 x 5 transition energies.
+ * post: (nblock + 1) columns of post_stride (>= 5) floats; column b holds the normalised state
+ * probabilities after block b - 1.  Note the reference's normaliser starts its fold at 0.0f (not
+ * at -inf), i.e. the probabilities of a column sum to S / (1 + S) -- kept as is. */
+int sb2o_posterior_crf(const float *trans, size_t nblock, size_t stride, float *post, size_t post_stride) {
+    if (NULL == trans || NULL == post) return -1;
+    enum { NS = 5 };
+    for (int st = 0; st < NS; st++) post[st] = 0.0f;
+    for (size_t blk = 0; blk < nblock; blk++) {
+        const float *tr = trans + blk * stride;
+        const float *prev = post + blk * post_stride;
+        float *curr = post + (blk + 1) * post_stride;
+        for (int st1 = 0; st1 < NS; st1++) {
+            curr[st1] = tr[st1 * NS] + prev[0];
+            for (int st2 = 1; st2 < NS; st2++) curr[st1] = sb2o_logsumexpf(curr[st1], tr[st1 * NS + st2] + prev[st2]);
+        }
+    }
+    float bufA[NS], bufB[NS];
+    float *prev = bufA, *curr = bufB;
+    for (int st = 0; st < NS; st++) curr[st] = 0.0f;
+    {
+        float *last = post + nblock * post_stride;
+        float tot = 0.0f;
+        for (int st = 0; st < NS; st++) tot = sb2o_logsumexpf(tot, last[st]);
+        for (int st = 0; st < NS; st++) last[st] = expf(last[st] - tot);
+    }
+    for (size_t blk = nblock; blk > 0; blk--) {
+        const float *tr = trans + (blk - 1) * stride;
+        float *col = post + (blk - 1) * post_stride;
+        float *tmp = curr; curr = prev; prev = tmp;
+        for (int st = 0; st < NS; st++) curr[st] = tr[st] + prev[0];
+        for (int st1 = 1; st1 < NS; st1++)
+            for (int st2 = 0; st2 < NS; st2++) curr[st2] = sb2o_logsumexpf(curr[st2], tr[st1 * NS + st2] + prev[st1]);
+        float tot = 0.0f;
+        for (int st = 0; st < NS; st++) {
+            col[st] += curr[st];
+            tot = sb2o_logsumexpf(tot, col[st]);
+        }
+        for (int st = 0; st < NS; st++) col[st] = expf(col[st] - tot);
+    }
+    return 0;
+}
+
 static const char BASES[4] = {'A', 'C', 'G', 'T'};
 
 /* overlap(), src/decode.c:367-382 */

@@ -89,6 +89,9 @@ def lib():
         "get_posterior_function": (C.c_void_p, [C.c_int]),
         "decode_transducer": (C.c_float, [mp, C.c_float, C.c_float, C.c_float, _i32p, C.c_bool]),
         "decode_crf": (C.c_float, [mp, _i32p]),
+        "posterior_crf": (mp, [mp]),
+        "sb2_batch_posterior_crf": (C.c_int, [C.c_void_p]),
+        "sb2_batch_download_base_probs": (C.c_int, [C.c_void_p, C.c_size_t, _f32p]),
         "overlapper": (C.c_void_p, [_i32p, C.c_size_t, C.c_int, _i32p]),
         "crfpath_to_basecall": (C.c_void_p, [_i32p, C.c_size_t, _i32p]),
         "homopolymer_path": (C.c_int, [mp, _i32p, C.c_int]),
@@ -324,14 +327,27 @@ def get_model_stride(model):
     return stride
 
 
-def basecall_raw(data, model='rgrgr_r94', **kwargs):
+def posterior_crf(post):
+    """Per-block base probabilities (ACGT-) of a CRF transition matrix as an (nblock + 1, 5) array
+    (`lib.posterior_crf`, python/scrappy/__init__.py:424-428)."""
+    ptr = lib().posterior_crf(post.data())
+    if not ptr:
+        raise RuntimeError("posterior_crf failed: %s" % last_error())
+    return ScrappyMatrix(ptr).data(as_numpy=True)
+
+
+def basecall_raw(data, model='rgrgr_r94', with_base_probs=False, **kwargs):
     """Trim, normalise, run the network and decode one read
-    (python/scrappy/__init__.py:403-430).  Returns (call, score, pos, start, end)."""
+    (python/scrappy/__init__.py:403-430).  Returns (call, score, pos, start, end, base_probs); the last item
+    is None unless `with_base_probs` (rnnrf_r94 only)."""
+    if with_base_probs and model != 'rnnrf_r94':
+        raise ValueError("Base probabilities can only be returned for model 'rnnrf_r94'.")
     raw = RawTable(data)
     raw.trim().scale()
     post = calc_post(raw, model, log=True)
     seq, score, pos = decode_post(post, model, **kwargs)
-    return seq, score, pos, raw.start, raw.end
+    base_probs = posterior_crf(post) if with_base_probs else None
+    return seq, score, pos, raw.start, raw.end, base_probs
 
 
 # ---------------------------------------------------------------------------
@@ -438,6 +454,14 @@ class Batch(object):
 
     def sync(self):
         self._check(lib().sb2_batch_sync(self._h), "sync")
+
+    def posterior_crf(self):
+        self._check(lib().sb2_batch_posterior_crf(self._h), "posterior_crf")
+
+    def base_probs(self, read):
+        out = np.zeros((self.nblock[read] + 1, 8), dtype=np.float32)
+        self._check(lib().sb2_batch_download_base_probs(self._h, read, _fp(out)), "download_base_probs")
+        return out[:, :5]
 
     def posterior(self, read):
         out = np.zeros((self.nblock[read], self.ostride), dtype=np.float32)

@@ -287,6 +287,7 @@ struct sb2_batch {
     // device
     float *d_raw = nullptr, *d_X[2]{}, *d_Xin = nullptr, *d_post = nullptr, *d_score = nullptr, *d_layers = nullptr;
     float *d_Xin2 = nullptr, *d_FF = nullptr;          // raw_r94 only
+    float *d_bprob = nullptr;                           // posterior_crf output, (total_cols + nread) x 8, on first use
     int *d_nsample = nullptr, *d_nblock = nullptr, *d_coloff = nullptr, *d_tbE = nullptr, *d_path = nullptr;
     int64_t *d_sampoff = nullptr;
     uint8_t *d_tb = nullptr;
@@ -337,6 +338,7 @@ extern "C" void sb2_batch_destroy(sb2_batch *b) {
     if (b->d_bases) cudaFree(b->d_bases);
     if (b->h_nbase) cudaFreeHost(b->h_nbase);
     if (b->h_bases) cudaFreeHost(b->h_bases);
+    if (b->d_bprob) cudaFree(b->d_bprob);
     if (b->d_Xin2) cudaFree(b->d_Xin2);
     if (b->d_FF) cudaFree(b->d_FF);
     if (b->d_gidx) cudaFree(b->d_gidx);
@@ -1160,6 +1162,68 @@ extern "C" float decode_crf(const_scrappie_matrix trans, int *path) {
     float score = NAN;
     if (0 != decode_single(trans, true, 0.f, 0.f, 0.f, false, path, &score)) return NAN;
     return score;
+}
+
+// posterior_crf (src/decode.c:928-1012) on a host matrix of 25 transition energies per block
+extern "C" scrappie_matrix posterior_crf(const_scrappie_matrix trans) {
+    if (nullptr == trans) return nullptr;
+    sb2_engine *eng = default_engine();
+    if (nullptr == eng) return nullptr;
+    if (cudaSetDevice(eng->device) != cudaSuccess) return nullptr;
+    if (trans->nr != 25) { sb2_set_error("posterior_crf: expected 25 transition rows"); return nullptr; }
+    const size_t nb = trans->nc, stride = trans->stride;
+    scrappie_matrix post = make_scrappie_matrix(5, nb + 1);
+    if (nullptr == post) return nullptr;
+    float *d_trans = nullptr, *d_out = nullptr;
+    int *d_meta = nullptr;
+    bool ok = 0 == dev_alloc(&d_trans, nb * stride) && 0 == dev_alloc(&d_out, (nb + 1) * 8) && 0 == dev_alloc(&d_meta, 4);
+    const int meta[4] = {(int)nb, 0, (int)nb, 0};        // nblock[0]; col_off[0..1]
+    ok = ok && cudaMemcpy(d_meta, meta, sizeof(meta), cudaMemcpyHostToDevice) == cudaSuccess &&
+         cudaMemcpy(d_trans, trans->data.f, nb * stride * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess;
+    if (ok) {
+        BatchDims d{};
+        d.nread = 1; d.total_cols = (int)nb; d.max_cols = (int)nb;
+        d.nblock = d_meta; d.col_off = d_meta + 1;
+        launch_posterior_crf(d_trans, d, (int)stride, d_out, 0);
+        eng->launches += 1;
+        ok = cudaGetLastError() == cudaSuccess &&
+             cudaMemcpy2D(post->data.f, post->stride * sizeof(float), d_out, 8 * sizeof(float),
+                          std::min((size_t)8, (size_t)post->stride) * sizeof(float), nb + 1, cudaMemcpyDeviceToHost) == cudaSuccess;
+    }
+    if (d_trans) cudaFree(d_trans);
+    if (d_out) cudaFree(d_out);
+    if (d_meta) cudaFree(d_meta);
+    if (!ok) {
+        sb2_set_error("posterior_crf: CUDA error %s", cudaGetErrorString(cudaGetLastError()));
+        return free_scrappie_matrix(post);
+    }
+    return post;
+}
+
+// The same for every read of an rnnrf_r94 batch, from the transitions the forward pass left on the device.
+extern "C" int sb2_batch_posterior_crf(sb2_batch *b) {
+    if (nullptr == b) return -1;
+    const sb2_host_model &h = b->m->host;
+    if (h.head != 1 || h.nstate != 25) { sb2_set_error("posterior_crf needs a CRF model (rnnrf_r94)"); return -1; }
+    CUDA_OK(cudaSetDevice(b->eng->device));
+    if (nullptr == b->d_bprob && dev_alloc(&b->d_bprob, ((size_t)b->total_cols + b->nread) * 8)) return -1;
+    launch_posterior_crf(b->d_post, b->dims, (int)h.ostride, b->d_bprob, b->stream);
+    b->eng->launches += 1;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// dst: (nblock + 1) x 8 floats (the reference's 5-row matrix, stride 8)
+extern "C" int sb2_batch_download_base_probs(sb2_batch *b, size_t read, float *dst) {
+    if (nullptr == b || nullptr == dst || read >= (size_t)b->nread || nullptr == b->d_bprob) {
+        sb2_set_error("base probabilities: run sb2_batch_posterior_crf first");
+        return -1;
+    }
+    CUDA_OK(cudaSetDevice(b->eng->device));
+    CUDA_OK(cudaStreamSynchronize(b->stream));
+    CUDA_OK(cudaMemcpy(dst, b->d_bprob + ((size_t)b->col_off[read] + read) * 8, ((size_t)b->nblock[read] + 1) * 8 * sizeof(float),
+                       cudaMemcpyDeviceToHost));
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------

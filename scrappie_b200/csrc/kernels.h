@@ -59,6 +59,10 @@ void launch_decode_transducer_warp(const float *post, const BatchDims &d, int os
                                    float skip_pen, float local_pen, uint8_t *tb, int *tb_end, int *path,
                                    float *score, cudaStream_t s);
 
+// posterior_crf (src/decode.c:928-1012): post = (total_cols + nread) columns of 8 floats, read r starts at
+// column col_off[r] + r and owns nblock[r] + 1 columns
+void launch_posterior_crf(const float *trans, const BatchDims &d, int ostride, float *post, cudaStream_t s);
+
 // decode_crf (src/decode.c:836-893)
 void launch_decode_crf(const float *trans, const BatchDims &d, int ostride, uint8_t *tb, int *path,
                        float *score, cudaStream_t s);

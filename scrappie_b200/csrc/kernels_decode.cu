@@ -296,6 +296,90 @@ decode_transducer_warp_kernel(const float *__restrict__ post, BatchDims d, int o
 
 }  // namespace
 
+// ---------------------------------------------------------------------------------
+// posterior_crf (src/decode.c:928-1012): forward-backward over the 5 x 5 transition energies of rnnrf_r94
+// ---------------------------------------------------------------------------------
+// One warp per read.  Lanes 0..24 fetch the 25 energies of a block with one coalesced load; lane s < 5 owns
+// state s: the forward value alpha[s] (written to the output column as the reference does, then read back by
+// the same lane in the backward sweep) and the backward value beta[s].  Every logsumexp fold runs in the
+// reference's order (ascending source state) with logsumexpf = fmaxf + log1pf(expf(-|x - y|)); the column
+// normaliser starts its fold at 0.0f exactly like the reference (its probabilities sum to S / (1 + S)).
+namespace {
+
+constexpr int PCRF_WARPS = 4;
+
+__device__ __forceinline__ float lse2(float x, float y) { return fmaxf(x, y) + log1pf(expf(-fabsf(x - y))); }
+
+__global__ void __launch_bounds__(32 * PCRF_WARPS)
+posterior_crf_kernel(const float *__restrict__ trans, BatchDims d, int ostride, float *__restrict__ post) {
+    constexpr int NS = 5, PS = 8;                   // states, output stride (4 * ceil(5 / 4))
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int r = blockIdx.x * PCRF_WARPS + warp;
+    if (r >= d.nread) return;
+    const int T = d.nblock[r];
+    const float *tr = trans + (size_t)d.col_off[r] * ostride;
+    float *out = post + ((size_t)d.col_off[r] + r) * PS;            // read r owns nblock + 1 columns
+    const bool own = lane < NS;
+    const int me = own ? lane : 0;
+    const unsigned FULL = 0xffffffffu;
+
+    // ---- forward sweep: alpha[0] = 0, alpha[b + 1][to] = LSE_from (trans[b][to][from] + alpha[b][from])
+    float a = 0.0f;
+    if (lane < PS) out[lane] = 0.0f;
+    float tv_next = (T > 0 && lane < NS * NS) ? tr[lane] : 0.0f;
+    for (int blk = 0; blk < T; blk++) {
+        const float tv = tv_next;
+        if (blk + 1 < T && lane < NS * NS) tv_next = tr[(size_t)(blk + 1) * ostride + lane];
+        float acc = 0.0f;
+#pragma unroll
+        for (int from = 0; from < NS; from++) {
+            const float v = __shfl_sync(FULL, tv, me * NS + from) + __shfl_sync(FULL, a, from);
+            acc = (from == 0) ? v : lse2(acc, v);
+        }
+        a = acc;
+        if (lane < PS) out[(size_t)(blk + 1) * PS + lane] = own ? a : 0.0f;
+    }
+
+    // ---- last column: normalise alpha[T]
+    {
+        float tot = 0.0f;
+#pragma unroll
+        for (int st = 0; st < NS; st++) tot = lse2(tot, __shfl_sync(FULL, a, st));
+        if (own) out[(size_t)T * PS + lane] = expf(a - tot);
+    }
+
+    // ---- backward sweep: beta[T] = 0, beta[b][from] = LSE_to (trans[b][to][from] + beta[b + 1][to]);
+    //      column b becomes exp(alpha[b] + beta[b] - normaliser)
+    float b = 0.0f;
+    float tvb_next = (T > 0 && lane < NS * NS) ? tr[(size_t)(T - 1) * ostride + lane] : 0.0f;
+    float al_next = (T > 0 && own) ? out[(size_t)(T - 1) * PS + lane] : 0.0f;
+    for (int blk = T; blk > 0; blk--) {
+        const float tv = tvb_next, al = al_next;
+        if (blk > 1) {
+            if (lane < NS * NS) tvb_next = tr[(size_t)(blk - 2) * ostride + lane];
+            if (own) al_next = out[(size_t)(blk - 2) * PS + lane];
+        }
+        float acc = 0.0f;
+#pragma unroll
+        for (int to = 0; to < NS; to++) {
+            const float v = __shfl_sync(FULL, tv, to * NS + me) + __shfl_sync(FULL, b, to);
+            acc = (to == 0) ? v : lse2(acc, v);
+        }
+        b = acc;
+        const float c = al + b;
+        float tot = 0.0f;
+#pragma unroll
+        for (int st = 0; st < NS; st++) tot = lse2(tot, __shfl_sync(FULL, c, st));
+        if (own) out[(size_t)(blk - 1) * PS + lane] = expf(c - tot);
+    }
+}
+
+}  // namespace
+
+void launch_posterior_crf(const float *trans, const BatchDims &d, int ostride, float *post, cudaStream_t s) {
+    posterior_crf_kernel<<<(d.nread + PCRF_WARPS - 1) / PCRF_WARPS, 32 * PCRF_WARPS, 0, s>>>(trans, d, ostride, post);
+}
+
 void launch_decode_transducer_warp(const float *post, const BatchDims &d, int ostride, float stay_pen,
                                    float skip_pen, float local_pen, uint8_t *tb, int *tb_end, int *path,
                                    float *score, cudaStream_t s) {

@@ -248,7 +248,8 @@ def test_bundled_reads_bit_identical_bases(sb, engine, golden, model):
 def test_scrappy_style_basecall_raw(sb, golden):
     """basecall_raw (python/test/test_scrappy.py:72-75 compares it with the CLI)."""
     raw = bundled_signal(golden, 2)
-    seq, score, pos, start, end = sb.basecall_raw(raw, "rgrgr_r94")
+    seq, score, pos, start, end, base_probs = sb.basecall_raw(raw, "rgrgr_r94")
+    assert base_probs is None
     rt = sb.RawTable(raw).trim().scale()
     post = sb.calc_post(rt, "rgrgr_r94", min_prob=1e-6)
     assert post.shape == (len(pos) - 1, 1025)
@@ -397,3 +398,49 @@ def test_error_paths(sb, engine):
     with pytest.raises(RuntimeError):
         sb.calc_post(rt, "rgrgr_r94")
     assert engine.launches > 0
+
+
+# ---- posterior_crf -------------------------------------------------
+PCRF_TOL = 2e-5     # absolute, on probabilities in [0, 1]; CUDA expf / log1pf differ from glibc by a few ulp
+
+
+@pytest.mark.parametrize("key", ["syn_300", "syn_1501", "hand"])
+def test_posterior_crf_vs_reference_fixture(sb, oracle, golden, key):
+    """posterior_crf through the C-ABI (host matrix in, host matrix out) against the compiled reference's output
+    (tests/golden/ref_posterior_crf.npz) and the oracle restatement on the same transitions."""
+    g = golden.ref_posterior_crf
+    trans = g[key + "_trans"]
+    m = sb.ScrappyMatrix.from_numpy(trans, nr=25)
+    got = sb.posterior_crf(m)
+    assert got.shape == (trans.shape[0] + 1, 5)
+    assert np.abs(got - g[key + "_post"][:, :5]).max() < PCRF_TOL
+    assert np.abs(got - oracle.posterior_crf(trans)[:, :5]).max() < PCRF_TOL
+    # the reference's normaliser quirk survives: a column sums to S / (1 + S), not to 1
+    assert np.allclose(got.sum(axis=1), g[key + "_post"][:, :5].sum(axis=1), atol=1e-4)
+
+
+def test_posterior_crf_batch_on_device(sb, engine, oracle):
+    """Batch path: transitions stay on the device; ragged reads, checked per read against the oracle run on the
+    transitions the same batch produced."""
+    lens = [1500, 300, 2001, 64]
+    sigs = [synthetic_read(300 + i, n) for i, n in enumerate(lens)]
+    b = engine.batch("rnnrf_r94", lens)
+    b.upload(sigs)
+    b.run()
+    b.posterior_crf()
+    for i in range(len(lens)):
+        trans = b.posterior(i)
+        got = b.base_probs(i)
+        want = oracle.posterior_crf(trans)[:, :5]
+        assert got.shape == want.shape
+        assert np.abs(got - want).max() < PCRF_TOL
+    b.close()
+
+
+def test_basecall_raw_with_base_probs(sb, golden):
+    raw = bundled_signal(golden, 2)
+    seq, score, pos, start, end, probs = sb.basecall_raw(raw, "rnnrf_r94", with_base_probs=True)
+    assert probs.shape == (len(pos), 5) and np.isfinite(probs).all()
+    with pytest.raises(ValueError):
+        sb.basecall_raw(raw, "rgrgr_r94", with_base_probs=True)
+    assert sb.lib().posterior_crf(None) is None or not sb.lib().posterior_crf(None)

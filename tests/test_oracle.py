@@ -157,3 +157,11 @@ def test_oracle_matches_live_reference(oracle, reference):
         sa, pa, ba, _ = oracle.basecall_raw(model, x)
         sb_, pb, bb, _ = reference.basecall_raw(model, x)
         assert ba == bb and np.array_equal(pa, pb)
+
+
+@pytest.mark.parametrize("key", ["syn_300", "syn_1501", "hand"])
+def test_posterior_crf_exact(oracle, golden, key):
+    """posterior_crf restatement vs the compiled reference's output (same libm, same order: bit-exact)."""
+    g = golden.ref_posterior_crf
+    got = oracle.posterior_crf(g[key + "_trans"])
+    assert np.array_equal(got[:, :5], g[key + "_post"][:, :5])

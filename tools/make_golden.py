@@ -157,8 +157,33 @@ def raw_r94_outputs():
     np.savez_compressed(os.path.join(OUT, "ref_raw_r94.npz"), **d)
 
 
+def posterior_crf_outputs():
+    """posterior_crf (src/decode.c:928-1012) of the reference on rnnrf_r94 transitions of seeded synthetic reads
+    and on hand-made energies with ties / large magnitudes.  The transitions are stored too, so the GPU test does
+    not depend on the network's own (tolerance-level) differences."""
+    ref = Reference()
+    d = {}
+    for n in (300, 1501):
+        x = synthetic_read(2000 + n, n)
+        trans = ref.posterior("rnnrf_r94", x)
+        key = "syn_%d" % n
+        d[key + "_trans"] = trans
+        d[key + "_post"] = ref.posterior_crf(trans)
+    rng = np.random.default_rng(77)
+    t = np.zeros((64, 28), dtype=np.float32)
+    t[:, :25] = rng.normal(0, 4, size=(64, 25)).astype(np.float32)
+    t[10:20, :25] = 0.0                  # exact ties
+    t[30:34, :25] *= 10.0                # one transition dominates
+    d["hand_trans"] = t
+    d["hand_post"] = ref.posterior_crf(t)
+    np.savez_compressed(os.path.join(OUT, "ref_posterior_crf.npz"), **d)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "posterior_crf":
+        posterior_crf_outputs()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "raw_r94":
         raw_r94_outputs()
         sys.exit(0)
