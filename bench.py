@@ -46,7 +46,7 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--cpu-sample-reads", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--sets", type=int, default=2,
+    ap.add_argument("--sets", type=int, default=4,
                     help="buffer sets: consecutive steps alternate between the sets and are not synchronised with each "
                          "other, so step n + 1 overlaps the tail of step n (1 = one set, L2 flushed between steps)")
     ap.add_argument("--workload", default="fixed", choices=["fixed", "mixed"],
@@ -228,7 +228,7 @@ def main_b200(args, rank, world, local_rank):
         sigs = make_workload(args.reads, args.samples, 1000 + rank * args.reads)
         nbatch = (args.reads + args.batch - 1) // args.batch
         groups = [sigs[i * args.batch:(i + 1) * args.batch] for i in range(nbatch)]
-    nsets = args.sets if (args.sets > 1 and args.steps % args.sets == 0) else 1
+    nsets = max(1, min(args.sets, args.steps))
     groups = groups * nsets                              # set k = batches[k * nbatch : (k + 1) * nbatch], same reads
     batches = [eng.batch(args.model, [len(s) for s in g]) for g in groups]
     pinned = []
@@ -255,10 +255,13 @@ def main_b200(args, rank, world, local_rank):
     # set of a step (GBs of activations) is far larger than L2, so nothing is served from cache across steps.
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if nsets > 1:
+        # set k runs steps k, k + nsets, ...: exactly args.steps steps in all
+        set_reps = [args.steps // nsets + (1 if k < args.steps % nsets else 0) for k in range(nsets)]
+        reps = [set_reps[i // nbatch] for i in range(len(batches))]
         sb.multi_stream_time(batches, params, nrep=max(3, (args.warmup + nsets - 1) // nsets))
         barrier()
         launches0 = eng.launches
-        step_ms = sb.multi_stream_time(batches, params, nrep=args.steps // nsets) / args.steps
+        step_ms = sb.multi_stream_time(batches, params, nrep=reps) / args.steps
         launches = eng.launches - launches0
         barrier()
         l2_note = ("not flushed: %d steps back to back, each streaming its own %.1f GB of activations through HBM "
@@ -287,17 +290,18 @@ def main_b200(args, rank, world, local_rank):
         for _ in range(nrep):
             results[i] = batches[i].basecall(pinned[i].ptr, True, params, lazy=True)
 
-    def e2e_run(nrep):
-        th = [threading.Thread(target=work, args=(i, nrep)) for i in range(len(batches))]
+    def e2e_run(reps_):
+        th = [threading.Thread(target=work, args=(i, reps_[i])) for i in range(len(batches))]
         for t in th:
             t.start()
         for t in th:
             t.join()
 
-    e2e_run(1)
+    e2e_reps = reps if nsets > 1 else [args.steps] * len(batches)
+    e2e_run([1] * len(batches))
     barrier()
     t0 = time.perf_counter()
-    e2e_run(args.steps // nsets)
+    e2e_run(e2e_reps)
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / args.steps
     nbases = int(sum(int(res.nbase.sum()) for res in results[:nbatch]))
@@ -326,6 +330,9 @@ def main_b200(args, rank, world, local_rank):
     scan_avg_ms = float(np.mean([solo["scan%d" % l] for l in range(1, 6)]))
     flop_per_launch = FLOP_PER_READ_STEP_RECURRENT[args.model] * cols
     achieved = flop_per_launch / (scan_avg_ms * 1e-3) / 1e12
+    reads_per_cta = 16 if (args.model != "rnnrf_r94" and batches[0].nread >= 128
+                           and os.environ.get("SCRAPPIE_B200_SCAN_GROUPS", "0") in ("0", "4")) else 8
+    scan_ctas = (batches[0].nread + reads_per_cta - 1) // reads_per_cta
     peak = pk["bf16_tflops"]
     hbm = pk["hbm_gbs"]
     traffic = None
@@ -376,6 +383,9 @@ def main_b200(args, rank, world, local_rank):
                      "peak_source": "%s bf16 dense burst (MEASURED_PEAKS.json), kernel timed alone; the scan is a chain of "
                                     "dependent 12-instruction UMMA groups, latency- not throughput-bound (DESIGN.md section 4)" % pk_src,
                      "flop_per_launch": flop_per_launch, "avg_launch_ms": scan_avg_ms,
+                     # a scan launch of one batch occupies one SM per 16 (H = 96) or 8 reads, not the GPU: the
+                     # other SMs run the other batches' kernels at the same time
+                     "sms_used_per_launch": scan_ctas, "frac_of_sm_share": achieved / (peak * min(scan_ctas, 148) / 148.0),
                      "stage_ms_solo_batch": solo, "stage_ms_per_batch_concurrent": stage_sum,
                      "other_kernels": kernels},
     }

@@ -221,9 +221,9 @@ int sb2_batch_basecall(sb2_batch *b, const float *concat, int pinned, const sb2_
 /* Time forward+decode of several batches running concurrently on their own streams (how a
  * job larger than one batch executes); CUDA events on the launching stream. */
 int sb2_multi_time(sb2_batch **batches, int nbatch, const sb2_params *p, int nrep, int flush_l2, float *ms_out);
-/* streaming throughput: nrep steps per batch back to back on the batches' own streams, no synchronisation
-   between steps; *ms_total = device time of all nbatch * nrep runs */
-int sb2_multi_stream_time(sb2_batch **batches, int nbatch, const sb2_params *p, int nrep, float *ms_total);
+/* streaming throughput: batch k runs nrep_per_batch[k] steps back to back on its own stream, no synchronisation
+   between steps or batches; *ms_total = device time of all the runs */
+int sb2_multi_stream_time(sb2_batch **batches, int nbatch, const sb2_params *p, const int *nrep_per_batch, float *ms_total);
 
 /* Diagnostic hook (SCRAPPIE_B200_TRACE=1 at engine creation): clock64() stamps recorded by CTA 0 of
  * the second GRU layer's scan at its hand-over points, steps 100..103, 16 slots per step. */

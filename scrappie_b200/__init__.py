@@ -129,7 +129,7 @@ def lib():
         "sb2_batch_basecall": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(Params), C.POINTER(_Call)]),
         "sb2_calls_free": (None, [C.POINTER(_Call), C.c_size_t]),
         "sb2_multi_time": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(Params), C.c_int, C.c_int, _f32p]),
-        "sb2_multi_stream_time": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(Params), C.c_int, _f32p]),
+        "sb2_multi_stream_time": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(Params), _i32p, _f32p]),
         "sb2_conv_plan_debug": (C.c_int, [C.c_size_t, C.c_size_t, C.c_size_t, _i32p, C.c_int]),
     }
     for name in MODELS:
@@ -579,12 +579,13 @@ def multi_time(batches, params=None, nrep=1, flush_l2=True):
 
 
 def multi_stream_time(batches, params=None, nrep=1):
-    """Device time (ms, total) of `nrep` forward+decode steps per batch, the batches free-running on their own
-    streams with no synchronisation between steps (streaming throughput)."""
+    """Device time (ms, total) of `nrep` forward+decode steps per batch (an int, or one count per batch), the
+    batches free-running on their own streams with no synchronisation between steps (streaming throughput)."""
     params = params or default_params()
     hs = (C.c_void_p * len(batches))(*[b._h for b in batches])
     ms = np.zeros(1, dtype=np.float32)
-    rc = lib().sb2_multi_stream_time(hs, len(batches), C.byref(params), nrep, _fp(ms))
+    reps = np.ascontiguousarray(np.broadcast_to(np.asarray(nrep, dtype=np.int32), (len(batches),)))
+    rc = lib().sb2_multi_stream_time(hs, len(batches), C.byref(params), _ip(reps), _fp(ms))
     if rc:
         raise RuntimeError("sb2_multi_stream_time failed: %s" % last_error())
     return float(ms[0])

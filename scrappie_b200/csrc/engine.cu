@@ -1012,8 +1012,12 @@ extern "C" int sb2_multi_time(sb2_batch **batches, int nbatch, const sb2_params 
 // cross-stream synchronisation between steps, so a batch's decode overlaps the other batches' next network
 // pass the way a continuously fed basecaller runs.  One event pair brackets all nbatch * nrep runs; the
 // per-step working set (GBs) is far larger than L2, so no flush is needed between steps.
-extern "C" int sb2_multi_stream_time(sb2_batch **batches, int nbatch, const sb2_params *p, int nrep, float *ms_total) {
-    if (nullptr == batches || nbatch <= 0 || nullptr == p || nrep <= 0 || nullptr == ms_total) return -1;
+extern "C" int sb2_multi_stream_time(sb2_batch **batches, int nbatch, const sb2_params *p, const int *nrep_per_batch,
+                                     float *ms_total) {
+    if (nullptr == batches || nbatch <= 0 || nullptr == p || nullptr == nrep_per_batch || nullptr == ms_total) return -1;
+    int nrep = 0;
+    for (int k = 0; k < nbatch; k++) nrep = std::max(nrep, nrep_per_batch[k]);
+    if (nrep <= 0) return -1;
     sb2_engine *eng = batches[0]->eng;
     CUDA_OK(cudaSetDevice(eng->device));
     cudaStream_t main_s = batches[0]->stream;
@@ -1026,7 +1030,8 @@ extern "C" int sb2_multi_stream_time(sb2_batch **batches, int nbatch, const sb2_
     cudaEventRecord(e0, main_s);
     for (int k = 1; k < nbatch; k++) cudaStreamWaitEvent(batches[k]->stream, e0, 0);
     for (int i = 0; i < nrep && 0 == rc; i++)
-        for (int k = 0; k < nbatch; k++) rc |= sb2_batch_run(batches[k], p);
+        for (int k = 0; k < nbatch; k++)
+            if (i < nrep_per_batch[k]) rc |= sb2_batch_run(batches[k], p);
     for (int k = 1; k < nbatch; k++) {
         cudaEventRecord(done[k], batches[k]->stream);
         cudaStreamWaitEvent(main_s, done[k], 0);

@@ -1042,13 +1042,14 @@ __device__ __forceinline__ void tanh4(const float (&x)[4], float (&y)[4]) {
     }
 }
 
-template <int H, int MATH>
-__global__ void __launch_bounds__((H > 96) ? 512 : 256, 1)
+template <int H, int MATH, int NG>
+__global__ void __launch_bounds__((H > 96) ? 512 : 128 * NG, 1)
 gru_scan_v4_kernel(const float *__restrict__ Xin, const float *__restrict__ sW, const float *__restrict__ sW2,
                    const float *__restrict__ resid, float *__restrict__ out, BatchDims d, int backward,
                    long long *__restrict__ trace) {
 #define SB2_TRACE(slot) do { if (trace != nullptr && blockIdx.x == 0 && grp == 0 && lane == 0 && s >= 100 && s < 104) trace[(s - 100) * 16 + (slot)] = clock64(); } while (0)
-    constexpr int NG = 2, RPG = 4, NM = 16;             // groups per CTA, reads per group, UMMA N
+    constexpr int RPG = 4, NM = 16;                     // NG groups per CTA; reads per group, UMMA N
+    static_assert(NG == 2 || (NG == 4 && H <= 96), "four groups need a scheduler free of gate math");
     constexpr uint32_t LBO_B = 16u * NM + 16u, SBO_B = 128u;
     constexpr uint32_t TILE_B = (H / 8) * LBO_B;
     constexpr int NKS = H / 16;
@@ -1114,12 +1115,13 @@ gru_scan_v4_kernel(const float *__restrict__ Xin, const float *__restrict__ sW, 
     __syncthreads();
     tc_fence_after();
 
-    // H <= 96: eight warps -- gate warps 0-2 / 4-6 (lane quarters 0-2 of group 0 / 1), issuers 3 / 7, i.e. on
-    // scheduler 3, which has no gate math; the small CTA leaves registers for decode / conv CTAs of other
-    // batches on the same SM.  H = 112: all eight warps 0-7 are gate warps, issuers are warps 11 / 15 (512 threads).
-    const bool is_issuer = (NQ < 4) ? (warp == 3 || warp == 7) : (warp == 11 || warp == 15);
-    const bool is_gate = (warp < 8) && ((warp & 3) < NQ);
-    const int grp = is_issuer ? ((NQ < 4) ? (warp == 7) : (warp == 15)) : (warp >> 2);
+    // H <= 96: four warps per group -- gate warps 4g .. 4g+2 (lane quarters 0-2), issuer 4g+3, i.e. every issuer
+    // sits on scheduler 3, which has no gate math; a CTA is 8 warps (two groups, 8 reads) or 16 warps (four
+    // groups, 16 reads: the gate math of four groups interleaves on each scheduler and one SM carries twice the
+    // reads).  H = 112: all eight warps 0-7 are gate warps, the issuers are warps 11 / 15 (512 threads).
+    const bool is_issuer = (NQ < 4) ? ((warp & 3) == 3 && warp < 4 * NG) : (warp == 11 || warp == 15);
+    const bool is_gate = (warp < 4 * NG) && ((warp & 3) < NQ);
+    const int grp = (NQ < 4) ? (warp >> 2) : (is_issuer ? (warp == 15) : (warp >> 2));
     uint8_t *b_h = b_ops + grp * 2 * TILE_B, *b_rh = b_h + TILE_B;
     uint64_t *bar_r = &bars[grp * 5 + 0], *bar_z = &bars[grp * 5 + 1], *bar_c = &bars[grp * 5 + 2],
              *bar_rh = &bars[grp * 5 + 3], *bar_h = &bars[grp * 5 + 4];
@@ -1132,9 +1134,10 @@ gru_scan_v4_kernel(const float *__restrict__ Xin, const float *__restrict__ sW, 
 
     if (is_issuer) {
         // ---- UMMA issuer of one group -----------------------------------------------------------
-        if (grp == 1) {                                  // start the second group half a step late
+        if (grp > 0) {                                   // stagger the groups over a step
             const long long t0 = clock64();
-            while (clock64() - t0 < 700) { }
+            const long long lag = (NG == 2) ? 700 : 450 * grp;
+            while (clock64() - t0 < lag) { }
         }
         const uint32_t idesc = umma_idesc_f16(128, NM);
         const uint64_t dBh = umma_desc(smem_u32(b_h), LBO_B, SBO_B), dBrh = umma_desc(smem_u32(b_rh), LBO_B, SBO_B);
@@ -1328,29 +1331,40 @@ gru_scan_v4_kernel(const float *__restrict__ Xin, const float *__restrict__ sW, 
     if (warp == 0) tmem_dealloc(tmem, TCOLS);
 }
 
-template <int H, int MATH>
+template <int H, int MATH, int NG>
 static int launch_scan_v4(const float *Xin, const float *sW, const float *sW2, const float *resid, float *out,
                           const BatchDims &d, int backward, long long *trace, cudaStream_t s) {
-    constexpr int EXCLUSIVE_SMEM = 120 * 1024;          // all 512 TMEM columns are allocated: one CTA per SM
+    // All 512 TMEM columns are allocated, so a second scan CTA on the same SM would stall in tcgen05.alloc: the
+    // dynamic shared-memory request keeps it off (2 x (104 + 14) KB > 228 KB) while leaving ~110 KB for the
+    // decode / conv CTAs of other batches that share the SM.
+    constexpr int EXCLUSIVE_SMEM = 104 * 1024;
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(gru_scan_v4_kernel<H, MATH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        if (cudaFuncSetAttribute(gru_scan_v4_kernel<H, MATH, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  EXCLUSIVE_SMEM) != cudaSuccess)
             return -1;
         configured = true;
     }
-    const int grid = (d.nread + 7) / 8;
-    gru_scan_v4_kernel<H, MATH><<<grid, (H > 96) ? 512 : 256, EXCLUSIVE_SMEM, s>>>(Xin, sW, sW2, resid, out, d, backward, trace);
+    const int grid = (d.nread + 4 * NG - 1) / (4 * NG);
+    gru_scan_v4_kernel<H, MATH, NG><<<grid, (H > 96) ? 512 : 128 * NG, EXCLUSIVE_SMEM, s>>>(Xin, sW, sW2, resid, out, d, backward, trace);
     return 0;
 }
 
 int launch_gru_scan_v4(const float *Xin, const float *sW, const float *sW2, const float *resid, float *out,
                        const BatchDims &d, int H, int backward, int math, long long *trace, cudaStream_t s) {
-#define SB2_CASE(HH, MM) if (H == HH && math == MM) return launch_scan_v4<HH, MM>(Xin, sW, sW2, resid, out, d, backward, trace, s)
+    // reads per CTA: 16 (four groups) once a batch has enough reads to fill the GPU twice over at 8 per CTA
+    // (SCRAPPIE_B200_SCAN_GROUPS=2|4 overrides)
+    static int groups = -1;
+    if (groups < 0) { const char *e = getenv("SCRAPPIE_B200_SCAN_GROUPS"); groups = e ? atoi(e) : 0; }
+    const bool four = (H == 96) && (groups == 4 || (groups == 0 && d.nread >= 128));
+#define SB2_CASE(HH, MM) if (H == HH && math == MM) return launch_scan_v4<HH, MM, 2>(Xin, sW, sW2, resid, out, d, backward, trace, s)
+#define SB2_CASE4(MM) if (four && math == MM) return launch_scan_v4<96, MM, 4>(Xin, sW, sW2, resid, out, d, backward, trace, s)
+    SB2_CASE4(5); SB2_CASE4(2); SB2_CASE4(0);
     SB2_CASE(96, 0); SB2_CASE(96, 1); SB2_CASE(96, 2);
     SB2_CASE(112, 0); SB2_CASE(112, 1); SB2_CASE(112, 2);
     SB2_CASE(96, 3); SB2_CASE(112, 3); SB2_CASE(96, 4); SB2_CASE(112, 4); SB2_CASE(96, 5); SB2_CASE(112, 5);
 #undef SB2_CASE
+#undef SB2_CASE4
     return -1;
 }
 
