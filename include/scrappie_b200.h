@@ -211,6 +211,23 @@ typedef struct {
     size_t nblock;
     size_t nbase;
 } sb2_call;
+/* Signal preparation of `scrappie raw` (src/scrappie_raw.c:98-121, :270-275): trim_and_segment_raw +
+ * medmad_normalise_array, on the device, bit-identical to the host functions of part 1. */
+typedef struct {
+    size_t trim_start, trim_end, varseg_chunk;
+    float varseg_thresh;
+} sb2_trim;
+sb2_trim sb2_default_trim(void);                     /* 200, 10, 100, 0.0 */
+/* start / end per read (both 0 when the read trims to nothing -- the case in which the reference frees it);
+ * normalised (may be NULL): normalised[r] receives end[r] - start[r] floats */
+int sb2_prepare_reads(sb2_engine *eng, const float *const *raws, const size_t *nsample, size_t nread,
+                      const sb2_trim *t, size_t *start, size_t *end, float *const *normalised);
+/* calculate_post (src/scrappie_raw.c:265-315) for a batch of untrimmed pA signals: everything from the trimmer to
+ * the base strings runs on the device.  start / end (may be NULL) as above; returns the number of reads called. */
+int sb2_basecall_raw_batch(sb2_engine *eng, enum raw_model_type model, const float *const *raws,
+                           const size_t *nsample, size_t nread, const sb2_trim *t, const sb2_params *p,
+                           sb2_call *out, size_t *start, size_t *end);
+
 int sb2_basecall_batch(sb2_engine *eng, enum raw_model_type model, const float *const *signals,
                        const size_t *nsample, size_t nread, const sb2_params *p, sb2_call *out);
 void sb2_calls_free(sb2_call *calls, size_t n);     /* free() every calls[i].bases */

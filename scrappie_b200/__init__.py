@@ -44,6 +44,12 @@ class Params(C.Structure):
                 ("allow_slip", C.c_int), ("homopolymer", C.c_int)]
 
 
+class Trim(C.Structure):
+    """sb2_trim: the signal-preparation options of `scrappie raw` (src/scrappie_raw.c:98-121)."""
+    _fields_ = [("trim_start", C.c_size_t), ("trim_end", C.c_size_t), ("varseg_chunk", C.c_size_t),
+                ("varseg_thresh", C.c_float)]
+
+
 class _Call(C.Structure):
     _fields_ = [("bases", C.c_void_p), ("score", C.c_float), ("nblock", C.c_size_t), ("nbase", C.c_size_t)]
 
@@ -128,6 +134,12 @@ def lib():
                                          C.POINTER(Params), C.POINTER(_Call)]),
         "sb2_batch_basecall": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(Params), C.POINTER(_Call)]),
         "sb2_calls_free": (None, [C.POINTER(_Call), C.c_size_t]),
+        "sb2_default_trim": (Trim, []),
+        "sb2_prepare_reads": (C.c_int, [C.c_void_p, C.POINTER(_f32p), C.POINTER(C.c_size_t), C.c_size_t, C.POINTER(Trim),
+                                        C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(_f32p)]),
+        "sb2_basecall_raw_batch": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(_f32p), C.POINTER(C.c_size_t), C.c_size_t,
+                                             C.POINTER(Trim), C.POINTER(Params), C.POINTER(_Call), C.POINTER(C.c_size_t),
+                                             C.POINTER(C.c_size_t)]),
         "sb2_multi_time": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(Params), C.c_int, C.c_int, _f32p]),
         "sb2_multi_stream_time": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(Params), _i32p, _f32p]),
         "sb2_conv_plan_debug": (C.c_int, [C.c_size_t, C.c_size_t, C.c_size_t, _i32p, C.c_int]),
@@ -382,6 +394,54 @@ class Engine(object):
 
     def batch(self, model, nsample):
         return Batch(self, model, nsample)
+
+    @staticmethod
+    def _trim(trim=None, **kw):
+        t = trim or lib().sb2_default_trim()
+        for k, v in kw.items():
+            setattr(t, k, v)
+        return t
+
+    def prepare_reads(self, raws, trim=None, normalise=True, **kw):
+        """trim_and_segment_raw + medmad_normalise_array on the device for a list of untrimmed signals.
+        Returns (start, end, normalised) -- `normalised[r]` is the scaled raws[r][start[r]:end[r]] (None when
+        the read trims to nothing)."""
+        t = self._trim(trim, **kw)
+        sigs = [np.ascontiguousarray(s, dtype=np.float32) for s in raws]
+        n = len(sigs)
+        ptrs = (_f32p * n)(*[_fp(s) for s in sigs])
+        lens = (C.c_size_t * n)(*[s.size for s in sigs])
+        start = (C.c_size_t * n)()
+        end = (C.c_size_t * n)()
+        outs = [np.zeros(s.size, dtype=np.float32) for s in sigs] if normalise else None
+        optrs = (_f32p * n)(*[_fp(o) for o in outs]) if normalise else None
+        rc = lib().sb2_prepare_reads(self._h, ptrs, lens, n, C.byref(t), start, end, optrs)
+        if rc:
+            raise RuntimeError("sb2_prepare_reads failed: %s" % last_error())
+        start, end = [int(x) for x in start], [int(x) for x in end]
+        norm = None
+        if normalise:
+            norm = [o[:e - s_] if e > s_ else None for o, s_, e in zip(outs, start, end)]
+        return start, end, norm
+
+    def basecall_raw_batch(self, model, raws, params=None, trim=None, **kw):
+        """calculate_post (src/scrappie_raw.c:265-315) for a list of untrimmed pA signals, everything on the
+        device.  Returns a list of (bases or None, score, nblock, start, end)."""
+        params = params or default_params()
+        t = self._trim(trim, **kw)
+        sigs = [np.ascontiguousarray(s, dtype=np.float32) for s in raws]
+        n = len(sigs)
+        ptrs = (_f32p * n)(*[_fp(s) for s in sigs])
+        lens = (C.c_size_t * n)(*[s.size for s in sigs])
+        start = (C.c_size_t * n)()
+        end = (C.c_size_t * n)()
+        out = (_Call * n)()
+        rc = lib().sb2_basecall_raw_batch(self._h, _MODEL_ENUM[model], ptrs, lens, n, C.byref(t), C.byref(params), out,
+                                          start, end)
+        if rc < 0:
+            raise RuntimeError("sb2_basecall_raw_batch failed: %s" % last_error())
+        return [(_take_string(o.bases), float(o.score), int(o.nblock), int(s_), int(e))
+                for o, s_, e in zip(out, start, end)]
 
     def basecall_batch(self, model, signals, params=None):
         """signals: list of trimmed + normalised float32 arrays.  Returns list of

@@ -956,6 +956,136 @@ extern "C" int sb2_basecall_batch(sb2_engine *eng, enum raw_model_type model, co
     return ncalled;
 }
 
+// ------------------------------------------------------------------------------------
+// signal preparation on the device (trim_and_segment_raw + medmad_normalise_array) and the raw-signal basecall
+// ------------------------------------------------------------------------------------
+extern "C" sb2_trim sb2_default_trim(void) {
+    sb2_trim t;
+    t.trim_start = 200; t.trim_end = 10; t.varseg_chunk = 100; t.varseg_thresh = 0.0f;   // src/scrappie_raw.c:98-121
+    return t;
+}
+
+namespace {
+struct RawStage {
+    float *d_raw = nullptr, *d_mads = nullptr;
+    int64_t *d_off = nullptr, *d_moff = nullptr;
+    int *d_n = nullptr, *d_se = nullptr;
+    std::vector<int64_t> off;
+    ~RawStage() {
+        void *ptrs[] = {d_raw, d_mads, d_off, d_moff, d_n, d_se};
+        for (void *p : ptrs) if (p) cudaFree(p);
+    }
+};
+}  // namespace
+
+// Upload the untrimmed signals and run the trimmer; start/end per read (end = 0: nothing left).
+static int stage_and_trim(sb2_engine *eng, const float *const *raws, const size_t *nsample, size_t nread,
+                          const sb2_trim *t, RawStage &st, std::vector<int> &start, std::vector<int> &end) {
+    CUDA_OK(cudaSetDevice(eng->device));
+    st.off.resize(nread);
+    std::vector<int64_t> moff(nread);
+    std::vector<int> n(nread);
+    int64_t so = 0, mo = 0;
+    const size_t chunk = t->varseg_chunk;
+    for (size_t r = 0; r < nread; r++) {
+        if (nullptr == raws[r] || nsample[r] > (size_t)1 << 30) { sb2_set_error("read %zu: bad signal", r); return -1; }
+        st.off[r] = so; moff[r] = mo; n[r] = (int)nsample[r];
+        so += (int64_t)((nsample[r] + 3) / 4 * 4);
+        mo += (int64_t)(chunk >= 2 ? nsample[r] / chunk : 0);
+    }
+    start.assign(nread, 0); end.assign(nread, 0);
+    if (chunk < 2 || chunk > (size_t)1 << 20) return 0;                 // trim_raw_by_mad fails: every read is dropped
+    if (dev_alloc(&st.d_raw, (size_t)so) || dev_alloc(&st.d_mads, (size_t)mo) || dev_alloc(&st.d_off, nread) ||
+        dev_alloc(&st.d_moff, nread) || dev_alloc(&st.d_n, nread) || dev_alloc(&st.d_se, 2 * nread))
+        return -1;
+    for (size_t r = 0; r < nread; r++)
+        CUDA_OK(cudaMemcpyAsync(st.d_raw + st.off[r], raws[r], nsample[r] * sizeof(float), cudaMemcpyHostToDevice, 0));
+    CUDA_OK(cudaMemcpyAsync(st.d_off, st.off.data(), nread * sizeof(int64_t), cudaMemcpyHostToDevice, 0));
+    CUDA_OK(cudaMemcpyAsync(st.d_moff, moff.data(), nread * sizeof(int64_t), cudaMemcpyHostToDevice, 0));
+    CUDA_OK(cudaMemcpyAsync(st.d_n, n.data(), nread * sizeof(int), cudaMemcpyHostToDevice, 0));
+    const int ts = (int)std::min(t->trim_start, (size_t)1 << 30), te = (int)std::min(t->trim_end, (size_t)1 << 30);
+    launch_trim(st.d_raw, st.d_off, st.d_n, (int)nread, (int)chunk, t->varseg_thresh, ts, te, st.d_mads, st.d_moff, st.d_se, 0);
+    eng->launches += 1;
+    CUDA_OK(cudaGetLastError());
+    std::vector<int> se(2 * nread);
+    CUDA_OK(cudaMemcpy(se.data(), st.d_se, 2 * nread * sizeof(int), cudaMemcpyDeviceToHost));
+    for (size_t r = 0; r < nread; r++) { start[r] = se[2 * r]; end[r] = se[2 * r + 1]; }
+    return 0;
+}
+
+extern "C" int sb2_prepare_reads(sb2_engine *eng, const float *const *raws, const size_t *nsample, size_t nread,
+                                 const sb2_trim *t, size_t *start_out, size_t *end_out, float *const *normalised) {
+    if (nullptr == eng || nullptr == raws || nullptr == nsample || nullptr == t || 0 == nread) return -1;
+    RawStage st;
+    std::vector<int> start, end;
+    if (0 != stage_and_trim(eng, raws, nsample, nread, t, st, start, end)) return -1;
+    for (size_t r = 0; r < nread; r++) {
+        if (start_out) start_out[r] = (size_t)start[r];
+        if (end_out) end_out[r] = (size_t)end[r];
+    }
+    if (nullptr == normalised || nullptr == st.d_raw) return 0;
+    std::vector<int64_t> src(nread);
+    std::vector<int> n(nread);
+    for (size_t r = 0; r < nread; r++) { src[r] = st.off[r] + start[r]; n[r] = end[r] - start[r]; }
+    float *d_out = nullptr;
+    int64_t *d_src = nullptr;
+    int *d_n = nullptr;
+    const size_t total = (size_t)(st.off[nread - 1] + (int64_t)((nsample[nread - 1] + 3) / 4 * 4));
+    int rc = (dev_alloc(&d_out, total) || dev_alloc(&d_src, nread) || dev_alloc(&d_n, nread)) ? -1 : 0;
+    if (0 == rc && (cudaMemcpy(d_src, src.data(), nread * sizeof(int64_t), cudaMemcpyHostToDevice) != cudaSuccess ||
+                    cudaMemcpy(d_n, n.data(), nread * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess))
+        rc = -1;
+    if (0 == rc) {
+        launch_medmad(st.d_raw, d_src, d_out, d_src, d_n, (int)nread, 0);
+        eng->launches += 1;
+        for (size_t r = 0; r < nread && 0 == rc; r++)
+            if (n[r] > 0 && nullptr != normalised[r] &&
+                cudaMemcpy(normalised[r], d_out + src[r], (size_t)n[r] * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess)
+                rc = -1;
+    }
+    if (d_out) cudaFree(d_out);
+    if (d_src) cudaFree(d_src);
+    if (d_n) cudaFree(d_n);
+    if (rc) sb2_set_error("prepare_reads: CUDA error %s", cudaGetErrorString(cudaGetLastError()));
+    return rc;
+}
+
+// calculate_post (src/scrappie_raw.c:265-315) for a batch of untrimmed pA signals: trim, normalise, network, decode,
+// homopolymer fix-up and base strings, all on the device.  Reads that trim to nothing get out[r].bases = NULL.
+extern "C" int sb2_basecall_raw_batch(sb2_engine *eng, enum raw_model_type model, const float *const *raws,
+                                      const size_t *nsample, size_t nread, const sb2_trim *t, const sb2_params *p,
+                                      sb2_call *out, size_t *start_out, size_t *end_out) {
+    if (nullptr == eng || nullptr == raws || nullptr == nsample || nullptr == t || nullptr == p || nullptr == out || 0 == nread) return -1;
+    for (size_t r = 0; r < nread; r++) out[r] = sb2_call{nullptr, NAN, 0, 0};
+    RawStage st;
+    std::vector<int> start, end;
+    if (0 != stage_and_trim(eng, raws, nsample, nread, t, st, start, end)) return -1;
+    std::vector<size_t> keep, len;
+    std::vector<int64_t> src;
+    for (size_t r = 0; r < nread; r++) {
+        if (start_out) start_out[r] = (size_t)start[r];
+        if (end_out) end_out[r] = (size_t)end[r];
+        if (end[r] > start[r]) { keep.push_back(r); len.push_back((size_t)(end[r] - start[r])); src.push_back(st.off[r] + start[r]); }
+    }
+    if (keep.empty()) return 0;
+    sb2_batch *b = sb2_batch_create(eng, model, len.data(), len.size());
+    if (nullptr == b) return -1;
+    int ncalled = -1;
+    int64_t *d_src = nullptr;
+    std::vector<sb2_call> calls(keep.size(), sb2_call{nullptr, NAN, 0, 0});
+    if (0 == dev_alloc(&d_src, keep.size()) &&
+        cudaMemcpyAsync(d_src, src.data(), keep.size() * sizeof(int64_t), cudaMemcpyHostToDevice, b->stream) == cudaSuccess) {
+        launch_medmad(st.d_raw, d_src, b->d_raw, b->d_sampoff, b->d_nsample, b->nread, b->stream);
+        eng->launches += 1;
+        ncalled = sb2_batch_basecall(b, nullptr, 0, p, calls.data());
+        for (size_t i = 0; i < keep.size(); i++) out[keep[i]] = calls[i];
+    }
+    if (b->stream) cudaStreamSynchronize(b->stream);
+    if (d_src) cudaFree(d_src);
+    sb2_batch_destroy(b);
+    return ncalled;
+}
+
 // Time forward+decode of several batches running concurrently, each on its own stream
 // (the way a job larger than one batch is executed).  The timed region is bracketed by
 // events on the first batch's stream: every other stream waits for the start event and

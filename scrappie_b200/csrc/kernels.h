@@ -63,6 +63,13 @@ void launch_decode_transducer_warp(const float *post, const BatchDims &d, int os
 // column col_off[r] + r and owns nblock[r] + 1 columns
 void launch_posterior_crf(const float *trans, const BatchDims &d, int ostride, float *post, cudaStream_t s);
 
+// signal preparation (kernels_prep.cu): trim_and_segment_raw (src/scrappie_common.c:5-73) -> start_end[2 r], [2 r + 1]
+// (both 0 when nothing is left), and medmad_normalise_array (src/util.c:190-204) from src + src_off[r] to dst + dst_off[r]
+void launch_trim(const float *raw, const int64_t *off, const int *nsample, int nread, int chunk, float perc,
+                 int trim_start, int trim_end, float *mads, const int64_t *mads_off, int *start_end, cudaStream_t s);
+void launch_medmad(const float *src, const int64_t *src_off, float *dst, const int64_t *dst_off, const int *nsample,
+                   int nread, cudaStream_t s);
+
 // decode_crf (src/decode.c:836-893)
 void launch_decode_crf(const float *trans, const BatchDims &d, int ostride, uint8_t *tb, int *path,
                        float *score, cudaStream_t s);

@@ -444,3 +444,66 @@ def test_basecall_raw_with_base_probs(sb, golden):
     with pytest.raises(ValueError):
         sb.basecall_raw(raw, "rgrgr_r94", with_base_probs=True)
     assert sb.lib().posterior_crf(None) is None or not sb.lib().posterior_crf(None)
+
+
+# ---- signal preparation on the device -------------------------------
+def _host_prep(sb, raw, start=200, end=10, chunk=100, thresh=0.0):
+    """The host functions of the library (bit-exact vs the oracle / upstream vectors, tests/test_host.py)."""
+    rt = sb.RawTable(raw)
+    try:
+        rt.trim(start, end, chunk, thresh)
+    except Exception:
+        return None
+    if rt.end <= rt.start:
+        return None
+    s_, e_ = rt.start, rt.end
+    rt.scale()
+    return s_, e_, np.array(rt.data(as_numpy=True), dtype=np.float32)
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(varseg_thresh=0.3), dict(varseg_chunk=50, varseg_thresh=0.1, trim_start=0, trim_end=0),
+                                dict(varseg_chunk=300, varseg_thresh=0.25)])
+def test_device_prep_bit_exact(sb, engine, golden, kw):
+    """trim_and_segment_raw + medmad_normalise_array on the device == the host functions, bit for bit: the bundled
+    reads (29k - 81k samples), the upstream test signal, synthetic pA-like reads incl. quiet stretches that the
+    trimmer removes, and reads too short to survive."""
+    rng = np.random.default_rng(5)
+    raws = [bundled_signal(golden, i) for i in range(3)]
+    raws.append(np.array(golden.upstream_signal["raw"], dtype=np.float32))
+    for n in (4000, 1234, 777, 211, 150, 10):
+        x = (synthetic_read(900 + n, n) * 12.0 + 90.0).astype(np.float32)
+        raws.append(x)
+    raws.append(np.array([93.5], dtype=np.float32))
+    quiet = (synthetic_read(7, 6000) * 12.0 + 90.0).astype(np.float32)
+    quiet[:900] = 90.0 + rng.normal(0, 0.01, 900).astype(np.float32)         # low-variance head and tail
+    quiet[-700:] = 85.0
+    raws.append(quiet)
+    hk = dict(start=kw.get("trim_start", 200), end=kw.get("trim_end", 10), chunk=kw.get("varseg_chunk", 100),
+              thresh=kw.get("varseg_thresh", 0.0))
+    start, end, norm = engine.prepare_reads(raws, **kw)
+    nsurv = 0
+    for i, raw in enumerate(raws):
+        want = _host_prep(sb, raw, **hk)
+        if want is None:
+            assert end[i] == 0 and norm[i] is None, i
+            continue
+        nsurv += 1
+        assert (start[i], end[i]) == want[:2], (i, start[i], end[i], want[:2])
+        assert np.array_equal(norm[i].view(np.uint32), want[2].view(np.uint32)), i
+    assert nsurv >= 8
+
+
+@pytest.mark.parametrize("model", ["rgrgr_r94", "rnnrf_r94"])
+def test_basecall_raw_batch_bundled_reads(sb, engine, golden, model):
+    """`scrappie raw` on the bundled reads with the whole of calculate_post on the device: untrimmed pA signal in,
+    md5-identical base sequences out."""
+    g = golden.ref_reads
+    raws = [bundled_signal(golden, i) for i in range(3)] + [np.full(150, 90.0, dtype=np.float32)]
+    calls = engine.basecall_raw_batch(model, raws)
+    for i in range(3):
+        k = "r%d_%s" % (i, model)
+        bases, score, nblock, start, end = calls[i]
+        assert hashlib.md5((bases + "\n").encode()).hexdigest() == str(g[k + "_md5"])
+        assert abs(score - float(g[k + "_score"])) < (0.02 if model == "rgrgr_r94" else 0.25)
+        assert [start, end] == list(g["r%d_trim" % i])
+    assert calls[3][0] is None and calls[3][4] == 0          # too short: dropped like the reference does
