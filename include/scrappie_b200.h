@@ -39,6 +39,23 @@ typedef struct {
     float *raw;
 } raw_table;
 
+/* src/scrappie_structures.h:8-22, interface/scrappie.h:13-27 */
+typedef struct {
+    uint64_t start;
+    float length;
+    float mean;
+    float stdv;
+    int pos;
+    int state;
+} event_t;
+
+typedef struct {
+    size_t n;
+    size_t start;
+    size_t end;
+    event_t *event;
+} event_table;
+
 /* src/scrappie_matrix.h:10-16.  Column-major fp32, every column padded to a multiple
  * of 4 floats (stride = 4 * nrq), 16-byte aligned, zero initialised.  The reference's
  * union {__m128 *v; float *f;} is a single pointer; `f` here has the same offset. */
@@ -99,6 +116,11 @@ posterior_function_ptr get_posterior_function(const enum raw_model_type model);
 /* -- network forward (GPU): src/networks.c:250-394, :567-615.
  *    Returns a new matrix [nstate x nblock] owned by the caller, or NULL. -- */
 /* raw_r94 (interface/scrappie.h:49-51, src/networks.c:196-247): two bidirectional GRU pairs */
+/* interface/scrappie.h:47-48, src/networks.c:146-194: the events (LSTM) model.  Features are made on the host
+ * (nanonet_features_from_events, src/nnfeatures.c:76-115, exported as well); window, LSTM layers and head on the GPU */
+scrappie_matrix nanonet_features_from_events(const event_table et, bool normalise);
+scrappie_matrix nanonet_posterior(const event_table events, float min_prob,
+                                  float tempW, float tempb, bool return_log);
 scrappie_matrix nanonet_raw_posterior(const raw_table signal, float min_prob,
                                       float tempW, float tempb, bool return_log);
 scrappie_matrix nanonet_rgrgr_r94_posterior(const raw_table signal, float min_prob,
@@ -227,6 +249,11 @@ int sb2_prepare_reads(sb2_engine *eng, const float *const *raws, const size_t *n
 int sb2_basecall_raw_batch(sb2_engine *eng, enum raw_model_type model, const float *const *raws,
                            const size_t *nsample, size_t nread, const sb2_trim *t, const sb2_params *p,
                            sb2_call *out, size_t *start, size_t *end);
+
+/* nanonet_posterior for several event tables in one pass (LSTM scans run 8 reads per CTA); out[i] is a new matrix
+ * owned by the caller or NULL.  Returns the number of posteriors made, -1 on failure. */
+int sb2_events_posterior_batch(sb2_engine *eng, const event_table *tables, size_t ntable, float min_prob,
+                               float tempW, float tempb, bool return_log, scrappie_matrix *out);
 
 int sb2_basecall_batch(sb2_engine *eng, enum raw_model_type model, const float *const *signals,
                        const size_t *nsample, size_t nread, const sb2_params *p, sb2_call *out);

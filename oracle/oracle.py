@@ -87,7 +87,29 @@ class Oracle:
                                             C.c_float, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
         L.sb2o_convolution.argtypes = [c_float_p, C.c_size_t, C.POINTER(_Tensor), C.POINTER(_Tensor),
                                        C.c_size_t, c_float_p]
+        L.sb2o_event_features.argtypes = [c_float_p, C.c_size_t, c_float_p]
+        L.sb2o_events_posterior.restype = C.c_size_t
+        L.sb2o_events_posterior.argtypes = [C.POINTER(_Model), c_float_p, C.c_size_t, C.c_float, C.c_float,
+                                            C.c_float, C.c_int, c_float_p]
         self._models = {}
+
+    # -- events model (src/networks.c:146-194) -------------------------------
+    def event_features(self, ev):
+        """ev: [n, 3] (mean, stdv, length) -> studentised features [n, 4]."""
+        ev = np.ascontiguousarray(ev, dtype=np.float32)
+        out = np.zeros((ev.shape[0], 4), dtype=np.float32)
+        self.lib.sb2o_event_features(_fp(ev), ev.shape[0], _fp(out))
+        return out
+
+    def events_posterior(self, ev, min_prob=1e-5, tempW=1.0, tempb=1.0, return_log=True):
+        m = self.model("nanonet_events")
+        ev = np.ascontiguousarray(ev, dtype=np.float32)
+        ns = self.nstate("nanonet_events")
+        out = np.zeros((ev.shape[0], 4 * ((ns + 3) // 4)), dtype=np.float32)
+        n = self.lib.sb2o_events_posterior(C.byref(m), _fp(ev), ev.shape[0], min_prob, tempW, tempb,
+                                           int(return_log), _fp(out))
+        assert n == ev.shape[0]
+        return out
 
     # -- models ------------------------------------------------------------
     def model(self, name):
@@ -214,6 +236,41 @@ class _Mat(C.Structure):
                 ("data", c_float_p)]
 
 
+class _Event(C.Structure):
+    """event_t, src/scrappie_structures.h:8-15."""
+    _fields_ = [("start", C.c_uint64), ("length", C.c_float), ("mean", C.c_float), ("stdv", C.c_float),
+                ("pos", C.c_int), ("state", C.c_int)]
+
+
+class _EventTable(C.Structure):
+    _fields_ = [("n", C.c_size_t), ("start", C.c_size_t), ("end", C.c_size_t), ("event", C.POINTER(_Event))]
+
+
+def make_event_table(ev, start=0, end=None):
+    """[n, 3] (mean, stdv, length) -> (event_table, keep-alive array)."""
+    ev = np.asarray(ev, dtype=np.float32)
+    arr = (_Event * ev.shape[0])()
+    pos = 0
+    for i in range(ev.shape[0]):
+        arr[i].start = pos
+        arr[i].length = float(ev[i, 2])
+        arr[i].mean = float(ev[i, 0])
+        arr[i].stdv = float(ev[i, 1])
+        arr[i].pos = -1
+        arr[i].state = -1
+        pos += int(ev[i, 2])
+    return _EventTable(ev.shape[0], start, ev.shape[0] if end is None else end, arr), arr
+
+
+def synthetic_events(seed, n):
+    """Event table of a synthetic read: [n, 3] = (mean pA, stdv, length in samples)."""
+    rng = np.random.default_rng(seed)
+    mean = (90.0 + 12.0 * rng.uniform(-1.5, 1.5, n)).astype(np.float32)
+    stdv = (0.3 + np.abs(rng.normal(1.5, 0.5, n))).astype(np.float32)
+    length = rng.geometric(1.0 / 9.0, n).astype(np.float32)
+    return np.stack([mean, stdv, length], axis=1).astype(np.float32)
+
+
 class _RawTable(C.Structure):
     _fields_ = [("uuid", C.c_char_p), ("n", C.c_size_t), ("start", C.c_size_t), ("end", C.c_size_t),
                 ("raw", c_float_p)]
@@ -254,6 +311,10 @@ class Reference:
         L.crfpath_to_basecall.argtypes = [c_int_p, C.c_size_t, c_int_p]
         L.posterior_crf.restype = C.POINTER(_Mat)
         L.posterior_crf.argtypes = [C.POINTER(_Mat)]
+        L.nanonet_posterior.restype = C.POINTER(_Mat)
+        L.nanonet_posterior.argtypes = [_EventTable, C.c_float, C.c_float, C.c_float, C.c_bool]
+        L.nanonet_features_from_events.restype = C.POINTER(_Mat)
+        L.nanonet_features_from_events.argtypes = [_EventTable, C.c_bool]
         L.homopolymer_path.argtypes = [C.POINTER(_Mat), c_int_p, C.c_int]
         L.medmad_normalise_array.argtypes = [c_float_p, C.c_size_t]
         L.trim_and_segment_raw.restype = _RawTable
@@ -311,6 +372,21 @@ class Reference:
         score = self.lib.decode_crf(mp, _ip(path))
         self.lib.free_scrappie_matrix(mp)
         return float(score), path
+
+    def events_posterior(self, ev, min_prob=1e-5, tempW=1.0, tempb=1.0, return_log=True):
+        et, keep = make_event_table(ev)
+        mp = self.lib.nanonet_posterior(et, min_prob, tempW, tempb, return_log)
+        assert mp, "reference returned NULL"
+        out, nr = self._to_np(mp)
+        self.lib.free_scrappie_matrix(mp)
+        return out
+
+    def event_features(self, ev):
+        et, keep = make_event_table(ev)
+        mp = self.lib.nanonet_features_from_events(et, True)
+        out, nr = self._to_np(mp)
+        self.lib.free_scrappie_matrix(mp)
+        return out
 
     def posterior_crf(self, trans):
         mp = self._mat(trans, 25)

@@ -120,9 +120,11 @@ int sb2o_model_from_blob(const void *blob, size_t nbytes, sb2o_model *m) {
     const blob_entry *tab = (const blob_entry *)(p + 40);
     const float *data = (const float *)(p + 40 + (size_t)nt * sizeof(blob_entry));
     int rc = 0;
-    rc |= find_tensor(tab, nt, data, "conv_W", &m->conv_W);
-    rc |= find_tensor(tab, nt, data, "conv_b", &m->conv_b);
-    if (m->arch == 1) {
+    if (m->arch != 2) {
+        rc |= find_tensor(tab, nt, data, "conv_W", &m->conv_W);
+        rc |= find_tensor(tab, nt, data, "conv_b", &m->conv_b);
+    }
+    if (m->arch >= 1) {
         const char *cn[2][3] = {{"comb1_Wf", "comb1_Wb", "comb1_b"}, {"comb2_Wf", "comb2_Wb", "comb2_b"}};
         for (int i = 0; i < 2; i++) {
             rc |= find_tensor(tab, nt, data, cn[i][0], &m->comb_Wf[i]);
@@ -130,7 +132,7 @@ int sb2o_model_from_blob(const void *blob, size_t nbytes, sb2o_model *m) {
             rc |= find_tensor(tab, nt, data, cn[i][2], &m->comb_b[i]);
         }
     }
-    for (int l = 0; l < (m->arch == 1 ? 4 : 5); l++) {
+    for (int l = 0; l < (m->arch >= 1 ? 4 : 5); l++) {
         char nm[24];
         const char *parts[4] = {"iW", "b", "sW", "sW2"};
         sb2o_tensor *dst[4] = {&m->iW[l], &m->b[l], &m->sW[l], &m->sW2[l]};
@@ -360,6 +362,112 @@ static size_t posterior_raw_r94(const sb2o_model *m, const float *raw, size_t n,
     head_softmax(ff, ncol, &m->FF_W, &m->FF_b, min_prob, tempW, tempb, return_log, out);
     free(gb); free(gf); free(xin); free(ff2); free(ff);
     return ncol;
+}
+
+/* ---- events model (src/networks.c:146-194) ------------------------------------------------ */
+
+/* nanonet_features_from_events + studentise_features_kahan, src/nnfeatures.c:47-115.
+ * ev: n events x (mean, stdv, length); out: n x 4.  The four SSE lanes of the reference are four
+ * independent scalar recurrences here; the reciprocal square root is the same RSQRTPS instruction. */
+#include <xmmintrin.h>
+void sb2o_event_features(const float *ev, size_t n, float *out) {
+    for (size_t e = 0; e < n; e++) {
+        out[4 * e + 0] = ev[3 * e + 0];
+        out[4 * e + 1] = ev[3 * e + 1];
+        out[4 * e + 2] = ev[3 * e + 2];
+        out[4 * e + 3] = (e + 1 < n) ? (float)fabs(ev[3 * e] - ev[3 * (e + 1)]) : 0.0f;
+    }
+    float sum[4] = {0}, sumsq[4] = {0}, comp[4] = {0}, compsq[4] = {0};
+    for (size_t e = 0; e < n; e++)
+        for (int l = 0; l < 4; l++) {
+            const float v = out[4 * e + l];
+            const float d1 = v - comp[l];
+            const float sum_tmp = sum[l] + d1;
+            comp[l] = (sum_tmp - sum[l]) - d1;
+            sum[l] = sum_tmp;
+            const float d2 = v * v - compsq[l];
+            const float sumsq_tmp = sumsq[l] + d2;
+            compsq[l] = (sumsq_tmp - sumsq[l]) - d2;
+            sumsq[l] = sumsq_tmp;
+        }
+    float var[4];
+    for (int l = 0; l < 4; l++) {
+        sum[l] /= (float)(int)n;
+        sumsq[l] /= (float)(int)n;
+        var[l] = sumsq[l] - sum[l] * sum[l];
+    }
+    float rs[4];
+    _mm_storeu_ps(rs, _mm_rsqrt_ps(_mm_loadu_ps(var)));
+    for (int l = 0; l < 4; l++) sum[l] *= rs[l];
+    for (size_t e = 0; e < n; e++)
+        for (int l = 0; l < 4; l++) out[4 * e + l] = rs[l] * out[4 * e + l] - sum[l];
+}
+
+/* window(features, 3, 1), src/layers.c:119-146: column c = [f[c-1], f[c], f[c+1]], zero beyond the end.
+ * Column 0 stays ALL ZERO in the reference: its loop `for (int w1 = icol - wh + 1; w1 <= icol + wh; ...)`
+ * compares the int w1 = -1 with a size_t, i.e. as a huge unsigned value, and never runs.  (The loop also
+ * visits a fourth position icol + 2, which lands in the next column's first rows and is overwritten there.) */
+static void window3(const float *f, size_t n, float *out) {
+    for (size_t c = 0; c < n; c++)
+        for (int w = -1; w <= 1; w++)
+            for (int l = 0; l < 4; l++) {
+                const long src = (long)c + w;
+                out[12 * c + 4 * (w + 1) + l] = (0 == c || src >= (long)n) ? 0.0f : f[4 * src + l];
+            }
+}
+
+/* lstm_forward / lstm_backward / lstm_step, src/layers.c:673-832.  Rows of Xin / columns of sW:
+ * [0,H) cell input (tanh), [H,2H) input gate, [2H,3H) forget gate, [3H,4H) output gate;
+ * peepholes p: [0,H) input gate, [H,2H) forget gate (both see the OLD cell), [2H,3H) output gate (NEW cell). */
+void sb2o_lstm(const float *Xin, size_t ncol, const sb2o_tensor *sW, const sb2o_tensor *p, int backward, float *out) {
+    const size_t H = sW->nr;
+    float *h = calloc(H, sizeof(float)), *c = calloc(H, sizeof(float));
+    float *xF = malloc(4 * H * sizeof(float));
+    for (size_t s = 0; s < ncol; s++) {
+        const size_t t = backward ? (ncol - 1 - s) : s;
+        const float *x = Xin + t * 4 * H;
+        for (size_t k = 0; k < 4 * H; k++) {
+            const float *w = sW->data + k * sW->stride;
+            float acc = 0.0f;
+            for (size_t i = 0; i < H; i++) acc += w[i] * h[i];
+            xF[k] = x[k] + acc;
+        }
+        float *o = out + t * H;
+        for (size_t i = 0; i < H; i++) {
+            const float forget = sb2o_logisticf(xF[2 * H + i] + c[i] * p->data[H + i]) * c[i];
+            const float update = sb2o_logisticf(xF[H + i] + c[i] * p->data[i]) * sb2o_tanhf(xF[i]);
+            c[i] = forget + update;
+            o[i] = sb2o_logisticf(xF[3 * H + i] + c[i] * p->data[2 * H + i]) * sb2o_tanhf(c[i]);
+        }
+        memcpy(h, o, H * sizeof(float));
+    }
+    free(xF); free(c); free(h);
+}
+
+/* nanonet_posterior, src/networks.c:146-194.  ev: n x (mean, stdv, length); out: n columns of out_stride floats */
+size_t sb2o_events_posterior(const sb2o_model *m, const float *ev, size_t n, float min_prob, float tempW,
+                             float tempb, int return_log, float *out) {
+    if (NULL == m || NULL == ev || 0 == n || NULL == out || m->arch != 2) return 0;
+    const size_t H = m->sW[0].nr, FW = m->comb_b[0].nr;
+    float *feat = malloc(n * 4 * sizeof(float)), *f3 = malloc(n * 12 * sizeof(float));
+    float *ff = malloc(n * FW * sizeof(float)), *ff2 = malloc(n * FW * sizeof(float));
+    float *xin = malloc(n * 4 * H * sizeof(float));
+    float *lf = malloc(n * H * sizeof(float)), *lb = malloc(n * H * sizeof(float));
+    sb2o_event_features(ev, n, feat);
+    window3(feat, n, f3);
+    const float *in = f3;
+    for (int pair = 0; pair < 2; pair++) {
+        sb2o_affine(in, n, &m->iW[2 * pair], &m->b[2 * pair], xin);
+        sb2o_lstm(xin, n, &m->sW[2 * pair], &m->sW2[2 * pair], 0, lf);
+        sb2o_affine(in, n, &m->iW[2 * pair + 1], &m->b[2 * pair + 1], xin);
+        sb2o_lstm(xin, n, &m->sW[2 * pair + 1], &m->sW2[2 * pair + 1], 1, lb);
+        float *dst = (pair == 0) ? ff : ff2;
+        affine2_tanh(lf, lb, n, &m->comb_Wf[pair], &m->comb_Wb[pair], &m->comb_b[pair], dst);
+        in = dst;
+    }
+    head_softmax(in, n, &m->FF_W, &m->FF_b, min_prob, tempW, tempb, return_log, out);
+    free(lb); free(lf); free(xin); free(ff2); free(ff); free(f3); free(feat);
+    return n;
 }
 
 /* nanonet_rgrgr_*_posterior (src/networks.c:250-296) / nanonet_rnnrf_r94_transitions (:567-615) */

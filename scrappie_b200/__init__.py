@@ -44,6 +44,30 @@ class Params(C.Structure):
                 ("allow_slip", C.c_int), ("homopolymer", C.c_int)]
 
 
+class _Event(C.Structure):
+    """event_t (src/scrappie_structures.h:8-15)."""
+    _fields_ = [("start", C.c_uint64), ("length", C.c_float), ("mean", C.c_float), ("stdv", C.c_float),
+                ("pos", C.c_int), ("state", C.c_int)]
+
+
+class _EventTable(C.Structure):
+    _fields_ = [("n", C.c_size_t), ("start", C.c_size_t), ("end", C.c_size_t), ("event", C.POINTER(_Event))]
+
+
+class EventTable(object):
+    """An event_table built from an [n, 3] array of (mean, stdv, length)."""
+
+    def __init__(self, events, start=0, end=None):
+        ev = np.asarray(events, dtype=np.float32)
+        self._arr = (_Event * ev.shape[0])()
+        pos = 0
+        for i in range(ev.shape[0]):
+            e = self._arr[i]
+            e.start, e.length, e.mean, e.stdv, e.pos, e.state = pos, float(ev[i, 2]), float(ev[i, 0]), float(ev[i, 1]), -1, -1
+            pos += int(ev[i, 2])
+        self.table = _EventTable(ev.shape[0], start, ev.shape[0] if end is None else end, self._arr)
+
+
 class Trim(C.Structure):
     """sb2_trim: the signal-preparation options of `scrappie raw` (src/scrappie_raw.c:98-121)."""
     _fields_ = [("trim_start", C.c_size_t), ("trim_end", C.c_size_t), ("varseg_chunk", C.c_size_t),
@@ -96,6 +120,10 @@ def lib():
         "decode_transducer": (C.c_float, [mp, C.c_float, C.c_float, C.c_float, _i32p, C.c_bool]),
         "decode_crf": (C.c_float, [mp, _i32p]),
         "posterior_crf": (mp, [mp]),
+        "nanonet_posterior": (mp, [_EventTable, C.c_float, C.c_float, C.c_float, C.c_bool]),
+        "nanonet_features_from_events": (mp, [_EventTable, C.c_bool]),
+        "sb2_events_posterior_batch": (C.c_int, [C.c_void_p, C.POINTER(_EventTable), C.c_size_t, C.c_float, C.c_float,
+                                                 C.c_float, C.c_bool, C.POINTER(mp)]),
         "sb2_batch_posterior_crf": (C.c_int, [C.c_void_p]),
         "sb2_batch_download_base_probs": (C.c_int, [C.c_void_p, C.c_size_t, _f32p]),
         "overlapper": (C.c_void_p, [_i32p, C.c_size_t, C.c_int, _i32p]),
@@ -259,7 +287,7 @@ class ScrappyMatrix(object):
         a = np.ctypeslib.as_array(m.f, shape=(m.nc, m.stride))[:, :m.nr]
         if sloika:
             a = np.hstack((a[:, m.nr - 1:m.nr], a[:, :m.nr - 1]))
-        return np.ascontiguousarray(a)
+        return np.array(a, dtype=np.float32, order="C")      # always a copy: the C matrix may be freed before its user is done
 
     def padded(self):
         m = self._ptr.contents
@@ -337,6 +365,24 @@ def get_model_stride(model):
     if stride == -1:
         raise ValueError("Invalid scrappie model '{}'.".format(model))
     return stride
+
+
+def event_features(events):
+    """Studentised event features [n, 4] (nanonet_features_from_events, src/nnfeatures.c:76-115; host)."""
+    et = events if isinstance(events, EventTable) else EventTable(events)
+    ptr = lib().nanonet_features_from_events(et.table, True)
+    if not ptr:
+        raise RuntimeError("nanonet_features_from_events failed")
+    return ScrappyMatrix(ptr).data(as_numpy=True)
+
+
+def calc_post_events(events, min_prob=1e-6, log=True, tempW=1.0, tempb=1.0):
+    """nanonet_posterior (interface/scrappie.h:47-48): posterior of the events (LSTM) model as a ScrappyMatrix."""
+    et = events if isinstance(events, EventTable) else EventTable(events)
+    ptr = lib().nanonet_posterior(et.table, min_prob, tempW, tempb, log)
+    if not ptr:
+        raise RuntimeError("nanonet_posterior failed: %s" % last_error())
+    return ScrappyMatrix(ptr)
 
 
 def posterior_crf(post):
@@ -442,6 +488,19 @@ class Engine(object):
             raise RuntimeError("sb2_basecall_raw_batch failed: %s" % last_error())
         return [(_take_string(o.bases), float(o.score), int(o.nblock), int(s_), int(e))
                 for o, s_, e in zip(out, start, end)]
+
+    def events_posterior_batch(self, tables, min_prob=1e-6, log=True, tempW=1.0, tempb=1.0):
+        """nanonet_posterior for a list of event tables ([n, 3] arrays or EventTable) in one pass; list of
+        ScrappyMatrix (None where the reference would return NULL)."""
+        ets = [t if isinstance(t, EventTable) else EventTable(t) for t in tables]
+        n = len(ets)
+        arr = (_EventTable * n)(*[e.table for e in ets])
+        mp = C.POINTER(_Mat)
+        out = (mp * n)()
+        rc = lib().sb2_events_posterior_batch(self._h, arr, n, min_prob, tempW, tempb, log, out)
+        if rc < 0:
+            raise RuntimeError("sb2_events_posterior_batch failed: %s" % last_error())
+        return [ScrappyMatrix(o) if o else None for o in out]
 
     def basecall_batch(self, model, signals, params=None):
         """signals: list of trimmed + normalised float32 arrays.  Returns list of

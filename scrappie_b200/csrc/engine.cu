@@ -7,6 +7,7 @@
 
 #include <time.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdio>
@@ -51,7 +52,7 @@ struct DevModel {
 
 struct sb2_engine {
     int device = 0;
-    DevModel models[SB2_NMODEL];
+    DevModel models[SB2_NMODEL + 1];            // [SB2_NMODEL] = the events (LSTM) model of nanonet_posterior
     char weights_dir[1024]{};
     std::atomic<uint64_t> launches{0};
     float *flush_buf = nullptr;
@@ -75,7 +76,7 @@ static int upload_model(sb2_engine *eng, DevModel *dm) {
         for (uint32_t c = 0; c < t.nc; c++) memcpy(&v[(size_t)c * t.nr], t.data + (size_t)c * t.stride, t.nr * sizeof(float));
         return v;
     };
-    {   // conv taps: reference stores filter f as a column of winlen*4 floats with the tap at
+    if (h.arch != 2) {   // conv taps: reference stores filter f as a column of winlen*4 floats with the tap at
         // every 4th slot (src/layers.c:155-157); device layout is [tap][filter]
         const size_t NF = h.nfilter;
         std::vector<float> taps((size_t)h.winlen * NF);
@@ -91,7 +92,7 @@ static int upload_model(sb2_engine *eng, DevModel *dm) {
         items.push_back({&dm->sW[l], compact(h.sW[l])});
         items.push_back({&dm->sW2[l], compact(h.sW2[l])});
     }
-    if (h.arch == 1)
+    if (h.arch >= 1)
         for (int i = 0; i < 2; i++) {
             items.push_back({&dm->comb_Wf[i], compact(h.comb_Wf[i])});
             items.push_back({&dm->comb_Wb[i], compact(h.comb_Wb[i])});
@@ -110,7 +111,7 @@ static int upload_model(sb2_engine *eng, DevModel *dm) {
         *it.first = dst;
         off += align_up(it.second.size() * sizeof(float), 256);
     }
-    if (h.arch == 1) {      // raw_r94: the scans read fp32 weights; its odd-shaped affine maps use the fp32 kernel
+    if (h.arch >= 1) {      // raw_r94 / events: the scans read fp32 weights; the odd-shaped affine maps use the fp32 kernel
         dm->loaded = true;
         return 0;
     }
@@ -1359,6 +1360,138 @@ extern "C" int sb2_batch_download_base_probs(sb2_batch *b, size_t read, float *d
     CUDA_OK(cudaMemcpy(dst, b->d_bprob + ((size_t)b->col_off[read] + read) * 8, ((size_t)b->nblock[read] + 1) * 8 * sizeof(float),
                        cudaMemcpyDeviceToHost));
     return 0;
+}
+
+// ------------------------------------------------------------------------------------
+// events (LSTM) model: nanonet_posterior (interface/scrappie.h:47-48, src/networks.c:146-194)
+// ------------------------------------------------------------------------------------
+static DevModel *get_events_model(sb2_engine *eng) {
+    DevModel *dm = &eng->models[SB2_NMODEL];
+    std::lock_guard<std::mutex> lock(eng->mu);
+    if (dm->loaded) return dm;
+    char path[1200];
+    snprintf(path, sizeof(path), "%s/nanonet_events.bin", eng->weights_dir);
+    void *blob = nullptr;
+    size_t nbytes = 0;
+    if (0 != sb2_read_file(path, &blob, &nbytes)) return nullptr;
+    int rc = sb2_host_model_parse(blob, nbytes, &dm->host);
+    free(blob);
+    if (0 == rc && (dm->host.arch != 2 || dm->host.H != 96)) { sb2_set_error("events model: unsupported shape"); rc = -1; }
+    if (0 == rc) rc = upload_model(eng, dm);
+    return (0 == rc) ? dm : nullptr;
+}
+
+namespace {
+struct EventsScratch {
+    std::vector<void *> ptrs;
+    template <typename T> T *get(size_t n) {
+        T *p = nullptr;
+        if (cudaMalloc(reinterpret_cast<void **>(&p), (n ? n : 1) * sizeof(T)) != cudaSuccess) return nullptr;
+        ptrs.push_back(p);
+        return p;
+    }
+    ~EventsScratch() { for (void *p : ptrs) cudaFree(p); }
+};
+}  // namespace
+
+extern "C" int sb2_events_posterior_batch(sb2_engine *eng, const event_table *tables, size_t ntable, float min_prob,
+                                          float tempW, float tempb, bool return_log, scrappie_matrix *out) {
+    if (nullptr == eng || nullptr == tables || nullptr == out || 0 == ntable) return -1;
+    if (!(min_prob >= 0.0f && min_prob <= 1.0f) || !(tempW > 0.0f) || !(tempb > 0.0f)) {
+        sb2_set_error("invalid min_prob / temperature");
+        return -1;
+    }
+    for (size_t i = 0; i < ntable; i++) out[i] = nullptr;
+    CUDA_OK(cudaSetDevice(eng->device));
+    DevModel *dm = get_events_model(eng);
+    if (nullptr == dm) return -1;
+    const sb2_host_model &h = dm->host;
+    const int H = (int)h.H, FW = (int)h.ffw, NF = (int)h.nfilter, NS = (int)h.nstate, OS = (int)h.ostride;
+
+    // features on the host, as the reference does (4 floats per event)
+    std::vector<size_t> keep;
+    std::vector<int> nblock, col_off(1, 0);
+    std::vector<float> feats;
+    for (size_t i = 0; i < ntable; i++) {
+        if (0 == tables[i].n || nullptr == tables[i].event || tables[i].end <= tables[i].start) continue;   // NULL like the reference
+        scrappie_matrix f = nanonet_features_from_events(tables[i], true);
+        if (nullptr == f) continue;
+        keep.push_back(i);
+        nblock.push_back((int)f->nc);
+        col_off.push_back(col_off.back() + (int)f->nc);
+        feats.insert(feats.end(), f->data.f, f->data.f + f->nc * 4);
+        free_scrappie_matrix(f);
+    }
+    if (keep.empty()) return 0;
+    const size_t N = (size_t)col_off.back();
+    EventsScratch sc;
+    float *d_feat = sc.get<float>(N * 4), *d_f3 = sc.get<float>(N * NF);
+    float *d_xf = sc.get<float>(N * 4 * H), *d_xb = sc.get<float>(N * 4 * H);
+    float *d_hf = sc.get<float>(N * H), *d_hb = sc.get<float>(N * H);
+    float *d_ff[2] = {sc.get<float>(N * FW), sc.get<float>(N * FW)};
+    float *d_post = sc.get<float>(N * OS);
+    int *d_nblock = sc.get<int>(keep.size()), *d_coloff = sc.get<int>(keep.size() + 1);
+    if (!d_feat || !d_f3 || !d_xf || !d_xb || !d_hf || !d_hb || !d_ff[0] || !d_ff[1] || !d_post || !d_nblock || !d_coloff) {
+        sb2_set_error("events posterior: out of device memory");
+        return -1;
+    }
+    CUDA_OK(cudaMemcpy(d_feat, feats.data(), N * 4 * sizeof(float), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(d_nblock, nblock.data(), keep.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(d_coloff, col_off.data(), (keep.size() + 1) * sizeof(int), cudaMemcpyHostToDevice));
+    BatchDims d{};
+    d.nread = (int)keep.size(); d.total_cols = (int)N;
+    d.max_cols = *std::max_element(nblock.begin(), nblock.end());
+    d.nblock = d_nblock; d.col_off = d_coloff;
+    cudaStream_t s = 0;
+    launch_window3(d_feat, d_f3, d, s);
+    const float *in = d_f3;
+    int K = NF;
+    uint64_t nl = 1;
+    for (int pair = 0; pair < 2; pair++) {
+        const int lf = 2 * pair, lb = 2 * pair + 1;
+        launch_affine(in, (int)N, K, dm->iW[lf], K, dm->b[lf], 4 * H, d_xf, 4 * H, 1.0f, 1.0f, 0, 0, s);
+        launch_affine(in, (int)N, K, dm->iW[lb], K, dm->b[lb], 4 * H, d_xb, 4 * H, 1.0f, 1.0f, 0, 0, s);
+        if (0 != launch_lstm_scan(d_xf, dm->sW[lf], dm->sW2[lf], d_hf, d, H, 0, s) ||
+            0 != launch_lstm_scan(d_xb, dm->sW[lb], dm->sW2[lb], d_hb, d, H, 1, s)) {
+            sb2_set_error("events posterior: unsupported LSTM width");
+            return -1;
+        }
+        // feedforward2_tanh: tanh(b + Wf lstmF + Wb lstmB)
+        launch_affine(d_hf, (int)N, H, dm->comb_Wf[pair], H, dm->comb_b[pair], FW, d_ff[pair], FW, 1.0f, 1.0f, 0, 0, s);
+        launch_affine(d_hb, (int)N, H, dm->comb_Wb[pair], H, nullptr, FW, d_ff[pair], FW, 1.0f, 1.0f, 2, 1, s);
+        nl += 6;
+        in = d_ff[pair];
+        K = FW;
+    }
+    launch_affine(in, (int)N, FW, dm->FF_W, FW, dm->FF_b, NS, d_post, OS, tempW / tempb, tempb, 1, 0, s);
+    launch_softmax_finish(d_post, (int)N, NS, OS, min_prob, return_log ? 1 : 0, s);
+    eng->launches += nl + 2;
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaStreamSynchronize(s));
+    int nmade = 0;
+    for (size_t i = 0; i < keep.size(); i++) {
+        scrappie_matrix post = make_scrappie_matrix((size_t)NS, (size_t)nblock[i]);
+        if (nullptr == post) continue;
+        if (cudaMemcpy2D(post->data.f, post->stride * sizeof(float), d_post + (size_t)col_off[i] * OS, OS * sizeof(float),
+                         std::min((size_t)OS, (size_t)post->stride) * sizeof(float), (size_t)nblock[i],
+                         cudaMemcpyDeviceToHost) != cudaSuccess) {
+            free_scrappie_matrix(post);
+            continue;
+        }
+        out[keep[i]] = post;
+        nmade++;
+    }
+    return nmade;
+}
+
+extern "C" scrappie_matrix nanonet_posterior(const event_table events, float min_prob, float tempW, float tempb,
+                                             bool return_log) {
+    if (0 == events.n || nullptr == events.event) return nullptr;
+    sb2_engine *eng = default_engine();
+    if (nullptr == eng) return nullptr;
+    scrappie_matrix post = nullptr;
+    if (1 != sb2_events_posterior_batch(eng, &events, 1, min_prob, tempW, tempb, return_log, &post)) return nullptr;
+    return post;
 }
 
 // ------------------------------------------------------------------------------------

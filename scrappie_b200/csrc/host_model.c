@@ -108,11 +108,14 @@ int sb2_host_model_parse(const void *blob, size_t nbytes, sb2_host_model *m) {
     const blob_entry *tab = (const blob_entry *)(p + 40);
     const float *data = (const float *)(p + 40 + table_bytes);
     const size_t nfloat = (nbytes - 40 - table_bytes) / sizeof(float);
-    if (m->arch > 1) { sb2_set_error("weight blob: unknown architecture %u", m->arch); sb2_host_model_free(m); return -1; }
+    if (m->arch > 2) { sb2_set_error("weight blob: unknown architecture %u", m->arch); sb2_host_model_free(m); return -1; }
     const int nlayer = (m->arch == 0) ? SB2_NLAYER : 4;
 
-    int rc = lookup(tab, nt, data, nfloat, "conv_W", &m->conv_W);
-    rc |= lookup(tab, nt, data, nfloat, "conv_b", &m->conv_b);
+    int rc = 0;
+    if (m->arch != 2) {
+        rc |= lookup(tab, nt, data, nfloat, "conv_W", &m->conv_W);
+        rc |= lookup(tab, nt, data, nfloat, "conv_b", &m->conv_b);
+    }
     for (int l = 0; l < nlayer; l++) {
         char nm[24];
         snprintf(nm, sizeof(nm), "gru%d_iW", l + 1);  rc |= lookup(tab, nt, data, nfloat, nm, &m->iW[l]);
@@ -120,7 +123,7 @@ int sb2_host_model_parse(const void *blob, size_t nbytes, sb2_host_model *m) {
         snprintf(nm, sizeof(nm), "gru%d_sW", l + 1);  rc |= lookup(tab, nt, data, nfloat, nm, &m->sW[l]);
         snprintf(nm, sizeof(nm), "gru%d_sW2", l + 1); rc |= lookup(tab, nt, data, nfloat, nm, &m->sW2[l]);
     }
-    if (m->arch == 1) {
+    if (m->arch >= 1) {
         for (int i = 0; i < 2; i++) {
             char nm[24];
             snprintf(nm, sizeof(nm), "comb%d_Wf", i + 1); rc |= lookup(tab, nt, data, nfloat, nm, &m->comb_Wf[i]);
@@ -134,6 +137,32 @@ int sb2_host_model_parse(const void *blob, size_t nbytes, sb2_host_model *m) {
         sb2_set_error("weight blob: missing or out-of-range tensor");
         sb2_host_model_free(m);
         return -1;
+    }
+    if (m->arch == 2) {
+        /* events model (src/networks.c:146-194): 12 windowed features -> 2 x (LSTM pair + feedforward2_tanh) -> softmax;
+         * sW[l] = [H][4H] recurrent weights, sW2[l] = the 3H peepholes */
+        m->H = m->sW[0].nr;
+        m->ffw = m->comb_b[0].nr;
+        m->nfilter = m->iW[0].nr;
+        m->nstate = m->FF_W.nc;
+        m->ostride = 4 * ((m->nstate + 3) / 4);
+        for (int l = 0; l < 4 && 0 == rc; l++) {
+            const uint32_t in = (l < 2) ? m->nfilter : m->ffw;
+            if (m->iW[l].nr != in || m->iW[l].stride != in || m->iW[l].nc != 4 * m->H || m->b[l].nr != 4 * m->H ||
+                m->sW[l].nr != m->H || m->sW[l].stride != m->H || m->sW[l].nc != 4 * m->H || m->sW2[l].nr != 3 * m->H)
+                rc = -1;
+        }
+        for (int i = 0; i < 2 && 0 == rc; i++)
+            if (m->comb_Wf[i].nr != m->H || m->comb_Wb[i].nr != m->H || m->comb_Wf[i].nc != m->ffw ||
+                m->comb_Wb[i].nc != m->ffw || m->comb_Wf[i].stride != m->H || m->comb_Wb[i].stride != m->H)
+                rc = -1;
+        if (m->FF_W.nr != m->ffw || m->FF_W.stride != m->ffw || m->nfilter % 4 != 0) rc = -1;
+        if (0 != rc) {
+            sb2_set_error("weight blob: unexpected shapes in the events model");
+            sb2_host_model_free(m);
+            return -1;
+        }
+        return 0;
     }
     m->winlen = m->conv_W.stride / 4;       /* taps sit at every 4th float of a filter column */
     m->nfilter = m->conv_W.nc;

@@ -70,6 +70,12 @@ void launch_trim(const float *raw, const int64_t *off, const int *nsample, int n
 void launch_medmad(const float *src, const int64_t *src_off, float *dst, const int64_t *dst_off, const int *nsample,
                    int nread, cudaStream_t s);
 
+// events model (kernels_lstm.cu): window(features, 3, 1) (src/layers.c:119-146) over [col][4] features -> [col][12],
+// and lstm_forward / lstm_backward (src/layers.c:673-832): Xin [col][4H], sW [4H][H], peep [3H] -> out [col][H]
+void launch_window3(const float *feat, float *out, const BatchDims &d, cudaStream_t s);
+int launch_lstm_scan(const float *Xin, const float *sW, const float *peep, float *out, const BatchDims &d, int H,
+                     int backward, cudaStream_t s);
+
 // decode_crf (src/decode.c:836-893)
 void launch_decode_crf(const float *trans, const BatchDims &d, int ostride, uint8_t *tb, int *path,
                        float *score, cudaStream_t s);

@@ -507,3 +507,36 @@ def test_basecall_raw_batch_bundled_reads(sb, engine, golden, model):
         assert abs(score - float(g[k + "_score"])) < (0.02 if model == "rgrgr_r94" else 0.25)
         assert [start, end] == list(g["r%d_trim" % i])
     assert calls[3][0] is None and calls[3][4] == 0          # too short: dropped like the reference does
+
+
+# ---- events (LSTM) model: nanonet_posterior of interface/scrappie.h ----------
+def test_events_posterior_vs_oracle_and_reference(sb, engine, oracle, golden):
+    """nanonet_posterior through the C-ABI: against the oracle restatement run on this host (same RSQRTPS, so the
+    features are bit-identical) and against the compiled reference's fixture; the k-mer argmax must agree."""
+    from oracle.oracle import synthetic_events
+    g = golden.ref_events
+    for n in (2, 50, 333, 1200):
+        ev = g["ev_%d_events" % n]
+        assert np.array_equal(ev, synthetic_events(n, n))
+        feat = sb.event_features(ev)
+        assert np.array_equal(feat.view(np.uint32), oracle.event_features(ev).view(np.uint32))
+        post = sb.calc_post_events(ev, min_prob=1e-5)
+        assert post.shape == (n, 1025)
+        got = post.data(as_numpy=True)
+        want = oracle.events_posterior(ev)[:, :1025]
+        assert np.abs(got - want).max() < LOG_TOL
+        assert np.array_equal(got.argmax(axis=1), want.argmax(axis=1))
+        # reference fixture: features made on the machine that generated it; only if this host's RSQRTPS gives the
+        # same bits is the tight tolerance meaningful
+        tol = LOG_TOL if np.array_equal(feat.view(np.uint32), g["ev_%d_features" % n][:, :4].view(np.uint32)) else 5e-2
+        assert np.abs(got[g["ev_%d_post_cols" % n]] - g["ev_%d_post_sub" % n][:, :1025]).max() < tol
+    # probabilities instead of logs; batch == singles; error paths
+    evs = [synthetic_events(7 + i, n) for i, n in enumerate((40, 1, 97, 513))]
+    posts = engine.events_posterior_batch(evs, min_prob=1e-5, log=False)
+    for ev, p in zip(evs, posts):
+        one = sb.calc_post_events(ev, min_prob=1e-5, log=False).data(as_numpy=True)
+        assert np.array_equal(p.data(as_numpy=True), one)
+        assert np.abs(one.sum(axis=1) - 1.0).max() < 1e-4
+        assert np.abs(one - oracle.events_posterior(ev, return_log=False)[:, :1025]).max() < 1e-5
+    empty = sb.EventTable(np.zeros((0, 3), dtype=np.float32))
+    assert not sb.lib().nanonet_posterior(empty.table, 1e-5, 1.0, 1.0, True)

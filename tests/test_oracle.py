@@ -165,3 +165,15 @@ def test_posterior_crf_exact(oracle, golden, key):
     g = golden.ref_posterior_crf
     got = oracle.posterior_crf(g[key + "_trans"])
     assert np.array_equal(got[:, :5], g[key + "_post"][:, :5])
+
+
+@pytest.mark.parametrize("n", [2, 50, 333, 1200])
+def test_events_model_against_reference_fixture(oracle, golden, n):
+    """Events (LSTM) model restatement vs the compiled reference (tests/golden/ref_events.npz)."""
+    g = golden.ref_events
+    ev = g["ev_%d_events" % n]
+    feat = oracle.event_features(ev)
+    same_cpu = np.array_equal(feat.view(np.uint32), g["ev_%d_features" % n][:, :4].view(np.uint32))
+    post = oracle.events_posterior(ev)
+    err = np.abs(post[g["ev_%d_post_cols" % n]][:, :1025] - g["ev_%d_post_sub" % n][:, :1025]).max()
+    assert err < (1e-4 if same_cpu else 5e-2), (err, same_cpu)

@@ -19,6 +19,9 @@ Blob layout (all little-endian):
     uint32   arch          0 = conv + 5 alternating unidirectional GRU layers + head (rgrgr / rnnrf),
                            1 = raw_r94: conv + 2 x (bidirectional GRU pair + feedforward2_tanh) + head
                                (src/networks.c:196-247); tensors gru1..4 = F1, B1, F2, B2, comb1/2 = FF1/FF2
+                           2 = nanonet events model (src/networks.c:146-194): no convolution; 2 x (bidirectional LSTM
+                               pair + feedforward2_tanh) + head; tensors gru1..4 = lstm F1, B1, F2, B2 with
+                               sW = [H][4H] recurrent weights and sW2 = the 3H peephole weights `p`
     uint32   reserved[2]
     n_tensor x { char name[24]; uint32 nr, nc, stride, offset }   offset in floats
     float    data[]      each tensor exactly as the reference stores it:
@@ -74,6 +77,20 @@ def extract_raw_r94(lib, outdir):
     write_blob("raw_r94", tensors, stride, 1, 0, 0, 1, outdir)
 
 
+def extract_events(lib, outdir):
+    """nanonet_posterior's weights (src/networks.c:146-194, src/models/nanonet_events.h)."""
+    tensors = []
+    for i, lay in enumerate(["lstmF1", "lstmB1", "lstmF2", "lstmB2"], 1):
+        for part, sym in (("iW", "iW"), ("b", "b"), ("sW", "sW"), ("sW2", "p")):
+            tensors.append(("gru%d_%s" % (i, part),) + read_mat(lib, "_%s_%s" % (lay, sym)))
+    for i in (1, 2):
+        for part in ("Wf", "Wb", "b"):
+            tensors.append(("comb%d_%s" % (i, part),) + read_mat(lib, "_FF%d_%s" % (i, part)))
+    tensors.append(("FF_W",) + read_mat(lib, "_FF3_W"))
+    tensors.append(("FF_b",) + read_mat(lib, "_FF3_b"))
+    write_blob("nanonet_events", tensors, 1, 0, 0, 0, 2, outdir)
+
+
 def write_blob(model, tensors, stride, conv_act, head, residual, arch, outdir):
     hdr = b"SB2WTS01" + struct.pack("<8I", len(tensors), stride, conv_act, head, residual, arch, 0, 0)
     table = b""
@@ -115,6 +132,7 @@ def main():
     for model in MODELS:
         extract(lib, model, outdir)
     extract_raw_r94(lib, outdir)
+    extract_events(lib, outdir)
 
 
 if __name__ == "__main__":

@@ -179,8 +179,28 @@ def posterior_crf_outputs():
     np.savez_compressed(os.path.join(OUT, "ref_posterior_crf.npz"), **d)
 
 
+def events_outputs():
+    """nanonet_posterior (interface/scrappie.h:47-48, the events / LSTM model) of the reference on seeded synthetic
+    event tables: studentised features (depend on the CPU's RSQRTPS approximation) and subsampled posterior columns."""
+    from oracle.oracle import synthetic_events
+    ref = Reference()
+    d = {}
+    for n in (2, 50, 333, 1200):
+        ev = synthetic_events(n, n)
+        post = ref.events_posterior(ev)
+        key = "ev_%d" % n
+        d[key + "_events"] = ev
+        d[key + "_features"] = ref.event_features(ev)
+        d[key + "_post_cols"] = np.arange(0, post.shape[0], 5)
+        d[key + "_post_sub"] = post[::5]
+    np.savez_compressed(os.path.join(OUT, "ref_events.npz"), **d)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "events":
+        events_outputs()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "posterior_crf":
         posterior_crf_outputs()
         sys.exit(0)
