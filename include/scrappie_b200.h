@@ -137,6 +137,21 @@ scrappie_matrix nanonet_rnnrf_r94_transitions(const raw_table signal, float min_
 float decode_transducer(const_scrappie_matrix logpost, float stay_pen, float skip_pen,
                         float local_pen, int *seq, bool allow_slip);
 float decode_crf(const_scrappie_matrix trans, int *path);
+/* python/pyscrap.h:44-61, src/decode.h:40-49 (src/decode.c:1420-1964, :1638): alignment of a log posterior to a
+   known k-mer sequence -- Viterbi (optionally with the path: nblock ints, -1 = start / end state) or forward score,
+   full or banded (poslow inclusive, poshigh exclusive, one pair per block).  NAN on failure.  The DP runs on the GPU.
+   encode_bases_to_integers (src/scrappie_seq_helpers.c:53-75): calloc'd array of n - state_len + 1 k-mer states. */
+float map_to_sequence_viterbi(const_scrappie_matrix logpost, float stay_pen, float skip_pen, float local_pen,
+                              int const *seq, size_t seqlen, int *path);
+float map_to_sequence_forward(const_scrappie_matrix logpost, float stay_pen, float skip_pen, float local_pen,
+                              int const *seq, size_t seqlen);
+float map_to_sequence_viterbi_banded(const_scrappie_matrix logpost, float stay_pen, float skip_pen, float local_pen,
+                                     int const *seq, size_t seqlen, size_t const *poslow, size_t const *poshigh);
+float map_to_sequence_forward_banded(const_scrappie_matrix logpost, float stay_pen, float skip_pen, float local_pen,
+                                     int const *seq, size_t seqlen, size_t const *poslow, size_t const *poshigh);
+bool are_bounds_sane(size_t const *low, size_t const *high, size_t nblock, size_t seqlen);
+int *encode_bases_to_integers(char const *seq, size_t n, size_t state_len);
+
 /* python/pyscrap.h:22, src/decode.h:30 (src/decode.c:928-1012): per-block state probabilities (ACGT-) of a CRF;
    new 5 x (nblock + 1) matrix owned by the caller, NULL on failure */
 scrappie_matrix posterior_crf(const_scrappie_matrix trans);

@@ -87,11 +87,32 @@ class Oracle:
                                             C.c_float, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
         L.sb2o_convolution.argtypes = [c_float_p, C.c_size_t, C.POINTER(_Tensor), C.POINTER(_Tensor),
                                        C.c_size_t, c_float_p]
+        L.sb2o_map_to_sequence.restype = C.c_float
+        L.sb2o_map_to_sequence.argtypes = [c_float_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_float, C.c_float, C.c_float,
+                                           c_int_p, C.c_size_t, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), c_int_p]
         L.sb2o_event_features.argtypes = [c_float_p, C.c_size_t, c_float_p]
         L.sb2o_events_posterior.restype = C.c_size_t
         L.sb2o_events_posterior.argtypes = [C.POINTER(_Model), c_float_p, C.c_size_t, C.c_float, C.c_float,
                                             C.c_float, C.c_int, c_float_p]
         self._models = {}
+
+    def map_to_sequence(self, post, nstate, seq, stay_pen=0.0, skip_pen=0.0, local_pen=4.0, forward=False, bands=None,
+                        want_path=False):
+        """post [nblock, stride] log posterior; seq: k-mer states.  Returns (score, path or None)."""
+        post = np.ascontiguousarray(post, dtype=np.float32)
+        seq = np.ascontiguousarray(seq, dtype=np.int32)
+        nblock, stride = post.shape
+        path = np.zeros(nblock, dtype=np.int32) if want_path else None
+        lo = hi = None
+        if bands is not None:
+            lo = np.ascontiguousarray(bands[0], dtype=np.uintp)
+            hi = np.ascontiguousarray(bands[1], dtype=np.uintp)
+        sp = C.POINTER(C.c_size_t)
+        score = self.lib.sb2o_map_to_sequence(_fp(post), nblock, nstate, stride, stay_pen, skip_pen, local_pen, _ip(seq),
+                                              seq.size, int(forward), lo.ctypes.data_as(sp) if lo is not None else None,
+                                              hi.ctypes.data_as(sp) if hi is not None else None,
+                                              _ip(path) if want_path else None)
+        return float(score), path
 
     # -- events model (src/networks.c:146-194) -------------------------------
     def event_features(self, ev):
@@ -311,6 +332,16 @@ class Reference:
         L.crfpath_to_basecall.argtypes = [c_int_p, C.c_size_t, c_int_p]
         L.posterior_crf.restype = C.POINTER(_Mat)
         L.posterior_crf.argtypes = [C.POINTER(_Mat)]
+        sp = C.POINTER(C.c_size_t)
+        L.map_to_sequence_viterbi.restype = C.c_float
+        L.map_to_sequence_viterbi.argtypes = [C.POINTER(_Mat), C.c_float, C.c_float, C.c_float, c_int_p, C.c_size_t, c_int_p]
+        L.map_to_sequence_forward.restype = C.c_float
+        L.map_to_sequence_forward.argtypes = [C.POINTER(_Mat), C.c_float, C.c_float, C.c_float, c_int_p, C.c_size_t]
+        for f in (L.map_to_sequence_viterbi_banded, L.map_to_sequence_forward_banded):
+            f.restype = C.c_float
+            f.argtypes = [C.POINTER(_Mat), C.c_float, C.c_float, C.c_float, c_int_p, C.c_size_t, sp, sp]
+        L.encode_bases_to_integers.restype = C.POINTER(C.c_int)
+        L.encode_bases_to_integers.argtypes = [C.c_char_p, C.c_size_t, C.c_size_t]
         L.nanonet_posterior.restype = C.POINTER(_Mat)
         L.nanonet_posterior.argtypes = [_EventTable, C.c_float, C.c_float, C.c_float, C.c_bool]
         L.nanonet_features_from_events.restype = C.POINTER(_Mat)
@@ -370,6 +401,34 @@ class Reference:
         mp = self._mat(trans, 25)
         path = np.zeros(trans.shape[0] + 1, dtype=np.int32)
         score = self.lib.decode_crf(mp, _ip(path))
+        self.lib.free_scrappie_matrix(mp)
+        return float(score), path
+
+    def encode_bases(self, bases, klen):
+        b = bases.encode()
+        ptr = self.lib.encode_bases_to_integers(b, len(b), klen)
+        out = np.ctypeslib.as_array(ptr, shape=(len(b) - klen + 1,)).copy()
+        self.libc.free(ptr)
+        return out
+
+    def map_to_sequence(self, post, nstate, seq, stay_pen=0.0, skip_pen=0.0, local_pen=4.0, forward=False, bands=None,
+                        want_path=False):
+        mp = self._mat(post, nstate)
+        seq = np.ascontiguousarray(seq, dtype=np.int32)
+        path = None
+        if bands is None:
+            if forward:
+                score = self.lib.map_to_sequence_forward(mp, stay_pen, skip_pen, local_pen, _ip(seq), seq.size)
+            else:
+                path = np.zeros(post.shape[0], dtype=np.int32) if want_path else None
+                score = self.lib.map_to_sequence_viterbi(mp, stay_pen, skip_pen, local_pen, _ip(seq), seq.size,
+                                                         _ip(path) if want_path else None)
+        else:
+            sp = C.POINTER(C.c_size_t)
+            lo = np.ascontiguousarray(bands[0], dtype=np.uintp)
+            hi = np.ascontiguousarray(bands[1], dtype=np.uintp)
+            f = self.lib.map_to_sequence_forward_banded if forward else self.lib.map_to_sequence_viterbi_banded
+            score = f(mp, stay_pen, skip_pen, local_pen, _ip(seq), seq.size, lo.ctypes.data_as(sp), hi.ctypes.data_as(sp))
         self.lib.free_scrappie_matrix(mp)
         return float(score), path
 

@@ -659,6 +659,79 @@ int sb2o_posterior_crf(const float *trans, size_t nblock, size_t stride, float *
     return 0;
 }
 
+/* map_to_sequence_viterbi / _forward / _viterbi_banded / _forward_banded, src/decode.c:1420-1964.
+ * One restatement with two switches: `forward` replaces max by logsumexpf, `low/high` (may be NULL) are the
+ * band limits per block.  The banded variants only rewrite the positions inside the band of each block, so
+ * positions outside it keep the value they had two blocks earlier (the two score vectors alternate) -- kept.
+ * path (viterbi, unbanded only; may be NULL): nblock ints, -1 for the start / end states. */
+float sb2o_map_to_sequence(const float *lp, size_t nblock, size_t nst, size_t stride, float stay_pen, float skip_pen,
+                           float local_pen, const int *seq, size_t seqlen, int forward, const size_t *low,
+                           const size_t *high, int *path) {
+    if (NULL == lp || NULL == seq || seqlen < 3 || 0 == nblock) return NAN;
+    const size_t STAY = nst - 1, START = seqlen, END = seqlen + 1, ns = seqlen + 2;
+    const int banded = (NULL != low && NULL != high);
+    float *c = calloc(ns, sizeof(float)), *p = calloc(ns, sizeof(float));
+    int *tb = (!forward && !banded && NULL != path) ? malloc(nblock * ns * sizeof(int)) : NULL;
+#define SB2O_COMB(a, b) (forward ? sb2o_logsumexpf((a), (b)) : fmaxf((a), (b)))
+    for (size_t i = 0; i < ns; i++) { c[i] = -1e30f; p[i] = -1e30f; }
+    if (banded) p[START] = 0.0f; else c[START] = 0.0f;
+    for (size_t blk = 0; blk < nblock; blk++) {
+        const float *l = lp + blk * stride;
+        int *t = tb ? tb + blk * ns : NULL;
+        if (!(banded && 0 == blk)) { float *tmp = p; p = c; c = tmp; }
+        const float loc = forward ? sb2o_logsumexpf(-local_pen, l[STAY]) : fmaxf(-local_pen, l[STAY]);
+        c[START] = p[START] + loc;
+        c[END] = p[END] + loc;
+        if (t) { t[START] = (int)START; t[END] = (int)END; }
+        if (!banded) {
+            for (size_t pos = 0; pos < seqlen; pos++) { c[pos] = p[pos] - stay_pen + l[STAY]; if (t) t[pos] = (int)pos; }
+            for (size_t pos = 1; pos < seqlen; pos++) {
+                const float sc = p[pos - 1] + l[seq[pos]];
+                if (forward) c[pos] = sb2o_logsumexpf(c[pos], sc);
+                else if (sc > c[pos]) { c[pos] = sc; if (t) t[pos] = (int)pos - 1; }
+            }
+            for (size_t pos = 2; pos < seqlen; pos++) {
+                const float sc = p[pos - 2] - skip_pen + l[seq[pos]];
+                if (forward) c[pos] = sb2o_logsumexpf(c[pos], sc);
+                else if (sc > c[pos]) { c[pos] = sc; if (t) t[pos] = (int)pos - 2; }
+            }
+            const float s0 = p[START] + l[seq[0]];
+            if (forward) c[0] = sb2o_logsumexpf(c[0], s0);
+            else if (s0 > c[0]) { c[0] = s0; if (t) t[0] = (int)START; }
+            const float se = p[seqlen - 1] - local_pen;
+            if (forward) c[END] = sb2o_logsumexpf(c[END], se);
+            else if (se > c[END]) { c[END] = se; if (t) t[END] = (int)seqlen - 1; }
+        } else if (0 == blk) {
+            c[0] = SB2O_COMB(c[0], p[0] + l[STAY] - stay_pen);
+            if (high[0] > 0) c[1] = l[seq[1]];
+            if (high[0] > 1) c[2] = l[seq[2]] - skip_pen;
+            c[END] = SB2O_COMB(c[END], p[START] - local_pen);
+            c[0] = SB2O_COMB(c[0], p[START] + l[seq[0]]);
+            c[END] = SB2O_COMB(c[END], p[seqlen - 1] - local_pen);
+        } else {
+            for (size_t pos = low[blk]; pos < high[blk - 1]; pos++) c[pos] = p[pos] - stay_pen + l[STAY];
+            size_t a = low[blk] > low[blk - 1] + 1 ? low[blk] : low[blk - 1] + 1;
+            size_t b = high[blk] < high[blk - 1] + 1 ? high[blk] : high[blk - 1] + 1;
+            for (size_t pos = a; pos < b; pos++) c[pos] = SB2O_COMB(p[pos - 1] + l[seq[pos]], c[pos]);
+            a = low[blk] > low[blk - 1] + 2 ? low[blk] : low[blk - 1] + 2;
+            b = high[blk] < high[blk - 1] + 2 ? high[blk] : high[blk - 1] + 2;
+            for (size_t pos = a; pos < b; pos++) c[pos] = SB2O_COMB(p[pos - 2] - skip_pen + l[seq[pos]], c[pos]);
+            if (0 == low[blk]) c[0] = SB2O_COMB(c[0], p[START] + l[seq[0]]);
+            c[END] = SB2O_COMB(c[END], p[seqlen - 1] - local_pen);
+        }
+    }
+    const float score = SB2O_COMB(c[seqlen - 1], c[END]);
+#undef SB2O_COMB
+    if (tb) {
+        path[nblock - 1] = (c[seqlen - 1] > c[END]) ? (int)seqlen - 1 : (int)END;
+        for (size_t blk = nblock - 1; blk > 0; blk--) path[blk - 1] = tb[blk * ns + path[blk]];
+        for (size_t blk = 0; blk < nblock; blk++)
+            if ((int)START == path[blk] || (int)END == path[blk]) path[blk] = -1;
+    }
+    free(tb); free(p); free(c);
+    return score;
+}
+
 static const char BASES[4] = {'A', 'C', 'G', 'T'};
 
 /* overlap(), src/decode.c:367-382 */

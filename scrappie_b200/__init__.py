@@ -120,6 +120,14 @@ def lib():
         "decode_transducer": (C.c_float, [mp, C.c_float, C.c_float, C.c_float, _i32p, C.c_bool]),
         "decode_crf": (C.c_float, [mp, _i32p]),
         "posterior_crf": (mp, [mp]),
+        "map_to_sequence_viterbi": (C.c_float, [mp, C.c_float, C.c_float, C.c_float, _i32p, C.c_size_t, _i32p]),
+        "map_to_sequence_forward": (C.c_float, [mp, C.c_float, C.c_float, C.c_float, _i32p, C.c_size_t]),
+        "map_to_sequence_viterbi_banded": (C.c_float, [mp, C.c_float, C.c_float, C.c_float, _i32p, C.c_size_t,
+                                                       C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+        "map_to_sequence_forward_banded": (C.c_float, [mp, C.c_float, C.c_float, C.c_float, _i32p, C.c_size_t,
+                                                       C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+        "are_bounds_sane": (C.c_bool, [C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.c_size_t, C.c_size_t]),
+        "encode_bases_to_integers": (C.c_void_p, [C.c_char_p, C.c_size_t, C.c_size_t]),
         "nanonet_posterior": (mp, [_EventTable, C.c_float, C.c_float, C.c_float, C.c_bool]),
         "nanonet_features_from_events": (mp, [_EventTable, C.c_bool]),
         "sb2_events_posterior_batch": (C.c_int, [C.c_void_p, C.POINTER(_EventTable), C.c_size_t, C.c_float, C.c_float,
@@ -383,6 +391,67 @@ def calc_post_events(events, min_prob=1e-6, log=True, tempW=1.0, tempb=1.0):
     if not ptr:
         raise RuntimeError("nanonet_posterior failed: %s" % last_error())
     return ScrappyMatrix(ptr)
+
+
+def guess_state_properties(nstate):
+    """(alphabet length, k-mer length) of a posterior with `nstate` rows (python/scrappy/__init__.py:25-44)."""
+    for alpha_len in (4,):
+        kmer_len = int(round(np.log(nstate - 1) / np.log(alpha_len)))
+        if alpha_len ** kmer_len + 1 == nstate:
+            return alpha_len, kmer_len
+    raise ValueError("Cannot guess state properties from %d states." % nstate)
+
+
+def encode_bases(sequence, kmer_len):
+    """k-mer states of a base sequence (encode_bases_to_integers)."""
+    b = sequence.encode()
+    ptr = lib().encode_bases_to_integers(b, len(b), kmer_len)
+    if not ptr:
+        raise RuntimeError('An unknown error occurred whilst encoding sequence.')
+    n = len(b) - kmer_len + 1
+    out = np.ctypeslib.as_array(C.cast(ptr, _i32p), shape=(n,)).copy()
+    _libc.free(C.c_void_p(ptr))
+    return out
+
+
+def map_post_to_sequence(post, sequence, stay_pen=0, skip_pen=0, local_pen=4.0, viterbi=False, path=False, bands=None):
+    """Local-global alignment of a posterior to a base sequence, forward or Viterbi, optionally banded
+    (python/scrappy/__init__.py:492-578; same arguments and return value: (score, path or None))."""
+    if path and not viterbi:
+        raise ValueError('Cannot calulate path with `viterbi==False`.')
+    if not isinstance(post, ScrappyMatrix):
+        raise TypeError('`post` should be a ScrappyMatrix.')
+    nblock, nstate = post.shape
+    alpha_len, kmer_len = guess_state_properties(nstate)
+    seq = encode_bases(sequence, kmer_len)
+    seq_len = seq.size
+    path_data = np.zeros(nblock, dtype=np.int32) if (viterbi and path) else None
+    sp = C.POINTER(C.c_size_t)
+    if bands is None:
+        if viterbi:
+            score = lib().map_to_sequence_viterbi(post.data(), stay_pen, skip_pen, local_pen, _ip(seq), seq_len,
+                                                  _ip(path_data) if path_data is not None else None)
+        else:
+            score = lib().map_to_sequence_forward(post.data(), stay_pen, skip_pen, local_pen, _ip(seq), seq_len)
+    else:
+        if isinstance(bands, int):
+            gradient = seq_len / nblock
+            hband = 2 * bands * gradient / 2
+            bands = [np.ascontiguousarray(np.array(x, dtype=np.uintp)) for x in (
+                [max(0, x * gradient - hband) for x in range(nblock)],
+                [min(seq_len, x * gradient + hband) for x in range(nblock)])]
+        elif len(bands) == 2:
+            bands = [np.ascontiguousarray(x, dtype=np.uintp) for x in bands]
+        else:
+            raise ValueError('`bands` should be `None`, an integer, or length 2.')
+        lo, hi = (x.ctypes.data_as(sp) for x in bands)
+        if not lib().are_bounds_sane(lo, hi, nblock, seq_len):
+            raise ValueError('Supplied banding structure is not valid.')
+        func = lib().map_to_sequence_viterbi_banded if viterbi else lib().map_to_sequence_forward_banded
+        score = func(post.data(), stay_pen, skip_pen, local_pen, _ip(seq), seq_len, lo, hi)
+    if score != score:
+        raise RuntimeError('An unknown error occurred during alignment.')
+    return score, path_data
 
 
 def posterior_crf(post):

@@ -1362,6 +1362,99 @@ extern "C" int sb2_batch_download_base_probs(sb2_batch *b, size_t read, float *d
     return 0;
 }
 
+namespace {
+struct EventsScratch {
+    std::vector<void *> ptrs;
+    template <typename T> T *get(size_t n) {
+        T *p = nullptr;
+        if (cudaMalloc(reinterpret_cast<void **>(&p), (n ? n : 1) * sizeof(T)) != cudaSuccess) return nullptr;
+        ptrs.push_back(p);
+        return p;
+    }
+    ~EventsScratch() { for (void *p : ptrs) cudaFree(p); }
+};
+}  // namespace
+
+// ------------------------------------------------------------------------------------
+// map_to_sequence_* (src/decode.c:1420-1964) on a host posterior
+// ------------------------------------------------------------------------------------
+static bool bounds_sane(const size_t *low, const size_t *high, size_t nblock, size_t seqlen) {
+    // are_bounds_sane, src/decode.c:1638-1691
+    if (nullptr == low || nullptr == high || 0 == nblock) return false;
+    bool ok = (low[0] == 0) && (high[nblock - 1] == seqlen);
+    for (size_t i = 0; i < nblock && ok; i++) ok = low[i] <= seqlen && high[i] <= seqlen && low[i] <= high[i];
+    for (size_t i = 1; i < nblock && ok; i++) ok = low[i] <= high[i - 1] && low[i] >= low[i - 1] && high[i] >= high[i - 1];
+    return ok;
+}
+
+extern "C" bool are_bounds_sane(size_t const *low, size_t const *high, size_t nblock, size_t seqlen) {
+    const bool ok = bounds_sane(low, high, nblock, seqlen);
+    if (!ok) fprintf(stderr, "scrappie_b200: banding structure is not valid\n");
+    return ok;
+}
+
+static float map_to_sequence_run(const_scrappie_matrix logpost, float stay_pen, float skip_pen, float local_pen,
+                                 const int *seq, size_t seqlen, bool forward, const size_t *low, const size_t *high,
+                                 int *path) {
+    if (nullptr == logpost || nullptr == seq || seqlen < 3 || 0 == logpost->nc || seqlen > (size_t)1 << 24) return NAN;
+    const bool banded = (nullptr != low || nullptr != high);
+    const size_t nb = logpost->nc, stride = logpost->stride;
+    if (banded && !are_bounds_sane(low, high, nb, seqlen)) return NAN;
+    for (size_t i = 0; i < seqlen; i++)
+        if (seq[i] < 0 || (size_t)seq[i] + 1 >= logpost->nr) { sb2_set_error("map_to_sequence: state out of range"); return NAN; }
+    sb2_engine *eng = default_engine();
+    if (nullptr == eng || cudaSetDevice(eng->device) != cudaSuccess) return NAN;
+    EventsScratch sc;
+    float *d_lp = sc.get<float>(nb * stride), *d_buf = sc.get<float>(2 * (seqlen + 2)), *d_score = sc.get<float>(1);
+    int *d_seq = sc.get<int>(seqlen), *d_low = nullptr, *d_high = nullptr, *d_path = nullptr;
+    uint8_t *d_tb = nullptr, *d_tbe = nullptr;
+    const bool want_path = (!forward && !banded && nullptr != path);
+    if (want_path) { d_tb = sc.get<uint8_t>(nb * seqlen); d_tbe = sc.get<uint8_t>(nb); d_path = sc.get<int>(nb); }
+    std::vector<int> lo32, hi32;
+    if (banded) {
+        lo32.assign(low, low + nb); hi32.assign(high, high + nb);
+        d_low = sc.get<int>(nb); d_high = sc.get<int>(nb);
+    }
+    if (!d_lp || !d_buf || !d_score || !d_seq || (want_path && (!d_tb || !d_tbe || !d_path)) || (banded && (!d_low || !d_high))) {
+        sb2_set_error("map_to_sequence: out of device memory");
+        return NAN;
+    }
+    bool ok = cudaMemcpy(d_lp, logpost->data.f, nb * stride * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess &&
+              cudaMemcpy(d_seq, seq, seqlen * sizeof(int), cudaMemcpyHostToDevice) == cudaSuccess;
+    if (ok && banded)
+        ok = cudaMemcpy(d_low, lo32.data(), nb * sizeof(int), cudaMemcpyHostToDevice) == cudaSuccess &&
+             cudaMemcpy(d_high, hi32.data(), nb * sizeof(int), cudaMemcpyHostToDevice) == cudaSuccess;
+    float score = NAN;
+    if (ok) {
+        launch_map_to_sequence(d_lp, (int)nb, (int)logpost->nr, (int)stride, stay_pen, skip_pen, local_pen, d_seq, (int)seqlen,
+                               d_low, d_high, forward ? 1 : 0, d_buf, d_tb, d_tbe, d_score, d_path, 0);
+        eng->launches += 1;
+        ok = cudaGetLastError() == cudaSuccess && cudaMemcpy(&score, d_score, sizeof(float), cudaMemcpyDeviceToHost) == cudaSuccess;
+        if (ok && want_path) ok = cudaMemcpy(path, d_path, nb * sizeof(int), cudaMemcpyDeviceToHost) == cudaSuccess;
+    }
+    if (!ok) { sb2_set_error("map_to_sequence: CUDA error %s", cudaGetErrorString(cudaGetLastError())); return NAN; }
+    return score;
+}
+
+extern "C" float map_to_sequence_viterbi(const_scrappie_matrix logpost, float stay_pen, float skip_pen, float local_pen,
+                                         int const *seq, size_t seqlen, int *path) {
+    return map_to_sequence_run(logpost, stay_pen, skip_pen, local_pen, seq, seqlen, false, nullptr, nullptr, path);
+}
+extern "C" float map_to_sequence_forward(const_scrappie_matrix logpost, float stay_pen, float skip_pen, float local_pen,
+                                         int const *seq, size_t seqlen) {
+    return map_to_sequence_run(logpost, stay_pen, skip_pen, local_pen, seq, seqlen, true, nullptr, nullptr, nullptr);
+}
+extern "C" float map_to_sequence_viterbi_banded(const_scrappie_matrix logpost, float stay_pen, float skip_pen, float local_pen,
+                                                int const *seq, size_t seqlen, size_t const *poslow, size_t const *poshigh) {
+    if (nullptr == poslow || nullptr == poshigh) return NAN;
+    return map_to_sequence_run(logpost, stay_pen, skip_pen, local_pen, seq, seqlen, false, poslow, poshigh, nullptr);
+}
+extern "C" float map_to_sequence_forward_banded(const_scrappie_matrix logpost, float stay_pen, float skip_pen, float local_pen,
+                                                int const *seq, size_t seqlen, size_t const *poslow, size_t const *poshigh) {
+    if (nullptr == poslow || nullptr == poshigh) return NAN;
+    return map_to_sequence_run(logpost, stay_pen, skip_pen, local_pen, seq, seqlen, true, poslow, poshigh, nullptr);
+}
+
 // ------------------------------------------------------------------------------------
 // events (LSTM) model: nanonet_posterior (interface/scrappie.h:47-48, src/networks.c:146-194)
 // ------------------------------------------------------------------------------------
@@ -1381,18 +1474,6 @@ static DevModel *get_events_model(sb2_engine *eng) {
     return (0 == rc) ? dm : nullptr;
 }
 
-namespace {
-struct EventsScratch {
-    std::vector<void *> ptrs;
-    template <typename T> T *get(size_t n) {
-        T *p = nullptr;
-        if (cudaMalloc(reinterpret_cast<void **>(&p), (n ? n : 1) * sizeof(T)) != cudaSuccess) return nullptr;
-        ptrs.push_back(p);
-        return p;
-    }
-    ~EventsScratch() { for (void *p : ptrs) cudaFree(p); }
-};
-}  // namespace
 
 extern "C" int sb2_events_posterior_batch(sb2_engine *eng, const event_table *tables, size_t ntable, float min_prob,
                                           float tempW, float tempb, bool return_log, scrappie_matrix *out) {

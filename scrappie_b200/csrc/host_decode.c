@@ -178,3 +178,28 @@ int homopolymer_path(const_scrappie_matrix post, int *viterbipath,
     free(runs);
     return 0;
 }
+
+/* encode_bases_to_integers, src/scrappie_seq_helpers.c:15-75: A/C/G/T (either case) -> base-4 k-mer states;
+ * NULL when a base is not recognised (the reference also warns on stderr). */
+int *encode_bases_to_integers(char const *seq, size_t n, size_t state_len) {
+    if (NULL == seq || 0 == state_len || n < state_len) return NULL;
+    const size_t nstate = n - state_len + 1;
+    int *iseq = calloc(nstate, sizeof(int));
+    if (NULL == iseq) return NULL;
+    for (size_t i = 0; i < nstate; i++) {
+        int ib = 0;
+        for (size_t j = 0; j < state_len; j++) {
+            int b;
+            switch (seq[i + j]) {
+            case 'A': case 'a': b = 0; break;
+            case 'C': case 'c': b = 1; break;
+            case 'G': case 'g': b = 2; break;
+            case 'T': case 't': b = 3; break;
+            default: free(iseq); return NULL;
+            }
+            ib = ib * 4 + b;
+        }
+        iseq[i] = ib;
+    }
+    return iseq;
+}

@@ -76,6 +76,12 @@ void launch_window3(const float *feat, float *out, const BatchDims &d, cudaStrea
 int launch_lstm_scan(const float *Xin, const float *sW, const float *peep, float *out, const BatchDims &d, int H,
                      int backward, cudaStream_t s);
 
+// map_to_sequence_{viterbi,forward}[_banded] (src/decode.c:1420-1964), kernels_map.cu.  buf: 2 * (seqlen + 2)
+// floats; tb (seqlen bytes per block) / tb_end (1 byte per block) / path only for the unbanded Viterbi path
+void launch_map_to_sequence(const float *lp, int nblock, int nst, int stride, float stay_pen, float skip_pen,
+                            float local_pen, const int *seq, int seqlen, const int *low, const int *high, int forward,
+                            float *buf, uint8_t *tb, uint8_t *tb_end, float *score, int *path, cudaStream_t s);
+
 // decode_crf (src/decode.c:836-893)
 void launch_decode_crf(const float *trans, const BatchDims &d, int ostride, uint8_t *tb, int *path,
                        float *score, cudaStream_t s);

@@ -540,3 +540,44 @@ def test_events_posterior_vs_oracle_and_reference(sb, engine, oracle, golden):
         assert np.abs(one - oracle.events_posterior(ev, return_log=False)[:, :1025]).max() < 1e-5
     empty = sb.EventTable(np.zeros((0, 3), dtype=np.float32))
     assert not sb.lib().nanonet_posterior(empty.table, 1e-5, 1.0, 1.0, True)
+
+
+# ---- map_to_sequence_*  ----------------------------------------------
+def test_map_to_sequence_vs_reference_fixture(sb, golden):
+    """All four alignment entry points through the C-ABI on the reference's own posterior: Viterbi scores and the
+    Viterbi path bit-exact, forward scores within 1e-3 (expf / log1pf differ from glibc by a few ulp per block)."""
+    g = golden.ref_map
+    post = sb.ScrappyMatrix.from_numpy(g["post"], nr=1025)
+    L = sb.lib()
+    import ctypes as C
+    sp = C.POINTER(C.c_size_t)
+    for name, sq in (("a", g["seq"]), ("b", g["seq2"])):
+        sq = np.ascontiguousarray(sq, dtype=np.int32)
+        lo = np.ascontiguousarray(g[name + "_low"], dtype=np.uintp)
+        hi = np.ascontiguousarray(g[name + "_high"], dtype=np.uintp)
+        for pens in ((0.0, 0.0, 4.0), (0.1, 0.3, 2.0)):
+            key = "%s_%g_%g_%g" % ((name,) + pens)
+            path = np.zeros(post.shape[0], dtype=np.int32)
+            sv = L.map_to_sequence_viterbi(post.data(), *pens, sb._ip(sq), sq.size, sb._ip(path))
+            assert np.float32(sv) == g[key + "_viterbi"]
+            assert np.array_equal(path, g[key + "_path"])
+            sf = L.map_to_sequence_forward(post.data(), *pens, sb._ip(sq), sq.size)
+            assert abs(sf - float(g[key + "_forward"])) < 1e-3
+            svb = L.map_to_sequence_viterbi_banded(post.data(), *pens, sb._ip(sq), sq.size, lo.ctypes.data_as(sp), hi.ctypes.data_as(sp))
+            assert np.float32(svb) == g[key + "_viterbi_banded"]
+            sfb = L.map_to_sequence_forward_banded(post.data(), *pens, sb._ip(sq), sq.size, lo.ctypes.data_as(sp), hi.ctypes.data_as(sp))
+            assert abs(sfb - float(g[key + "_forward_banded"])) < 1e-3
+    # scrappy-style wrapper (python/test/test_scrappy.py:77-103 style): own basecall maps onto itself
+    bases = str(g["bases"])
+    score, path = sb.map_post_to_sequence(post, bases, viterbi=True, path=True)
+    assert np.float32(score) == g["a_0_0_4_viterbi"] and np.array_equal(path, g["a_0_0_4_path"])
+    fscore, none = sb.map_post_to_sequence(post, bases, viterbi=False)
+    assert none is None and fscore >= score - 1e-3           # the forward score sums over all paths
+    bscore, _ = sb.map_post_to_sequence(post, bases, viterbi=True, bands=40)
+    assert np.isfinite(bscore)
+    with pytest.raises(ValueError):
+        sb.map_post_to_sequence(post, bases, viterbi=False, path=True)
+    with pytest.raises(ValueError):
+        sb.map_post_to_sequence(post, bases, bands=(np.ones(post.shape[0]), np.zeros(post.shape[0])))
+    with pytest.raises(RuntimeError):
+        sb.map_post_to_sequence(post, "ACGTNACGT")

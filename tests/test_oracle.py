@@ -177,3 +177,18 @@ def test_events_model_against_reference_fixture(oracle, golden, n):
     post = oracle.events_posterior(ev)
     err = np.abs(post[g["ev_%d_post_cols" % n]][:, :1025] - g["ev_%d_post_sub" % n][:, :1025]).max()
     assert err < (1e-4 if same_cpu else 5e-2), (err, same_cpu)
+
+
+def test_map_to_sequence_exact(oracle, golden):
+    """map_to_sequence restatement (all four variants) vs the compiled reference: same libm, same order -> exact."""
+    g = golden.ref_map
+    post = g["post"]
+    for name, sq in (("a", g["seq"]), ("b", g["seq2"])):
+        bands = (g[name + "_low"], g[name + "_high"])
+        for pens in ((0.0, 0.0, 4.0), (0.1, 0.3, 2.0)):
+            key = "%s_%g_%g_%g" % ((name,) + pens)
+            sv, pv = oracle.map_to_sequence(post, 1025, sq, *pens, forward=False, want_path=True)
+            assert np.float32(sv) == g[key + "_viterbi"] and np.array_equal(pv, g[key + "_path"])
+            assert np.float32(oracle.map_to_sequence(post, 1025, sq, *pens, forward=True)[0]) == g[key + "_forward"]
+            assert np.float32(oracle.map_to_sequence(post, 1025, sq, *pens, forward=False, bands=bands)[0]) == g[key + "_viterbi_banded"]
+            assert np.float32(oracle.map_to_sequence(post, 1025, sq, *pens, forward=True, bands=bands)[0]) == g[key + "_forward_banded"]

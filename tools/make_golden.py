@@ -196,8 +196,41 @@ def events_outputs():
     np.savez_compressed(os.path.join(OUT, "ref_events.npz"), **d)
 
 
+def map_outputs():
+    """map_to_sequence_{viterbi,forward}[_banded] of the reference on the posterior of a seeded synthetic read,
+    against its own basecall and a perturbed copy; bands = a diagonal band of half-width 30 positions."""
+    ref = Reference()
+    x = synthetic_read(4242, 3000)
+    score, path, bases, post = ref.basecall_raw("rgrgr_r94", x)
+    seq = ref.encode_bases(bases, 5)
+    seq2 = seq.copy()
+    seq2[10] = (seq2[10] + 37) % 1024
+    seq2 = np.delete(seq2, [50, 51, 52])
+    nb = post.shape[0]
+    d = {"post": post, "bases": np.array(bases), "seq": seq, "seq2": seq2}
+    for name, sq in (("a", seq), ("b", seq2)):
+        grad = sq.size / nb
+        hb = 30 * grad
+        lo = np.array([max(0, i * grad - hb) for i in range(nb)], dtype=np.uintp)
+        hi = np.array([min(sq.size, i * grad + hb) for i in range(nb)], dtype=np.uintp)
+        lo[0] = 0
+        hi[-1] = sq.size
+        d[name + "_low"], d[name + "_high"] = lo, hi
+        for pens in ((0.0, 0.0, 4.0), (0.1, 0.3, 2.0)):
+            key = "%s_%g_%g_%g" % ((name,) + pens)
+            sv, pv = ref.map_to_sequence(post, 1025, sq, *pens, forward=False, want_path=True)
+            d[key + "_viterbi"], d[key + "_path"] = np.float32(sv), pv
+            d[key + "_forward"] = np.float32(ref.map_to_sequence(post, 1025, sq, *pens, forward=True)[0])
+            d[key + "_viterbi_banded"] = np.float32(ref.map_to_sequence(post, 1025, sq, *pens, forward=False, bands=(lo, hi))[0])
+            d[key + "_forward_banded"] = np.float32(ref.map_to_sequence(post, 1025, sq, *pens, forward=True, bands=(lo, hi))[0])
+    np.savez_compressed(os.path.join(OUT, "ref_map.npz"), **d)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "map":
+        map_outputs()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "events":
         events_outputs()
         sys.exit(0)
