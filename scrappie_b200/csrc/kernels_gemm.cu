@@ -4,8 +4,8 @@
 //                      affine_map, src/layers.c:248-252, src/scrappie_matrix.c:323-351): the input
 //                      transform of every GRU layer for ALL time steps of ALL reads of a batch.
 //
-// Roles inside a CTA (persistent, one CTA per SM, 288 threads):
-//   warps 5-8  producers  load a chunk of NT activation columns (fp32, coalesced), split each value
+// Roles inside a CTA (persistent, one CTA per SM, 416 threads):
+//   warps 5-12 producers  load a chunk of NT activation columns (fp32, coalesced), split each value
 //                         into fp16 hi + lo and store it as the canonical K-major UMMA B operand
 //   warp  4    issuer     one elected lane issues tcgen05.mma: A = weight tile (shared memory,
 //                         resident for the whole kernel, fetched once by a TMA bulk copy),
@@ -97,7 +97,7 @@ __device__ __forceinline__ void split8(const float4 &a, const float4 &b, float s
 }
 
 template <int K, int ROWS, int NTILE, int NT, int LDC>
-__global__ void __launch_bounds__(288, 1)
+__global__ void __launch_bounds__(416, 1)
 affine_tc_kernel(const float *__restrict__ X, int ncol, const uint8_t *__restrict__ wimg, const float *__restrict__ bias,
                  int M, float *__restrict__ C) {
     using G = GemmCfg<K, ROWS, NTILE, NT>;
@@ -112,7 +112,7 @@ affine_tc_kernel(const float *__restrict__ X, int ncol, const uint8_t *__restric
     const int nchunk = (ncol + NT - 1) / NT;
 
     if (tid == 0) {
-        mbar_init(&full[0], 4); mbar_init(&full[1], 4);
+        mbar_init(&full[0], 8); mbar_init(&full[1], 8);
         mbar_init(&empty[0], 1); mbar_init(&empty[1], 1);
         mbar_init(&accf[0], 1); mbar_init(&accf[1], 1);
         mbar_init(&acce[0], 4); mbar_init(&acce[1], 4);
@@ -166,30 +166,44 @@ affine_tc_kernel(const float *__restrict__ X, int ncol, const uint8_t *__restric
         }
     } else if (warp >= 5) {
         // ---- producers: fp32 activations -> split fp16 canonical B operand ---------------
-        const int pt = tid - 160;                       // 0..127
+        // eight producer warps, and every load of a thread's share of the chunk is issued before the first value is
+        // converted: the whole 49 KB chunk is in flight at once (the kernel was bound by the exposed latency of
+        // these loads, profiles/r24)
+        const int pt = tid - 160;                       // 0..255
         constexpr int K8 = K / 8;
         constexpr int UNITS = NT * K8;
+        constexpr int NPROD = 256;
+        constexpr int PER = (UNITS + NPROD - 1) / NPROD;
         uint32_t it = 0;
         for (int c = blockIdx.x; c < nchunk; c += gridDim.x, it++) {
             const uint32_t s = it & 1;
-            mbar_wait(&empty[s], ((it >> 1) & 1) ^ 1);
-            uint8_t *b_hi = b_ring + s * G::STAGE_B, *b_lo = b_hi + G::TILE_B;
             const int col0 = c * NT;
             const float *src = X + (size_t)col0 * K;
             const int nvalid = min(NT, ncol - col0) * K8;
-#pragma unroll 4
-            for (int u = pt; u < UNITS; u += 128) {
-                float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+            float4 va[PER], vb[PER];
+#pragma unroll
+            for (int i = 0; i < PER; i++) {
+                const int u = pt + i * NPROD;
+                va[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                vb[i] = va[i];
                 if (u < nvalid) {
-                    a = *reinterpret_cast<const float4 *>(src + (size_t)u * 8);
-                    b = *reinterpret_cast<const float4 *>(src + (size_t)u * 8 + 4);
+                    va[i] = __ldg(reinterpret_cast<const float4 *>(src + (size_t)u * 8));
+                    vb[i] = __ldg(reinterpret_cast<const float4 *>(src + (size_t)u * 8 + 4));
                 }
-                const int n = u / K8, k8 = u % K8;
-                uint4 hi, lo;
-                split8(a, b, OPERAND_SCALE, hi, lo);
-                const uint32_t off = (uint32_t)(n >> 3) * G::SBO_B + (uint32_t)k8 * G::LBO_B + (uint32_t)(n & 7) * 16;
-                *reinterpret_cast<uint4 *>(b_hi + off) = hi;
-                *reinterpret_cast<uint4 *>(b_lo + off) = lo;
+            }
+            mbar_wait(&empty[s], ((it >> 1) & 1) ^ 1);
+            uint8_t *b_hi = b_ring + s * G::STAGE_B, *b_lo = b_hi + G::TILE_B;
+#pragma unroll
+            for (int i = 0; i < PER; i++) {
+                const int u = pt + i * NPROD;
+                if (u < UNITS) {
+                    const int n = u / K8, k8 = u % K8;
+                    uint4 hi, lo;
+                    split8(va[i], vb[i], OPERAND_SCALE, hi, lo);
+                    const uint32_t off = (uint32_t)(n >> 3) * G::SBO_B + (uint32_t)k8 * G::LBO_B + (uint32_t)(n & 7) * 16;
+                    *reinterpret_cast<uint4 *>(b_hi + off) = hi;
+                    *reinterpret_cast<uint4 *>(b_lo + off) = lo;
+                }
             }
             fence_async_smem();
             __syncwarp();
@@ -261,7 +275,7 @@ static int launch_affine_cfg(const float *X, int ncol, const uint8_t *wimg, cons
     }
     const int nchunk = (ncol + NT - 1) / NT;
     const int grid = nchunk < 148 ? nchunk : 148;
-    affine_tc_kernel<K, ROWS, NTILE, NT, LDC><<<grid, 288, G::SMEM, s>>>(X, ncol, wimg, bias, M, C);
+    affine_tc_kernel<K, ROWS, NTILE, NT, LDC><<<grid, 416, G::SMEM, s>>>(X, ncol, wimg, bias, M, C);
     return 0;
 }
 
