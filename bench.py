@@ -330,8 +330,11 @@ def main_b200(args, rank, world, local_rank):
     scan_avg_ms = float(np.mean([solo["scan%d" % l] for l in range(1, 6)]))
     flop_per_launch = FLOP_PER_READ_STEP_RECURRENT[args.model] * cols
     achieved = flop_per_launch / (scan_avg_ms * 1e-3) / 1e12
-    reads_per_cta = 16 if (args.model != "rnnrf_r94" and batches[0].nread >= 128
-                           and os.environ.get("SCRAPPIE_B200_SCAN_GROUPS", "0") in ("0", "4")) else 8
+    grp_env = os.environ.get("SCRAPPIE_B200_SCAN_GROUPS", "0")
+    if args.model == "rnnrf_r94":
+        reads_per_cta = 12 if (batches[0].nread >= 96 and grp_env in ("0", "3")) else 8
+    else:
+        reads_per_cta = 16 if (batches[0].nread >= 128 and grp_env in ("0", "4")) else 8
     scan_ctas = (batches[0].nread + reads_per_cta - 1) // reads_per_cta
     peak = pk["bf16_tflops"]
     hbm = pk["hbm_gbs"]

@@ -1049,7 +1049,7 @@ gru_scan_v4_kernel(const float *__restrict__ Xin, const float *__restrict__ sW, 
                    long long *__restrict__ trace) {
 #define SB2_TRACE(slot) do { if (trace != nullptr && blockIdx.x == 0 && grp == 0 && lane == 0 && s >= 100 && s < 104) trace[(s - 100) * 16 + (slot)] = clock64(); } while (0)
     constexpr int RPG = 4, NM = 16;                     // NG groups per CTA; reads per group, UMMA N
-    static_assert(NG == 2 || (NG == 4 && H <= 96), "four groups need a scheduler free of gate math");
+    static_assert(NG == 2 || (NG == 4 && H <= 96) || (NG == 3 && H > 96), "groups per CTA: TMEM columns and warp slots");
     constexpr uint32_t LBO_B = 16u * NM + 16u, SBO_B = 128u;
     constexpr uint32_t TILE_B = (H / 8) * LBO_B;
     constexpr int NKS = H / 16;
@@ -1119,9 +1119,11 @@ gru_scan_v4_kernel(const float *__restrict__ Xin, const float *__restrict__ sW, 
     // sits on scheduler 3, which has no gate math; a CTA is 8 warps (two groups, 8 reads) or 16 warps (four
     // groups, 16 reads: the gate math of four groups interleaves on each scheduler and one SM carries twice the
     // reads).  H = 112: all eight warps 0-7 are gate warps, the issuers are warps 11 / 15 (512 threads).
-    const bool is_issuer = (NQ < 4) ? ((warp & 3) == 3 && warp < 4 * NG) : (warp == 11 || warp == 15);
+    // H = 112 with three groups (12 reads, 336 + 144 TMEM columns): gate warps 0-11, issuers 13 / 14 / 15.
+    const bool is_issuer = (NQ < 4) ? ((warp & 3) == 3 && warp < 4 * NG)
+                                    : ((NG == 2) ? (warp == 11 || warp == 15) : (warp >= 13 && warp < 13 + NG));
     const bool is_gate = (warp < 4 * NG) && ((warp & 3) < NQ);
-    const int grp = (NQ < 4) ? (warp >> 2) : (is_issuer ? (warp == 15) : (warp >> 2));
+    const int grp = (NQ < 4) ? (warp >> 2) : (is_issuer ? ((NG == 2) ? (warp == 15) : (warp - 13)) : (warp >> 2));
     uint8_t *b_h = b_ops + grp * 2 * TILE_B, *b_rh = b_h + TILE_B;
     uint64_t *bar_r = &bars[grp * 5 + 0], *bar_z = &bars[grp * 5 + 1], *bar_c = &bars[grp * 5 + 2],
              *bar_rh = &bars[grp * 5 + 3], *bar_h = &bars[grp * 5 + 4];
@@ -1136,7 +1138,7 @@ gru_scan_v4_kernel(const float *__restrict__ Xin, const float *__restrict__ sW, 
         // ---- UMMA issuer of one group -----------------------------------------------------------
         if (grp > 0) {                                   // stagger the groups over a step
             const long long t0 = clock64();
-            const long long lag = (NG == 2) ? 700 : 450 * grp;
+            const long long lag = (NG == 2) ? 700 : ((NG == 3) ? 650 : 450) * grp;
             while (clock64() - t0 < lag) { }
         }
         const uint32_t idesc = umma_idesc_f16(128, NM);
@@ -1357,6 +1359,10 @@ int launch_gru_scan_v4(const float *Xin, const float *sW, const float *sW2, cons
     static int groups = -1;
     if (groups < 0) { const char *e = getenv("SCRAPPIE_B200_SCAN_GROUPS"); groups = e ? atoi(e) : 0; }
     const bool four = (H == 96) && (groups == 4 || (groups == 0 && d.nread >= 128));
+    const bool three = (H == 112) && (groups == 3 || (groups == 0 && d.nread >= 96));
+#define SB2_CASE3(MM) if (three && math == MM) return launch_scan_v4<112, MM, 3>(Xin, sW, sW2, resid, out, d, backward, trace, s)
+    SB2_CASE3(5); SB2_CASE3(2); SB2_CASE3(0);
+#undef SB2_CASE3
 #define SB2_CASE(HH, MM) if (H == HH && math == MM) return launch_scan_v4<HH, MM, 2>(Xin, sW, sW2, resid, out, d, backward, trace, s)
 #define SB2_CASE4(MM) if (four && math == MM) return launch_scan_v4<96, MM, 4>(Xin, sW, sW2, resid, out, d, backward, trace, s)
     SB2_CASE4(5); SB2_CASE4(2); SB2_CASE4(0);
