@@ -183,6 +183,26 @@ def test_transducer_decode_ties_and_extremes(sb, oracle):
             assert np.array_equal(path, opath) and score == oscore
 
 
+def test_transducer_decode_end_state_rounding_collisions(sb, oracle):
+    """The end state takes max_s fl(prev[s] - local_pen) with the LOWEST s among equal ROUNDED candidates
+    (src/decode.c:345-356).  With a huge local penalty the subtraction rounds coarsely, distinct scores collide
+    after rounding and the first-index rule decides the traceback; the warp-per-read decoder's exact path for that
+    case must agree with the reference's scan bit for bit.  Also long reads (several backtrace rounds) and
+    penalties that make the path leave through the end state early."""
+    rng = np.random.default_rng(11)
+    for nblock, scale in ((40, 1.0), (300, 3.0), (1300, 1.0)):
+        p = rng.dirichlet(np.ones(1025) * 0.05, size=nblock).astype(np.float32)
+        post = np.zeros((nblock, 1028), dtype=np.float32)
+        post[:, :1025] = robustlog(p, 1e-5) * np.float32(scale)
+        m = sb.ScrappyMatrix.from_numpy(post, 1025)
+        for pens in ((0, 0, 1e6, False), (0.5, 1.25, 3e4, False), (0, 0, 7e7, False), (2.0, 0.0, 0.0, False),
+                     (0, 0, 1e-3, False)):
+            score, path = sb.decode_path(m, "rgrgr_r94", *pens)
+            oscore, opath = oracle.decode_transducer(post, 1025, *pens)
+            assert np.array_equal(path, opath), (nblock, pens)
+            assert score == oscore, (nblock, pens)
+
+
 def test_transducer_decode_4096_states(sb, oracle):
     rng = np.random.default_rng(9)
     p = rng.dirichlet(np.ones(4097) * 0.02, size=120).astype(np.float32)
