@@ -21,6 +21,7 @@
 // CTAs of other batches instead of waiting for free SMs.
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "kernels.h"
 
@@ -58,11 +59,21 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// if (s < cand) { s = cand; code = c; } -- strict improvement only, like the reference's masked max
-// (ptxas turns this into FSETP + FSEL + SEL whichever way it is written; the half-rate ALU pipe they run on is
-// what bounds the kernel, profiles/r18)
-__device__ __forceinline__ void take_if_better(float &s, uint32_t &code, float cand, uint32_t c) {
-    if (s < cand) { s = cand; code = c; }
+// Traceback codes travel through the update as floats whose bit pattern is CODE_BIAS | code (2^23 + code: exact),
+// so that "if (s < cand) { s = cand; code = c; }" -- strict improvement only, like the reference's masked max -- can
+// be ONE compare on the half-rate ALU pipe plus two predicated FFMAs (x * 1.0f + -0.0f == x exactly) on the FMA
+// pipe.  Written as a C conditional ptxas emits FSETP + FSEL + SEL, three ALU-pipe instructions, and that pipe
+// bounds the kernel (profiles/r18); the multiplier and addend are kernel arguments so they cannot be folded away.
+constexpr uint32_t CODE_BIAS = 0x4B000000u;
+__device__ __forceinline__ float code_f(uint32_t code) { return __uint_as_float(CODE_BIAS | code); }
+template <bool FMA>
+__device__ __forceinline__ void take_if_better(float &s, float &code, float cand, float c, float one, float negzero) {
+    if (FMA) {
+        asm("{\n\t.reg .pred p;\n\tsetp.lt.f32 p, %0, %2;\n\t@p fma.rn.f32 %0, %2, %4, %5;\n\t@p fma.rn.f32 %1, %3, %4, %5;\n\t}"
+            : "+f"(s), "+f"(code) : "f"(cand), "f"(c), "f"(one), "f"(negzero));
+    } else {
+        if (s < cand) { s = cand; code = c; }
+    }
 }
 
 // byte position of state s inside a 1024-byte traceback row
@@ -71,11 +82,11 @@ __device__ __forceinline__ int tb_offset(int s) {
     return (g >> 2) * 512 + L * 16 + (g & 3) * 4 + j;
 }
 
-template <int WPC>
+template <int WPC, bool FMA>
 __global__ void __launch_bounds__(32 * WPC)
 decode_transducer_warp_kernel(const float *__restrict__ post, BatchDims d, int ostride, float stay_pen,
                               float skip_pen, float local_pen, uint8_t *tb, int *tb_end, int *path,
-                              float *__restrict__ score) {
+                              float *__restrict__ score, float one, float negzero) {
     __shared__ __align__(16) WarpTables tables[WPC];
     __shared__ __align__(16) float rings[WPC][NS * RING_ROW];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -126,17 +137,17 @@ decode_transducer_warp_kernel(const float *__restrict__ post, BatchDims d, int o
 #pragma unroll
             for (int j0 = 0; j0 < 4; j0++) {
                 float b = cur[g0][j0];
-                uint32_t q4 = 0;
+                float q4 = code_f(0);
 #pragma unroll
-                for (int q = 1; q < 4; q++) take_if_better(b, q4, cur[2 * q + g0][j0], (uint32_t)q);
+                for (int q = 1; q < 4; q++) take_if_better<FMA>(b, q4, cur[2 * q + g0][j0], code_f((uint32_t)q), one, negzero);
                 m4v[g0][j0] = b;
-                m4r[g0][j0] = (int)q4;
+                m4r[g0][j0] = (int)(__float_as_uint(q4) & 3u);
             }
 #pragma unroll
         for (int g0 = 0; g0 < 2; g0++) {
             float4 *dst = reinterpret_cast<float4 *>(&ws.m4[buf][128 * g0 + 4 * lane]);
-            dst[0] = make_float4(m4v[g0][0], __int_as_float(TB_STEP + m4r[g0][0]), m4v[g0][1], __int_as_float(TB_STEP + m4r[g0][1]));
-            dst[1] = make_float4(m4v[g0][2], __int_as_float(TB_STEP + m4r[g0][2]), m4v[g0][3], __int_as_float(TB_STEP + m4r[g0][3]));
+            dst[0] = make_float4(m4v[g0][0], code_f(TB_STEP + m4r[g0][0]), m4v[g0][1], code_f(TB_STEP + m4r[g0][1]));
+            dst[1] = make_float4(m4v[g0][2], code_f(TB_STEP + m4r[g0][2]), m4v[g0][3], code_f(TB_STEP + m4r[g0][3]));
         }
 
         // ---- skip maxima: suffix u = 4 (lane & 15) + j0 combines m4[u + 64 b], b = 2 g0 + (lane >> 4);
@@ -158,8 +169,8 @@ decode_transducer_warp_kernel(const float *__restrict__ post, BatchDims d, int o
         }
         if (lane < 16) {
             float4 *dst = reinterpret_cast<float4 *>(&ws.m16[buf][4 * lane]);
-            dst[0] = make_float4(m16v[0], __int_as_float(m16c[0]), m16v[1], __int_as_float(m16c[1]));
-            dst[1] = make_float4(m16v[2], __int_as_float(m16c[2]), m16v[3], __int_as_float(m16c[3]));
+            dst[0] = make_float4(m16v[0], code_f(m16c[0]), m16v[1], code_f(m16c[1]));
+            dst[1] = make_float4(m16v[2], code_f(m16c[2]), m16v[3], code_f(m16c[3]));
         }
 
         // ---- end state (src/decode.c:345-356): best of "stay in end" and max_s (prev[s] - local_pen), the
@@ -207,18 +218,21 @@ decode_transducer_warp_kernel(const float *__restrict__ post, BatchDims d, int o
             const float2 e16 = ws.m16[buf][8 * g + (lane >> 2)];
             const float4 l4 = *reinterpret_cast<const float4 *>(colv + 128 * g + 4 * lane);
             const float lpj[4] = {l4.x, l4.y, l4.z, l4.w};
-            const uint32_t c4 = (uint32_t)__float_as_int(e4.y), c16 = (uint32_t)__float_as_int(e16.y);
-            uint32_t cw = 0;
+            float cj[4];
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 float s = cur[g][j] + stay;
-                uint32_t code = TB_STAY;
-                take_if_better(s, code, lpj[j] + e4.x, c4);
-                take_if_better(s, code, (lpj[j] + e16.x) - skip_pen, c16);
-                take_if_better(s, code, curS + lpj[j], TB_START);
+                float code = code_f(TB_STAY);
+                take_if_better<FMA>(s, code, lpj[j] + e4.x, e4.y, one, negzero);
+                take_if_better<FMA>(s, code, (lpj[j] + e16.x) - skip_pen, e16.y, one, negzero);
+                take_if_better<FMA>(s, code, curS + lpj[j], code_f(TB_START), one, negzero);
                 cur[g][j] = s;
-                cw |= code << (8 * j);
+                cj[j] = code;
             }
+            // low bytes of the four biased codes -> one 32-bit word
+            const uint32_t lo2 = __byte_perm(__float_as_uint(cj[0]), __float_as_uint(cj[1]), 0x0040);
+            const uint32_t hi2 = __byte_perm(__float_as_uint(cj[2]), __float_as_uint(cj[3]), 0x0040);
+            const uint32_t cw = __byte_perm(lo2, hi2, 0x5410);
             codes[g] = cw;
         }
         *reinterpret_cast<uint4 *>(tb_cur) = make_uint4(codes[0], codes[1], codes[2], codes[3]);
@@ -385,11 +399,13 @@ void launch_decode_transducer_warp(const float *post, const BatchDims &d, int os
                                    float *score, cudaStream_t s) {
     static int wpc = 0;
     if (wpc == 0) { const char *e = getenv("SCRAPPIE_B200_DECODE_WPC"); wpc = e ? atoi(e) : 2; }
-#define SB2_LAUNCH_WARP_DECODE(WPC)                                                                       \
-    decode_transducer_warp_kernel<WPC><<<(d.nread + WPC - 1) / WPC, 32 * WPC, 0, s>>>(                     \
-        post, d, ostride, stay_pen, skip_pen, local_pen, tb, tb_end, path, score)
-    if (wpc == 1) SB2_LAUNCH_WARP_DECODE(1);
-    else SB2_LAUNCH_WARP_DECODE(2);
+    static int fma = -1;
+    if (fma < 0) { const char *e = getenv("SCRAPPIE_B200_DECODE_SEL"); fma = (e && 0 == strcmp(e, "sel")) ? 0 : 1; }
+#define SB2_LAUNCH_WARP_DECODE(WPC, FMA)                                                                  \
+    decode_transducer_warp_kernel<WPC, FMA><<<(d.nread + WPC - 1) / WPC, 32 * WPC, 0, s>>>(                \
+        post, d, ostride, stay_pen, skip_pen, local_pen, tb, tb_end, path, score, 1.0f, -0.0f)
+    if (wpc == 1) { if (fma) SB2_LAUNCH_WARP_DECODE(1, true); else SB2_LAUNCH_WARP_DECODE(1, false); }
+    else { if (fma) SB2_LAUNCH_WARP_DECODE(2, true); else SB2_LAUNCH_WARP_DECODE(2, false); }
 #undef SB2_LAUNCH_WARP_DECODE
 }
 
