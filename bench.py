@@ -306,10 +306,14 @@ def main_b200(args, rank, world, local_rank):
     e2e_s = (time.perf_counter() - t0) / args.steps
     nbases = int(sum(int(res.nbase.sum()) for res in results[:nbatch]))
     h2d = sum(b.total_samples_padded * 4 for b in batches[:nbatch])
-    # device -> host per batch: base count + score per read, then the base strings as one 2-D copy whose width is
-    # the longest call rounded up to 16 bytes (finish_on_device, csrc/engine.cu)
-    d2h = sum(b.nread * 8 + b.nread * ((int(res.nbase.max()) + 1 + 15) // 16 * 16)
-              for b, res in zip(batches[:nbatch], results[:nbatch]))
+    def d2h_bytes(b, res):
+        # finish_on_device (csrc/engine.cu): base count + score per read, then either the whole base-string area
+        # (batches whose area is <= 2 MB) or a 2-D copy as wide as the longest call
+        klen = 1 if args.model == "rnnrf_r94" else (6 if args.model == "rgrgr_r10" else 5)
+        stride = (klen * (max(b.nblock) + 1) + 1 + 15) // 16 * 16
+        area = b.nread * stride
+        return b.nread * 8 + (area if area <= (2 << 20) else b.nread * ((int(res.nbase.max()) + 1 + 15) // 16 * 16))
+    d2h = sum(d2h_bytes(b, res) for b, res in zip(batches[:nbatch], results[:nbatch]))
 
     # ---- reduce over ranks (max time) ------------------------------------------------------
     step_ms, e2e_s = max_over_ranks([step_ms, e2e_s], dist, device="cuda" if world > 1 else "cpu")

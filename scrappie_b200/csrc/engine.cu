@@ -315,6 +315,7 @@ struct sb2_batch {
     int eager_runs = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[ST_COUNT + 1]{};
+    cudaEvent_t ev_done = nullptr;          // blocking-sync event the basecall path waits on
     float stage_ms[ST_COUNT]{};
     float stage_at[ST_COUNT + 1]{};          // start of each stage relative to the first batch of a timed multi-batch run
     BatchDims dims{};
@@ -347,6 +348,7 @@ extern "C" void sb2_batch_destroy(sb2_batch *b) {
     void *hptrs[] = {b->h_paths, b->h_scores, b->h_gidx, b->h_gval};
     for (void *p : hptrs) if (p) cudaFreeHost(p);
     for (auto &e : b->ev) if (e) cudaEventDestroy(e);
+    if (b->ev_done) cudaEventDestroy(b->ev_done);
     if (b->stream) cudaStreamDestroy(b->stream);
     delete b;
 }
@@ -810,13 +812,26 @@ static int finish_on_device(sb2_batch *b, const sb2_params *p, sb2_call *out) {
     b->eng->launches += 1;
     CUDA_OK(cudaMemcpyAsync(b->h_nbase, b->d_nbase, (size_t)b->nread * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
     CUDA_OK(cudaMemcpyAsync(b->h_scores, b->d_score, (size_t)b->nread * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
-    CUDA_OK(cudaStreamSynchronize(b->stream));
-    int maxlen = 0;
-    for (int r = 0; r < b->nread; r++) maxlen = std::max(maxlen, b->h_nbase[r]);
-    const size_t width = std::min((size_t)b->bases_stride, align_up((size_t)maxlen + 1, 16));
-    CUDA_OK(cudaMemcpy2DAsync(b->h_bases, b->bases_stride, b->d_bases, b->bases_stride, width, (size_t)b->nread,
-                              cudaMemcpyDeviceToHost, b->stream));
-    CUDA_OK(cudaStreamSynchronize(b->stream));
+    // Host threads wait on a blocking-sync event (they sleep instead of spinning: with one thread per batch and
+    // several ranks per host the spinning waits starved each other).  Small batches fetch the whole base-string
+    // area in the same pass; large ones first learn the longest call, then copy only that width.
+    if (nullptr == b->ev_done) CUDA_OK(cudaEventCreateWithFlags(&b->ev_done, cudaEventBlockingSync | cudaEventDisableTiming));
+    const size_t all_bytes = (size_t)b->nread * b->bases_stride;
+    if (all_bytes <= ((size_t)2 << 20)) {
+        CUDA_OK(cudaMemcpyAsync(b->h_bases, b->d_bases, all_bytes, cudaMemcpyDeviceToHost, b->stream));
+        CUDA_OK(cudaEventRecord(b->ev_done, b->stream));
+        CUDA_OK(cudaEventSynchronize(b->ev_done));
+    } else {
+        CUDA_OK(cudaEventRecord(b->ev_done, b->stream));
+        CUDA_OK(cudaEventSynchronize(b->ev_done));
+        int maxlen = 0;
+        for (int r = 0; r < b->nread; r++) maxlen = std::max(maxlen, b->h_nbase[r]);
+        const size_t width = std::min((size_t)b->bases_stride, align_up((size_t)maxlen + 1, 16));
+        CUDA_OK(cudaMemcpy2DAsync(b->h_bases, b->bases_stride, b->d_bases, b->bases_stride, width, (size_t)b->nread,
+                                  cudaMemcpyDeviceToHost, b->stream));
+        CUDA_OK(cudaEventRecord(b->ev_done, b->stream));
+        CUDA_OK(cudaEventSynchronize(b->ev_done));
+    }
     int ncalled = 0;
     for (int r = 0; r < b->nread; r++) {
         const int nbase = b->h_nbase[r];
