@@ -26,7 +26,9 @@ def test_library_exports_every_declared_symbol(sb):
     for must in ("nanonet_rgrgr_r94_posterior", "nanonet_rnnrf_r94_transitions", "decode_transducer", "decode_crf",
                  "overlapper", "crfpath_to_basecall", "homopolymer_path", "trim_and_segment_raw",
                  "medmad_normalise_array", "mat_from_array", "free_scrappie_matrix", "get_raw_model_stride_from_string",
-                 "sb2_basecall_batch", "sb2_batch_forward", "sb2_batch_decode"):
+                 "sb2_basecall_batch", "sb2_batch_forward", "sb2_batch_decode", "nanonet_posterior", "nanonet_raw_posterior",
+                 "posterior_crf", "map_to_sequence_viterbi", "map_to_sequence_forward_banded", "encode_bases_to_integers",
+                 "sb2_basecall_raw_batch", "sb2_prepare_reads", "sb2_events_posterior_batch", "sb2_multi_stream_time"):
         assert must in names
     missing = [n for n in names if not hasattr(L, n)]
     assert not missing, missing
@@ -237,3 +239,46 @@ def test_product_never_touches_oracle():
                 txt = open(os.path.join(dirpath, fn)).read()
                 assert "sb2o_" not in txt and "liboracle" not in txt and "scrappie_oracle" not in txt, fn
                 assert "import oracle" not in txt and "from oracle" not in txt, fn
+
+
+def test_event_features_bit_exact_vs_oracle(sb, oracle):
+    """nanonet_features_from_events (host; Kahan sums + RSQRTPS, src/nnfeatures.c:47-115) == the oracle restatement
+    on this CPU, bit for bit; sub-range tables use et.start / et.end like the reference."""
+    from oracle.oracle import synthetic_events
+    for n in (2, 3, 50, 1000):
+        ev = synthetic_events(100 + n, n)
+        got = sb.event_features(ev)
+        assert got.shape == (n, 4)
+        assert np.array_equal(got.view(np.uint32), oracle.event_features(ev).view(np.uint32))
+    ev = synthetic_events(5, 60)
+    sub = sb.EventTable(ev, start=10, end=45)
+    assert np.array_equal(sb.event_features(sub).view(np.uint32), oracle.event_features(ev[10:45]).view(np.uint32))
+    empty = sb.EventTable(ev, start=7, end=7)
+    assert not sb.lib().nanonet_features_from_events(empty.table, True)
+
+
+def test_encode_bases_and_bounds(sb, reference):
+    """encode_bases_to_integers (src/scrappie_seq_helpers.c:53-75) and are_bounds_sane (src/decode.c:1638-1691)."""
+    seq = "ACGTTGCAAACCGGTTacgt"
+    for k in (1, 3, 5):
+        got = sb.encode_bases(seq, k)
+        want = [sum("ACGT".index(c) * 4 ** (k - 1 - j) for j, c in enumerate(seq.upper()[i:i + k])) for i in range(len(seq) - k + 1)]
+        assert got.tolist() == want
+        if reference is not None:
+            assert np.array_equal(got, reference.encode_bases(seq, k))
+    with pytest.raises(RuntimeError):
+        sb.encode_bases("ACGNT", 2)
+    sp = C.POINTER(C.c_size_t)
+
+    def sane(lo, hi, seqlen):
+        lo = np.ascontiguousarray(lo, dtype=np.uintp)
+        hi = np.ascontiguousarray(hi, dtype=np.uintp)
+        return bool(sb.lib().are_bounds_sane(lo.ctypes.data_as(sp), hi.ctypes.data_as(sp), lo.size, seqlen))
+    assert sane([0, 0, 1, 2], [2, 3, 4, 5], 5)
+    assert sane([0, 2], [2, 5], 5)                   # touching, not overlapping: a step is still possible
+    assert not sane([1, 1], [3, 5], 5)               # first band must start at 0
+    assert not sane([0, 1], [3, 4], 5)               # last band must end at seqlen
+    assert not sane([0, 4], [3, 5], 5)               # gap between consecutive bands
+    assert not sane([0, 2, 1], [3, 4, 5], 5)         # low bounds must not decrease
+    assert not sane([0, 1, 2], [4, 3, 5], 5)         # high bounds must not decrease
+    assert not sane([0, 1], [6, 5], 5)               # beyond the sequence
