@@ -462,22 +462,29 @@ head_softmax_tc_kernel(const float *__restrict__ X, int ncol, const uint8_t *__r
         // FAST: exp((acc * 2^-16 + b) / cdiv) = 2^(acc * sc + b * bsc), one FFMA in front of ex2.approx
         const float inv_cdiv = 1.0f / cdiv;
         const float sc = RESULT_SCALE * inv_cdiv * 1.4426950408889634f, bsc = inv_cdiv * 1.4426950408889634f;
+        float4 xs4[KQ / 4];
+        auto load_stay_x = [&](int chunk) {
+            const int col = min(chunk * NT + ch * 32 + lane, ncol - 1);     // clamped: out-of-range columns are never stored
+            const float4 *xp = reinterpret_cast<const float4 *>(X + (size_t)col * K + q * KQ);
+#pragma unroll
+            for (int i = 0; i < KQ / 4; i++) xs4[i] = __ldg(xp + i);
+        };
+        load_stay_x(blockIdx.x);
         uint32_t it = 0;
         for (int c = blockIdx.x; c < nchunk; c += gridDim.x, it++) {
             const int col0 = c * NT + ch * 32;            // first column of this warp's half
             const int mycol = col0 + lane;
-            // stay logit, partial over k in [q*KQ, (q+1)*KQ) for column `mycol`
+            // stay logit, partial over k in [q*KQ, (q+1)*KQ) for column `mycol`: the activations were fetched while
+            // the previous chunk was being finished (xs4), the next chunk's are requested right away
             float sp = 0.0f;
-            if (mycol < ncol) {
-                const float4 *xp = reinterpret_cast<const float4 *>(X + (size_t)mycol * K + q * KQ);
 #pragma unroll
-                for (int i = 0; i < KQ / 4; i++) {
-                    float4 x4 = xp[i];
-                    if (xdiv != 1.0f) { x4.x /= xdiv; x4.y /= xdiv; x4.z /= xdiv; x4.w /= xdiv; }
-                    sp = fmaf(ws[4 * i], x4.x, sp); sp = fmaf(ws[4 * i + 1], x4.y, sp);
-                    sp = fmaf(ws[4 * i + 2], x4.z, sp); sp = fmaf(ws[4 * i + 3], x4.w, sp);
-                }
+            for (int i = 0; i < KQ / 4; i++) {
+                float4 x4 = xs4[i];
+                if (xdiv != 1.0f) { x4.x /= xdiv; x4.y /= xdiv; x4.z /= xdiv; x4.w /= xdiv; }
+                sp = fmaf(ws[4 * i], x4.x, sp); sp = fmaf(ws[4 * i + 1], x4.y, sp);
+                sp = fmaf(ws[4 * i + 2], x4.z, sp); sp = fmaf(ws[4 * i + 3], x4.w, sp);
             }
+            load_stay_x(c + (int)gridDim.x);
             // pass A: e = exp(logit), column sums over this thread's 8 rows
             float cs[32];
 #pragma unroll
