@@ -17,8 +17,11 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libscrappie_b200.so")
+# SCRAPPIE_B200_LIB selects an alternative build of the library (A/B measurements); the weights stay where they are
+LIB_PATH = os.environ.get("SCRAPPIE_B200_LIB") or os.path.join(_HERE, "libscrappie_b200.so")
 WEIGHTS_DIR = os.path.join(_HERE, "weights")
+if os.environ.get("SCRAPPIE_B200_LIB"):
+    os.environ.setdefault("SCRAPPIE_B200_WEIGHTS", WEIGHTS_DIR)     # the library looks for weights next to itself
 
 MODELS = ("raw_r94", "rgrgr_r94", "rgrgr_r941", "rgrgr_r10", "rnnrf_r94")
 _MODEL_ENUM = {"raw_r94": 0, "rgrgr_r94": 1, "rgrgr_r941": 2, "rgrgr_r10": 3, "rnnrf_r94": 4}
