@@ -6,6 +6,7 @@ Tolerances (SURVEY.md section 0.5 / BASELINE north star): decoders bit-exact (in
 fp32 score given the same posterior); posterior max-abs-err <= 1e-4 in log space, <= 1e-5 in
 probability space; base sequences identical to the reference's."""
 import hashlib
+import os
 
 import numpy as np
 import pytest
@@ -601,3 +602,25 @@ def test_map_to_sequence_vs_reference_fixture(sb, golden):
         sb.map_post_to_sequence(post, bases, bands=(np.ones(post.shape[0]), np.zeros(post.shape[0])))
     with pytest.raises(RuntimeError):
         sb.map_post_to_sequence(post, "ACGTNACGT")
+
+
+def test_c_caller_basecalls_bundled_reads(sb, golden, tmp_path):
+    """examples/raw_basecall.c (plain C, C-ABI only) on the bundled reads written as float32 files: the FASTA records
+    carry the reference's bases (md5) and trim bounds."""
+    import subprocess
+    from test_host import _build_example
+    exe = _build_example(sb, tmp_path)
+    files = []
+    for i in range(3):
+        f = tmp_path / ("read%d.f32" % i)
+        bundled_signal(golden, i).astype("<f4").tofile(str(f))
+        files.append(str(f))
+    env = dict(os.environ, SCRAPPIE_B200_WEIGHTS=sb.WEIGHTS_DIR)
+    out = subprocess.run([exe, "rgrgr_r94"] + files, check=True, capture_output=True, text=True, env=env).stdout.splitlines()
+    recs = [(out[i], out[i + 1]) for i in range(1, len(out), 2)]
+    assert len(recs) == 3
+    g = golden.ref_reads
+    for i, (hdr, bases) in enumerate(recs):
+        assert hashlib.md5((bases + "\n").encode()).hexdigest() == str(g["r%d_rgrgr_r94_md5" % i])
+        lo, hi = [int(v) for v in g["r%d_trim" % i]]
+        assert '"trim" : [ %d, %d ]' % (lo, hi) in hdr and '"sequence_length" : %d' % len(bases) in hdr

@@ -282,3 +282,23 @@ def test_encode_bases_and_bounds(sb, reference):
     assert not sane([0, 2, 1], [3, 4, 5], 5)         # low bounds must not decrease
     assert not sane([0, 1, 2], [4, 3, 5], 5)         # high bounds must not decrease
     assert not sane([0, 1], [6, 5], 5)               # beyond the sequence
+
+
+def _build_example(sb, tmp_path):
+    import subprocess
+    exe = str(tmp_path / "raw_basecall")
+    libdir = os.path.dirname(sb.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "raw_basecall.c"), "-L" + libdir, "-lscrappie_b200",
+                    "-Wl,-rpath," + libdir, "-lm", "-o", exe], check=True)
+    return exe
+
+
+def test_c_caller_compiles_and_runs_host_side(sb, tmp_path):
+    """The header is plain C99 and a C program links against the library: examples/raw_basecall.c in its host-only
+    mode (registry, containers, trim + scale) -- no GPU call."""
+    import subprocess
+    exe = _build_example(sb, tmp_path)
+    out = subprocess.run([exe, "rnnrf_r94"], check=True, capture_output=True, text=True).stdout
+    assert "model rnnrf_r94 stride 1" in out and "trimmed to [200, 390)" in out
+    assert subprocess.run([exe, "no_such_model"], capture_output=True).returncode != 0
