@@ -116,6 +116,17 @@ posterior_function_ptr get_posterior_function(const enum raw_model_type model);
 /* -- network forward (GPU): src/networks.c:250-394, :567-615.
  *    Returns a new matrix [nstate x nblock] owned by the caller, or NULL. -- */
 /* raw_r94 (interface/scrappie.h:49-51, src/networks.c:196-247): two bidirectional GRU pairs */
+/* src/event_detection.h:6-25, src/event_detection.c:270-320: segmentation of a raw signal into events (host code, as in
+ * the reference); the table's `event` array is calloc'd and owned by the caller */
+typedef struct {
+    size_t window_length1;
+    size_t window_length2;
+    float threshold1;
+    float threshold2;
+    float peak_height;
+} detector_param;
+event_table detect_events(raw_table const rt, detector_param const edparam);
+
 /* interface/scrappie.h:47-48, src/networks.c:146-194: the events (LSTM) model.  Features are made on the host
  * (nanonet_features_from_events, src/nnfeatures.c:76-115, exported as well); window, LSTM layers and head on the GPU */
 scrappie_matrix nanonet_features_from_events(const event_table et, bool normalise);

@@ -292,6 +292,12 @@ def synthetic_events(seed, n):
     return np.stack([mean, stdv, length], axis=1).astype(np.float32)
 
 
+class _DetectorParam(C.Structure):
+    """detector_param, src/event_detection.h:6-12; defaults :15-21."""
+    _fields_ = [("window_length1", C.c_size_t), ("window_length2", C.c_size_t), ("threshold1", C.c_float),
+                ("threshold2", C.c_float), ("peak_height", C.c_float)]
+
+
 class _RawTable(C.Structure):
     _fields_ = [("uuid", C.c_char_p), ("n", C.c_size_t), ("start", C.c_size_t), ("end", C.c_size_t),
                 ("raw", c_float_p)]
@@ -342,6 +348,8 @@ class Reference:
             f.argtypes = [C.POINTER(_Mat), C.c_float, C.c_float, C.c_float, c_int_p, C.c_size_t, sp, sp]
         L.encode_bases_to_integers.restype = C.POINTER(C.c_int)
         L.encode_bases_to_integers.argtypes = [C.c_char_p, C.c_size_t, C.c_size_t]
+        L.detect_events.restype = _EventTable
+        L.detect_events.argtypes = [_RawTable, _DetectorParam]
         L.nanonet_posterior.restype = C.POINTER(_Mat)
         L.nanonet_posterior.argtypes = [_EventTable, C.c_float, C.c_float, C.c_float, C.c_bool]
         L.nanonet_features_from_events.restype = C.POINTER(_Mat)
@@ -431,6 +439,16 @@ class Reference:
             score = f(mp, stay_pen, skip_pen, local_pen, _ip(seq), seq.size, lo.ctypes.data_as(sp), hi.ctypes.data_as(sp))
         self.lib.free_scrappie_matrix(mp)
         return float(score), path
+
+    def detect_events(self, raw, w1=3, w2=6, t1=1.4, t2=9.0, peak_height=0.2):
+        """[n, 4] array (start, length, mean, stdv) of the reference's event detector."""
+        raw = np.ascontiguousarray(raw, dtype=np.float32)
+        rt = _RawTable(None, raw.size, 0, raw.size, _fp(raw))
+        et = self.lib.detect_events(rt, _DetectorParam(w1, w2, t1, t2, peak_height))
+        out = np.array([[et.event[i].start, et.event[i].length, et.event[i].mean, et.event[i].stdv] for i in range(et.n)],
+                       dtype=np.float64)
+        self.libc.free(C.cast(et.event, C.c_void_p))
+        return out
 
     def events_posterior(self, ev, min_prob=1e-5, tempW=1.0, tempb=1.0, return_log=True):
         et, keep = make_event_table(ev)

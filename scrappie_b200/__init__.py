@@ -57,6 +57,15 @@ class _EventTable(C.Structure):
     _fields_ = [("n", C.c_size_t), ("start", C.c_size_t), ("end", C.c_size_t), ("event", C.POINTER(_Event))]
 
 
+class DetectorParam(C.Structure):
+    """detector_param (src/event_detection.h:6-21); the defaults are the reference's event_detection_defaults."""
+    _fields_ = [("window_length1", C.c_size_t), ("window_length2", C.c_size_t), ("threshold1", C.c_float),
+                ("threshold2", C.c_float), ("peak_height", C.c_float)]
+
+    def __init__(self, window_length1=3, window_length2=6, threshold1=1.4, threshold2=9.0, peak_height=0.2):
+        super().__init__(window_length1, window_length2, threshold1, threshold2, peak_height)
+
+
 class EventTable(object):
     """An event_table built from an [n, 3] array of (mean, stdv, length)."""
 
@@ -133,6 +142,7 @@ def lib():
         "encode_bases_to_integers": (C.c_void_p, [C.c_char_p, C.c_size_t, C.c_size_t]),
         "nanonet_posterior": (mp, [_EventTable, C.c_float, C.c_float, C.c_float, C.c_bool]),
         "nanonet_features_from_events": (mp, [_EventTable, C.c_bool]),
+        "detect_events": (_EventTable, [_RawTable, DetectorParam]),
         "sb2_events_posterior_batch": (C.c_int, [C.c_void_p, C.POINTER(_EventTable), C.c_size_t, C.c_float, C.c_float,
                                                  C.c_float, C.c_bool, C.POINTER(mp)]),
         "sb2_batch_posterior_crf": (C.c_int, [C.c_void_p]),
@@ -376,6 +386,19 @@ def get_model_stride(model):
     if stride == -1:
         raise ValueError("Invalid scrappie model '{}'.".format(model))
     return stride
+
+
+def detect_events(rt, param=None):
+    """Segment a raw signal (a RawTable, trimmed range) into events: [n, 4] array of (start, length, mean, stdv)
+    (detect_events, src/event_detection.c:270-320; host code)."""
+    rt = rt if isinstance(rt, RawTable) else RawTable(rt)
+    et = lib().detect_events(rt.data(), param or DetectorParam())
+    if not et.event:
+        raise RuntimeError("detect_events failed")
+    out = np.array([[et.event[i].start, et.event[i].length, et.event[i].mean, et.event[i].stdv] for i in range(et.n)],
+                   dtype=np.float64)
+    _libc.free(C.cast(et.event, C.c_void_p))
+    return out
 
 
 def event_features(events):

@@ -624,3 +624,24 @@ def test_c_caller_basecalls_bundled_reads(sb, golden, tmp_path):
         assert hashlib.md5((bases + "\n").encode()).hexdigest() == str(g["r%d_rgrgr_r94_md5" % i])
         lo, hi = [int(v) for v in g["r%d_trim" % i]]
         assert '"trim" : [ %d, %d ]' % (lo, hi) in hdr and '"sequence_length" : %d' % len(bases) in hdr
+
+
+def test_events_path_from_raw_signal(sb, oracle, golden):
+    """The `scrappie events` chain on a bundled read: trim -> detect_events (host) -> nanonet_posterior (GPU) ->
+    decode_transducer (GPU), against the oracle run on the same event table."""
+    rt = sb.RawTable(bundled_signal(golden, 2)).trim()
+    ev = sb.detect_events(rt)
+    assert ev.shape[0] > 1000
+    table = np.stack([ev[:, 2], ev[:, 3], ev[:, 1]], axis=1).astype(np.float32)          # (mean, stdv, length)
+    post = sb.calc_post_events(table, min_prob=1e-5)
+    got = post.data(as_numpy=True)
+    want = oracle.events_posterior(table)[:, :1025]
+    # 5 787 events through two stacked bidirectional LSTM pairs in fp32 with a different summation order: 1.5e-4 in
+    # log space on entries near the 1e-5 probability floor (the oracle itself is 2e-5 from the reference's OpenBLAS
+    # build on this table); the probability-space bound is the meaningful one
+    assert np.abs(got - want).max() < 5e-4
+    assert np.abs(np.exp(got) - np.exp(want)).max() < 1e-5
+    assert np.array_equal(got.argmax(axis=1), want.argmax(axis=1))
+    score, path = sb.decode_path(post, "rgrgr_r94", 0.0, 0.0, 2.0, False)
+    oscore, opath = oracle.decode_transducer(post.padded(), 1025, 0.0, 0.0, 2.0)
+    assert np.array_equal(path, opath) and score == oscore

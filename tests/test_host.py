@@ -302,3 +302,30 @@ def test_c_caller_compiles_and_runs_host_side(sb, tmp_path):
     out = subprocess.run([exe, "rnnrf_r94"], check=True, capture_output=True, text=True).stdout
     assert "model rnnrf_r94 stride 1" in out and "trimmed to [200, 390)" in out
     assert subprocess.run([exe, "no_such_model"], capture_output=True).returncode != 0
+
+
+def test_detect_events_bit_exact(sb, golden, reference):
+    """detect_events (host; src/event_detection.c:24-320) against the compiled reference's event tables: fixtures for
+    synthetic signals and the bundled reads, the live reference (where built) for odd lengths and parameters."""
+    import hashlib
+    g = golden.ref_detect
+    for seed, n in ((1, 4000), (2, 1234)):
+        x = (synthetic_read(seed, n) * 12 + 90).astype(np.float32)
+        got = sb.detect_events(x).astype(np.float32)
+        assert np.array_equal(got.view(np.uint32), g["syn_%d_events" % n].view(np.uint32))
+    for i in range(3):
+        got = sb.detect_events(bundled_signal(golden, i)).astype(np.float32)
+        assert got.shape[0] == int(g["r%d_nevent" % i])
+        assert hashlib.md5(np.ascontiguousarray(got).tobytes()).hexdigest() == str(g["r%d_md5" % i])
+        assert got[0, 0] == 0 and np.all(np.diff(got[:, 0]) == got[:-1, 1])            # contiguous events from 0
+    if reference is not None:
+        for n, kw in ((50, {}), (13, {}), (5000, dict(w1=4, w2=9, t1=2.0, t2=5.0, peak_height=0.5)),
+                      (5000, dict(w1=2, w2=3, t1=0.5, t2=1.0, peak_height=0.05))):
+            x = (synthetic_read(90 + n, n) * 12 + 90).astype(np.float32)
+            par = sb.DetectorParam(kw.get("w1", 3), kw.get("w2", 6), kw.get("t1", 1.4), kw.get("t2", 9.0), kw.get("peak_height", 0.2))
+            got = sb.detect_events(x, par).astype(np.float32)
+            want = reference.detect_events(x, **kw).astype(np.float32)
+            assert got.shape == want.shape and np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    flat = np.full(300, 90.0, dtype=np.float32)                   # no boundary at all: one event over the whole signal
+    ev = sb.detect_events(flat)
+    assert ev.shape == (1, 4) and ev[0, 0] == 0 and ev[0, 1] == 300 and ev[0, 2] == 90.0 and ev[0, 3] == 0.0

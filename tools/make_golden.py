@@ -226,8 +226,30 @@ def map_outputs():
     np.savez_compressed(os.path.join(OUT, "ref_map.npz"), **d)
 
 
+def detect_outputs():
+    """detect_events (src/event_detection.c) of the reference: full event tables for two synthetic pA signals,
+    count + md5 of the float32 (start, length, mean, stdv) rows for the bundled reads."""
+    ref = Reference()
+    d = {}
+    for seed, n in ((1, 4000), (2, 1234)):
+        x = (synthetic_read(seed, n) * 12 + 90).astype(np.float32)
+        d["syn_%d_events" % n] = ref.detect_events(x).astype(np.float32)
+    reads = np.load(os.path.join(OUT, "reads.npz"))
+    for i in range(3):
+        sig = reads["r%d_signal" % i]
+        dig, off, rng = [np.float32(v) for v in reads["r%d_meta" % i]]
+        x = ((sig.astype(np.float32) + off) * np.float32(rng / dig)).astype(np.float32)
+        ev = ref.detect_events(x).astype(np.float32)
+        d["r%d_nevent" % i] = np.int64(ev.shape[0])
+        d["r%d_md5" % i] = np.array(hashlib.md5(np.ascontiguousarray(ev).tobytes()).hexdigest())
+    np.savez_compressed(os.path.join(OUT, "ref_detect.npz"), **d)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "detect":
+        detect_outputs()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "map":
         map_outputs()
         sys.exit(0)
