@@ -31,6 +31,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FLOP_PER_READ_STEP_RECURRENT = {"rgrgr_r94": 55296, "rgrgr_r941": 55296, "rgrgr_r10": 55296, "rnnrf_r94": 75264}
+# algorithmic HBM bytes per block when every intermediate is materialised once:
+# conv out H*4 W; per layer X H*4 R + Xin 3H*4 W, then Xin 3H*4 R + X H*4 W; posterior stride*4 W + R; traceback W
+BYTES_PER_BLOCK = {"rgrgr_r94": 96 * 4 + 5 * (2 * 96 * 4 + 2 * 288 * 4) + 2 * 1028 * 4 + 1028,
+                   "rgrgr_r941": 96 * 4 + 5 * (2 * 96 * 4 + 2 * 288 * 4) + 2 * 1028 * 4 + 1028,
+                   "rnnrf_r94": 112 * 4 + 5 * (3 * 112 * 4 + 2 * 336 * 4) + 2 * 28 * 4 + 8}
 FLOP_PER_BLOCK_TOTAL = {"rgrgr_r94": 753408, "rnnrf_r94": 760704}
 
 
@@ -381,6 +386,11 @@ def main_b200(args, rank, world, local_rank):
         "network_tflops": world * FLOP_PER_BLOCK_TOTAL.get(args.model, 0) * total_blocks / (step_ms * 1e-3) / 1e12,
         "e2e": {"value": world * total_samples / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3},
+        # the whole step against the HBM roofline: algorithmic bytes if every intermediate is written and read once
+        # (conv out, X / Xin per layer, posterior, traceback) over the measured step time
+        "step_hbm": {"bytes_per_block": BYTES_PER_BLOCK.get(args.model), "achieved": (BYTES_PER_BLOCK.get(args.model, 0) * total_blocks
+                     / (step_ms * 1e-3) / 1e9), "peak": hbm, "unit": "GB/s",
+                     "frac": BYTES_PER_BLOCK.get(args.model, 0) * total_blocks / (step_ms * 1e-3) / 1e9 / hbm},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"kernel": "gru_scan (recurrent sW/sW2 products + gates): 5 of the 13 launches per batch, "
