@@ -17,6 +17,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "device_math.cuh"
@@ -329,19 +330,35 @@ __device__ __forceinline__ float head_log(float x) {
     return lg2_approx(x) * 0.6931471805599453f;
 }
 
-template <int K, bool FAST>
-__global__ void __launch_bounds__(448, 1)
+// EW = column slices of a chunk among the epilogue warps: 4 EW epilogue warps (TMEM lane quarter q = warp % 4,
+// slice ch = warp / 4, CW = NT / EW columns each).  EW = 4 (16 warps, 16 columns each) keeps twice as many TMEM loads,
+// stores and global loads in flight as EW = 2: the epilogue, not the tensor pipe or L2, sets this kernel's pace.
+template <int CW>
+__device__ __forceinline__ void tmem_ld_cw(uint32_t taddr, float (&v)[CW]) {
+    if constexpr (CW == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
+}
+template <int CW>
+__device__ __forceinline__ void tmem_st_cw(uint32_t taddr, const float (&v)[CW]) {
+    if constexpr (CW == 32) tmem_st32(taddr, v); else tmem_st16(taddr, v);
+}
+
+template <int K, bool FAST, int EW>
+__global__ void __launch_bounds__(32 * (4 * EW + 6), 1)
 head_softmax_tc_kernel(const float *__restrict__ X, int ncol, const uint8_t *__restrict__ wimg,
                        const float *__restrict__ w_stay, const float *__restrict__ bias, float *__restrict__ post,
                        int ostride, float xdiv, float cdiv, float min_prob, int return_log) {
     using G = HeadCfg<K>;
     constexpr int NT = G::NT, NTILE = G::NTILE;
+    constexpr int CW = NT / EW;                         // columns per epilogue warp
+    constexpr int KSPLIT = 32 / CW;                     // lanes per column: they split the stay dot product
+    constexpr int NEW = 4 * EW;                         // epilogue warps
+    static_assert(CW == 32 || CW == 16, "column slice");
     constexpr int OSTRIDE = NTILE * 128 + 4;            // 1028 = 4 * ceil(1025 / 4), the reference's column stride
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t *w_ring = smem;
     uint8_t *b_ring = smem + G::OFF_B;
-    float *part_sum = reinterpret_cast<float *>(smem + G::OFF_PART);            // [2][2][4][32]
-    float *part_stay = part_sum + 2 * 2 * 4 * 32;
+    float *part_sum = reinterpret_cast<float *>(smem + G::OFF_PART);            // [2][EW][4][CW]
+    float *part_stay = part_sum + 2 * EW * 4 * CW;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + G::OFF_BAR);
     uint64_t *full_b = bars, *empty_b = bars + 2, *wfull = bars + 4, *wempty = bars + 7, *tile_full = bars + 10,
              *tile_free = bars + 18;
@@ -353,7 +370,7 @@ head_softmax_tc_kernel(const float *__restrict__ X, int ncol, const uint8_t *__r
     if (tid == 0) {
         for (int i = 0; i < 2; i++) { mbar_init(&full_b[i], 4); mbar_init(&empty_b[i], 1); }
         for (int i = 0; i < G::WSTAGES; i++) { mbar_init(&wfull[i], 1); mbar_init(&wempty[i], 1); }
-        for (int i = 0; i < NTILE; i++) { mbar_init(&tile_full[i], 1); mbar_init(&tile_free[i], 8); }
+        for (int i = 0; i < NTILE; i++) { mbar_init(&tile_full[i], 1); mbar_init(&tile_free[i], NEW); }
         mbar_fence_init();
     }
     if (warp == 0) tmem_alloc(tmem_slot, 512);
@@ -362,7 +379,7 @@ head_softmax_tc_kernel(const float *__restrict__ X, int ncol, const uint8_t *__r
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp == 8) {
+    if (warp == NEW) {
         // ---- UMMA issuer ------------------------------------------------------------------
         const uint32_t idesc = umma_idesc_f16(128, NT);
         constexpr uint64_t TA = G::TILE_A >> 4, KA = (2 * G::LBO_A) >> 4, KB = (2 * G::LBO_B) >> 4, TB = G::TILE_B >> 4;
@@ -394,7 +411,7 @@ head_softmax_tc_kernel(const float *__restrict__ X, int ncol, const uint8_t *__r
             if (elect_one()) umma_commit(&empty_b[s]);
             __syncwarp();
         }
-    } else if (warp == 9) {
+    } else if (warp == NEW + 1) {
         // ---- weight streamer: 8 tile images per chunk through a 3-deep TMA ring ------------
         uint32_t wslot = 0, wphase = 0;
         for (int c = blockIdx.x; c < nchunk; c += gridDim.x) {
@@ -412,9 +429,9 @@ head_softmax_tc_kernel(const float *__restrict__ X, int ncol, const uint8_t *__r
                 if (++wslot == G::WSTAGES) { wslot = 0; wphase ^= 1; }
             }
         }
-    } else if (warp >= 10) {
+    } else if (warp >= NEW + 2) {
         // ---- producers ------------------------------------------------------------------------
-        const int pt = tid - 320;
+        const int pt = tid - 32 * (NEW + 2);
         constexpr int K8 = K / 8;
         constexpr int UNITS = NT * K8;
         const float scale = OPERAND_SCALE;
@@ -452,55 +469,60 @@ head_softmax_tc_kernel(const float *__restrict__ X, int ncol, const uint8_t *__r
         // ---- epilogue ---------------------------------------------------------------------------
         const int q = warp & 3, ch = warp >> 2;
         const int m = q * 32 + lane;
-        const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + ch * 32;
-        constexpr int KQ = K / 4;                         // the stay dot product is split over the 4 q-warps
+        const int cl = lane & (CW - 1);                   // this lane's column inside the slice (sums, stay row)
+        const int kh = lane / CW;                         // which part of the stay dot product this lane takes
+        const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + ch * CW;
+        constexpr int KQ = K / 4;                         // the stay dot product is split over the 4 q-warps ...
+        constexpr int KL = KQ / KSPLIT;                   // ... and over the KSPLIT lanes that share a column
+        static_assert(KL % 4 == 0, "stay split");
         const float b_stay = bias[NTILE * 128];
-        float ws[KQ];
+        float ws[KL];
 #pragma unroll
-        for (int i = 0; i < KQ; i++) ws[i] = w_stay[q * KQ + i];
+        for (int i = 0; i < KL; i++) ws[i] = w_stay[q * KQ + kh * KL + i];
         const float keep = 1.0f - min_prob;
         // FAST: exp((acc * 2^-16 + b) / cdiv) = 2^(acc * sc + b * bsc), one FFMA in front of ex2.approx
         const float inv_cdiv = 1.0f / cdiv;
         const float sc = RESULT_SCALE * inv_cdiv * 1.4426950408889634f, bsc = inv_cdiv * 1.4426950408889634f;
-        float4 xs4[KQ / 4];
+        float4 xs4[KL / 4];
         auto load_stay_x = [&](int chunk) {
-            const int col = min(chunk * NT + ch * 32 + lane, ncol - 1);     // clamped: out-of-range columns are never stored
-            const float4 *xp = reinterpret_cast<const float4 *>(X + (size_t)col * K + q * KQ);
+            const int col = min(chunk * NT + ch * CW + cl, ncol - 1);      // clamped: out-of-range columns are never stored
+            const float4 *xp = reinterpret_cast<const float4 *>(X + (size_t)col * K + q * KQ + kh * KL);
 #pragma unroll
-            for (int i = 0; i < KQ / 4; i++) xs4[i] = __ldg(xp + i);
+            for (int i = 0; i < KL / 4; i++) xs4[i] = __ldg(xp + i);
         };
         load_stay_x(blockIdx.x);
         uint32_t it = 0;
         for (int c = blockIdx.x; c < nchunk; c += gridDim.x, it++) {
-            const int col0 = c * NT + ch * 32;            // first column of this warp's half
-            const int mycol = col0 + lane;
-            // stay logit, partial over k in [q*KQ, (q+1)*KQ) for column `mycol`: the activations were fetched while
+            const int col0 = c * NT + ch * CW;            // first column of this warp's slice
+            const int mycol = col0 + cl;
+            // stay logit, partial over this lane's part of k for column `mycol`: the activations were fetched while
             // the previous chunk was being finished (xs4), the next chunk's are requested right away
             float sp = 0.0f;
 #pragma unroll
-            for (int i = 0; i < KQ / 4; i++) {
+            for (int i = 0; i < KL / 4; i++) {
                 float4 x4 = xs4[i];
                 if (xdiv != 1.0f) { x4.x /= xdiv; x4.y /= xdiv; x4.z /= xdiv; x4.w /= xdiv; }
                 sp = fmaf(ws[4 * i], x4.x, sp); sp = fmaf(ws[4 * i + 1], x4.y, sp);
                 sp = fmaf(ws[4 * i + 2], x4.z, sp); sp = fmaf(ws[4 * i + 3], x4.w, sp);
             }
+            if (KSPLIT == 2) sp += __shfl_xor_sync(0xffffffffu, sp, 16);
             load_stay_x(c + (int)gridDim.x);
             // pass A: e = exp(logit), column sums over this thread's 8 rows
-            float cs[32];
+            float cs[CW];
 #pragma unroll
-            for (int j = 0; j < 32; j++) cs[j] = 0.0f;
+            for (int j = 0; j < CW; j++) cs[j] = 0.0f;
 #pragma unroll 1
             for (int t = 0; t < NTILE; t++) {
                 mbar_wait(&tile_full[t], it & 1);
                 tc_fence_after();
-                float v[32];
-                tmem_ld32(tbase + t * NT, v);
+                float v[CW];
+                tmem_ld_cw<CW>(tbase + t * NT, v);
                 tmem_ld_wait();
                 const float bt = __ldg(bias + t * 128 + m);
                 if (FAST) {
                     const float bt2 = bt * bsc;
 #pragma unroll
-                    for (int j = 0; j < 32; j++) {
+                    for (int j = 0; j < CW; j++) {
                         // clamp = the reference's exp_ps input clamp (+-88.376) expressed in base 2
                         const float e = ex2_approx(fminf(fmaxf(fmaf(v[j], sc, bt2), -127.5f), 127.5f));
                         cs[j] += e;
@@ -508,18 +530,19 @@ head_softmax_tc_kernel(const float *__restrict__ X, int ncol, const uint8_t *__r
                     }
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 32; j++) {
+                    for (int j = 0; j < CW; j++) {
                         const float e = exp_cephes((fmaf(v[j], RESULT_SCALE, bt)) / cdiv);
                         cs[j] += e;
                         v[j] = e;
                     }
                 }
-                tmem_st32(tbase + t * NT, v);
+                tmem_st_cw<CW>(tbase + t * NT, v);
             }
             tmem_st_wait();
-            // column sums over the 32 lanes: halving butterfly (31 shuffles); lane L ends with column L
+            // column sums over the 32 lanes (= 32 rows): halving butterfly over the CW columns, then (CW = 16) the two
+            // half-warps are added; lane L ends with the sum of column L % CW
 #pragma unroll
-            for (int w = 16; w > 0; w >>= 1) {
+            for (int w = CW / 2; w > 0; w >>= 1) {
                 const bool up = (lane & w) != 0;
 #pragma unroll
                 for (int j = 0; j < w; j++) {
@@ -529,17 +552,20 @@ head_softmax_tc_kernel(const float *__restrict__ X, int ncol, const uint8_t *__r
                     cs[j] = mine_v + __shfl_xor_sync(0xffffffffu, send, w);
                 }
             }
-            const int pb = ((it & 1) * 2 + ch) * 4 * 32;
-            part_sum[pb + q * 32 + lane] = cs[0];
-            part_stay[pb + q * 32 + lane] = sp;
+            if (KSPLIT == 2) cs[0] += __shfl_xor_sync(0xffffffffu, cs[0], 16);
+            const int pb = ((it & 1) * EW + ch) * 4 * CW;
+            if (lane < CW) {
+                part_sum[pb + q * CW + cl] = cs[0];
+                part_stay[pb + q * CW + cl] = sp;
+            }
             named_bar_sync(1 + ch, 128);
             float tot = 0.0f, sl = 0.0f;
 #pragma unroll
-            for (int qq = 0; qq < 4; qq++) { tot += part_sum[pb + qq * 32 + lane]; sl += part_stay[pb + qq * 32 + lane]; }
+            for (int qq = 0; qq < 4; qq++) { tot += part_sum[pb + qq * CW + cl]; sl += part_stay[pb + qq * CW + cl]; }
             const float e_stay = FAST ? ex2_approx(fminf(fmaxf((b_stay + sl) * bsc, -127.5f), 127.5f))
                                       : exp_cephes((b_stay + sl) / cdiv);
             const float recip = __fdiv_rn(1.0f, tot + e_stay);
-            if (q == 0 && mycol < ncol) {
+            if (q == 0 && lane < CW && mycol < ncol) {
                 // stay state and the three padding lanes (exp(0) = 1 in the reference, normalised like the rest)
                 float ps = e_stay * recip, pp = recip;
                 if (return_log) { ps = head_log<FAST>(min_prob + keep * ps); pp = head_log<FAST>(min_prob + keep * pp); }
@@ -548,14 +574,14 @@ head_softmax_tc_kernel(const float *__restrict__ X, int ncol, const uint8_t *__r
             }
             // pass B: normalise, robust log, store.  out = log(min_prob + keep * e * recip)
             const float krc_mine = return_log ? keep * recip : recip;
-            float rc[32];
+            float rc[CW];
 #pragma unroll
-            for (int j = 0; j < 32; j++) rc[j] = __shfl_sync(0xffffffffu, krc_mine, j);
-            const int nok = min(32, ncol - col0);
+            for (int j = 0; j < CW; j++) rc[j] = __shfl_sync(0xffffffffu, krc_mine, j);
+            const int nok = min(CW, ncol - col0);
 #pragma unroll 1
             for (int t = 0; t < NTILE; t++) {
-                float v[32];
-                tmem_ld32(tbase + t * NT, v);
+                float v[CW];
+                tmem_ld_cw<CW>(tbase + t * NT, v);
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
@@ -563,17 +589,17 @@ head_softmax_tc_kernel(const float *__restrict__ X, int ncol, const uint8_t *__r
                 float *dst = post + (size_t)col0 * OSTRIDE + t * 128 + m;
                 if (return_log) {
 #pragma unroll
-                    for (int j = 0; j < 32; j++) v[j] = head_log<FAST>(fmaf(v[j], rc[j], min_prob));
+                    for (int j = 0; j < CW; j++) v[j] = head_log<FAST>(fmaf(v[j], rc[j], min_prob));
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 32; j++) v[j] = v[j] * rc[j];
+                    for (int j = 0; j < CW; j++) v[j] = v[j] * rc[j];
                 }
-                if (nok == 32) {
+                if (nok == CW) {
 #pragma unroll
-                    for (int j = 0; j < 32; j++) dst[j * OSTRIDE] = v[j];
+                    for (int j = 0; j < CW; j++) dst[j * OSTRIDE] = v[j];
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 32; j++)
+                    for (int j = 0; j < CW; j++)
                         if (j < nok) dst[j * OSTRIDE] = v[j];
                 }
             }
@@ -593,18 +619,24 @@ int launch_head_softmax_tc(const float *X, int ncol, int K, const uint8_t *wimg,
     if (K != 96 || ostride != 1028) return -1;
     using G = HeadCfg<96>;
     static bool configured = false;
+    static int ew = 0;
     if (!configured) {
-        if (cudaFuncSetAttribute(head_softmax_tc_kernel<96, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM) != cudaSuccess ||
-            cudaFuncSetAttribute(head_softmax_tc_kernel<96, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM) != cudaSuccess)
+        const char *e = getenv("SCRAPPIE_B200_HEAD_SLICES");
+        ew = (e && atoi(e) == 2) ? 2 : 4;
+        if (cudaFuncSetAttribute(head_softmax_tc_kernel<96, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM) != cudaSuccess ||
+            cudaFuncSetAttribute(head_softmax_tc_kernel<96, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM) != cudaSuccess ||
+            cudaFuncSetAttribute(head_softmax_tc_kernel<96, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM) != cudaSuccess)
             return -1;
         configured = true;
     }
     const int nchunk = (ncol + G::NT - 1) / G::NT;
     const int grid = nchunk < 148 ? nchunk : 148;
     if (exact_math)
-        head_softmax_tc_kernel<96, false><<<grid, 448, G::SMEM, s>>>(X, ncol, wimg, w_stay, bias, post, ostride, xdiv, cdiv, min_prob, return_log);
+        head_softmax_tc_kernel<96, false, 2><<<grid, 448, G::SMEM, s>>>(X, ncol, wimg, w_stay, bias, post, ostride, xdiv, cdiv, min_prob, return_log);
+    else if (ew == 2)
+        head_softmax_tc_kernel<96, true, 2><<<grid, 448, G::SMEM, s>>>(X, ncol, wimg, w_stay, bias, post, ostride, xdiv, cdiv, min_prob, return_log);
     else
-        head_softmax_tc_kernel<96, true><<<grid, 448, G::SMEM, s>>>(X, ncol, wimg, w_stay, bias, post, ostride, xdiv, cdiv, min_prob, return_log);
+        head_softmax_tc_kernel<96, true, 4><<<grid, 704, G::SMEM, s>>>(X, ncol, wimg, w_stay, bias, post, ostride, xdiv, cdiv, min_prob, return_log);
     return 0;
 }
 
