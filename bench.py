@@ -355,15 +355,26 @@ def main_b200(args, rank, world, local_rank):
         if k.startswith("gru_scan") and args.model != "rnnrf_r94":
             traffic = v["dram_read_bytes"] + v["dram_write_bytes"]
 
-    def hbm_kernel(name, ms, nbytes):
-        return {"kernel": name, "bound": "hbm", "avg_launch_ms": ms, "bytes_per_launch": nbytes,
-                "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s", "frac": nbytes / (ms * 1e-3) / 1e9 / hbm}
+    # write-only HBM bandwidth of this pool's B200 (tools/hbm_write_probe.py, r29): kernels that mostly write are
+    # bounded by it rather than by the half-read half-write copy figure of MEASURED_PEAKS.json
+    HBM_WRITE_GBS = 3904.0
+
+    def hbm_kernel(name, ms, nbytes, wbytes=None):
+        k = {"kernel": name, "bound": "hbm", "avg_launch_ms": ms, "bytes_per_launch": nbytes,
+             "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s", "frac": nbytes / (ms * 1e-3) / 1e9 / hbm}
+        if wbytes is not None:
+            k["write_bytes_per_launch"] = wbytes
+            k["write_achieved"] = wbytes / (ms * 1e-3) / 1e9
+            k["write_peak"] = HBM_WRITE_GBS
+            k["write_frac"] = k["write_achieved"] / HBM_WRITE_GBS
+        return k
     aff_ms = float(np.mean([solo["affine%d" % l] for l in range(1, 6)]))
     tb_bytes = (nstate_stride - 4 + 4) if args.model != "rnnrf_r94" else 8
     kernels = [
         hbm_kernel("conv_act", solo["conv"], nsamp0 * 4 + cols * H * 4),
-        hbm_kernel("affine_tc (GRU input transform)", aff_ms, cols * (H + 3 * H) * 4),
-        hbm_kernel("head (FF + softmax + robust log)", solo["head_gemm"] + solo["head_finish"], cols * (H + nstate_stride) * 4),
+        hbm_kernel("affine_tc (GRU input transform)", aff_ms, cols * (H + 3 * H) * 4, cols * 3 * H * 4),
+        hbm_kernel("head (FF + softmax + robust log)", solo["head_gemm"] + solo["head_finish"], cols * (H + nstate_stride) * 4,
+                   cols * nstate_stride * 4),
         hbm_kernel("decode (Viterbi + traceback)", solo["decode"], cols * (nstate_stride * 4 + tb_bytes + 4)),
     ]
     stage_sum = {k: float(np.mean([st[k] for st in stage])) for k in stage[0]}
