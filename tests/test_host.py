@@ -329,3 +329,19 @@ def test_detect_events_bit_exact(sb, golden, reference):
     flat = np.full(300, 90.0, dtype=np.float32)                   # no boundary at all: one event over the whole signal
     ev = sb.detect_events(flat)
     assert ev.shape == (1, 4) and ev[0, 0] == 0 and ev[0, 1] == 300 and ev[0, 2] == 90.0 and ev[0, 3] == 0.0
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours): one JSON line with the contract's keys,
+    timed on the compiled reference where it is built (oracle/_ref), else on the oracle port.  Tiny sample here."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--reads", "8",
+                          "--samples", "1000", "--steps", "1", "--warmup", "1"], check=True, capture_output=True, text=True).stdout
+    line = json.loads(out.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "samples/s" and line["higher_is_better"] is True
+    assert line["metric"] == "raw samples/sec (rgrgr_r94)" and line["value"] > 0 and line["gpu_launches"] == 0
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert abs(line["e2e"]["value"] - line["value"]) < 1e-6 * line["value"]
