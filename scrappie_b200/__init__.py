@@ -157,6 +157,7 @@ def lib():
         "sb2_engine_load_blob": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
         "sb2_last_error": (C.c_char_p, []),
         "sb2_engine_launch_count": (C.c_uint64, [C.c_void_p]),
+        "sb2_engine_set_scan_generation": (C.c_int, [C.c_void_p, C.c_int]),
         "sb2_batch_create": (C.c_void_p, [C.c_void_p, C.c_int, C.POINTER(C.c_size_t), C.c_size_t]),
         "sb2_batch_destroy": (None, [C.c_void_p]),
         "sb2_batch_nblock": (C.c_size_t, [C.c_void_p, C.c_size_t]),
@@ -266,9 +267,15 @@ class RawTable(object):
     def trim(self, start=200, end=10, varseg_chunk=100, varseg_thresh=0.0):
         """Trim by MAD segmentation then fixed amounts (trim_and_segment_raw).  The C
         routine frees its buffer when nothing is left, so it works on a malloc'd copy."""
+        if varseg_chunk < 2:
+            # trim_raw_by_mad fails here WITHOUT freeing the buffer, while "nothing left" frees it: rejected before
+            # the call so that the two cases cannot be confused (and nothing leaks)
+            raise ValueError("varseg_chunk must be at least 2")
         _libc.malloc.restype = C.c_void_p
         _libc.malloc.argtypes = [C.c_size_t]
         buf = _libc.malloc(max(self._data.nbytes, 4))
+        if not buf:
+            raise MemoryError("trim: cannot allocate the working copy")
         C.memmove(buf, self._data.ctypes.data, self._data.nbytes)
         rt = _RawTable(None, self._rt.n, self._rt.start, self._rt.end, C.cast(buf, _f32p))
         out = lib().trim_and_segment_raw(rt, start, end, varseg_chunk, varseg_thresh)
@@ -532,6 +539,11 @@ class Engine(object):
     @property
     def launches(self):
         return int(lib().sb2_engine_launch_count(self._h))
+
+    def set_scan_generation(self, gen):
+        """0 automatic, 4 / 5: force the GRU scan kernel generation (affects batches that have not run yet)."""
+        if lib().sb2_engine_set_scan_generation(self._h, int(gen)):
+            raise ValueError("scan generation must be 0, 4 or 5")
 
     def batch(self, model, nsample):
         return Batch(self, model, nsample)

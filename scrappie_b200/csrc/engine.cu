@@ -43,8 +43,6 @@ struct DevModel {
     float *iW[SB2_NLAYER]{}, *b[SB2_NLAYER]{}, *sW[SB2_NLAYER]{}, *sW2[SB2_NLAYER]{};
     float *FF_W = nullptr, *FF_b = nullptr;
     float *comb_Wf[2]{}, *comb_Wb[2]{}, *comb_b[2]{};    // raw_r94: feedforward2_tanh layers
-    uint8_t *scan_img[SB2_NLAYER]{};     // tensor-core scan: per-layer weight image
-    uint8_t *d_img_all = nullptr;
     uint8_t *iw_img[SB2_NLAYER]{};       // tensor-core affine: per-layer input-transform image
     uint8_t *d_gemm_img_all = nullptr;
     uint8_t *head_img = nullptr;         // fused output head (1025-state models, K = 96)
@@ -58,10 +56,14 @@ struct sb2_engine {
     float *flush_buf = nullptr;
     size_t flush_n = 0;
     std::mutex mu;
-    int scan_impl = 0;      // 0 = ffma, 1 = tcgen05
+    int scan_impl = 5;      // gate math of the tcgen05 scan (5 / 2 / 0), or -1 = fp32 CUDA-core scan
+    std::atomic<int> scan_gen{0};   // 0 automatic (v5 for >= 48 reads), 4 / 5 forced
     int gemm_impl = 0;
     long long *d_trace = nullptr;   // diagnostic: hand-over timestamps of the scan kernel (SCRAPPIE_B200_TRACE=1)
     int head_exact = 0;     // 1: cephes exp / log in the fused head (bit-level mirror of the reference's maths)
+    // idle workspaces of sb2_basecall_batch / sb2_basecall_raw_batch, per model: device buffers, pinned staging and
+    // CUDA graphs survive between calls, so the documented drop-in call allocates nothing in steady state
+    std::vector<struct sb2_batch *> pool[SB2_NMODEL];
 };
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -115,19 +117,6 @@ static int upload_model(sb2_engine *eng, DevModel *dm) {
         dm->loaded = true;
         return 0;
     }
-    {   // tensor-core scan images
-        const size_t nb = align_up(scan_image_bytes((int)H), 256);
-        std::vector<uint8_t> img(nb * SB2_NLAYER, 0);
-        std::vector<float> sw, sw2;
-        for (int l = 0; l < SB2_NLAYER; l++) {
-            sw = compact(h.sW[l]);
-            sw2 = compact(h.sW2[l]);
-            build_scan_image(sw.data(), sw2.data(), (int)H, img.data() + nb * l);
-        }
-        CUDA_OK(cudaMalloc(&dm->d_img_all, img.size()));
-        CUDA_OK(cudaMemcpy(dm->d_img_all, img.data(), img.size(), cudaMemcpyHostToDevice));
-        for (int l = 0; l < SB2_NLAYER; l++) dm->scan_img[l] = dm->d_img_all + nb * l;
-    }
     {   // tensor-core affine images (input transforms)
         const size_t nb = align_up(gemm_image_bytes(3, (int)H, (int)H), 256);
         std::vector<uint8_t> img(nb * SB2_NLAYER, 0);
@@ -150,23 +139,39 @@ static int upload_model(sb2_engine *eng, DevModel *dm) {
     return 0;
 }
 
+// Free everything a (possibly partial) model load allocated; the slot can be loaded again afterwards.
+static void release_model(sb2_engine *eng, DevModel *dm) {
+    cudaSetDevice(eng->device);
+    if (dm->d_all) cudaFree(dm->d_all);
+    if (dm->d_gemm_img_all) cudaFree(dm->d_gemm_img_all);
+    if (dm->head_img) cudaFree(dm->head_img);
+    sb2_host_model_free(&dm->host);
+    *dm = DevModel{};
+}
+
 extern "C" int sb2_engine_load_blob(sb2_engine *eng, enum raw_model_type model, const void *blob, size_t nbytes) {
     if (nullptr == eng || model < 0 || model >= SCRAPPIE_MODEL_INVALID) return -1;
     std::lock_guard<std::mutex> lock(eng->mu);
     DevModel *dm = &eng->models[model];
     if (dm->loaded) return 0;
     if (0 != sb2_host_model_parse(blob, nbytes, &dm->host)) return -1;
+    int rc = 0;
     if (dm->host.H != 96 && dm->host.H != 112) {
         sb2_set_error("unsupported GRU width %u", dm->host.H);
-        return -1;
+        rc = -1;
     }
-    return upload_model(eng, dm);
+    if (0 == rc) rc = upload_model(eng, dm);
+    if (0 != rc) release_model(eng, dm);             // a retry must not find half a model (or leak it)
+    return rc;
 }
 
 static DevModel *get_model(sb2_engine *eng, enum raw_model_type model) {
     if (nullptr == eng || model < 0 || model >= SCRAPPIE_MODEL_INVALID) return nullptr;
     DevModel *dm = &eng->models[model];
-    if (dm->loaded) return dm;
+    {
+        std::lock_guard<std::mutex> lock(eng->mu);  // `loaded` is published under the engine's mutex
+        if (dm->loaded) return dm;
+    }
     char path[1200];
     snprintf(path, sizeof(path), "%s/%s.bin", eng->weights_dir, sb2_model_file_stem(model));
     void *blob = nullptr;
@@ -196,31 +201,25 @@ extern "C" sb2_engine *sb2_engine_create(int device, const char *weights_dir) {
     else if (0 != sb2_default_weights_dir(eng->weights_dir, sizeof(eng->weights_dir))) eng->weights_dir[0] = '\0';
     const char *scan = getenv("SCRAPPIE_B200_SCAN");
     const char *gemm = getenv("SCRAPPIE_B200_GEMM");
-    // tcgen05 with weights in TMEM: 1 cephes gates, 2 SFU gates, 3 polynomial gates (default);
-    // 4 tcgen05 with weights in shared memory (SFU gates); 0 fp32 CUDA cores (debug cross-check)
-    // 5..7: v3 kernel (two-pass, reset gate first) with cephes / SFU / polynomial gates
-    // 8..13: v4 kernel (v3 + two read groups per CTA); gate math 0 cephes, 1 SFU ex2 + rcp, 2 polynomial exp2 +
-    //        refined rcp, 3 / 4 compensated-argument ex2 with / without the Newton step, 5 plain ex2.approx +
-    //        Newton-refined rcp (13 = default: as accurate as the polynomial, shortest dependent chain that is)
-    eng->scan_impl = 13;
-    if (scan && 0 == strcmp(scan, "v4_poly")) eng->scan_impl = 10;
-    if (scan && 0 == strcmp(scan, "v3")) eng->scan_impl = 7;
-    if (scan && 0 == strcmp(scan, "v4_cephes")) eng->scan_impl = 8;
-    if (scan && 0 == strcmp(scan, "v4_fast")) eng->scan_impl = 9;
-    if (scan && 0 == strcmp(scan, "v4_sfu")) eng->scan_impl = 11;   // ex2.approx with compensated argument
-    if (scan && 0 == strcmp(scan, "v4_sfu2")) eng->scan_impl = 13;  // plain ex2.approx, Newton-refined reciprocal
-    if (scan && 0 == strcmp(scan, "v4_sfu1")) eng->scan_impl = 12;  // same without the Newton step on rcp.approx
-    if (scan && 0 == strcmp(scan, "ffma")) eng->scan_impl = 0;
-    if (scan && 0 == strcmp(scan, "v3_cephes")) eng->scan_impl = 5;
-    if (scan && 0 == strcmp(scan, "v3_fast")) eng->scan_impl = 6;
-    if (scan && 0 == strcmp(scan, "tc")) eng->scan_impl = 1;
-    if (scan && 0 == strcmp(scan, "tc_fast")) eng->scan_impl = 2;
-    if (scan && 0 == strcmp(scan, "tc_poly")) eng->scan_impl = 3;
-    if (scan && 0 == strcmp(scan, "tc_smem")) eng->scan_impl = 4;
+    // GRU scan: tcgen05 kernels (weights in TMEM) with gate math 5 = SFU ex2 + Newton-refined reciprocal (default),
+    // 2 = polynomial exp2, 0 = cephes-identical gates; -1 = fp32 CUDA cores (debug cross-check).  Read once per engine.
+    eng->scan_impl = 5;
+    if (scan && (0 == strcmp(scan, "poly") || 0 == strcmp(scan, "v4_poly"))) eng->scan_impl = 2;
+    if (scan && (0 == strcmp(scan, "cephes") || 0 == strcmp(scan, "v4_cephes"))) eng->scan_impl = 0;
+    if (scan && 0 == strcmp(scan, "ffma")) eng->scan_impl = -1;
+    if (const char *g = getenv("SCRAPPIE_B200_SCAN_GEN")) eng->scan_gen = atoi(g);
     eng->gemm_impl = (gemm && 0 == strcmp(gemm, "ffma")) ? 0 : 1;    // 1 = tcgen05 (default), 0 = fp32 CUDA cores
     const char *headm = getenv("SCRAPPIE_B200_HEAD");
     eng->head_exact = (headm && 0 == strcmp(headm, "exact")) ? 1 : 0;
     if (cudaSetDevice(device) != cudaSuccess) { delete eng; return nullptr; }
+    // dynamic shared-memory limits are a per-device attribute of each kernel: set them for THIS device now, so that
+    // no launch path ever configures anything (first use may be under stream capture, or from several host threads)
+    if (0 != configure_scan_kernels() || 0 != configure_gemm_kernels() || 0 != configure_v1_kernels()) {
+        sb2_set_error("device %d: cannot configure kernels (%s); sm_100a required", device, cudaGetErrorString(cudaGetLastError()));
+        fprintf(stderr, "scrappie_b200: %s\n", sb2_last_error());
+        delete eng;
+        return nullptr;
+    }
     if (getenv("SCRAPPIE_B200_TRACE") && cudaMalloc(&eng->d_trace, 64 * sizeof(long long)) == cudaSuccess)
         cudaMemset(eng->d_trace, 0, 64 * sizeof(long long));
     return eng;
@@ -229,13 +228,11 @@ extern "C" sb2_engine *sb2_engine_create(int device, const char *weights_dir) {
 extern "C" void sb2_engine_destroy(sb2_engine *eng) {
     if (nullptr == eng) return;
     cudaSetDevice(eng->device);
-    for (auto &dm : eng->models) {
-        if (dm.d_all) cudaFree(dm.d_all);
-        if (dm.d_img_all) cudaFree(dm.d_img_all);
-        if (dm.d_gemm_img_all) cudaFree(dm.d_gemm_img_all);
-        if (dm.head_img) cudaFree(dm.head_img);
-        sb2_host_model_free(&dm.host);
+    for (auto &free_list : eng->pool) {
+        for (sb2_batch *b : free_list) sb2_batch_destroy(b);
+        free_list.clear();
     }
+    for (auto &dm : eng->models) release_model(eng, &dm);
     if (eng->flush_buf) cudaFree(eng->flush_buf);
     if (eng->d_trace) cudaFree(eng->d_trace);
     delete eng;
@@ -247,6 +244,14 @@ extern "C" int sb2_engine_read_trace(sb2_engine *eng, long long *out, int n) {
     CUDA_OK(cudaSetDevice(eng->device));
     CUDA_OK(cudaDeviceSynchronize());
     CUDA_OK(cudaMemcpy(out, eng->d_trace, sizeof(long long) * (size_t)std::min(n, 64), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// Force a GRU scan kernel generation (4: four reads per group, 5: eight reads per group + TMA input ring; 0 = automatic).
+// Batches that already captured a CUDA graph keep replaying it: set this before their first run.
+extern "C" int sb2_engine_set_scan_generation(sb2_engine *eng, int gen) {
+    if (nullptr == eng || (gen != 0 && gen != 4 && gen != 5)) return -1;
+    eng->scan_gen = gen;
     return 0;
 }
 
@@ -313,6 +318,15 @@ struct sb2_batch {
     sb2_params graph_params{};
     uint64_t graph_launches = 0;
     int eager_runs = 0;
+    // capacities of the device buffers: a pooled workspace is re-shaped for every call and only ever grows
+    size_t cap_reads = 0, cap_cols = 0, cap_samples = 0, cap_bases = 0, cap_finish_cols = 0, cap_finish_reads = 0;
+    bool pooled = false;
+    uint8_t *h_meta = nullptr, *d_meta = nullptr;       // nsample | nblock | col_off | samp_off | conv tails: one H2D copy
+    size_t meta_bytes = 0;
+    float *h_stage = nullptr;                           // pinned staging of the signals in the padded layout
+    size_t stage_cap = 0;
+    int64_t *d_src = nullptr;                           // raw-signal basecall: source offset of every kept read
+    int graph_dims[3]{};                                // (nread, total_cols, max_cols) the captured graph was made for
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[ST_COUNT + 1]{};
     cudaEvent_t ev_done = nullptr;          // blocking-sync event the basecall path waits on
@@ -327,38 +341,43 @@ static int dev_alloc(T **p, size_t n) {
     return 0;
 }
 
+static void batch_free_device(sb2_batch *b) {
+    void *ptrs[] = {b->d_raw, b->d_X[0], b->d_X[1], b->d_Xin, b->d_post, b->d_score, b->d_layers, b->d_tbE, b->d_path,
+                    b->d_tb, b->d_meta, b->d_path2, b->d_nbase, b->d_bases, b->d_bprob, b->d_Xin2, b->d_FF, b->d_gidx,
+                    b->d_gval, b->d_src};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    b->d_raw = b->d_X[0] = b->d_X[1] = b->d_Xin = b->d_post = b->d_score = b->d_layers = nullptr;
+    b->d_tbE = b->d_path = nullptr; b->d_tb = nullptr; b->d_meta = nullptr; b->d_path2 = b->d_nbase = nullptr;
+    b->d_bases = nullptr; b->d_bprob = b->d_Xin2 = b->d_FF = nullptr; b->d_gidx = nullptr; b->d_gval = nullptr; b->d_src = nullptr;
+    void *hptrs[] = {b->h_paths, b->h_scores, b->h_gidx, b->h_gval, b->h_nbase, b->h_bases, b->h_meta};
+    for (void *p : hptrs) if (p) cudaFreeHost(p);
+    b->h_paths = nullptr; b->h_scores = nullptr; b->h_gidx = nullptr; b->h_gval = nullptr; b->h_nbase = nullptr;
+    b->h_bases = nullptr; b->h_meta = nullptr;
+    if (b->graph) { cudaGraphExecDestroy(b->graph); b->graph = nullptr; }
+    b->cap_reads = b->cap_cols = b->cap_samples = b->cap_bases = b->cap_finish_cols = b->cap_finish_reads = 0;
+    b->gcap = 0;
+    b->eager_runs = 0;
+}
+
 extern "C" void sb2_batch_destroy(sb2_batch *b) {
     if (nullptr == b) return;
     cudaSetDevice(b->eng->device);
     if (b->stream) cudaStreamSynchronize(b->stream);
-    void *ptrs[] = {b->d_raw, b->d_X[0], b->d_X[1], b->d_Xin, b->d_post, b->d_score, b->d_layers, b->d_nsample,
-                    b->d_nblock, b->d_coloff, b->d_tbE, b->d_path, b->d_sampoff, b->d_tb, b->d_tails};
-    for (void *p : ptrs) if (p) cudaFree(p);
-    if (b->graph) cudaGraphExecDestroy(b->graph);
-    if (b->d_path2) cudaFree(b->d_path2);
-    if (b->d_nbase) cudaFree(b->d_nbase);
-    if (b->d_bases) cudaFree(b->d_bases);
-    if (b->h_nbase) cudaFreeHost(b->h_nbase);
-    if (b->h_bases) cudaFreeHost(b->h_bases);
-    if (b->d_bprob) cudaFree(b->d_bprob);
-    if (b->d_Xin2) cudaFree(b->d_Xin2);
-    if (b->d_FF) cudaFree(b->d_FF);
-    if (b->d_gidx) cudaFree(b->d_gidx);
-    if (b->d_gval) cudaFree(b->d_gval);
-    void *hptrs[] = {b->h_paths, b->h_scores, b->h_gidx, b->h_gval};
-    for (void *p : hptrs) if (p) cudaFreeHost(p);
+    batch_free_device(b);
+    if (b->h_stage) cudaFreeHost(b->h_stage);
     for (auto &e : b->ev) if (e) cudaEventDestroy(e);
     if (b->ev_done) cudaEventDestroy(b->ev_done);
     if (b->stream) cudaStreamDestroy(b->stream);
     delete b;
 }
 
-static int batch_init(sb2_batch *b, const size_t *nsample, size_t nread) {
+// Host-side layout of a batch: offsets of every read in the sample and column dimensions, conv tail plans.
+static int batch_layout(sb2_batch *b, const size_t *nsample, size_t nread, std::vector<sb2_conv_tail> &tails) {
     const sb2_host_model &h = b->m->host;
-    const size_t H = h.H;
     b->nread = (int)nread;
+    b->max_cols = 0;
     b->nsample.resize(nread); b->nblock.resize(nread); b->samp_off.resize(nread); b->col_off.resize(nread + 1);
-    std::vector<sb2_conv_tail> tails(nread);
+    tails.resize(nread);
     int64_t so = 0;
     int64_t co = 0;
     for (size_t r = 0; r < nread; r++) {
@@ -376,30 +395,69 @@ static int batch_init(sb2_batch *b, const size_t *nsample, size_t nread) {
     b->col_off[nread] = (int)co;
     b->total_cols = (int)co;
     b->total_samples = so;
+    return 0;
+}
 
-    CUDA_OK(cudaSetDevice(b->eng->device));
-    CUDA_OK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
-    for (auto &e : b->ev) CUDA_OK(cudaEventCreate(&e));
-    const size_t ncol = (size_t)b->total_cols;
+static size_t meta_offsets(size_t cap_reads, size_t off[5]) {
+    size_t o = 0;
+    off[0] = o; o += align_up(cap_reads * sizeof(int), 16);               // nsample
+    off[1] = o; o += align_up(cap_reads * sizeof(int), 16);               // nblock
+    off[2] = o; o += align_up((cap_reads + 1) * sizeof(int), 16);         // col_off
+    off[3] = o; o += align_up(cap_reads * sizeof(int64_t), 16);           // samp_off
+    off[4] = o; o += align_up(cap_reads * sizeof(sb2_conv_tail), 16);     // conv tails
+    return o;
+}
+
+// Make the device buffers large enough for the current layout.  Fresh batches get exactly what they need; pooled
+// workspaces grow with 1/8 head room and keep what they have when the next call is smaller.
+static int batch_reserve(sb2_batch *b) {
+    const sb2_host_model &h = b->m->host;
+    const size_t H = h.H;
+    const size_t nread = (size_t)b->nread, ncol_need = (size_t)b->total_cols, nsamp_need = (size_t)b->total_samples;
+    if (nread <= b->cap_reads && ncol_need <= b->cap_cols && nsamp_need <= b->cap_samples) return 0;
+    if (b->stream) CUDA_OK(cudaStreamSynchronize(b->stream));
+    const bool keep_layers = b->keep_layers;
+    auto grow = [&](size_t need, size_t have) { return std::max(have, b->pooled ? need + need / 8 : need); };
+    const size_t cap_reads = grow(nread, b->cap_reads), ncol = grow(ncol_need, b->cap_cols), nsamp = grow(nsamp_need, b->cap_samples);
+    batch_free_device(b);
     // raw_r94 keeps both directions of a bidirectional pair alive and merges them into `ffw` features
     if (h.arch == 1 && (dev_alloc(&b->d_Xin2, ncol * 3 * H) || dev_alloc(&b->d_FF, ncol * std::max(h.ffw, h.nfilter)))) return -1;
-    if (dev_alloc(&b->d_raw, (size_t)so) || dev_alloc(&b->d_X[0], ncol * H) || dev_alloc(&b->d_X[1], ncol * H) ||
+    if (dev_alloc(&b->d_raw, nsamp) || dev_alloc(&b->d_X[0], ncol * H) || dev_alloc(&b->d_X[1], ncol * H) ||
         dev_alloc(&b->d_Xin, ncol * 3 * H) || dev_alloc(&b->d_post, ncol * h.ostride) ||
-        dev_alloc(&b->d_score, nread) || dev_alloc(&b->d_nsample, nread) || dev_alloc(&b->d_nblock, nread) ||
-        dev_alloc(&b->d_coloff, nread + 1) || dev_alloc(&b->d_sampoff, nread) || dev_alloc(&b->d_tails, nread) ||
-        dev_alloc(&b->d_path, ncol + nread))
+        dev_alloc(&b->d_score, cap_reads) || dev_alloc(&b->d_path, ncol + cap_reads))
         return -1;
     if (h.head == 0) {
         if (dev_alloc(&b->d_tb, ncol * (h.nstate - 1)) || dev_alloc(&b->d_tbE, ncol)) return -1;
     } else {
         if (dev_alloc(&b->d_tb, ncol * 8)) return -1;
     }
-    CUDA_OK(cudaMemcpy(b->d_nsample, b->nsample.data(), nread * sizeof(int), cudaMemcpyHostToDevice));
-    CUDA_OK(cudaMemcpy(b->d_nblock, b->nblock.data(), nread * sizeof(int), cudaMemcpyHostToDevice));
-    CUDA_OK(cudaMemcpy(b->d_coloff, b->col_off.data(), (nread + 1) * sizeof(int), cudaMemcpyHostToDevice));
-    CUDA_OK(cudaMemcpy(b->d_sampoff, b->samp_off.data(), nread * sizeof(int64_t), cudaMemcpyHostToDevice));
-    CUDA_OK(cudaMemcpy(b->d_tails, tails.data(), nread * sizeof(sb2_conv_tail), cudaMemcpyHostToDevice));
-    CUDA_OK(cudaMemset(b->d_raw, 0, (size_t)so * sizeof(float)));
+    size_t off[5];
+    b->meta_bytes = meta_offsets(cap_reads, off);
+    if (dev_alloc(&b->d_meta, b->meta_bytes)) return -1;
+    CUDA_OK(cudaMallocHost(reinterpret_cast<void **>(&b->h_meta), b->meta_bytes));
+    b->d_nsample = reinterpret_cast<int *>(b->d_meta + off[0]);
+    b->d_nblock = reinterpret_cast<int *>(b->d_meta + off[1]);
+    b->d_coloff = reinterpret_cast<int *>(b->d_meta + off[2]);
+    b->d_sampoff = reinterpret_cast<int64_t *>(b->d_meta + off[3]);
+    b->d_tails = reinterpret_cast<sb2_conv_tail *>(b->d_meta + off[4]);
+    CUDA_OK(cudaMemset(b->d_raw, 0, nsamp * sizeof(float)));
+    b->cap_reads = cap_reads; b->cap_cols = ncol; b->cap_samples = nsamp;
+    if (keep_layers && dev_alloc(&b->d_layers, (size_t)6 * ncol * H)) return -1;
+    return 0;
+}
+
+// One H2D copy of the batch's dimension tables (asynchronous on the batch's stream: h_meta is pinned and is not
+// touched again before the next re-shape, which only happens after the stream has been synchronised).
+static int batch_upload_meta(sb2_batch *b, const std::vector<sb2_conv_tail> &tails) {
+    size_t off[5];
+    meta_offsets(b->cap_reads, off);
+    const size_t nread = (size_t)b->nread;
+    memcpy(b->h_meta + off[0], b->nsample.data(), nread * sizeof(int));
+    memcpy(b->h_meta + off[1], b->nblock.data(), nread * sizeof(int));
+    memcpy(b->h_meta + off[2], b->col_off.data(), (nread + 1) * sizeof(int));
+    memcpy(b->h_meta + off[3], b->samp_off.data(), nread * sizeof(int64_t));
+    memcpy(b->h_meta + off[4], tails.data(), nread * sizeof(sb2_conv_tail));
+    CUDA_OK(cudaMemcpyAsync(b->d_meta, b->h_meta, b->meta_bytes, cudaMemcpyHostToDevice, b->stream));
     b->dims.nread = b->nread;
     b->dims.total_cols = b->total_cols;
     b->dims.max_cols = b->max_cols;
@@ -408,6 +466,34 @@ static int batch_init(sb2_batch *b, const size_t *nsample, size_t nread) {
     b->dims.samp_off = b->d_sampoff;
     b->dims.col_off = b->d_coloff;
     b->dims.col_read = nullptr;
+    return 0;
+}
+
+// (Re-)shape a batch for `nread` reads of the given lengths.
+static int batch_shape(sb2_batch *b, const size_t *nsample, size_t nread) {
+    std::vector<sb2_conv_tail> tails;
+    const int prev[3] = {b->nread, b->total_cols, b->max_cols};
+    if (0 != batch_layout(b, nsample, nread, tails)) return -1;
+    CUDA_OK(cudaSetDevice(b->eng->device));
+    if (nullptr == b->stream) {
+        CUDA_OK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+        for (auto &e : b->ev) CUDA_OK(cudaEventCreate(&e));
+    }
+    if (0 != batch_reserve(b)) return -1;
+    if (0 != batch_upload_meta(b, tails)) return -1;
+    // A captured graph bakes in grid sizes and the dimension arguments: it is kept only for an identical shape, and a
+    // new shape runs eagerly once before it is captured (a stream of differently shaped batches never pays for
+    // capture + instantiation).
+    if (prev[0] != b->nread || prev[1] != b->total_cols || prev[2] != b->max_cols) {
+        if (b->graph) { cudaGraphExecDestroy(b->graph); b->graph = nullptr; }
+        b->eager_runs = 0;
+    }
+    return 0;
+}
+
+static int batch_init(sb2_batch *b, const size_t *nsample, size_t nread) {
+    if (0 != batch_shape(b, nsample, nread)) return -1;
+    CUDA_OK(cudaStreamSynchronize(b->stream));
     return 0;
 }
 
@@ -433,7 +519,7 @@ extern "C" int sb2_batch_keep_layers(sb2_batch *b, int keep) {
     if (nullptr == b) return -1;
     if (b->m->host.arch != 0) { sb2_set_error("per-layer dumps are only available for the rgrgr / rnnrf topology"); return -1; }
     CUDA_OK(cudaSetDevice(b->eng->device));
-    if (keep && nullptr == b->d_layers && dev_alloc(&b->d_layers, (size_t)6 * b->total_cols * b->m->host.H)) return -1;
+    if (keep && nullptr == b->d_layers && dev_alloc(&b->d_layers, (size_t)6 * b->cap_cols * b->m->host.H)) return -1;
     b->keep_layers = keep != 0;
     return 0;
 }
@@ -465,20 +551,11 @@ static int run_scan(sb2_batch *b, const float *Xin, const DevModel &m, int l, co
     const int H = (int)b->m->host.H;
     cudaStream_t s = b->stream;
     const int impl = b->eng->scan_impl;
-    if (impl == 0) {
+    if (impl < 0) {
         launch_gru_scan_ffma(Xin, m.sW[l], m.sW2[l], resid, out, b->dims, H, backward, s);
         return 0;
     }
-    int rc;
-    if (impl == 4) {
-        rc = (nullptr == m.scan_img[l]) ? -1 : launch_gru_scan_tc(Xin, m.scan_img[l], resid, out, b->dims, H, backward, 1, s);
-    } else if (impl >= 8) {
-        rc = launch_gru_scan_v4(Xin, m.sW[l], m.sW2[l], resid, out, b->dims, H, backward, impl - 8, trace, s);
-    } else if (impl >= 5) {
-        rc = launch_gru_scan_v3(Xin, m.sW[l], m.sW2[l], resid, out, b->dims, H, backward, impl - 5, trace, s);
-    } else {
-        rc = launch_gru_scan_tmem(Xin, m.sW[l], m.sW2[l], resid, out, b->dims, H, backward, impl - 1, s);
-    }
+    const int rc = launch_gru_scan_tc(Xin, m.sW[l], m.sW2[l], resid, out, b->dims, H, backward, impl, b->eng->scan_gen.load(), trace, s);
     if (0 != rc) sb2_set_error("tensor-core scan: unsupported configuration");
     return rc;
 }
@@ -649,6 +726,7 @@ extern "C" int sb2_batch_run(sb2_batch *b, const sb2_params *p) {
     cudaGraphDestroy(g);
     if (ei != cudaSuccess) { b->graph = nullptr; sb2_set_error("CUDA graph instantiation failed: %s", cudaGetErrorString(ei)); return -1; }
     b->graph_params = *p;
+    b->graph_dims[0] = b->nread; b->graph_dims[1] = b->total_cols; b->graph_dims[2] = b->max_cols;
     // the launches counted while capturing were recorded, not executed: they run now, with the graph
     b->graph_launches = b->eng->launches.load() - l0;
     CUDA_OK(cudaGraphLaunch(b->graph, b->stream));
@@ -774,12 +852,12 @@ static int host_threads() {
 }
 
 static int basecall_buffers(sb2_batch *b) {
-    if (nullptr != b->h_paths) return 0;
-    const size_t np = (size_t)b->total_cols + b->nread;
+    if (nullptr != b->h_paths) return 0;                // freed together with the device buffers when a workspace grows
+    const size_t np = b->cap_cols + b->cap_reads;
     // every run position needs (stay, repeat k-mer) of one column; runs can overlap, so leave head room
-    b->gcap = 4 * (size_t)b->total_cols + 64;
+    b->gcap = 4 * b->cap_cols + 64;
     CUDA_OK(cudaMallocHost(reinterpret_cast<void **>(&b->h_paths), np * sizeof(int)));
-    CUDA_OK(cudaMallocHost(reinterpret_cast<void **>(&b->h_scores), (size_t)b->nread * sizeof(float)));
+    if (nullptr == b->h_scores) CUDA_OK(cudaMallocHost(reinterpret_cast<void **>(&b->h_scores), b->cap_reads * sizeof(float)));
     CUDA_OK(cudaMallocHost(reinterpret_cast<void **>(&b->h_gidx), b->gcap * 2 * sizeof(int)));
     CUDA_OK(cudaMallocHost(reinterpret_cast<void **>(&b->h_gval), b->gcap * sizeof(float)));
     if (dev_alloc(&b->d_gidx, b->gcap * 2) || dev_alloc(&b->d_gval, b->gcap)) return -1;
@@ -787,17 +865,23 @@ static int basecall_buffers(sb2_batch *b) {
 }
 
 static int finish_buffers(sb2_batch *b) {
-    if (nullptr != b->d_bases) return 0;
     const sb2_host_model &h = b->m->host;
     const int klen = (h.head == 0) ? (int)(logf((float)h.nstate) / logf(4.0f)) : 1;
     // worst case: every block moves by a full k-mer
     b->bases_stride = (int)align_up((size_t)klen * ((size_t)b->max_cols + 1) + 1, 16);
     const size_t nbytes = (size_t)b->nread * b->bases_stride;
-    if (dev_alloc(&b->d_path2, (size_t)b->total_cols + b->nread) || dev_alloc(&b->d_nbase, b->nread) ||
-        dev_alloc(&b->d_bases, nbytes))
-        return -1;
-    CUDA_OK(cudaMallocHost(reinterpret_cast<void **>(&b->h_nbase), (size_t)b->nread * sizeof(int)));
-    CUDA_OK(cudaMallocHost(reinterpret_cast<void **>(&b->h_bases), nbytes));
+    if (nullptr == b->d_path2) {
+        if (dev_alloc(&b->d_path2, b->cap_cols + b->cap_reads) || dev_alloc(&b->d_nbase, b->cap_reads)) return -1;
+        CUDA_OK(cudaMallocHost(reinterpret_cast<void **>(&b->h_nbase), b->cap_reads * sizeof(int)));
+        if (nullptr == b->h_scores) CUDA_OK(cudaMallocHost(reinterpret_cast<void **>(&b->h_scores), b->cap_reads * sizeof(float)));
+    }
+    if (nbytes > b->cap_bases) {
+        if (b->d_bases) { CUDA_OK(cudaStreamSynchronize(b->stream)); cudaFree(b->d_bases); cudaFreeHost(b->h_bases); b->d_bases = nullptr; b->h_bases = nullptr; }
+        const size_t cap = b->pooled ? nbytes + nbytes / 4 : nbytes;
+        if (dev_alloc(&b->d_bases, cap)) return -1;
+        CUDA_OK(cudaMallocHost(reinterpret_cast<void **>(&b->h_bases), cap));
+        b->cap_bases = cap;
+    }
     return 0;
 }
 
@@ -871,7 +955,18 @@ static int homopolymer_fixup(sb2_batch *b, int *paths) {
     for (int r = 0; r < nread; r++) need[r + 1] += need[r];
     const size_t nent = 2 * need[nread];
     int rc = bad ? -1 : 0;
-    if (0 == rc && nent > b->gcap) { sb2_set_error("homopolymer gather buffer too small"); rc = -1; }
+    if (0 == rc && nent > b->gcap) {                    // overlapping runs can exceed the estimate: grow, do not fail
+        cudaStreamSynchronize(b->stream);
+        cudaFreeHost(b->h_gidx); cudaFreeHost(b->h_gval); cudaFree(b->d_gidx); cudaFree(b->d_gval);
+        b->h_gidx = nullptr; b->h_gval = nullptr; b->d_gidx = nullptr; b->d_gval = nullptr;
+        b->gcap = nent + nent / 2;
+        if (cudaMallocHost(reinterpret_cast<void **>(&b->h_gidx), b->gcap * 2 * sizeof(int)) != cudaSuccess ||
+            cudaMallocHost(reinterpret_cast<void **>(&b->h_gval), b->gcap * sizeof(float)) != cudaSuccess ||
+            dev_alloc(&b->d_gidx, b->gcap * 2) || dev_alloc(&b->d_gval, b->gcap)) {
+            sb2_set_error("homopolymer gather buffers: out of memory");
+            rc = -1;
+        }
+    }
     if (0 == rc && nent > 0) {
 #pragma omp parallel for schedule(static) num_threads(host_threads())
         for (int r = 0; r < nread; r++) {
@@ -917,7 +1012,6 @@ extern "C" int sb2_batch_basecall(sb2_batch *b, const float *concat, int pinned,
     static const bool timing = getenv("SCRAPPIE_B200_TIMING") != nullptr;
     const double t0 = now_ms();
     CUDA_OK(cudaSetDevice(b->eng->device));
-    if (0 != basecall_buffers(b)) return -1;
     if (nullptr != concat && 0 != sb2_batch_upload_concat(b, concat, pinned)) return -1;
     // SCRAPPIE_B200_FINISH=host keeps the homopolymer fix-up and the overlapper on the CPU (cross-check path)
     static const bool finish_host = getenv("SCRAPPIE_B200_FINISH") && 0 == strcmp(getenv("SCRAPPIE_B200_FINISH"), "host");
@@ -928,6 +1022,7 @@ extern "C" int sb2_batch_basecall(sb2_batch *b, const float *concat, int pinned,
         if (timing) fprintf(stderr, "scrappie_b200: basecall %d reads: launch %.2f ms, gpu + finishing + copies %.2f ms\n", nread, tg - t0, now_ms() - tg);
         return n;
     }
+    if (0 != basecall_buffers(b)) return -1;
     if (0 != sb2_batch_run(b, p) || 0 != sb2_batch_download_paths(b, b->h_paths, b->h_scores)) return -1;
     const double t1 = now_ms();
     const sb2_host_model &h = b->m->host;
@@ -960,15 +1055,87 @@ extern "C" void sb2_calls_free(sb2_call *calls, size_t n) {
     for (size_t i = 0; i < n; i++) { free(calls[i].bases); calls[i].bases = nullptr; }
 }
 
+// ---- workspace pool -------------------------------------------------------------------------------------------
+// sb2_basecall_batch / sb2_basecall_raw_batch take an idle workspace of the model (or make one), re-shape it for the
+// call and hand it back afterwards: device buffers, pinned staging areas, the stream and -- while consecutive calls
+// have the same shape -- the captured CUDA graph are reused, so a steady stream of calls allocates nothing.
+// Concurrent callers each get their own workspace.
+static sb2_batch *pool_acquire(sb2_engine *eng, enum raw_model_type model) {
+    DevModel *dm = get_model(eng, model);
+    if (nullptr == dm) return nullptr;
+    {
+        std::lock_guard<std::mutex> lock(eng->mu);
+        auto &free_list = eng->pool[model];
+        if (!free_list.empty()) {
+            sb2_batch *b = free_list.back();
+            free_list.pop_back();
+            return b;
+        }
+    }
+    sb2_batch *b = new sb2_batch();
+    b->eng = eng;
+    b->model_type = model;
+    b->m = dm;
+    b->pooled = true;
+    return b;
+}
+
+static void pool_release(sb2_engine *eng, sb2_batch *b, bool healthy) {
+    if (nullptr == b) return;
+    if (!healthy) { sb2_batch_destroy(b); return; }    // never recycle a workspace a CUDA error went through
+    std::lock_guard<std::mutex> lock(eng->mu);
+    eng->pool[b->model_type].push_back(b);
+}
+
+// Shortest signal the model's convolution accepts; shorter reads are dropped from a batch (bases NULL, score NAN)
+// instead of failing it -- the reference handles reads one at a time, so a bad read never loses the others.
+static size_t min_read_samples(sb2_engine *eng, enum raw_model_type model) {
+    DevModel *dm = get_model(eng, model);
+    return dm ? (size_t)dm->host.winlen : 0;
+}
+
+// Signals from ordinary (pageable) host memory: gathered into the workspace's pinned staging area in the batch's
+// padded layout (pads zeroed), then one asynchronous H2D copy.
+static int stage_signals(sb2_batch *b, const float *const *signals, const std::vector<size_t> &keep) {
+    const size_t total = (size_t)b->total_samples;
+    if (total > b->stage_cap) {
+        if (b->h_stage) cudaFreeHost(b->h_stage);
+        b->h_stage = nullptr;
+        const size_t cap = total + total / 8;
+        CUDA_OK(cudaMallocHost(reinterpret_cast<void **>(&b->h_stage), cap * sizeof(float)));
+        b->stage_cap = cap;
+    }
+    const int n = b->nread;
+#pragma omp parallel for schedule(static) num_threads(host_threads()) if (total > (size_t)1 << 18)
+    for (int r = 0; r < n; r++) {
+        float *dst = b->h_stage + b->samp_off[r];
+        const size_t len = (size_t)b->nsample[r], padded = (len + 3) / 4 * 4;
+        memcpy(dst, signals[keep[r]], len * sizeof(float));
+        for (size_t i = len; i < padded; i++) dst[i] = 0.0f;
+    }
+    CUDA_OK(cudaMemcpyAsync(b->d_raw, b->h_stage, total * sizeof(float), cudaMemcpyHostToDevice, b->stream));
+    return 0;
+}
+
 extern "C" int sb2_basecall_batch(sb2_engine *eng, enum raw_model_type model, const float *const *signals,
                                   const size_t *nsample, size_t nread, const sb2_params *p, sb2_call *out) {
     if (nullptr == eng || nullptr == signals || nullptr == nsample || nullptr == p || nullptr == out) return -1;
     for (size_t r = 0; r < nread; r++) out[r] = sb2_call{nullptr, NAN, 0, 0};
-    sb2_batch *b = sb2_batch_create(eng, model, nsample, nread);
+    const size_t min_len = min_read_samples(eng, model);
+    if (0 == min_len) return -1;
+    std::vector<size_t> keep, len;
+    for (size_t r = 0; r < nread; r++)
+        if (nullptr != signals[r] && nsample[r] >= min_len) { keep.push_back(r); len.push_back(nsample[r]); }
+    if (keep.empty()) return 0;
+    sb2_batch *b = pool_acquire(eng, model);
     if (nullptr == b) return -1;
     int ncalled = -1;
-    if (0 == sb2_batch_upload(b, signals)) ncalled = sb2_batch_basecall(b, nullptr, 0, p, out);
-    sb2_batch_destroy(b);
+    std::vector<sb2_call> calls(keep.size(), sb2_call{nullptr, NAN, 0, 0});
+    if (0 == batch_shape(b, len.data(), len.size()) && 0 == stage_signals(b, signals, keep)) {
+        ncalled = sb2_batch_basecall(b, nullptr, 0, p, calls.data());
+        if (ncalled >= 0) for (size_t i = 0; i < keep.size(); i++) out[keep[i]] = calls[i];
+    }
+    pool_release(eng, b, ncalled >= 0);
     return ncalled;
 }
 
@@ -1076,29 +1243,39 @@ extern "C" int sb2_basecall_raw_batch(sb2_engine *eng, enum raw_model_type model
     RawStage st;
     std::vector<int> start, end;
     if (0 != stage_and_trim(eng, raws, nsample, nread, t, st, start, end)) return -1;
+    const size_t min_len = min_read_samples(eng, model);
+    if (0 == min_len) return -1;
     std::vector<size_t> keep, len;
     std::vector<int64_t> src;
     for (size_t r = 0; r < nread; r++) {
         if (start_out) start_out[r] = (size_t)start[r];
         if (end_out) end_out[r] = (size_t)end[r];
-        if (end[r] > start[r]) { keep.push_back(r); len.push_back((size_t)(end[r] - start[r])); src.push_back(st.off[r] + start[r]); }
+        // reads that trim to nothing, or to less than one convolution window, are dropped (bases NULL, score NAN):
+        // one bad read must not lose the rest of the batch
+        if (end[r] > start[r] && (size_t)(end[r] - start[r]) >= min_len) {
+            keep.push_back(r); len.push_back((size_t)(end[r] - start[r])); src.push_back(st.off[r] + start[r]);
+        }
     }
     if (keep.empty()) return 0;
-    sb2_batch *b = sb2_batch_create(eng, model, len.data(), len.size());
+    sb2_batch *b = pool_acquire(eng, model);
     if (nullptr == b) return -1;
     int ncalled = -1;
-    int64_t *d_src = nullptr;
     std::vector<sb2_call> calls(keep.size(), sb2_call{nullptr, NAN, 0, 0});
-    if (0 == dev_alloc(&d_src, keep.size()) &&
-        cudaMemcpyAsync(d_src, src.data(), keep.size() * sizeof(int64_t), cudaMemcpyHostToDevice, b->stream) == cudaSuccess) {
-        launch_medmad(st.d_raw, d_src, b->d_raw, b->d_sampoff, b->d_nsample, b->nread, b->stream);
+    bool ok = 0 == batch_shape(b, len.data(), len.size());
+    if (ok && (nullptr == b->d_src || keep.size() > b->cap_reads)) ok = 0 == dev_alloc(&b->d_src, b->cap_reads);
+    // the trimmer ran on the legacy stream: order this workspace's stream after it
+    ok = ok && cudaStreamSynchronize(0) == cudaSuccess;
+    ok = ok && cudaMemcpyAsync(b->d_src, src.data(), keep.size() * sizeof(int64_t), cudaMemcpyHostToDevice, b->stream) == cudaSuccess;
+    if (ok) {
+        launch_medmad(st.d_raw, b->d_src, b->d_raw, b->d_sampoff, b->d_nsample, b->nread, b->stream);
         eng->launches += 1;
-        ncalled = sb2_batch_basecall(b, nullptr, 0, p, calls.data());
-        for (size_t i = 0; i < keep.size(); i++) out[keep[i]] = calls[i];
+        ok = cudaStreamSynchronize(b->stream) == cudaSuccess;      // src (pageable) and st.d_raw must outlive the copies
     }
-    if (b->stream) cudaStreamSynchronize(b->stream);
-    if (d_src) cudaFree(d_src);
-    sb2_batch_destroy(b);
+    if (ok) {
+        ncalled = sb2_batch_basecall(b, nullptr, 0, p, calls.data());
+        if (ncalled >= 0) for (size_t i = 0; i < keep.size(); i++) out[keep[i]] = calls[i];
+    }
+    pool_release(eng, b, ncalled >= 0);
     return ncalled;
 }
 
@@ -1357,7 +1534,7 @@ extern "C" int sb2_batch_posterior_crf(sb2_batch *b) {
     const sb2_host_model &h = b->m->host;
     if (h.head != 1 || h.nstate != 25) { sb2_set_error("posterior_crf needs a CRF model (rnnrf_r94)"); return -1; }
     CUDA_OK(cudaSetDevice(b->eng->device));
-    if (nullptr == b->d_bprob && dev_alloc(&b->d_bprob, ((size_t)b->total_cols + b->nread) * 8)) return -1;
+    if (nullptr == b->d_bprob && dev_alloc(&b->d_bprob, (b->cap_cols + b->cap_reads) * 8)) return -1;
     launch_posterior_crf(b->d_post, b->dims, (int)h.ostride, b->d_bprob, b->stream);
     b->eng->launches += 1;
     CUDA_OK(cudaGetLastError());
@@ -1486,7 +1663,8 @@ static DevModel *get_events_model(sb2_engine *eng) {
     free(blob);
     if (0 == rc && (dm->host.arch != 2 || dm->host.H != 96)) { sb2_set_error("events model: unsupported shape"); rc = -1; }
     if (0 == rc) rc = upload_model(eng, dm);
-    return (0 == rc) ? dm : nullptr;
+    if (0 != rc) { release_model(eng, dm); return nullptr; }
+    return dm;
 }
 
 

@@ -100,21 +100,16 @@ void launch_small_head(const float *X, int ncol, int K, const float *W, const fl
 void launch_gather(const float *post, int ostride, const int *col_state_pairs, int n, float *out, cudaStream_t s);
 
 // ---- tensor-core path (kernels_tc.cu) ----
-// shared-memory image of one layer's recurrent weights (split fp16, canonical UMMA layout)
-size_t scan_image_bytes(int H);
-void build_scan_image(const float *sW, const float *sW2, int H, uint8_t *img);
-// gru_forward / gru_backward on tcgen05; returns -1 if the kernel could not be configured
-int launch_gru_scan_tc(const float *Xin, const uint8_t *wimg, const float *resid, float *out, const BatchDims &d,
-                       int H, int backward, int fast_math, cudaStream_t s);
-// same with the weights resident in TMEM (A operand from tensor memory); math: 0 cephes, 1 SFU, 2 polynomial
-int launch_gru_scan_tmem(const float *Xin, const float *sW, const float *sW2, const float *resid, float *out,
-                         const BatchDims &d, int H, int backward, int math, cudaStream_t s);
-// v3: hi|lo of the state packed in the UMMA N dimension (two passes), reset gate first, 8 gate warps
-int launch_gru_scan_v3(const float *Xin, const float *sW, const float *sW2, const float *resid, float *out,
-                       const BatchDims &d, int H, int backward, int math, long long *trace, cudaStream_t s);
-// v4: v3 + two independent groups of 4 reads per CTA (own operands / accumulators / issuer warp), ILP-friendly gates
-int launch_gru_scan_v4(const float *Xin, const float *sW, const float *sW2, const float *resid, float *out,
-                       const BatchDims &d, int H, int backward, int math, long long *trace, cudaStream_t s);
+// gru_forward / gru_backward on tcgen05 with the recurrent weights resident in TMEM (A operand from tensor memory).
+// math: 0 cephes gates, 2 polynomial exp2, 5 SFU ex2 + Newton-refined reciprocal.  Batches of >= 48 reads run the
+// v5 kernel (8 reads per group, inputs through a TMA ring), smaller ones v4 (4 reads per group).
+// gen: 0 automatic, 4 / 5 force a kernel generation (parity tests run both on the same batch)
+int launch_gru_scan_tc(const float *Xin, const float *sW, const float *sW2, const float *resid, float *out,
+                       const BatchDims &d, int H, int backward, int math, int gen, long long *trace, cudaStream_t s);
+// per-device kernel attributes (dynamic shared-memory limits); called by sb2_engine_create for its device
+int configure_scan_kernels();
+int configure_gemm_kernels();
+int configure_v1_kernels();
 // D[128][N] = A[128][K] B[N][K]^T through the scan's operand path (validation / latency probe)
 int launch_tc_selftest(const float *A, const float *B, float *D, int K, int N, int reps, long long *cycles,
                        cudaStream_t s);

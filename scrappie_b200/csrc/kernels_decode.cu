@@ -397,10 +397,9 @@ void launch_posterior_crf(const float *trans, const BatchDims &d, int ostride, f
 void launch_decode_transducer_warp(const float *post, const BatchDims &d, int ostride, float stay_pen,
                                    float skip_pen, float local_pen, uint8_t *tb, int *tb_end, int *path,
                                    float *score, cudaStream_t s) {
-    static int wpc = 0;
-    if (wpc == 0) { const char *e = getenv("SCRAPPIE_B200_DECODE_WPC"); wpc = e ? atoi(e) : 2; }
-    static int fma = -1;
-    if (fma < 0) { const char *e = getenv("SCRAPPIE_B200_DECODE_SEL"); fma = (e && 0 == strcmp(e, "sel")) ? 0 : 1; }
+    // read once (thread-safe static initialisation): warps per CTA, and "sel" = selects on the ALU pipe (cross-check)
+    static const int wpc = [] { const char *e = getenv("SCRAPPIE_B200_DECODE_WPC"); return e ? atoi(e) : 2; }();
+    static const int fma = [] { const char *e = getenv("SCRAPPIE_B200_DECODE_SEL"); return (e && 0 == strcmp(e, "sel")) ? 0 : 1; }();
 #define SB2_LAUNCH_WARP_DECODE(WPC, FMA)                                                                  \
     decode_transducer_warp_kernel<WPC, FMA><<<(d.nread + WPC - 1) / WPC, 32 * WPC, 0, s>>>(                \
         post, d, ostride, stay_pen, skip_pen, local_pen, tb, tb_end, path, score, 1.0f, -0.0f)

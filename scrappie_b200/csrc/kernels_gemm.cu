@@ -74,7 +74,7 @@ struct GemmCfg {
     static constexpr uint32_t LBO_B = 16 * NT + 16, SBO_B = 128;
     static constexpr uint32_t TILE_B = (K / 8) * LBO_B;
     static constexpr uint32_t STAGE_B = 2 * TILE_B;            // hi, lo
-    static constexpr uint32_t SMEM = WBYTES + 2 * STAGE_B + 128;
+    static constexpr uint32_t SMEM = WBYTES + 2 * STAGE_B + 128 + 32;   // barriers + TMEM slot, then 4 scales + 3 maxima
     static constexpr int NKS = K / 16;
     static constexpr uint32_t TCOLS = (2 * NT <= 32) ? 32 : (2 * NT <= 64 ? 64 : (2 * NT <= 128 ? 128 : (2 * NT <= 256 ? 256 : 512)));
     static_assert(K % 16 == 0 && ROWS % 8 == 0 && ROWS <= 128 && NT % 16 == 0 && NT <= 256, "tile shape");
@@ -108,11 +108,19 @@ affine_tc_kernel(const float *__restrict__ X, int ncol, const uint8_t *__restric
     uint64_t *bars = reinterpret_cast<uint64_t *>(b_ring + 2 * G::STAGE_B);
     uint64_t *full = bars, *empty = bars + 2, *accf = bars + 4, *acce = bars + 6, *wbar = bars + 8;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 9);
+    // Range safety of the split-fp16 operands: activations are scaled by 2^8 before the fp16 split, so |x| >= 2^7.99
+    // would overflow to inf where the reference's fp32 GEMM stays finite (conv + ELU output and rnnrf's residual
+    // stream are unbounded).  The producers take the chunk's max |x|; chunks below 128 use the usual 2^8 (bit-identical
+    // to a build without this guard), others the power of two that puts the maximum in [2^14, 2^15).  The epilogue
+    // undoes it.  cscale[it % 4] = 2^-8 (weights) / operand scale of chunk `it`; cmax[it % 3] = bits of max |x|.
+    float *cscale = reinterpret_cast<float *>(b_ring + 2 * G::STAGE_B + 128);
+    uint32_t *cmax = reinterpret_cast<uint32_t *>(cscale + 4);
 
     const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
     const int nchunk = (ncol + NT - 1) / NT;
 
     if (tid == 0) {
+        cmax[0] = 0; cmax[1] = 0; cmax[2] = 0;
         mbar_init(&full[0], 8); mbar_init(&full[1], 8);
         mbar_init(&empty[0], 1); mbar_init(&empty[1], 1);
         mbar_init(&accf[0], 1); mbar_init(&accf[1], 1);
@@ -192,6 +200,28 @@ affine_tc_kernel(const float *__restrict__ X, int ncol, const uint8_t *__restric
                     vb[i] = __ldg(reinterpret_cast<const float4 *>(src + (size_t)u * 8 + 4));
                 }
             }
+            // chunk-wide max |x| (integer compare of the sign-stripped bits; NaN / inf sort above every finite value)
+            uint32_t mx = 0;
+#pragma unroll
+            for (int i = 0; i < PER; i++) {
+                const float4 a = va[i], b = vb[i];
+                const float m = fmaxf(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))),
+                                      fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w))));
+                mx = max(mx, __float_as_uint(m));
+                // a NaN is dropped by fmaxf: catch it through the exponent test on each element's bits instead
+                mx = max(mx, max(max(__float_as_uint(a.x), __float_as_uint(a.y)), max(__float_as_uint(a.z), __float_as_uint(a.w))) & 0x7fffffffu);
+                mx = max(mx, max(max(__float_as_uint(b.x), __float_as_uint(b.y)), max(__float_as_uint(b.z), __float_as_uint(b.w))) & 0x7fffffffu);
+            }
+            mx = __reduce_max_sync(0xffffffffu, mx);
+            const uint32_t ms = it % 3;
+            if (lane == 0 && mx >= 0x43000000u) atomicMax(&cmax[ms], mx);      // only chunks with |x| >= 128 touch the slot
+            if (pt == 0) cmax[(it + 1) % 3] = 0;                               // last read two chunks ago (see above)
+            named_bar_sync(1, NPROD);
+            const uint32_t cm = cmax[ms];
+            float opscale = OPERAND_SCALE;
+            if (cm >= 0x43000000u && cm < 0x7f800000u)                          // finite, >= 128: max * scale in [2^14, 2^15)
+                opscale = __uint_as_float((uint32_t)(127 + 14 + 127 - (int)(cm >> 23)) << 23);
+            if (pt == 0) cscale[it & 3] = (1.0f / OPERAND_SCALE) / opscale;
             mbar_wait(&empty[s], ((it >> 1) & 1) ^ 1);
             uint8_t *b_hi = b_ring + s * G::STAGE_B, *b_lo = b_hi + G::TILE_B;
 #pragma unroll
@@ -200,7 +230,7 @@ affine_tc_kernel(const float *__restrict__ X, int ncol, const uint8_t *__restric
                 if (u < UNITS) {
                     const int n = u / K8, k8 = u % K8;
                     uint4 hi, lo;
-                    split8(va[i], vb[i], OPERAND_SCALE, hi, lo);
+                    split8(va[i], vb[i], opscale, hi, lo);
                     const uint32_t off = (uint32_t)(n >> 3) * G::SBO_B + (uint32_t)k8 * G::LBO_B + (uint32_t)(n & 7) * 16;
                     *reinterpret_cast<uint4 *>(b_hi + off) = hi;
                     *reinterpret_cast<uint4 *>(b_lo + off) = lo;
@@ -222,14 +252,16 @@ affine_tc_kernel(const float *__restrict__ X, int ncol, const uint8_t *__restric
             ok[g] = (m < ROWS) && (g * ROWS + m < M);
             bg[g] = ok[g] ? bias[g * ROWS + m] : 0.0f;
         }
-        uint32_t acc_it = 0;
-        for (int c = blockIdx.x; c < nchunk; c += gridDim.x) {
+        uint32_t acc_it = 0, it = 0;
+        for (int c = blockIdx.x; c < nchunk; c += gridDim.x, it++) {
             const int col0 = c * NT;
 #pragma unroll
             for (int g = 0; g < NTILE; g++, acc_it++) {
                 const uint32_t a = acc_it & 1;
                 mbar_wait(&accf[a], (acc_it >> 1) & 1);
                 tc_fence_after();
+                // written by the producers before they released this chunk's operand; 2^-16 unless the chunk held |x| >= 128
+                const float rscale = *reinterpret_cast<volatile float *>(&cscale[it & 3]);
                 if (warp_valid) {
                     // ldc is a compile-time constant: every store address is base + immediate
                     float *dst = C + (size_t)col0 * LDC + g * ROWS + m;
@@ -243,11 +275,11 @@ affine_tc_kernel(const float *__restrict__ X, int ncol, const uint8_t *__restric
                             float *d0 = dst + (size_t)n0 * LDC;
                             if (full) {
 #pragma unroll
-                                for (int j = 0; j < 32; j++) d0[j * LDC] = fmaf(v[j], RESULT_SCALE, bg[g]);
+                                for (int j = 0; j < 32; j++) d0[j * LDC] = fmaf(v[j], rscale, bg[g]);
                             } else {
 #pragma unroll
                                 for (int j = 0; j < 32; j++)
-                                    if (col0 + n0 + j < ncol) d0[j * LDC] = fmaf(v[j], RESULT_SCALE, bg[g]);
+                                    if (col0 + n0 + j < ncol) d0[j * LDC] = fmaf(v[j], rscale, bg[g]);
                             }
                         }
                     }
@@ -267,13 +299,6 @@ template <int K, int ROWS, int NTILE, int NT, int LDC>
 static int launch_affine_cfg(const float *X, int ncol, const uint8_t *wimg, const float *bias, int M, float *C,
                              cudaStream_t s) {
     using G = GemmCfg<K, ROWS, NTILE, NT>;
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(affine_tc_kernel<K, ROWS, NTILE, NT, LDC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)G::SMEM) != cudaSuccess)
-            return -1;
-        configured = true;
-    }
     const int nchunk = (ncol + NT - 1) / NT;
     const int grid = nchunk < 148 ? nchunk : 148;
     affine_tc_kernel<K, ROWS, NTILE, NT, LDC><<<grid, 416, G::SMEM, s>>>(X, ncol, wimg, bias, M, C);
@@ -618,17 +643,7 @@ int launch_head_softmax_tc(const float *X, int ncol, int K, const uint8_t *wimg,
     if (ncol <= 0) return 0;
     if (K != 96 || ostride != 1028) return -1;
     using G = HeadCfg<96>;
-    static bool configured = false;
-    static int ew = 0;
-    if (!configured) {
-        const char *e = getenv("SCRAPPIE_B200_HEAD_SLICES");
-        ew = (e && atoi(e) == 2) ? 2 : 4;
-        if (cudaFuncSetAttribute(head_softmax_tc_kernel<96, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM) != cudaSuccess ||
-            cudaFuncSetAttribute(head_softmax_tc_kernel<96, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM) != cudaSuccess ||
-            cudaFuncSetAttribute(head_softmax_tc_kernel<96, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM) != cudaSuccess)
-            return -1;
-        configured = true;
-    }
+    static const int ew = [] { const char *e = getenv("SCRAPPIE_B200_HEAD_SLICES"); return (e && atoi(e) == 2) ? 2 : 4; }();
     const int nchunk = (ncol + G::NT - 1) / G::NT;
     const int grid = nchunk < 148 ? nchunk : 148;
     if (exact_math)
@@ -638,6 +653,18 @@ int launch_head_softmax_tc(const float *X, int ncol, int K, const uint8_t *wimg,
     else
         head_softmax_tc_kernel<96, true, 4><<<grid, 704, G::SMEM, s>>>(X, ncol, wimg, w_stay, bias, post, ostride, xdiv, cdiv, min_prob, return_log);
     return 0;
+}
+
+// Per-device function attributes of this file's kernels (called once per engine, after cudaSetDevice): the
+// attribute belongs to the device, so a process-wide "configured" flag would leave a second GPU unconfigured.
+int configure_gemm_kernels() {
+    const cudaFuncAttribute A = cudaFuncAttributeMaxDynamicSharedMemorySize;
+    bool ok = cudaFuncSetAttribute(affine_tc_kernel<96, 96, 3, 128, 288>, A, (int)GemmCfg<96, 96, 3, 128>::SMEM) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(affine_tc_kernel<112, 112, 3, 64, 336>, A, (int)GemmCfg<112, 112, 3, 64>::SMEM) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(head_softmax_tc_kernel<96, true, 2>, A, (int)HeadCfg<96>::SMEM) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(head_softmax_tc_kernel<96, true, 4>, A, (int)HeadCfg<96>::SMEM) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(head_softmax_tc_kernel<96, false, 2>, A, (int)HeadCfg<96>::SMEM) == cudaSuccess;
+    return ok ? 0 : -1;
 }
 
 }  // namespace sb2

@@ -426,78 +426,6 @@ __device__ __forceinline__ float pick5(const float (&v)[5], int i) {
     return r;
 }
 
-__global__ void __launch_bounds__(128)
-globalnorm_kernel(float *__restrict__ trans, BatchDims d, int ostride) {
-    const int r = blockIdx.x * 4 + threadIdx.x / 32;
-    const int lane = threadIdx.x % 32;
-    if (r >= d.nread) return;
-    const int T = d.nblock[r];
-    float *tr = trans + (size_t)d.col_off[r] * ostride;
-    const int l = (lane < 25) ? lane : 24;
-    const int to = l / 5, from = l % 5;
-    float prev[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-    float nxt = (T > 0) ? tr[l] : 0.0f;
-    for (int t = 0; t < T; t++) {
-        const float e = nxt;
-        if (t + 1 < T) nxt = tr[(size_t)(t + 1) * ostride + l];
-        const float a = e + pick5(prev, from);
-        float v = __shfl_sync(0xffffffffu, a, to * 5);
-#pragma unroll
-        for (int f = 1; f < 5; f++) v = logsumexp2(v, __shfl_sync(0xffffffffu, a, to * 5 + f));
-#pragma unroll
-        for (int q = 0; q < 5; q++) prev[q] = __shfl_sync(0xffffffffu, v, q * 5);
-    }
-    float logZ = prev[0];
-#pragma unroll
-    for (int q = 1; q < 5; q++) logZ = logsumexp2(logZ, prev[q]);
-    logZ = logZ / (float)T;
-    for (int t = 0; t < T; t++)
-        if (lane < 25) tr[(size_t)t * ostride + lane] -= logZ;
-}
-
-
-__global__ void __launch_bounds__(128)
-decode_crf_kernel(const float *__restrict__ trans, BatchDims d, int ostride, uint8_t *__restrict__ tb,
-                  int *__restrict__ path, float *__restrict__ score) {
-    const int r = blockIdx.x * 4 + threadIdx.x / 32;
-    const int lane = threadIdx.x % 32;
-    if (r >= d.nread) return;
-    const int T = d.nblock[r];
-    const float *tr = trans + (size_t)d.col_off[r] * ostride;
-    uint8_t *tbr = tb + (size_t)d.col_off[r] * 8;
-    const int l = (lane < 25) ? lane : 24;
-    const int to = l / 5, from = l % 5;
-    float prev[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-    float nxt = (T > 0) ? tr[l] : 0.0f;
-    for (int t = 0; t < T; t++) {
-        const float e = nxt;
-        if (t + 1 < T) nxt = tr[(size_t)(t + 1) * ostride + l];
-        const float a = e + pick5(prev, from);
-        float best = __shfl_sync(0xffffffffu, a, to * 5);
-        int arg = 0;
-#pragma unroll
-        for (int f = 1; f < 5; f++) {
-            const float c = __shfl_sync(0xffffffffu, a, to * 5 + f);
-            if (c > best) { best = c; arg = f; }           // strict: lowest `from` wins ties
-        }
-        if (lane < 25 && from == 0) tbr[(size_t)t * 8 + to] = (uint8_t)arg;
-#pragma unroll
-        for (int q = 0; q < 5; q++) prev[q] = __shfl_sync(0xffffffffu, best, q * 5);
-    }
-    __syncwarp();
-    if (lane == 0) {
-        int last = 0;
-        for (int q = 1; q < 5; q++) if (prev[q] > prev[last]) last = q;
-        score[r] = pick5(prev, last);
-        int *p = path + d.col_off[r] + r;
-        p[T] = last;
-        for (int t = T; t > 0; t--) {
-            last = tbr[(size_t)(t - 1) * 8 + last];
-            p[t - 1] = last;
-        }
-    }
-}
-
 // ---------------------------------------------------------------------------------
 // CRF (rnnrf_r94), second generation: transitions staged through shared memory
 // ---------------------------------------------------------------------------------
@@ -563,15 +491,10 @@ globalnorm_v2_kernel(float *__restrict__ trans, BatchDims d, int ostride) {
 }
 
 void launch_globalnorm(float *trans, const BatchDims &d, int ostride, cudaStream_t s) {
-    static int gen = -1;
-    if (gen < 0) { const char *e = getenv("SCRAPPIE_B200_CRF"); gen = (e && 0 == strcmp(e, "v1")) ? 1 : 2; }
-    if (gen == 2 && ostride == 28)
-        globalnorm_v2_kernel<<<(d.nread + CRF_WARPS - 1) / CRF_WARPS, 32 * CRF_WARPS, 0, s>>>(trans, d, ostride);
-    else
-        globalnorm_kernel<<<(d.nread + 3) / 4, 128, 0, s>>>(trans, d, ostride);
+    globalnorm_v2_kernel<<<(d.nread + CRF_WARPS - 1) / CRF_WARPS, 32 * CRF_WARPS, 0, s>>>(trans, d, ostride);
 }
 
-// decode_crf (src/decode.c:836-893): identical arithmetic and tie-breaking as decode_crf_kernel.
+// decode_crf (src/decode.c:836-893): the reference's arithmetic and tie-breaking.
 __global__ void __launch_bounds__(32 * CRF_WARPS)
 decode_crf_v2_kernel(const float *__restrict__ trans, BatchDims d, int ostride, uint8_t *__restrict__ tb,
                      int *__restrict__ path, float *__restrict__ score) {
@@ -646,12 +569,7 @@ decode_crf_v2_kernel(const float *__restrict__ trans, BatchDims d, int ostride, 
 
 void launch_decode_crf(const float *trans, const BatchDims &d, int ostride, uint8_t *tb, int *path,
                        float *score, cudaStream_t s) {
-    static int gen = -1;
-    if (gen < 0) { const char *e = getenv("SCRAPPIE_B200_CRF"); gen = (e && 0 == strcmp(e, "v1")) ? 1 : 2; }
-    if (gen == 2 && ostride == 28)
-        decode_crf_v2_kernel<<<(d.nread + CRF_WARPS - 1) / CRF_WARPS, 32 * CRF_WARPS, 0, s>>>(trans, d, ostride, tb, path, score);
-    else
-        decode_crf_kernel<<<(d.nread + 3) / 4, 128, 0, s>>>(trans, d, ostride, tb, path, score);
+    decode_crf_v2_kernel<<<(d.nread + CRF_WARPS - 1) / CRF_WARPS, 32 * CRF_WARPS, 0, s>>>(trans, d, ostride, tb, path, score);
 }
 
 // CRF head: C[col][0:25] = b + W^T x (feedforward_linear inside globalnorm, src/layers.c:874-880), M = 25 rows.
@@ -713,181 +631,6 @@ void launch_small_head(const float *X, int ncol, int K, const float *W, const fl
 // and every maximum keeps the lowest index, so the result is bit-identical.
 constexpr float DEC_BIG = 1.e30f;
 enum { TB_STAY = 0, TB_STEP = 1, TB_SKIP = 5, TB_SLIP = 21, TB_START = 85 };
-
-template <int NH>
-__global__ void __launch_bounds__(NH / 4)
-decode_transducer_kernel(const float *__restrict__ post, BatchDims d, int ostride, float stay_pen,
-                         float skip_pen, float local_pen, int allow_slip, uint8_t *__restrict__ tb,
-                         int *__restrict__ tb_end, int *__restrict__ path, float *__restrict__ score) {
-    constexpr int NT = NH / 4;
-    constexpr int NW = NT / 32;
-    __shared__ __align__(16) float sc[2][NH];
-    __shared__ float w_val[2][NW];
-    __shared__ int w_idx[2][NW];
-    __shared__ float fin_val[NW];
-    __shared__ int fin_idx[NW];
-
-    const int r = blockIdx.x;
-    const int t = threadIdx.x;
-    const int lane = t % 32, warp = t / 32;
-    const int T = d.nblock[r];
-    const float *lp = post + (size_t)d.col_off[r] * ostride;
-    uint8_t *tbr = tb + (size_t)d.col_off[r] * NH;
-    int *tbe = tb_end + d.col_off[r];
-    const float slip_pen = (float)(2.0 * (double)skip_pen);
-
-    float cur[4] = {-DEC_BIG, -DEC_BIG, -DEC_BIG, -DEC_BIG};
-    float curS = 0.0f, curE = -DEC_BIG;         // replicated in every thread
-    float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
-    float nxt_stay = 0.0f;
-    if (T > 0) {
-        nxt = *reinterpret_cast<const float4 *>(lp + 4 * t);
-        nxt_stay = lp[NH];
-    }
-    for (int blk = 0; blk < T; blk++) {
-        const int buf = blk & 1;
-        const float4 l4 = nxt;
-        const float lstay = nxt_stay;
-        if (blk + 1 < T) {
-            nxt = *reinterpret_cast<const float4 *>(lp + (size_t)(blk + 1) * ostride + 4 * t);
-            nxt_stay = lp[(size_t)(blk + 1) * ostride + NH];
-        }
-        // publish the previous scores; find this warp's best "enter end" candidate
-        *reinterpret_cast<float4 *>(&sc[buf][4 * t]) = make_float4(cur[0], cur[1], cur[2], cur[3]);
-        {
-            float bv = cur[0] - local_pen;
-            int bi = 4 * t;
-#pragma unroll
-            for (int j = 1; j < 4; j++) {
-                const float v = cur[j] - local_pen;
-                if (v > bv) { bv = v; bi = 4 * t + j; }
-            }
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-            }
-            if (lane == 0) { w_val[buf][warp] = bv; w_idx[buf][warp] = bi; }
-        }
-        __syncthreads();
-
-        // end state: stay in it, or enter it from the best-scoring state (lowest index on ties)
-        {
-            float bv = w_val[buf][0];
-            int bi = w_idx[buf][0];
-#pragma unroll
-            for (int w = 1; w < NW; w++) {
-                const float v = w_val[buf][w];
-                const int i = w_idx[buf][w];
-                if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
-            }
-            const float hold = fmaxf(-local_pen, lstay - stay_pen);
-            float e = curE + hold;
-            int from = NH + 1;
-            if (bv > e) { e = bv; from = bi; }
-            if (t == 0) tbe[blk] = from;
-            curE = e;
-        }
-
-        const float *prev = sc[buf];
-        // step: best over the 4 states sharing suffix t
-        float b4 = prev[t];
-        int r4 = 0;
-#pragma unroll
-        for (int q = 1; q < 4; q++) {
-            const float v = prev[q * (NH / 4) + t];
-            if (b4 < v) { b4 = v; r4 = q; }
-        }
-        // skip: best over 16 states sharing suffix t / 4
-        float b16 = prev[t / 4];
-        int r16 = 0;
-#pragma unroll
-        for (int q = 1; q < 16; q++) {
-            const float v = prev[q * (NH / 16) + t / 4];
-            if (b16 < v) { b16 = v; r16 = q; }
-        }
-        float b64 = 0.0f;
-        int r64 = 0;
-        if (allow_slip) {
-            b64 = prev[t / 16];
-            for (int q = 1; q < 64; q++) {
-                const float v = prev[q * (NH / 64) + t / 16];
-                if (b64 < v) { b64 = v; r64 = q; }
-            }
-        }
-        const float stay = lstay - stay_pen;
-        const float lpj[4] = {l4.x, l4.y, l4.z, l4.w};
-        uint32_t codes = 0;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            float s = cur[j] + stay;
-            uint32_t code = TB_STAY;
-            const float st = lpj[j] + b4;
-            if (s < st) { s = st; code = TB_STEP + r4; }
-            const float sk = (lpj[j] + b16) - skip_pen;
-            if (s < sk) { s = sk; code = TB_SKIP + r16; }
-            if (allow_slip) {
-                const float sl = (lpj[j] + b64) - slip_pen;
-                if (s < sl) { s = sl; code = TB_SLIP + r64; }
-            }
-            const float ss = curS + lpj[j];
-            if (ss > s) { s = ss; code = TB_START; }
-            cur[j] = s;
-            codes |= code << (8 * j);
-        }
-        *reinterpret_cast<uint32_t *>(tbr + (size_t)blk * NH + 4 * t) = codes;
-        curS = curS + fmaxf(-local_pen, lstay - stay_pen);
-    }
-
-    // final argmax over (states..., start, end): first maximum wins
-    {
-        float bv = cur[0];
-        int bi = 4 * t;
-#pragma unroll
-        for (int j = 1; j < 4; j++) if (cur[j] > bv) { bv = cur[j]; bi = 4 * t + j; }
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-        }
-        if (lane == 0) { fin_val[warp] = bv; fin_idx[warp] = bi; }
-    }
-    __syncthreads();
-    if (t == 0) {
-        float bv = fin_val[0];
-        int last = fin_idx[0];
-        for (int w = 1; w < NW; w++)
-            if (fin_val[w] > bv || (fin_val[w] == bv && fin_idx[w] < last)) { bv = fin_val[w]; last = fin_idx[w]; }
-        if (curS > bv) { bv = curS; last = NH; }
-        if (curE > bv) { bv = curE; last = NH + 1; }
-        score[r] = bv;
-        int *seq = path + d.col_off[r] + r;
-        for (int blk = T - 1; blk >= 0; blk--) {
-            int out = -1;
-            if (last == NH) {
-                out = NH;                                   // start stays in start
-            } else if (last == NH + 1) {
-                out = NH + 1;
-                last = tbe[blk];
-            } else {
-                const int code = tbr[(size_t)blk * NH + last];
-                if (code != TB_STAY) {
-                    out = last;
-                    if (code >= TB_START) last = NH;
-                    else if (code >= TB_SLIP) last = (code - TB_SLIP) * (NH / 64) + last / 64;
-                    else if (code >= TB_SKIP) last = (code - TB_SKIP) * (NH / 16) + last / 16;
-                    else last = (code - TB_STEP) * (NH / 4) + last / 4;
-                }
-            }
-            seq[blk + 1] = out;
-        }
-        seq[0] = last;
-        for (int i = 0; i < T; i++) { if (seq[i] == NH) seq[i] = -1; else break; }
-        for (int i = T; i >= 0; i--) { if (seq[i] == NH + 1) seq[i] = -1; else break; }
-    }
-}
 
 // ---------------------------------------------------------------------------------
 // transducer Viterbi, second generation (same results, ~40 % fewer instructions per block)
@@ -1112,254 +855,25 @@ decode_transducer_v2_kernel(const float *__restrict__ post, BatchDims d, int ost
     }
 }
 
-// ---------------------------------------------------------------------------------
-// transducer Viterbi, third generation: eight states per thread
-// ---------------------------------------------------------------------------------
-// NH / 8 threads per read; thread t owns states 8t .. 8t+7, i.e. the two step suffixes 2t, 2t+1 and the
-// skip suffix t / 2.  The per-block work that is shared by a thread's states (publishing, the
-// hierarchical maxima, the end-state candidate) is paid once per 8 states instead of once per 4, and
-// the smaller CTA lets a whole 1024-read job be resident in one wave.
-// Results are bit-identical to the v1 / v2 kernels (tests/test_gpu_parity.py).
-template <int NH>
-__global__ void __launch_bounds__(NH / 8)
-decode_transducer_v3_kernel(const float *__restrict__ post, BatchDims d, int ostride, float stay_pen,
-                            float skip_pen, float local_pen, int allow_slip, uint8_t *__restrict__ tb,
-                            int *__restrict__ tb_end, int *__restrict__ path, float *__restrict__ score) {
-    constexpr int NT = NH / 8;
-    constexpr int NW = NT / 32;
-    constexpr int BT_ROWS = 16384 / NH;
-    constexpr int BIG_IDX = 0x7fffffff;
-    constexpr int SC_BYTES = 2 * NH * 4, BT_BYTES = BT_ROWS * NH;
-    __shared__ __align__(16) uint8_t sc_or_bt[SC_BYTES > BT_BYTES ? SC_BYTES : BT_BYTES];
-    __shared__ __align__(16) float2 m4s[NH / 4];        // (max over the 4 step predecessors, its r) per suffix
-    __shared__ float w_val[NW];
-    __shared__ int w_idx[NW];
-    __shared__ int s_last;
-    float (*sc)[NH] = reinterpret_cast<float (*)[NH]>(sc_or_bt);
-    uint8_t *bt_rows = sc_or_bt;
-
-    const int r = blockIdx.x;
-    const int t = threadIdx.x;
-    const int lane = t % 32, warp = t / 32;
-    const int T = d.nblock[r];
-    const float *lp = post + (size_t)d.col_off[r] * ostride;
-    uint8_t *tbr = tb + (size_t)d.col_off[r] * NH;
-    int *tbe = tb_end + d.col_off[r];
-    const float slip_pen = (float)(2.0 * (double)skip_pen);
-
-    float cur[8];
-#pragma unroll
-    for (int j = 0; j < 8; j++) cur[j] = -DEC_BIG;
-    float curS = 0.0f, curE = -DEC_BIG;
-    float4 nxa = make_float4(0.f, 0.f, 0.f, 0.f), nxb = nxa;
-    float nxt_stay = 0.0f;
-    if (T > 0) {
-        nxa = *reinterpret_cast<const float4 *>(lp + 8 * t);
-        nxb = *reinterpret_cast<const float4 *>(lp + 8 * t + 4);
-        nxt_stay = lp[NH];
-    }
-    const float *lp_next = lp + ostride + 8 * t;
-    const float *stay_next = lp + ostride + NH;
-    uint8_t *tb_cur = tbr + 8 * t;
-    int *tbe_cur = tbe;
-    for (int blk = 0; blk < T; blk++, lp_next += ostride, stay_next += ostride, tb_cur += NH, tbe_cur++) {
-        const int buf = blk & 1;
-        const float lpj[8] = {nxa.x, nxa.y, nxa.z, nxa.w, nxb.x, nxb.y, nxb.z, nxb.w};
-        const float lstay = nxt_stay;
-        if (blk + 1 < T) {
-            nxa = *reinterpret_cast<const float4 *>(lp_next);
-            nxb = *reinterpret_cast<const float4 *>(lp_next + 4);
-            nxt_stay = *stay_next;
-        }
-        // ---- phase A: publish the previous scores; this warp's best "enter end" candidate
-        *reinterpret_cast<float4 *>(&sc[buf][8 * t]) = make_float4(cur[0], cur[1], cur[2], cur[3]);
-        *reinterpret_cast<float4 *>(&sc[buf][8 * t + 4]) = make_float4(cur[4], cur[5], cur[6], cur[7]);
-        {
-            float v[8];
-#pragma unroll
-            for (int j = 0; j < 8; j++) v[j] = cur[j] - local_pen;
-            const float lm = fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7])));
-            const float wv = redux_max_f32(lm);
-            int cand = BIG_IDX;
-#pragma unroll
-            for (int j = 7; j >= 0; j--) cand = (v[j] == wv) ? 8 * t + j : cand;
-            const int wi = redux_min_s32(cand);          // lowest state index among the maximal ones
-            if (lane == 0) { w_val[warp] = wv; w_idx[warp] = wi; }
-        }
-        __syncthreads();
-
-        // ---- phase B: the two step maxima this thread's states need; warp 0 advances the end state
-        const float *prev = sc[buf];
-        float b4[2];
-        int r4[2];
-        {
-            float2 e = *reinterpret_cast<const float2 *>(&prev[2 * t]);
-            b4[0] = e.x; b4[1] = e.y; r4[0] = 0; r4[1] = 0;
-#pragma unroll
-            for (int q = 1; q < 4; q++) {
-                e = *reinterpret_cast<const float2 *>(&prev[q * (NH / 4) + 2 * t]);
-                if (b4[0] < e.x) { b4[0] = e.x; r4[0] = q; }
-                if (b4[1] < e.y) { b4[1] = e.y; r4[1] = q; }
-            }
-            *reinterpret_cast<float4 *>(&m4s[2 * t]) = make_float4(b4[0], __int_as_float(r4[0]), b4[1], __int_as_float(r4[1]));
-        }
-        if (warp == 0) {
-            const float v = (lane < NW) ? w_val[lane] : -INFINITY;
-            const int i = (lane < NW) ? w_idx[lane] : BIG_IDX;
-            const float bv = redux_max_f32(v);
-            const int bi = redux_min_s32((v == bv) ? i : BIG_IDX);
-            float e = curE + fmaxf(-local_pen, lstay - stay_pen);
-            int from = NH + 1;
-            if (bv > e) { e = bv; from = bi; }
-            if (lane == 0) *tbe_cur = from;
-            curE = e;
-        }
-        __syncthreads();
-
-        // ---- phase C: skip maximum from four step maxima, then the state updates
-        float b16;
-        int r16;
-        {
-            const float2 e0 = m4s[t / 2], e1 = m4s[(NH / 16) + t / 2], e2 = m4s[2 * (NH / 16) + t / 2], e3 = m4s[3 * (NH / 16) + t / 2];
-            b16 = fmaxf(fmaxf(e0.x, e1.x), fmaxf(e2.x, e3.x));
-            const int c0 = (e0.x == b16) ? 4 * __float_as_int(e0.y) : 99;
-            const int c1 = (e1.x == b16) ? 4 * __float_as_int(e1.y) + 1 : 99;
-            const int c2 = (e2.x == b16) ? 4 * __float_as_int(e2.y) + 2 : 99;
-            const int c3 = (e3.x == b16) ? 4 * __float_as_int(e3.y) + 3 : 99;
-            r16 = min(min(c0, c1), min(c2, c3));
-        }
-        float b64 = 0.0f;
-        int r64 = 0;
-        if (allow_slip) {
-            b64 = prev[t / 8];
-            for (int q = 1; q < 64; q++) {
-                const float v = prev[q * (NH / 64) + t / 8];
-                if (b64 < v) { b64 = v; r64 = q; }
-            }
-        }
-        const float stay = lstay - stay_pen;
-        uint32_t codes[2] = {0, 0};
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const int g = j >> 2;                          // which of the thread's two step suffixes
-            float s = cur[j] + stay;
-            uint32_t code = TB_STAY;
-            const float st = lpj[j] + b4[g];
-            if (s < st) { s = st; code = TB_STEP + r4[g]; }
-            const float sk = (lpj[j] + b16) - skip_pen;
-            if (s < sk) { s = sk; code = TB_SKIP + r16; }
-            if (allow_slip) {
-                const float sl = (lpj[j] + b64) - slip_pen;
-                if (s < sl) { s = sl; code = TB_SLIP + r64; }
-            }
-            const float ss = curS + lpj[j];
-            if (ss > s) { s = ss; code = TB_START; }
-            cur[j] = s;
-            codes[g] |= code << (8 * (j & 3));
-        }
-        *reinterpret_cast<uint2 *>(tb_cur) = make_uint2(codes[0], codes[1]);
-        curS = curS + fmaxf(-local_pen, lstay - stay_pen);
-    }
-
-    // ---- final argmax over (states..., start, end): first maximum wins
-    {
-        const float lm = fmaxf(fmaxf(fmaxf(cur[0], cur[1]), fmaxf(cur[2], cur[3])), fmaxf(fmaxf(cur[4], cur[5]), fmaxf(cur[6], cur[7])));
-        const float wv = redux_max_f32(lm);
-        int cand = BIG_IDX;
-#pragma unroll
-        for (int j = 7; j >= 0; j--) cand = (cur[j] == wv) ? 8 * t + j : cand;
-        const int wi = redux_min_s32(cand);
-        __syncthreads();
-        if (lane == 0) { w_val[warp] = wv; w_idx[warp] = wi; }
-    }
-    __syncthreads();
-    if (warp == 0) {
-        const float v = (lane < NW) ? w_val[lane] : -INFINITY;
-        const int i = (lane < NW) ? w_idx[lane] : BIG_IDX;
-        float bv = redux_max_f32(v);
-        int last = redux_min_s32((v == bv) ? i : BIG_IDX);
-        if (curS > bv) { bv = curS; last = NH; }
-        if (curE > bv) { bv = curE; last = NH + 1; }
-        if (lane == 0) { score[r] = bv; s_last = last; }
-    }
-    __syncthreads();
-
-    // ---- backtrace: chunks of BT_ROWS traceback rows staged in shared memory
-    int *seq = path + d.col_off[r] + r;
-    int last = s_last;
-    for (int hi_blk = T; hi_blk > 0; hi_blk -= BT_ROWS) {
-        const int lo_blk = max(hi_blk - BT_ROWS, 0);
-        const int nrow = hi_blk - lo_blk;
-        {
-            const uint4 *src = reinterpret_cast<const uint4 *>(tbr + (size_t)lo_blk * NH);
-            uint4 *dst = reinterpret_cast<uint4 *>(bt_rows);
-            for (int i = t; i < nrow * (NH / 16); i += NT) dst[i] = src[i];
-        }
-        __syncthreads();
-        if (t == 0) {
-            for (int blk = hi_blk - 1; blk >= lo_blk; blk--) {
-                int out = -1;
-                if (last == NH) {
-                    out = NH;                                   // start stays in start
-                } else if (last == NH + 1) {
-                    out = NH + 1;
-                    last = tbe[blk];
-                } else {
-                    const int code = bt_rows[(blk - lo_blk) * NH + last];
-                    if (code != TB_STAY) {
-                        out = last;
-                        if (code >= TB_START) last = NH;
-                        else if (code >= TB_SLIP) last = (code - TB_SLIP) * (NH / 64) + last / 64;
-                        else if (code >= TB_SKIP) last = (code - TB_SKIP) * (NH / 16) + last / 16;
-                        else last = (code - TB_STEP) * (NH / 4) + last / 4;
-                    }
-                }
-                seq[blk + 1] = out;
-            }
-        }
-        __syncthreads();
-    }
-    if (t == 0) {
-        seq[0] = last;
-        for (int i = 0; i < T; i++) { if (seq[i] == NH) seq[i] = -1; else break; }
-        for (int i = T; i >= 0; i--) { if (seq[i] == NH + 1) seq[i] = -1; else break; }
-    }
+// SCRAPPIE_B200_DECODE (read once): "v2" forces the CTA-per-read kernel, "none" skips decoding (timing experiments,
+// tools/exp_timeline.py).  Default: one warp per read with the scores in registers (kernels_decode.cu) for the
+// 1024-history models without slip; the CTA-per-read kernel serves 4096 histories and slip.
+static int decode_generation() {
+    static const int gen = [] {
+        const char *e = getenv("SCRAPPIE_B200_DECODE");
+        return (e && 0 == strcmp(e, "none")) ? 0 : ((e && 0 == strcmp(e, "v2")) ? 2 : 4);
+    }();
+    return gen;
 }
 
 void launch_decode_transducer(const float *post, const BatchDims &d, int nstate, int ostride,
                               float stay_pen, float skip_pen, float local_pen, int allow_slip,
                               uint8_t *tb, int *tb_end, int *path, float *score, cudaStream_t s) {
-    static int gen = -1;
-    if (gen < 0) {
-        const char *e = getenv("SCRAPPIE_B200_DECODE");
-        // v2 is the default: v3 (eight states per thread) executes fewer instructions but measures the same --
-        // the kernel is bound by the ALU pipe (compare / select), not by issue slots (profiles/)
-        // default: one warp per read with the scores in registers (kernels_decode.cu) for the 1024-history
-        // models without slip; the CTA-per-read generations stay selectable and serve 4096 histories / slip
-        gen = (e && 0 == strcmp(e, "none")) ? 0 : (e && 0 == strcmp(e, "v1")) ? 1 : ((e && 0 == strcmp(e, "v3")) ? 3 : ((e && 0 == strcmp(e, "v2")) ? 2 : 4));
-    }
+    const int gen = decode_generation();
     const int nh = nstate - 1;
-    if (gen == 0) return;                           // "none": timing experiments only (tools/exp_timeline.py)
+    if (gen == 0) return;
     if (gen == 4 && nh == 1024 && !allow_slip) {
         launch_decode_transducer_warp(post, d, ostride, stay_pen, skip_pen, local_pen, tb, tb_end, path, score, s);
-        return;
-    }
-    if (gen == 3) {
-        if (nh == 1024)
-            decode_transducer_v3_kernel<1024><<<d.nread, 128, 0, s>>>(post, d, ostride, stay_pen, skip_pen, local_pen,
-                                                                     allow_slip, tb, tb_end, path, score);
-        else if (nh == 4096)
-            decode_transducer_v3_kernel<4096><<<d.nread, 512, 0, s>>>(post, d, ostride, stay_pen, skip_pen, local_pen,
-                                                                     allow_slip, tb, tb_end, path, score);
-        return;
-    }
-    if (gen == 1) {
-        if (nh == 1024)
-            decode_transducer_kernel<1024><<<d.nread, 256, 0, s>>>(post, d, ostride, stay_pen, skip_pen, local_pen,
-                                                                  allow_slip, tb, tb_end, path, score);
-        else if (nh == 4096)
-            decode_transducer_kernel<4096><<<d.nread, 1024, 0, s>>>(post, d, ostride, stay_pen, skip_pen, local_pen,
-                                                                   allow_slip, tb, tb_end, path, score);
         return;
     }
     if (nh == 1024)
@@ -1491,6 +1005,7 @@ finish_reads_kernel(const float *__restrict__ post, BatchDims d, int nstate, int
 // rule "ZXYYY" at the same position, bases outermost -- i.e. in exactly the host's order.  Used when a
 // read's path fits the staging area; longer reads take finish_reads_kernel.
 constexpr int FIN_WARPS = 4;
+constexpr size_t FIN_SMEM_MAX = 200 * 1024;
 
 __global__ void __launch_bounds__(32 * FIN_WARPS)
 finish_reads_warp_kernel(const float *__restrict__ post, BatchDims d, int nstate, int ostride, int head, int homopolymer,
@@ -1603,17 +1118,10 @@ void launch_finish_reads(const float *post, const BatchDims &d, int nstate, int 
     const int maxb = d.max_cols;
     const size_t per_warp = (size_t)2 * (maxb + 1) * sizeof(int) + (size_t)((klen * (maxb + 1) + 1 + 15) / 16 * 16);
     const size_t smem = per_warp * FIN_WARPS;
-    static size_t configured = 0;
-    if (smem <= 200 * 1024) {
-        if (smem > configured) {
-            if (cudaFuncSetAttribute(finish_reads_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess)
-                configured = smem;
-        }
-        if (smem <= configured || smem <= 48 * 1024) {
-            finish_reads_warp_kernel<<<(d.nread + FIN_WARPS - 1) / FIN_WARPS, 32 * FIN_WARPS, smem, s>>>(
-                post, d, nstate, ostride, head, homopolymer, klen, maxb, path_in, bases, bases_stride, nbase);
-            return;
-        }
+    if (smem <= FIN_SMEM_MAX) {     // the attribute is set for every device in configure_v1_kernels()
+        finish_reads_warp_kernel<<<(d.nread + FIN_WARPS - 1) / FIN_WARPS, 32 * FIN_WARPS, smem, s>>>(
+            post, d, nstate, ostride, head, homopolymer, klen, maxb, path_in, bases, bases_stride, nbase);
+        return;
     }
     finish_reads_kernel<<<(d.nread + 31) / 32, 32, 0, s>>>(post, d, nstate, ostride, head, homopolymer, klen, path_in,
                                                         path_work, bases, bases_stride, nbase);
@@ -1642,5 +1150,10 @@ __global__ void flush_kernel(float *buf, size_t n) {
 }
 
 void launch_flush(float *buf, size_t nfloat, cudaStream_t s) { flush_kernel<<<148 * 8, 256, 0, s>>>(buf, nfloat); }
+
+// Per-device function attributes of this file's kernels (called once per engine, after cudaSetDevice).
+int configure_v1_kernels() {
+    return cudaFuncSetAttribute(finish_reads_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FIN_SMEM_MAX) == cudaSuccess ? 0 : -1;
+}
 
 }  // namespace sb2

@@ -645,3 +645,203 @@ def test_events_path_from_raw_signal(sb, oracle, golden):
     score, path = sb.decode_path(post, "rgrgr_r94", 0.0, 0.0, 2.0, False)
     oscore, opath = oracle.decode_transducer(post.padded(), 1025, 0.0, 0.0, 2.0)
     assert np.array_equal(path, opath) and score == oscore
+
+
+# ----------------------------------------------------------------------------- round 2: batch-size kernels
+
+def _ragged_lengths(n, lo, hi, seed):
+    rng = np.random.default_rng(seed)
+    return [int(x) for x in rng.integers(lo, hi, size=n)]
+
+
+@pytest.mark.parametrize("gen", [5, 4])
+def test_rnnrf_batch_size_kernels(sb, oracle, gen):
+    """BASELINE config 3's hot kernels: rnnrf_r94 (src/networks.c:567-615) with >= 96 ragged reads, so that the scan
+    runs with 8 reads per group / 3 groups per CTA (v5) or 12 reads per CTA (gru_scan_v4<112, ., 3>) instead of the
+    two-group kernel every small test uses.  Posterior vs oracle, per-layer activations for reads in every group
+    position (incl. indices 8-11 and the ragged last CTA), decode_crf exact, bases == the reference algorithm."""
+    eng = sb.Engine(0)
+    eng.set_scan_generation(gen)
+    lens = _ragged_lengths(100, 1000, 1400, 11)
+    lens[9] = 1399
+    lens[10] = 1000
+    sigs = [synthetic_read(2000 + i, n) for i, n in enumerate(lens)]
+    b = eng.batch("rnnrf_r94", lens)
+    b.keep_layers()
+    b.upload(sigs)
+    b.forward()
+    b.decode()
+    paths, scores = b.paths()
+    check = [0, 5, 8, 9, 10, 11, 13, 23, 24, 47, 95, 96, 99]
+    for i in check:
+        want, layers = oracle.posterior("rnnrf_r94", sigs[i], layers=True)
+        got = b.posterior(i)
+        assert got.shape == want.shape
+        assert np.abs(got[:, :25] - want[:, :25]).max() < CRF_TOL, (gen, i)
+        for l in range(6):
+            tol = 2e-6 if l == 0 else 5e-5 * max(1.0, float(np.abs(layers[l]).max()))
+            assert np.abs(b.layer(l, i, 112) - layers[l]).max() < tol, (gen, i, l)
+        oscore, opath = oracle.decode_crf(got)
+        assert np.array_equal(opath, paths[i]) and oscore == float(scores[i])
+    b.close()
+    calls = eng.basecall_batch("rnnrf_r94", sigs)
+    for i in (0, 8, 11, 50, 99):
+        assert calls[i][0] == oracle.basecall_raw("rnnrf_r94", sigs[i])[2], (gen, i)
+    eng.close()
+
+
+@pytest.mark.parametrize("gen", [5, 4])
+def test_rgrgr_ragged_large_batch(sb, oracle, gen):
+    """rgrgr_r94 with 130 RAGGED reads (src/networks.c:250-296): different lengths inside every read group and
+    across groups, last CTA partly empty -- 8-read groups of v5 and the four-group v4 kernel.  Posterior and layers
+    vs oracle, decoder exact on the GPU's posterior, bases == reference algorithm, and every read equal to the same
+    read basecalled alone (batch composition must not change a bit)."""
+    eng = sb.Engine(0)
+    eng.set_scan_generation(gen)
+    lens = _ragged_lengths(130, 1000, 4000, 5)
+    lens[3], lens[64], lens[129] = 19, 3999, 1003
+    sigs = [synthetic_read(3000 + i, n) for i, n in enumerate(lens)]
+    b = eng.batch("rgrgr_r94", lens)
+    b.keep_layers()
+    b.upload(sigs)
+    b.forward()
+    b.decode()
+    paths, scores = b.paths()
+    for i in (0, 3, 7, 8, 31, 32, 64, 127, 128, 129):
+        want, layers = oracle.posterior("rgrgr_r94", sigs[i], layers=True)
+        got = b.posterior(i)
+        assert np.abs(got[:, :1025] - want[:, :1025]).max() < LOG_TOL, (gen, i)
+        for l in range(6):
+            assert np.abs(b.layer(l, i, 96) - layers[l]).max() < (2e-6 if l == 0 else 5e-5), (gen, i, l)
+        oscore, opath = oracle.decode_transducer(got, 1025)
+        assert np.array_equal(opath, paths[i]) and oscore == float(scores[i])
+    post64, post129 = b.posterior(64).copy(), b.posterior(129).copy()
+    b.close()
+    for i, want in ((64, post64), (129, post129)):       # solo batches run the small-batch (v4, two groups) kernel
+        solo = eng.batch("rgrgr_r94", [lens[i]])
+        solo.upload([sigs[i]])
+        solo.forward()
+        assert np.array_equal(solo.posterior(0), want), (gen, i)
+        solo.close()
+    calls = eng.basecall_batch("rgrgr_r94", sigs)
+    for i in (0, 3, 8, 64, 129):
+        assert calls[i][0] == oracle.basecall_raw("rgrgr_r94", sigs[i])[2], (gen, i)
+    eng.close()
+
+
+# ----------------------------------------------------------------------------- round 2: operand range
+
+@pytest.mark.parametrize("model", ["rgrgr_r94", "rnnrf_r94"])
+def test_outliers_and_unnormalised_signal_stay_finite(sb, oracle, model):
+    """The tensor-core operands are fp16 pairs scaled by 2^8: activations >= 128 would overflow where the reference's
+    fp32 GEMMs (src/scrappie_matrix.c:323-351) stay finite.  A normalised read with +-60 spikes and an un-normalised
+    pA-scale read must come out finite and within tolerance of the oracle (affine_tc rescales such chunks)."""
+    ns = oracle.nstate(model)
+    tol = LOG_TOL if model == "rgrgr_r94" else CRF_TOL
+    x = synthetic_read(77, 1500).copy()
+    x[[100, 101, 700, 1203]] = [60.0, -60.0, 45.0, -52.0]
+    pa = (synthetic_read(78, 1200) * np.float32(12.0) + np.float32(95.0)).astype(np.float32)   # ~ raw pA levels, not scaled
+    for name, sig in (("spikes", x), ("pA", pa)):
+        got = sb.calc_post(sb.RawTable(sig), model, min_prob=1e-5).padded()
+        want = oracle.posterior(model, sig)
+        assert np.isfinite(got[:, :ns]).all(), (model, name)
+        err = np.abs(got[:, :ns] - want[:, :ns])
+        scale = np.maximum(1.0, np.abs(want[:, :ns]))
+        assert (err / scale).max() < 5 * tol, (model, name, float(err.max()))
+
+
+# ----------------------------------------------------------------------------- round 2: batch robustness / pool
+
+def test_short_read_does_not_fail_the_batch(sb, engine, oracle):
+    """A read shorter than the convolution window (19 samples for rgrgr) is dropped -- bases None, score NaN -- and the
+    rest of the batch is called as if it were not there (the reference's calculate_post handles reads one at a time,
+    src/scrappie_raw.c:265-315)."""
+    sigs = [synthetic_read(41, 1500), synthetic_read(42, 10), synthetic_read(43, 777), np.zeros(0, dtype=np.float32)]
+    calls = engine.basecall_batch("rgrgr_r94", sigs)
+    assert calls[1][0] is None and np.isnan(calls[1][1]) and calls[3][0] is None
+    for i in (0, 2):
+        assert calls[i][0] == oracle.basecall_raw("rgrgr_r94", sigs[i])[2]
+    # raw-signal entry point: a read that trims to 15 samples (chunk 5) between two good ones
+    rng = np.random.default_rng(3)
+    raws = [(synthetic_read(50 + i, n) * np.float32(10) + np.float32(90)).astype(np.float32) for i, n in enumerate((3000, 225, 2600))]
+    res = engine.basecall_raw_batch("rgrgr_r94", raws, varseg_chunk=5)
+    assert res[1][0] is None and 0 < res[1][4] - res[1][3] < 19
+    solo = [engine.basecall_raw_batch("rgrgr_r94", [raws[i]], varseg_chunk=5)[0] for i in (0, 2)]
+    assert res[0][0] == solo[0][0] and res[2][0] == solo[1][0] and res[0][0] and res[2][0]
+    assert all(engine.basecall_batch("rgrgr_r94", [synthetic_read(42, 10)])[0][0] is None for _ in range(2))
+
+
+def test_workspace_pool_reuse_is_invisible(sb, engine, oracle):
+    """sb2_basecall_batch recycles device workspaces between calls: results must not depend on what the workspace
+    held before (bigger batch, smaller batch, other lengths, same shape again = CUDA-graph replay)."""
+    a = [synthetic_read(600 + i, 2000 + 37 * i) for i in range(12)]
+    b_ = [synthetic_read(700 + i, 900 + 11 * i) for i in range(5)]
+    first = engine.basecall_batch("rgrgr_r94", a)
+    small = engine.basecall_batch("rgrgr_r94", b_)
+    for _ in range(3):
+        assert engine.basecall_batch("rgrgr_r94", a) == first
+    assert engine.basecall_batch("rgrgr_r94", b_) == small
+    assert engine.basecall_batch("rgrgr_r94", a[:5]) == first[:5]
+    assert first[7][0] == oracle.basecall_raw("rgrgr_r94", a[7])[2]
+    assert small[2][0] == oracle.basecall_raw("rgrgr_r94", b_[2])[2]
+    crf = engine.basecall_batch("rnnrf_r94", b_)
+    assert crf[1][0] == oracle.basecall_raw("rnnrf_r94", b_[1])[2]
+
+
+def test_concurrent_host_threads(sb, engine):
+    """The reference's entry points are re-entrant and called from OpenMP threads, one read each
+    (src/scrappie_raw.c:355-387).  Single-read symbols and the pooled batch call from eight threads at once must give
+    the results of the same calls made one after the other."""
+    import threading
+    sigs = [synthetic_read(900 + i, 800 + 53 * i) for i in range(16)]
+    want_post = [sb.calc_post(sb.RawTable(s), "rgrgr_r94").padded() for s in sigs]
+    want_calls = [engine.basecall_batch("rgrgr_r94", [s])[0] for s in sigs]
+    got_post, got_calls, errors = [None] * 16, [None] * 16, []
+
+    def work(t):
+        try:
+            for i in range(t, 16, 8):
+                got_post[i] = sb.calc_post(sb.RawTable(sigs[i]), "rgrgr_r94").padded()
+                got_calls[i] = engine.basecall_batch("rgrgr_r94", [sigs[i]])[0]
+        except Exception as e:          # noqa: BLE001 - reported below
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(8)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for i in range(16):
+        assert np.array_equal(got_post[i], want_post[i]) and got_calls[i] == want_calls[i]
+
+
+def test_two_engines_in_one_process(sb, oracle):
+    """Kernel attributes (dynamic shared-memory limits) are per device: a second engine on another GPU of the same
+    process must work, concurrently with the first.  Skipped on a one-GPU box."""
+    import ctypes as C
+    import threading
+    try:
+        cudart = C.CDLL("libcudart.so")
+    except OSError:
+        cudart = C.CDLL("libcudart.so.12")
+    n = C.c_int(0)
+    cudart.cudaGetDeviceCount(C.byref(n))
+    if n.value < 2:
+        pytest.skip("needs two GPUs")
+    sigs = [synthetic_read(100 + i, 1500 + 7 * i) for i in range(64)]
+    engines = [sb.Engine(0), sb.Engine(1)]
+    out = [None, None]
+
+    def work(k):
+        out[k] = engines[k].basecall_batch("rgrgr_r94", sigs)
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert out[0] == out[1]
+    assert out[1][5][0] == oracle.basecall_raw("rgrgr_r94", sigs[5])[2]
+    for e in engines:
+        e.close()
