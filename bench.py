@@ -4,22 +4,28 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle/_ref)
 
-One "step" = one pass of the hot path (network forward + Viterbi decode) over the whole
-workload on each GPU: `--reads` synthetic reads of `--samples` samples, processed in batches
-of `--batch` reads that run concurrently on their own CUDA streams (BASELINE config 2:
-rgrgr_r94, 1024 x 4000-sample reads, batch 256).  With N > 1 (torchrun, one rank per GPU) every
-rank processes its own `--reads` reads (weak scaling); rank 0 loads the weight blob and
+One "step" = one pass of the hot path (network forward + Viterbi decode) over the whole workload on each GPU:
+`--reads` synthetic reads of `--samples` samples, processed in batches of `--batch` reads that run concurrently on
+their own CUDA streams (BASELINE config 2: rgrgr_r94, 1024 x 4000-sample reads, batch 256).  With N > 1 (torchrun,
+one rank per GPU) every rank processes its own `--reads` reads (weak scaling); rank 0 loads the weight blob and
 broadcasts it over NCCL at start-up; there is no collective on the per-read path.
 
-  value  samples/s with the signals already resident in HBM; device time from CUDA events on
-         the launching stream (L2 flushed between steps, outside the timed region), max over ranks.
-  e2e    samples/s through the C-ABI batch basecall with HOST buffers: pinned H2D of the
-         signals, forward, decode, D2H of paths/scores, homopolymer fix-up and overlapper on
-         the host, all inside the timed region (wall clock, max over ranks).
+  value   samples/s with the signals already resident in HBM; device time from CUDA events on the launching stream,
+          K steps streamed back to back over `--sets` buffer sets, max over ranks.
+  e2e     samples/s through the documented drop-in call, sb2_basecall_batch, from ORDINARY
+          (pageable) host arrays: staging into pinned memory, H2D, forward, decode, homopolymer fix-up + overlapper on
+          the device, D2H of the base strings, all inside the timed region (wall clock, max over ranks).  Workspaces
+          come from the engine's pool, so the call allocates nothing in steady state.  `e2e.persistent` is the same
+          work through caller-owned sb2_batch objects with pre-filled pinned buffers (round 1's figure).
+  parity  base strings of the timed e2e run compared with the reference's own CPU implementation (oracle/_ref) on the
+          same reads; a mismatch makes the run exit non-zero.
+  other_configs   BASELINE configs 3 (rnnrf_r94) and 4 (mixed lengths), and with N > 1 config 5 (100 000 reads dealt
+          out by shard_reads), measured after the headline with the same method.
 """
 import argparse
 import json
 import os
+import queue
 import subprocess
 import sys
 import threading
@@ -51,12 +57,18 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--cpu-sample-reads", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true",
+                    help="only the headline workload (default: configs 3 and 4, and config 5 when N > 1, are measured too)")
+    ap.add_argument("--sustained-seconds", type=float, default=5.0,
+                    help="length of the additional long run that shows the figure under sustained clocks (0 = skip)")
     ap.add_argument("--sets", type=int, default=4,
                     help="buffer sets: consecutive steps alternate between the sets and are not synchronised with each "
                          "other, so step n + 1 overlaps the tail of step n (1 = one set, L2 flushed between steps)")
-    ap.add_argument("--workload", default="fixed", choices=["fixed", "mixed"],
+    ap.add_argument("--workload", default="fixed", choices=["fixed", "mixed", "sharded"],
                     help="fixed: --reads reads of --samples samples (BASELINE config 2); mixed: --reads reads with "
-                         "log-normal lengths in [1k, 200k] samples, length-bucketed dynamic batching (config 4)")
+                         "log-normal lengths in [1k, 200k] samples, length-bucketed dynamic batching (config 4); sharded: "
+                         "--total-reads reads of --samples samples dealt out to the ranks by shard_reads (config 5)")
+    ap.add_argument("--total-reads", type=int, default=100000)
     return ap.parse_args()
 
 
@@ -91,20 +103,21 @@ class ClockSampler(object):
         except Exception:
             self.proc.kill()
             out = ""
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in out.strip().splitlines():
             f = [x.strip() for x in line.split(",")]
             if len(f) < 7:
                 continue
             try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
             except ValueError:
                 continue
             for nm, v in zip(names, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_min_mhz": min(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "power_w_median": float(np.median(pw)) if pw else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
@@ -114,20 +127,63 @@ def make_workload(nreads, nsamples, seed0):
 
 
 # ------------------------------------------------------------------------------------
-# reference arm / cpu baseline (the only place bench.py touches oracle/)
+# reference arm / cpu baseline / parity check (the only place bench.py touches oracle/)
 # ------------------------------------------------------------------------------------
 
-def run_reference(model, sigs, nthreads=0):
-    """Times oracle/_ref (the reference's own C sources + OpenBLAS, one read per OpenMP thread).
-    Returns (seconds, nbases, nblocks, threads)."""
+def _cpu_flags():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("flags"):
+                return set(line.split(":", 1)[1].split())
+    except OSError:
+        pass
+    return set()
+
+
+def reference_library():
+    """(path, -march label) of the compiled reference for THIS host: the x86-64-v4 (AVX-512) build when the CPU has
+    it -- the closest shippable stand-in for the reference's -march=native (CMakeLists.txt:97) -- else x86-64-v3."""
+    base = os.path.join(ROOT, "oracle", "_ref")
+    v4 = os.path.join(base, "v4", "libref_bench.so")
+    if os.path.exists(v4) and {"avx512f", "avx512bw", "avx512cd", "avx512dq", "avx512vl"} <= _cpu_flags():
+        return v4, "x86-64-v4"
+    v3 = os.path.join(base, "libref_bench.so")
+    return (v3, "x86-64-v3") if os.path.exists(v3) else (None, None)
+
+
+_REF = {}
+
+
+def _ref_lib():
     import ctypes as C
-    so = os.path.join(ROOT, "oracle", "_ref", "libref_bench.so")
-    if not os.path.exists(so):
+    if "lib" not in _REF:
+        so, march = reference_library()
+        L = None
+        if so is not None:
+            L = C.CDLL(so)
+            L.ref_bench_run.restype = C.c_double
+            L.ref_bench_run.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int,
+                                        C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.c_void_p]
+            L.ref_bench_free.argtypes = [C.c_void_p]
+            blas = None
+            try:
+                L.ref_bench_blas_config.restype = C.c_char_p
+                blas = L.ref_bench_blas_config().decode().strip()
+            except AttributeError:
+                pass
+            _REF["build"] = {"march": march, "blas": blas, "flags": "-O3 -march=%s -fopenmp -DUSE_SSE2 -DNDEBUG "
+                             "(reference: -O3 -march=native, CMakeLists.txt:97)" % march}
+        _REF["lib"] = L
+    return _REF["lib"]
+
+
+def run_reference(model, sigs, nthreads=0, want_bases=False):
+    """Times oracle/_ref (the reference's own C sources + OpenBLAS, one read per OpenMP thread).
+    Returns (seconds, nbases, nblocks, threads[, bases])."""
+    import ctypes as C
+    L = _ref_lib()
+    if L is None:
         return None
-    L = C.CDLL(so)
-    L.ref_bench_run.restype = C.c_double
-    L.ref_bench_run.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int,
-                                C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.c_void_p]
     concat = np.concatenate(sigs).astype(np.float32)
     lens = np.array([len(s) for s in sigs], dtype=np.uint64)
     offs = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.uint64)
@@ -135,9 +191,17 @@ def run_reference(model, sigs, nthreads=0):
     # all host threads this process may use (torchrun exports OMP_NUM_THREADS=1, which is not what the
     # reference's own recommendation -- one read per core -- means; README.md:66-71)
     threads = nthreads or len(os.sched_getaffinity(0))
+    out = (C.c_void_p * len(sigs))() if want_bases else None
     secs = L.ref_bench_run(model.encode(), concat.ctypes.data, offs.ctypes.data, lens.ctypes.data, len(sigs),
-                           threads, C.byref(nb), C.byref(nk), None)
-    return secs, nb.value, nk.value, threads
+                           threads, C.byref(nb), C.byref(nk), out)
+    if not want_bases:
+        return secs, nb.value, nk.value, threads
+    bases = []
+    for p in out:
+        bases.append(C.string_at(p).decode() if p else None)
+        if p:
+            L.ref_bench_free(p)
+    return secs, nb.value, nk.value, threads, bases
 
 
 def run_oracle_port(model, sigs):
@@ -145,11 +209,26 @@ def run_oracle_port(model, sigs):
     from oracle.oracle import Oracle
     o = Oracle()
     t0 = time.time()
-    nb = 0
+    nb, bases = 0, []
     for s in sigs:
-        _, _, bases, _ = o.basecall_raw(model, s)
-        nb += len(bases or "")
-    return time.time() - t0, nb, 0, 1
+        _, _, b, _ = o.basecall_raw(model, s)
+        bases.append(b)
+        nb += len(b or "")
+    return time.time() - t0, nb, 0, 1, bases
+
+
+def check_parity(model, sigs, got_bases):
+    """Base strings of the GPU run vs the CPU reference on the same reads (python/test/test_scrappy.py:72-75 makes
+    the same comparison for the reference's own Python binding)."""
+    res = run_reference(model, sigs, want_bases=True)
+    against = "reference (oracle/_ref)"
+    if res is None:
+        res = run_oracle_port(model, sigs)
+        against = "oracle port"
+    want = res[4]
+    bad = [i for i, (g, w) in enumerate(zip(got_bases, want)) if g != w]
+    return {"reads_checked": len(sigs), "bases_identical": not bad, "mismatching_reads": bad[:8], "against": against,
+            "bases_checked": int(sum(len(w or "") for w in want))}
 
 
 def cpu_baseline(model, sigs, nreads_sample):
@@ -160,12 +239,14 @@ def cpu_baseline(model, sigs, nreads_sample):
         sample = sigs[:max(8, nreads_sample // 16)]
         res = run_oracle_port(model, sample)
         kind = "port"
-    secs, nbases, _, threads = res
+    secs, nbases, _, threads = res[:4]
     nsamp = sum(len(s) for s in sample)
-    return {"value": nsamp / secs, "unit": "samples/s", "cores": threads, "kind": kind,
-            "kbases_per_s": nbases / secs / 1e3,
-            "sample": "%d of the workload's reads (%d samples), one read per OpenMP thread, 1 BLAS thread, %.2f s wall"
-                      % (len(sample), nsamp, secs)}
+    out = {"value": nsamp / secs, "unit": "samples/s", "cores": threads, "kind": kind,
+           "kbases_per_s": nbases / secs / 1e3,
+           "sample": "%d of the workload's reads (%d samples), one read per OpenMP thread, 1 BLAS thread, %.2f s wall"
+                     % (len(sample), nsamp, secs)}
+    out.update(_REF.get("build", {}))
+    return out
 
 
 def main_reference(args, rank, world):
@@ -174,8 +255,9 @@ def main_reference(args, rank, world):
     # one step = one pass over the same workload as the GPU arm (args.reads reads), capped so that K steps stay bounded
     nstep_reads = min(args.reads, args.cpu_sample_reads)
     sigs = make_workload(nstep_reads, args.samples, 1000)
+    have_ref = _ref_lib() is not None
     for _ in range(max(1, min(args.warmup, 1))):
-        run_reference(args.model, sigs[:32]) if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_bench.so")) else None
+        run_reference(args.model, sigs[:32]) if have_ref else None
     times, kind, threads, nbases = [], "reference", 1, 0
     for _ in range(args.steps):
         res = run_reference(args.model, sigs)
@@ -188,14 +270,17 @@ def main_reference(args, rank, world):
         times.append(res[0]); nbases = res[1]; threads = res[3]
     ms = 1e3 * float(np.mean(times))
     value = nsamp / (ms / 1e3)
+    cpu = {"value": value, "unit": "samples/s", "cores": threads, "kind": kind,
+           "sample": "%d reads x %d samples per step" % (len(sigs), args.samples)}
+    cpu.update(_REF.get("build", {}))
     line = {"impl": "reference", "metric": "raw samples/sec (%s)" % args.model, "value": value, "unit": "samples/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "%s raw, synthetic %d-sample reads (bounded sample: %d reads per step), CPU %s"
-                                   % (args.model, args.samples, len(sigs), kind)},
+            "config": {"workload": "%s raw, %d synthetic %d-sample reads per GPU, batch=%d; CPU %s arm: bounded sample of "
+                                   "%d reads per step, one read per OpenMP thread"
+                                   % (args.model, args.reads, args.samples, args.batch, kind, len(sigs))},
             "kbases_per_s": nbases / (ms / 1e3) / 1e3,
-            "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "kind": kind,
-                             "sample": "%d reads x %d samples per step" % (len(sigs), args.samples)},
+            "cpu_baseline": cpu,
             "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -205,159 +290,351 @@ def main_reference(args, rank, world):
 # this repo's arm
 # ------------------------------------------------------------------------------------
 
-def main_b200(args, rank, world, local_rank):
-    import torch
-    import scrappie_b200 as sb
+class Ranks(object):
+    """torch.distributed plumbing of the bench: barrier, max / gather of timings."""
 
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    def __init__(self, rank, world, local_rank):
+        import torch
+        self.torch, self.rank, self.world = torch, rank, world
+        self.dist = None
+        if world > 1:
+            import torch.distributed as dist
+            torch.cuda.set_device(local_rank)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            self.dist = dist
 
-    eng = sb.Engine(local_rank)
-    # weights: rank 0 reads the blob, every other rank receives it over NCCL (init only)
-    from scrappie_b200.sharding import broadcast_blob, max_over_ranks
-    blob_path = os.path.join(sb.WEIGHTS_DIR, args.model + ".bin")
-    eng.load_blob(args.model, broadcast_blob(blob_path, rank, dist, device="cuda" if world > 1 else "cpu"))
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.dist is not None:
+            self.dist.barrier()
 
-    if args.workload == "mixed":
-        from scrappie_b200.sharding import lognormal_lengths, plan_batches
-        from scrappie_b200.synthetic import synthetic_read
+    def gather(self, value):
+        """`value` of every rank, as a list (every rank gets it)."""
+        if self.dist is None:
+            return [float(value)]
+        t = self.torch.tensor([float(value)], dtype=self.torch.float64, device="cuda")
+        out = [self.torch.zeros_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t)
+        return [float(x.item()) for x in out]
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.destroy_process_group()
+
+
+def spread(values):
+    v = sorted(values)
+    return {"min": v[0], "median": float(np.median(v)), "max": v[-1]}
+
+
+def d2h_bytes(model, nread, max_nblock, max_nbase):
+    # finish_on_device (csrc/engine.cu): base count + score per read, then either the whole base-string area
+    # (batches whose area is <= 2 MB) or a 2-D copy as wide as the longest call
+    klen = 1 if model == "rnnrf_r94" else (6 if model == "rgrgr_r10" else 5)
+    stride = (klen * (max_nblock + 1) + 1 + 15) // 16 * 16
+    area = nread * stride
+    return nread * 8 + (area if area <= (2 << 20) else nread * ((max_nbase + 1 + 15) // 16 * 16))
+
+
+def build_groups(args, model, workload, rank, world):
+    """The rank's reads and their division into batches.  Returns (sigs, groups, description)."""
+    import scrappie_b200 as sb  # noqa: F401
+    from scrappie_b200.sharding import lognormal_lengths, plan_batches, shard_reads
+    from scrappie_b200.synthetic import synthetic_read
+    if workload == "mixed":
         lens = lognormal_lengths(args.reads, seed=4 + rank)
         sigs = [synthetic_read(1000 + rank * args.reads + i, int(n)) for i, n in enumerate(lens)]
         plan = plan_batches(lens, max_reads=args.batch, max_samples=args.batch * 4096)
         groups = [[sigs[i] for i in idx] for idx in plan]
-        nbatch = len(groups)
+        desc = ("%s raw, %d synthetic reads per GPU with log-normal lengths (median 8000, sigma 1.0, clipped to [1k, 200k] "
+                "samples; %d samples in total, longest %d), length-bucketed dynamic batching into %d batches of <= %d reads"
+                % (model, args.reads, sum(len(s) for s in sigs), max(len(x) for x in sigs), len(groups), args.batch))
+    elif workload == "sharded":
+        # config 5 literally: read i of the job has seed 1000 + i; the job's reads are dealt out by shard_reads and each
+        # rank batches what it owns.  Only 2048 distinct signals are synthesised (read i uses signal i % 2048): the
+        # content of a read does not change what the path costs, generating 100 000 of them in Python would.
+        owned = shard_reads([args.samples] * args.total_reads, rank, world)
+        distinct = make_workload(min(2048, args.total_reads), args.samples, 1000)
+        sigs = [distinct[int(i) % len(distinct)] for i in owned]
+        groups = [sigs[i:i + args.batch] for i in range(0, len(sigs), args.batch)]
+        desc = ("%s raw, %d synthetic %d-sample reads sharded over %d GPU(s) by shard_reads (%d on this rank, batches of %d)"
+                % (model, args.total_reads, args.samples, world, len(sigs), args.batch))
     else:
         sigs = make_workload(args.reads, args.samples, 1000 + rank * args.reads)
-        nbatch = (args.reads + args.batch - 1) // args.batch
-        groups = [sigs[i * args.batch:(i + 1) * args.batch] for i in range(nbatch)]
-    nsets = max(1, min(args.sets, args.steps))
-    groups = groups * nsets                              # set k = batches[k * nbatch : (k + 1) * nbatch], same reads
-    batches = [eng.batch(args.model, [len(s) for s in g]) for g in groups]
-    pinned = []
-    for b, g in zip(batches, groups):
+        groups = [sigs[i:i + args.batch] for i in range(0, len(sigs), args.batch)]
+        desc = ("%s raw, %d synthetic %d-sample reads per GPU, batch=%d (%d concurrent batches), forward + Viterbi decode"
+                % (model, args.reads, args.samples, args.batch, len(groups)))
+    return sigs, groups, desc
+
+
+def measure(eng, ranks, args, model, workload, steps, warmup, nsets, detail):
+    """One workload through all three measurements: device-resident streaming (`value`), the documented call from
+    pageable host arrays (`e2e`), the persistent-batch path (`e2e.persistent`), plus the parity check of the e2e run's
+    base strings.  Returns a dict; `detail` adds the per-kernel figures of the headline."""
+    import scrappie_b200 as sb
+    torch = ranks.torch
+    rank = ranks.rank
+    sigs, groups, desc = build_groups(args, model, workload, rank, ranks.world)
+    nbatch = len(groups)
+    if workload == "sharded":
+        nsets, steps, warmup = 1, max(1, min(steps, 2)), 1          # one pass = the whole shard, already many batches
+    nsets = max(1, min(nsets, steps))
+    params = sb.default_params()
+    total_samples = sum(len(s) for s in sigs)
+
+    # ---- device-resident throughput -------------------------------------------------------------------------------
+    # Set k = batches[k * nbatch : (k + 1) * nbatch] (same reads).  The steps alternate between the sets and run back
+    # to back on the batches' own streams with no synchronisation in between (a continuously fed basecaller): step
+    # n + 1 starts while step n is still decoding.  A step streams GBs of activations, far more than L2 holds.
+    batches, pinned = [], []
+    for g in groups * nsets:
+        b = eng.batch(model, [len(s) for s in g])
         pb = sb.PinnedBuffer(b.total_samples_padded)
         pb.array[:] = 0
         for r, s in enumerate(g):
             pb.array[b.sample_offset[r]:b.sample_offset[r] + len(s)] = s
-        pinned.append(pb)
         b.upload_concat(pb.ptr, pinned_async=False)
-    params = sb.default_params()
-    total_samples = sum(len(s) for s in sigs)
+        batches.append(b)
+        pinned.append(pb)
     total_blocks = sum(b.total_blocks for b in batches[:nbatch])
-
-    def barrier():
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-
-    # ---- device-resident throughput ------------------------------------------------
-    # One step = one pass over the rank's `--reads` reads (nbatch concurrent batches).  With two buffer sets the
-    # steps alternate between the sets and run back to back on the batches' own streams with no synchronisation
-    # in between (a continuously fed basecaller): step n + 1 starts while step n is still decoding.  The working
-    # set of a step (GBs of activations) is far larger than L2, so nothing is served from cache across steps.
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    if nsets > 1:
-        # set k runs steps k, k + nsets, ...: exactly args.steps steps in all
-        set_reps = [args.steps // nsets + (1 if k < args.steps % nsets else 0) for k in range(nsets)]
-        reps = [set_reps[i // nbatch] for i in range(len(batches))]
-        sb.multi_stream_time(batches, params, nrep=max(3, (args.warmup + nsets - 1) // nsets))
-        barrier()
+    set_reps = [steps // nsets + (1 if k < steps % nsets else 0) for k in range(nsets)]
+    reps = [set_reps[i // nbatch] for i in range(len(batches))]
+    sampler = ClockSampler(torch.cuda.current_device()) if rank == 0 else None
+    if nsets > 1 or workload == "sharded":
+        sb.multi_stream_time(batches, params, nrep=max(1 if workload == "sharded" else 3, (warmup + nsets - 1) // nsets))
+        ranks.barrier()
         launches0 = eng.launches
-        step_ms = sb.multi_stream_time(batches, params, nrep=reps) / args.steps
+        step_ms = sb.multi_stream_time(batches, params, nrep=reps) / steps
         launches = eng.launches - launches0
-        barrier()
+        ranks.barrier()
         l2_note = ("not flushed: %d steps back to back, each streaming its own %.1f GB of activations through HBM "
-                   "(L2 is 126 MB); %d buffer sets alternate" %
-                   (args.steps, sum(b.total_blocks for b in batches[:nbatch]) * 26e3 / 1e9, nsets))
+                   "(L2 is 126 MB); %d buffer sets alternate" % (steps, total_blocks * 26e3 / 1e9, nsets))
     else:
-        sb.multi_time(batches, params, nrep=max(3, args.warmup), flush_l2=True)
-        barrier()
+        sb.multi_time(batches, params, nrep=max(3, warmup), flush_l2=True)
+        ranks.barrier()
         launches0 = eng.launches
-        ms = sb.multi_time(batches, params, nrep=args.steps, flush_l2=True)
+        ms = sb.multi_time(batches, params, nrep=steps, flush_l2=True)
         launches = eng.launches - launches0
-        barrier()
+        ranks.barrier()
         step_ms = float(np.mean(ms))
         l2_note = "flushed between timed steps (384 MB overwrite, outside the timed region)"
     clocks = sampler.stop() if sampler else None
-    # stage intervals of one synchronised step of the first set (diagnostics, outside the timed region)
-    sb.multi_time(batches[:nbatch], params, nrep=1, flush_l2=True)
-    stage = [b.stage_ms() for b in batches[:nbatch]]
+    out = {"workload": desc, "l2": l2_note, "buffer_sets": nsets, "steps": steps, "nbatch": nbatch,
+           "total_samples": total_samples, "total_blocks": total_blocks, "launches": int(launches), "clocks": clocks}
 
-    # ---- end to end through the C-ABI batch basecall, host buffers ------------------------
-    # One host thread per batch object; each basecalls its batch steps / nsets times (pinned host signal in, base
-    # strings out, every time), the threads free-running like the streams above.
+    # ---- sustained: the same streaming loop for >= N seconds (power-capped clocks instead of the burst's) ---------
+    if detail and args.sustained_seconds > 0:
+        n_long = int(np.ceil(args.sustained_seconds * 1e3 / step_ms / nsets)) * nsets
+        sampler = ClockSampler(torch.cuda.current_device()) if rank == 0 else None
+        ranks.barrier()
+        long_ms = sb.multi_stream_time(batches, params, nrep=[n_long // nsets] * len(batches))
+        ranks.barrier()
+        lc = sampler.stop() if sampler else None
+        long_all = ranks.gather(long_ms)
+        out["sustained"] = {"value": ranks.world * total_samples * n_long / (max(long_all) * 1e-3), "unit": "samples/s",
+                            "steps": n_long, "seconds": max(long_all) * 1e-3, "ms_per_step": max(long_all) / n_long,
+                            "clocks": lc}
+
+    # stage intervals of one synchronised step of the first set (diagnostics, outside the timed region)
+    if detail:
+        sb.multi_time(batches[:nbatch], params, nrep=1, flush_l2=True)
+        out["stage_concurrent"] = [b.stage_ms() for b in batches[:nbatch]]
+
+    # ---- end to end, persistent batch objects + pre-filled pinned buffers (round 1's e2e) ---------------------------
     results = [None] * len(batches)
 
-    def work(i, nrep):
+    def work_persistent(i, nrep):
         for _ in range(nrep):
             results[i] = batches[i].basecall(pinned[i].ptr, True, params, lazy=True)
 
-    def e2e_run(reps_):
-        th = [threading.Thread(target=work, args=(i, reps_[i])) for i in range(len(batches))]
+    def run_threads(fn, reps_):
+        th = [threading.Thread(target=fn, args=(i, reps_[i])) for i in range(len(reps_))]
         for t in th:
             t.start()
         for t in th:
             t.join()
 
-    e2e_reps = reps if nsets > 1 else [args.steps] * len(batches)
-    e2e_run([1] * len(batches))
-    barrier()
+    run_threads(work_persistent, [1] * len(batches))
+    ranks.barrier()
     t0 = time.perf_counter()
-    e2e_run(e2e_reps)
+    run_threads(work_persistent, reps)
     torch.cuda.synchronize()
-    e2e_s = (time.perf_counter() - t0) / args.steps
+    e2e_persistent_s = (time.perf_counter() - t0) / steps
     nbases = int(sum(int(res.nbase.sum()) for res in results[:nbatch]))
     h2d = sum(b.total_samples_padded * 4 for b in batches[:nbatch])
-    def d2h_bytes(b, res):
-        # finish_on_device (csrc/engine.cu): base count + score per read, then either the whole base-string area
-        # (batches whose area is <= 2 MB) or a 2-D copy as wide as the longest call
-        klen = 1 if args.model == "rnnrf_r94" else (6 if args.model == "rgrgr_r10" else 5)
-        stride = (klen * (max(b.nblock) + 1) + 1 + 15) // 16 * 16
-        area = b.nread * stride
-        return b.nread * 8 + (area if area <= (2 << 20) else b.nread * ((int(res.nbase.max()) + 1 + 15) // 16 * 16))
-    d2h = sum(d2h_bytes(b, res) for b, res in zip(batches[:nbatch], results[:nbatch]))
+    d2h = sum(d2h_bytes(model, b.nread, max(b.nblock), int(res.nbase.max())) for b, res in zip(batches[:nbatch], results[:nbatch]))
+    persistent_bases = results[0].bases(0)
 
-    # ---- reduce over ranks (max time) ------------------------------------------------------
-    step_ms, e2e_s = max_over_ranks([step_ms, e2e_s], dist, device="cuda" if world > 1 else "cpu")
+    if detail:
+        # Per-kernel figures from ONE batch timed alone (CUDA events on its stream, L2 flushed), after the timed region:
+        # in the concurrent step the stage intervals of different batches overlap, so they are not launch durations.
+        batches[0].time(params, nrep=3, flush_l2=True)
+        out["stage_solo"] = batches[0].stage_ms()
+        out["batch0"] = {"nread": batches[0].nread, "cols": batches[0].total_blocks, "ostride": batches[0].ostride,
+                         "nsamp": batches[0].total_samples_padded}
+    results = None
+    for b in batches:
+        b.close()
+    for pb in pinned:
+        pb.close()
+    batches, pinned = None, None
+
+    # ---- end to end through the documented call: sb2_basecall_batch from pageable host arrays ----------------------
+    # Work items = (step, batch); worker threads (one per concurrent batch slot) take them longest batch first and make
+    # one call each, exactly what INTEGRATION.md section 2.1 tells a maintainer to do.
+    order = sorted(range(nbatch), key=lambda k: -sum(len(s) for s in groups[k]))
+    prepared = [eng.prepare_call(g) for g in groups]
+    nworker = min(nbatch * nsets, 16)
+    last = [None] * nbatch
+
+    def run_documented(nstep):
+        q = queue.Queue()
+        for _ in range(nstep):
+            for k in order:
+                q.put(k)
+        err = []
+
+        def worker():
+            while True:
+                try:
+                    k = q.get_nowait()
+                except queue.Empty:
+                    return
+                try:
+                    last[k] = eng.basecall_prepared(model, prepared[k], params)
+                except Exception as e:      # noqa: BLE001 - re-raised on the main thread
+                    err.append(e)
+                    return
+        th = [threading.Thread(target=worker) for _ in range(nworker)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        if err:
+            raise err[0]
+
+    run_documented(max(2, (warmup + 1) // 2))           # pool warm-up: workspaces, pinned staging, graphs
+    ranks.barrier()
+    t0 = time.perf_counter()
+    run_documented(steps)
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / steps
+    ranks.barrier()
+
+    # ---- parity gate on the base strings the timed run produced -----------------------------------------------------
+    pick = []
+    if workload == "fixed":
+        pick = [(0, r) for r in range(len(groups[0]))] + [(k, r) for k in range(1, nbatch) for r in range(0, len(groups[k]), 8)]
+    else:
+        rng = np.random.default_rng(17)
+        flat = [(k, r) for k in range(nbatch) for r in range(len(groups[k]))]
+        pick = [flat[i] for i in sorted(rng.choice(len(flat), size=min(48, len(flat)), replace=False))]
+    pool_workspaces = None
+    if rank == 0:
+        got = [last[k].bases(r) for k, r in pick]
+        parity = check_parity(model, [groups[k][r] for k, r in pick], got)
+        parity["persistent_path_agrees"] = (persistent_bases == last[0].bases(0))
+        out["parity"] = parity
+
+    last = None
+    eng.trim_pool()                                     # the next workload sizes its own workspaces
+    step_all = ranks.gather(step_ms)
+    e2e_all = ranks.gather(e2e_s)
+    e2ep_all = ranks.gather(e2e_persistent_s)
+    W = ranks.world
+    out.update({
+        "ms_per_step": max(step_all), "value": W * total_samples / (max(step_all) * 1e-3),
+        "ms_per_step_ranks": spread(step_all),
+        "blocks_per_s": W * total_blocks / (max(step_all) * 1e-3),
+        "kbases_per_s": W * nbases / max(e2e_all) / 1e3,
+        "e2e": {"value": W * total_samples / max(e2e_all), "unit": "samples/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": max(e2e_all) * 1e3, "ms_per_step_ranks": spread([x * 1e3 for x in e2e_all]),
+                "api": "sb2_basecall_batch (pooled workspaces) from pageable host arrays, %d host threads" % nworker,
+                "persistent": {"value": W * total_samples / max(e2ep_all), "ms_per_step": max(e2ep_all) * 1e3,
+                               "api": "sb2_batch_basecall on caller-owned batches, pre-filled pinned buffers"}},
+    })
+    return out
+
+
+def write_peak_gbs(torch):
+    """Write-only HBM bandwidth measured now (fill of a 4 GiB buffer, best of 5): kernels that mostly write are bounded
+    by it rather than by the half-read half-write copy figure of MEASURED_PEAKS.json."""
+    x = torch.empty(1 << 30, dtype=torch.float32, device="cuda")
+    best = 0.0
+    for _ in range(6):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        x.fill_(1.0)
+        e1.record()
+        torch.cuda.synchronize()
+        best = max(best, x.numel() * 4 / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+    del x
+    torch.cuda.empty_cache()
+    return best
+
+
+def main_b200(args, rank, world, local_rank):
+    import scrappie_b200 as sb
+    from scrappie_b200.sharding import broadcast_blob
+
+    ranks = Ranks(rank, world, local_rank)
+    torch = ranks.torch
+    torch.cuda.set_device(local_rank)
+    eng = sb.Engine(local_rank)
+    default_run = (args.workload == "fixed" and args.model == "rgrgr_r94" and not args.no_other_configs)
+    models = [args.model] + (["rnnrf_r94"] if default_run else [])
+    # weights: rank 0 reads the blobs, every other rank receives them over NCCL (init only)
+    for m in models:
+        eng.load_blob(m, broadcast_blob(os.path.join(sb.WEIGHTS_DIR, m + ".bin"), rank, ranks.dist,
+                                        device="cuda" if world > 1 else "cpu"))
+
+    head = measure(eng, ranks, args, args.model, args.workload, args.steps, args.warmup, args.sets, detail=True)
+
+    others = {}
+    if default_run:
+        def brief(m):
+            keys = ("workload", "value", "ms_per_step", "ms_per_step_ranks", "kbases_per_s", "steps", "buffer_sets", "parity", "launches")
+            d = {k: m[k] for k in keys if k in m}
+            d["e2e"] = {k: m["e2e"][k] for k in ("value", "ms_per_step", "api", "h2d_bytes_per_step", "d2h_bytes_per_step")}
+            d["e2e"]["persistent"] = m["e2e"]["persistent"]["value"]
+            d["unit"] = "samples/s"
+            return d
+        others["rnnrf_r94 (config 3)"] = brief(measure(eng, ranks, args, "rnnrf_r94", "fixed", 8, 4, args.sets, detail=False))
+        others["mixed lengths (config 4)"] = brief(measure(eng, ranks, args, "rgrgr_r94", "mixed", 12, 6, 6, detail=False))
+        if world > 1:
+            others["sharded 100k (config 5)"] = brief(measure(eng, ranks, args, "rgrgr_r94", "sharded", 2, 1, 1, detail=False))
+
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
+        ranks.close()
         return
 
     pk, pk_src = peaks()
-    # Per-kernel figures from ONE batch timed alone (CUDA events on its stream, L2 flushed), after the timed region:
-    # in the concurrent step the stage intervals of different batches overlap, so they are not launch durations.
-    _, _, _ = batches[0].time(params, nrep=3, flush_l2=True)
-    solo = batches[0].stage_ms()
-    H = 112 if args.model == "rnnrf_r94" else 96
-    nstate_stride = batches[0].ostride
-    cols = batches[0].total_blocks
-    nsamp0 = batches[0].total_samples_padded
-    scan_avg_ms = float(np.mean([solo["scan%d" % l] for l in range(1, 6)]))
-    flop_per_launch = FLOP_PER_READ_STEP_RECURRENT[args.model] * cols
-    achieved = flop_per_launch / (scan_avg_ms * 1e-3) / 1e12
-    grp_env = os.environ.get("SCRAPPIE_B200_SCAN_GROUPS", "0")
-    if args.model == "rnnrf_r94":
-        reads_per_cta = 12 if (batches[0].nread >= 96 and grp_env in ("0", "3")) else 8
-    else:
-        reads_per_cta = 16 if (batches[0].nread >= 128 and grp_env in ("0", "4")) else 8
-    scan_ctas = (batches[0].nread + reads_per_cta - 1) // reads_per_cta
-    peak = pk["bf16_tflops"]
     hbm = pk["hbm_gbs"]
+    solo, b0 = head["stage_solo"], head["batch0"]
+    model = args.model
+    H = 112 if model == "rnnrf_r94" else 96
+    cols, nstate_stride, nsamp0 = b0["cols"], b0["ostride"], b0["nsamp"]
+    scan_avg_ms = float(np.mean([solo["scan%d" % l] for l in range(1, 6)]))
+    flop_per_launch = FLOP_PER_READ_STEP_RECURRENT[model] * cols
+    achieved = flop_per_launch / (scan_avg_ms * 1e-3) / 1e12
+    gen = int(os.environ.get("SCRAPPIE_B200_SCAN_GEN", "0"))
+    v5 = gen == 5 or (gen != 4 and b0["nread"] >= 48)
+    if v5:
+        reads_per_cta = 24 if H == 112 else 32
+    elif H == 112:
+        reads_per_cta = 12 if b0["nread"] >= 96 else 8
+    else:
+        reads_per_cta = 16 if b0["nread"] >= 128 else 8
+    scan_ctas = (b0["nread"] + reads_per_cta - 1) // reads_per_cta
+    peak = pk["bf16_tflops"]
     traffic = None
     tfiles = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_traffic.json")) \
         if os.path.isdir(os.path.join(ROOT, "profiles")) else []
     measured = json.load(open(os.path.join(ROOT, "profiles", tfiles[-1]))) if tfiles else {}
     for k, v in measured.items():
-        if k.startswith("gru_scan") and args.model != "rnnrf_r94":
+        if k.startswith("gru_scan") and model != "rnnrf_r94":
             traffic = v["dram_read_bytes"] + v["dram_write_bytes"]
-
-    # write-only HBM bandwidth of this pool's B200 (tools/hbm_write_probe.py, r29): kernels that mostly write are
-    # bounded by it rather than by the half-read half-write copy figure of MEASURED_PEAKS.json
-    HBM_WRITE_GBS = 3904.0
+    wpeak = write_peak_gbs(torch)
 
     def hbm_kernel(name, ms, nbytes, wbytes=None):
         k = {"kernel": name, "bound": "hbm", "avg_launch_ms": ms, "bytes_per_launch": nbytes,
@@ -365,11 +642,12 @@ def main_b200(args, rank, world, local_rank):
         if wbytes is not None:
             k["write_bytes_per_launch"] = wbytes
             k["write_achieved"] = wbytes / (ms * 1e-3) / 1e9
-            k["write_peak"] = HBM_WRITE_GBS
-            k["write_frac"] = k["write_achieved"] / HBM_WRITE_GBS
+            k["write_peak"] = wpeak
+            k["write_peak_source"] = "fill of a 4 GiB buffer measured in this run (not a driver-written peak)"
+            k["write_frac"] = k["write_achieved"] / wpeak
         return k
     aff_ms = float(np.mean([solo["affine%d" % l] for l in range(1, 6)]))
-    tb_bytes = (nstate_stride - 4 + 4) if args.model != "rnnrf_r94" else 8
+    tb_bytes = (nstate_stride - 4 + 4) if model != "rnnrf_r94" else 8
     kernels = [
         hbm_kernel("conv_act", solo["conv"], nsamp0 * 4 + cols * H * 4),
         hbm_kernel("affine_tc (GRU input transform)", aff_ms, cols * (H + 3 * H) * 4, cols * 3 * H * 4),
@@ -377,51 +655,57 @@ def main_b200(args, rank, world, local_rank):
                    cols * nstate_stride * 4),
         hbm_kernel("decode (Viterbi + traceback)", solo["decode"], cols * (nstate_stride * 4 + tb_bytes + 4)),
     ]
+    stage = head["stage_concurrent"]
     stage_sum = {k: float(np.mean([st[k] for st in stage])) for k in stage[0]}
+    step_ms = head["ms_per_step"]
+    bpb = BYTES_PER_BLOCK.get(model, 0)
     line = {
-        "metric": "raw samples/sec (%s)" % args.model, "value": world * total_samples / (step_ms * 1e-3),
-        "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
+        "metric": "raw samples/sec (%s)" % model, "value": head["value"],
+        "unit": "samples/s", "n_gpus": world, "steps": head["steps"], "warmup": args.warmup, "ms_per_step": step_ms,
+        "ms_per_step_ranks": head["ms_per_step_ranks"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": ("%s raw, %d synthetic %d-sample reads per GPU, batch=%d (%d concurrent batches), "
-                                "forward + Viterbi decode" % (args.model, args.reads, args.samples, args.batch, nbatch))
-                               if args.workload == "fixed" else
-                               ("%s raw, %d synthetic reads per GPU with log-normal lengths (median 8000, sigma 1.0, clipped "
-                                "to [1k, 200k] samples; %d samples in total, longest %d), length-bucketed dynamic batching "
-                                "into %d concurrent batches of <= %d reads" % (args.model, args.reads, total_samples,
-                                                                              max(len(x) for x in sigs), nbatch, args.batch)),
-                   "l2": l2_note, "buffer_sets": nsets,
+        "config": {"workload": head["workload"], "l2": head["l2"], "buffer_sets": head["buffer_sets"],
                    "scan_impl": os.environ.get("SCRAPPIE_B200_SCAN", "default"),
+                   "scan_generation": "v5 (8 reads per group, TMA input ring)" if v5 else "v4 (4 reads per group)",
                    "parallelism": "reads sharded, %d rank(s), NCCL weight broadcast at init only" % world},
-        "kbases_per_s": world * nbases / e2e_s / 1e3,
-        "blocks_per_s": world * total_blocks / (step_ms * 1e-3),
-        "network_tflops": world * FLOP_PER_BLOCK_TOTAL.get(args.model, 0) * total_blocks / (step_ms * 1e-3) / 1e12,
-        "e2e": {"value": world * total_samples / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3},
+        "kbases_per_s": head["kbases_per_s"],
+        "blocks_per_s": head["blocks_per_s"],
+        "network_tflops": FLOP_PER_BLOCK_TOTAL.get(model, 0) * head["blocks_per_s"] / 1e12,
+        "e2e": head["e2e"],
+        "parity": head.get("parity"),
+        "sustained": head.get("sustained"),
         # the whole step against the HBM roofline: algorithmic bytes if every intermediate is written and read once
         # (conv out, X / Xin per layer, posterior, traceback) over the measured step time
-        "step_hbm": {"bytes_per_block": BYTES_PER_BLOCK.get(args.model), "achieved": (BYTES_PER_BLOCK.get(args.model, 0) * total_blocks
-                     / (step_ms * 1e-3) / 1e9), "peak": hbm, "unit": "GB/s",
-                     "frac": BYTES_PER_BLOCK.get(args.model, 0) * total_blocks / (step_ms * 1e-3) / 1e9 / hbm},
-        "gpu_launches": int(launches),
-        "clocks": clocks,
+        "step_hbm": {"bytes_per_block": bpb, "achieved": bpb * head["blocks_per_s"] / 1e9, "peak": hbm, "unit": "GB/s",
+                     "frac": bpb * head["blocks_per_s"] / 1e9 / hbm / world},
+        "gpu_launches": head["launches"],
+        "clocks": head["clocks"],
         "roofline": {"kernel": "gru_scan (recurrent sW/sW2 products + gates): 5 of the 13 launches per batch, "
-                               "the largest share of the step (profiles/*_summary.md)",
+                               "the largest share of the step's SM time (profiles/*_summary.md)",
                      "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                      "frac": achieved / peak, "traffic": traffic,
                      "peak_source": "%s bf16 dense burst (MEASURED_PEAKS.json), kernel timed alone; the scan is a chain of "
                                     "dependent 12-instruction UMMA groups, latency- not throughput-bound (DESIGN.md section 4)" % pk_src,
                      "flop_per_launch": flop_per_launch, "avg_launch_ms": scan_avg_ms,
-                     # a scan launch of one batch occupies one SM per 16 (H = 96) or 8 reads, not the GPU: the
+                     # a scan launch of one batch occupies one SM per `reads_per_cta` reads, not the GPU: the
                      # other SMs run the other batches' kernels at the same time
+                     "reads_per_cta": reads_per_cta,
                      "sms_used_per_launch": scan_ctas, "frac_of_sm_share": achieved / (peak * min(scan_ctas, 148) / 148.0),
                      "stage_ms_solo_batch": solo, "stage_ms_per_batch_concurrent": stage_sum,
                      "other_kernels": kernels},
     }
+    if others:
+        line["other_configs"] = others
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(args.model, sigs, args.cpu_sample_reads)
+        sigs = make_workload(min(args.reads, 1024), args.samples, 1000)
+        line["cpu_baseline"] = cpu_baseline(model, sigs, args.cpu_sample_reads)
     print(json.dumps(line))
-    if dist is not None:
-        dist.destroy_process_group()
+    ranks.close()
+    bad = [name for name, p in [("headline", line.get("parity"))] + [(k, v.get("parity")) for k, v in others.items()]
+           if p is not None and not p["bases_identical"]]
+    if bad:
+        sys.stderr.write("bench.py: base sequences differ from the reference in: %s\n" % ", ".join(bad))
+        sys.exit(3)
 
 
 def main():

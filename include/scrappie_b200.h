@@ -287,6 +287,10 @@ int sb2_events_posterior_batch(sb2_engine *eng, const event_table *tables, size_
 int sb2_basecall_batch(sb2_engine *eng, enum raw_model_type model, const float *const *signals,
                        const size_t *nsample, size_t nread, const sb2_params *p, sb2_call *out);
 void sb2_calls_free(sb2_call *calls, size_t n);     /* free() every calls[i].bases */
+/* sb2_basecall_batch / sb2_basecall_raw_batch keep their device workspaces (buffers, pinned staging, CUDA graphs) in a
+ * per-engine pool between calls, so a steady stream of calls allocates nothing; concurrent callers each get their own.
+ * sb2_engine_trim_pool releases the idle ones (returns how many); sb2_engine_destroy releases all. */
+int sb2_engine_trim_pool(sb2_engine *eng);
 /* Same on an existing batch workspace (no device allocation per call).  concat: signals in
  * the batch's padded layout (pinned != 0 if it came from sb2_host_alloc_pinned), or NULL
  * when the signals are already resident. */

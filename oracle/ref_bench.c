@@ -30,6 +30,7 @@ int homopolymer_path(const ref_mat *, int *, int);
 char *overlapper(const int *, size_t, int, int *);
 char *crfpath_to_basecall(const int *, size_t, int *);
 void scipy_openblas_set_num_threads(int);
+char *scipy_openblas_get_config(void);
 
 static double now(void) {
     struct timespec ts;
@@ -79,4 +80,6 @@ double ref_bench_run(const char *model, const float *concat, const size_t *offse
 }
 
 void ref_bench_free(void *p) { free(p); }
+/* name + version + kernel of the BLAS the reference was linked against (e.g. "OpenBLAS 0.3.31 ... SkylakeX") */
+const char *ref_bench_blas_config(void) { return scipy_openblas_get_config(); }
 int ref_bench_max_threads(void) { return omp_get_max_threads(); }

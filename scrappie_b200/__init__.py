@@ -158,6 +158,7 @@ def lib():
         "sb2_last_error": (C.c_char_p, []),
         "sb2_engine_launch_count": (C.c_uint64, [C.c_void_p]),
         "sb2_engine_set_scan_generation": (C.c_int, [C.c_void_p, C.c_int]),
+        "sb2_engine_trim_pool": (C.c_int, [C.c_void_p]),
         "sb2_batch_create": (C.c_void_p, [C.c_void_p, C.c_int, C.POINTER(C.c_size_t), C.c_size_t]),
         "sb2_batch_destroy": (None, [C.c_void_p]),
         "sb2_batch_nblock": (C.c_size_t, [C.c_void_p, C.c_size_t]),
@@ -540,6 +541,10 @@ class Engine(object):
     def launches(self):
         return int(lib().sb2_engine_launch_count(self._h))
 
+    def trim_pool(self):
+        """Free the idle workspaces basecall_batch keeps between calls; returns how many."""
+        return int(lib().sb2_engine_trim_pool(self._h))
+
     def set_scan_generation(self, gen):
         """0 automatic, 4 / 5: force the GRU scan kernel generation (affects batches that have not run yet)."""
         if lib().sb2_engine_set_scan_generation(self._h, int(gen)):
@@ -608,6 +613,24 @@ class Engine(object):
         if rc < 0:
             raise RuntimeError("sb2_events_posterior_batch failed: %s" % last_error())
         return [ScrappyMatrix(o) if o else None for o in out]
+
+    def prepare_call(self, signals):
+        """The argument arrays of sb2_basecall_batch for a list of (ordinary, pageable) float32 signals, built once so
+        that a caller who basecalls the same buffers repeatedly pays no Python work per call."""
+        sigs = [np.ascontiguousarray(s, dtype=np.float32) for s in signals]
+        n = len(sigs)
+        return (sigs, (_f32p * n)(*[_fp(s) for s in sigs]), (C.c_size_t * n)(*[s.size for s in sigs]), n)
+
+    def basecall_prepared(self, model, prepared, params=None):
+        """sb2_basecall_batch (the documented drop-in call: workspace from the engine's pool, signals staged from
+        pageable memory) on arguments made by prepare_call.  Returns a CallSet."""
+        params = params or default_params()
+        _, ptrs, lens, n = prepared
+        out = (_Call * n)()
+        rc = lib().sb2_basecall_batch(self._h, _MODEL_ENUM[model], ptrs, lens, n, C.byref(params), out)
+        if rc < 0:
+            raise RuntimeError("sb2_basecall_batch failed: %s" % last_error())
+        return CallSet(out, n)
 
     def basecall_batch(self, model, signals, params=None):
         """signals: list of trimmed + normalised float32 arrays.  Returns list of

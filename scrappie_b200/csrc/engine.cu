@@ -1087,6 +1087,22 @@ static void pool_release(sb2_engine *eng, sb2_batch *b, bool healthy) {
     eng->pool[b->model_type].push_back(b);
 }
 
+// Release every idle pooled workspace (device memory, pinned staging, graphs).  Workspaces in use by a concurrent call are
+// unaffected.  Returns the number released.
+extern "C" int sb2_engine_trim_pool(sb2_engine *eng) {
+    if (nullptr == eng) return -1;
+    std::vector<sb2_batch *> idle;
+    {
+        std::lock_guard<std::mutex> lock(eng->mu);
+        for (auto &free_list : eng->pool) {
+            idle.insert(idle.end(), free_list.begin(), free_list.end());
+            free_list.clear();
+        }
+    }
+    for (sb2_batch *b : idle) sb2_batch_destroy(b);
+    return (int)idle.size();
+}
+
 // Shortest signal the model's convolution accepts; shorter reads are dropped from a batch (bases NULL, score NAN)
 // instead of failing it -- the reference handles reads one at a time, so a bad read never loses the others.
 static size_t min_read_samples(sb2_engine *eng, enum raw_model_type model) {

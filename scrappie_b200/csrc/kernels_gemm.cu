@@ -299,8 +299,11 @@ template <int K, int ROWS, int NTILE, int NT, int LDC>
 static int launch_affine_cfg(const float *X, int ncol, const uint8_t *wimg, const float *bias, int M, float *C,
                              cudaStream_t s) {
     using G = GemmCfg<K, ROWS, NTILE, NT>;
+    // persistent CTAs: one per SM unless SCRAPPIE_B200_AFFINE_CTAS caps it (read once) -- the kernel is HBM-bound and
+    // holds a whole SM (216 KB of shared memory) for as long as it runs
+    static const int max_ctas = [] { const char *e = getenv("SCRAPPIE_B200_AFFINE_CTAS"); const int v = e ? atoi(e) : 0; return (v > 0 && v < 148) ? v : 148; }();
     const int nchunk = (ncol + NT - 1) / NT;
-    const int grid = nchunk < 148 ? nchunk : 148;
+    const int grid = nchunk < max_ctas ? nchunk : max_ctas;
     affine_tc_kernel<K, ROWS, NTILE, NT, LDC><<<grid, 416, G::SMEM, s>>>(X, ncol, wimg, bias, M, C);
     return 0;
 }
@@ -644,8 +647,9 @@ int launch_head_softmax_tc(const float *X, int ncol, int K, const uint8_t *wimg,
     if (K != 96 || ostride != 1028) return -1;
     using G = HeadCfg<96>;
     static const int ew = [] { const char *e = getenv("SCRAPPIE_B200_HEAD_SLICES"); return (e && atoi(e) == 2) ? 2 : 4; }();
+    static const int max_ctas = [] { const char *e = getenv("SCRAPPIE_B200_HEAD_CTAS"); const int v = e ? atoi(e) : 0; return (v > 0 && v < 148) ? v : 148; }();
     const int nchunk = (ncol + G::NT - 1) / G::NT;
-    const int grid = nchunk < 148 ? nchunk : 148;
+    const int grid = nchunk < max_ctas ? nchunk : max_ctas;
     if (exact_math)
         head_softmax_tc_kernel<96, false, 2><<<grid, 448, G::SMEM, s>>>(X, ncol, wimg, w_stay, bias, post, ostride, xdiv, cdiv, min_prob, return_log);
     else if (ew == 2)
