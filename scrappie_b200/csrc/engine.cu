@@ -250,7 +250,7 @@ extern "C" int sb2_engine_read_trace(sb2_engine *eng, long long *out, int n) {
 // Force a GRU scan kernel generation (4: four reads per group, 5: eight reads per group + TMA input ring; 0 = automatic).
 // Batches that already captured a CUDA graph keep replaying it: set this before their first run.
 extern "C" int sb2_engine_set_scan_generation(sb2_engine *eng, int gen) {
-    if (nullptr == eng || (gen != 0 && gen != 4 && gen != 5)) return -1;
+    if (nullptr == eng || (gen != 0 && gen != 4 && gen != 5 && gen != 6)) return -1;
     eng->scan_gen = gen;
     return 0;
 }
@@ -1060,15 +1060,30 @@ extern "C" void sb2_calls_free(sb2_call *calls, size_t n) {
 // call and hand it back afterwards: device buffers, pinned staging areas, the stream and -- while consecutive calls
 // have the same shape -- the captured CUDA graph are reused, so a steady stream of calls allocates nothing.
 // Concurrent callers each get their own workspace.
-static sb2_batch *pool_acquire(sb2_engine *eng, enum raw_model_type model) {
+static sb2_batch *pool_acquire(sb2_engine *eng, enum raw_model_type model, const size_t *nsample, size_t nread) {
     DevModel *dm = get_model(eng, model);
     if (nullptr == dm) return nullptr;
+    // what the call will need, to pick the idle workspace that fits best (a stream of differently sized batches must
+    // not make every workspace grow to the largest, nor re-allocate on every call)
+    size_t need_cols = 0, need_samples = 0;
+    for (size_t r = 0; r < nread; r++) {
+        need_cols += (nsample[r] + dm->host.conv_stride - 1) / dm->host.conv_stride;
+        need_samples += (nsample[r] + 3) / 4 * 4;
+    }
     {
         std::lock_guard<std::mutex> lock(eng->mu);
         auto &free_list = eng->pool[model];
-        if (!free_list.empty()) {
-            sb2_batch *b = free_list.back();
-            free_list.pop_back();
+        int best = -1, largest = -1;
+        for (int i = 0; i < (int)free_list.size(); i++) {
+            const sb2_batch *w = free_list[i];
+            const bool fits = w->cap_cols >= need_cols && w->cap_samples >= need_samples && w->cap_reads >= nread;
+            if (fits && (best < 0 || w->cap_cols < free_list[best]->cap_cols)) best = i;
+            if (largest < 0 || w->cap_cols > free_list[largest]->cap_cols) largest = i;
+        }
+        const int pick = best >= 0 ? best : largest;
+        if (pick >= 0) {
+            sb2_batch *b = free_list[pick];
+            free_list.erase(free_list.begin() + pick);
             return b;
         }
     }
@@ -1143,7 +1158,7 @@ extern "C" int sb2_basecall_batch(sb2_engine *eng, enum raw_model_type model, co
     for (size_t r = 0; r < nread; r++)
         if (nullptr != signals[r] && nsample[r] >= min_len) { keep.push_back(r); len.push_back(nsample[r]); }
     if (keep.empty()) return 0;
-    sb2_batch *b = pool_acquire(eng, model);
+    sb2_batch *b = pool_acquire(eng, model, len.data(), len.size());
     if (nullptr == b) return -1;
     int ncalled = -1;
     std::vector<sb2_call> calls(keep.size(), sb2_call{nullptr, NAN, 0, 0});
@@ -1273,7 +1288,7 @@ extern "C" int sb2_basecall_raw_batch(sb2_engine *eng, enum raw_model_type model
         }
     }
     if (keep.empty()) return 0;
-    sb2_batch *b = pool_acquire(eng, model);
+    sb2_batch *b = pool_acquire(eng, model, len.data(), len.size());
     if (nullptr == b) return -1;
     int ncalled = -1;
     std::vector<sb2_call> calls(keep.size(), sb2_call{nullptr, NAN, 0, 0});

@@ -654,7 +654,7 @@ def _ragged_lengths(n, lo, hi, seed):
     return [int(x) for x in rng.integers(lo, hi, size=n)]
 
 
-@pytest.mark.parametrize("gen", [5, 4])
+@pytest.mark.parametrize("gen", [6, 5, 4])
 def test_rnnrf_batch_size_kernels(sb, oracle, gen):
     """BASELINE config 3's hot kernels: rnnrf_r94 (src/networks.c:567-615) with >= 96 ragged reads, so that the scan
     runs with 8 reads per group / 3 groups per CTA (v5) or 12 reads per CTA (gru_scan_v4<112, ., 3>) instead of the
@@ -690,7 +690,7 @@ def test_rnnrf_batch_size_kernels(sb, oracle, gen):
     eng.close()
 
 
-@pytest.mark.parametrize("gen", [5, 4])
+@pytest.mark.parametrize("gen", [6, 5, 4])
 def test_rgrgr_ragged_large_batch(sb, oracle, gen):
     """rgrgr_r94 with 130 RAGGED reads (src/networks.c:250-296): different lengths inside every read group and
     across groups, last CTA partly empty -- 8-read groups of v5 and the four-group v4 kernel.  Posterior and layers
