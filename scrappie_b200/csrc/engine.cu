@@ -4,6 +4,7 @@
 // kernels (kernels_v1.cu, kernels_tc.cu).  There is deliberately no CPU fallback; when
 // CUDA is unusable the entry points fail with NULL / NAN / -1 and sb2_last_error().
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <time.h>
 
@@ -67,6 +68,14 @@ struct sb2_engine {
 };
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// NVTX range around a host-side stage (header-only NVTX3: a no-op unless a profiler is attached).  Kernel launches are
+// asynchronous, so a range brackets the ENQUEUE of a stage; in an Nsight timeline the kernels of the stage line up
+// under it through the CUDA correlation ids.
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 static int upload_model(sb2_engine *eng, DevModel *dm) {
     const sb2_host_model &h = dm->host;
@@ -220,8 +229,8 @@ extern "C" sb2_engine *sb2_engine_create(int device, const char *weights_dir) {
         delete eng;
         return nullptr;
     }
-    if (getenv("SCRAPPIE_B200_TRACE") && cudaMalloc(&eng->d_trace, 64 * sizeof(long long)) == cudaSuccess)
-        cudaMemset(eng->d_trace, 0, 64 * sizeof(long long));
+    if (getenv("SCRAPPIE_B200_TRACE") && cudaMalloc(&eng->d_trace, 512 * sizeof(long long)) == cudaSuccess)
+        cudaMemset(eng->d_trace, 0, 512 * sizeof(long long));
     return eng;
 }
 
@@ -243,7 +252,7 @@ extern "C" int sb2_engine_read_trace(sb2_engine *eng, long long *out, int n) {
     if (nullptr == eng || nullptr == eng->d_trace || nullptr == out) return -1;
     CUDA_OK(cudaSetDevice(eng->device));
     CUDA_OK(cudaDeviceSynchronize());
-    CUDA_OK(cudaMemcpy(out, eng->d_trace, sizeof(long long) * (size_t)std::min(n, 64), cudaMemcpyDeviceToHost));
+    CUDA_OK(cudaMemcpy(out, eng->d_trace, sizeof(long long) * (size_t)std::min(n, 512), cudaMemcpyDeviceToHost));
     return 0;
 }
 
@@ -545,6 +554,18 @@ extern "C" int sb2_batch_upload_concat(sb2_batch *b, const float *concat, int pi
 
 static inline void stage_mark(sb2_batch *b, int i) { if (b->timing) cudaEventRecord(b->ev[i], b->stream); }
 
+// Launch-configuration errors surface at the launch site (cudaPeekAtLastError costs nothing: no synchronisation), so a
+// failure names the stage instead of the end of the pass.
+#define LAUNCH_OK(what)                                                                           \
+    do {                                                                                          \
+        cudaError_t e_ = cudaPeekAtLastError();                                                   \
+        if (e_ != cudaSuccess) {                                                                  \
+            sb2_set_error("CUDA error %s after launching %s (%s:%d)", cudaGetErrorString(e_), what, __FILE__, __LINE__); \
+            cudaGetLastError();                                                                   \
+            return -1;                                                                            \
+        }                                                                                         \
+    } while (0)
+
 // One GRU layer scan with the engine's selected kernel generation.
 static int run_scan(sb2_batch *b, const float *Xin, const DevModel &m, int l, const float *resid, float *out, int backward,
                     long long *trace) {
@@ -616,6 +637,8 @@ extern "C" int sb2_batch_forward(sb2_batch *b, const sb2_params *p, bool return_
         return -1;
     }
     CUDA_OK(cudaSetDevice(b->eng->device));
+    NvtxRange range("sb2_batch_forward");
+    LAUNCH_OK("(an earlier call on this thread)");
     if (h.arch == 1) return forward_raw_r94(b, p, return_log);
     const int H = (int)h.H;
     cudaStream_t s = b->stream;
@@ -624,11 +647,13 @@ extern "C" int sb2_batch_forward(sb2_batch *b, const sb2_params *p, bool return_
     stage_mark(b, ST_CONV);
     launch_conv_act(b->d_raw, b->dims, b->d_tails, m.conv_taps, m.conv_b, (int)h.winlen, H, (int)h.conv_stride,
                     (int)h.conv_act, b->d_X[0], s);
+    LAUNCH_OK("conv_act");
     nl++;
     int cur = 0;
     const size_t layer_bytes = (size_t)b->total_cols * H * sizeof(float);
     if (b->keep_layers) CUDA_OK(cudaMemcpyAsync(b->d_layers, b->d_X[0], layer_bytes, cudaMemcpyDeviceToDevice, s));
     for (int l = 0; l < SB2_NLAYER; l++) {
+        NvtxRange layer_range("gru layer: affine + scan");
         stage_mark(b, ST_AFFINE(l));
         if (b->eng->gemm_impl == 0) {
             launch_affine(b->d_X[cur], b->total_cols, H, m.iW[l], H, m.b[l], 3 * H, b->d_Xin, 3 * H, 1.0f, 1.0f, 0, 0, s);
@@ -636,10 +661,12 @@ extern "C" int sb2_batch_forward(sb2_batch *b, const sb2_params *p, bool return_
             sb2_set_error("tensor-core affine kernel could not be configured");
             return -1;
         }
+        LAUNCH_OK("affine (GRU input transform)");
         stage_mark(b, ST_SCAN(l));
         if (0 != run_scan(b, b->d_Xin, m, l, h.residual ? b->d_X[cur] : nullptr, b->d_X[cur ^ 1], (l % 2) == 0,
                           (l == 1) ? b->eng->d_trace : nullptr))
             return -1;
+        LAUNCH_OK("gru_scan");
         nl += 2;
         cur ^= 1;
         if (b->keep_layers)
@@ -647,6 +674,7 @@ extern "C" int sb2_batch_forward(sb2_batch *b, const sb2_params *p, bool return_
                                     cudaMemcpyDeviceToDevice, s));
     }
     b->final_x = cur;
+    NvtxRange head_range("head: FF + softmax / globalnorm");
     stage_mark(b, ST_HEAD);
     if (h.head == 0 && b->eng->gemm_impl != 0 && nullptr != m.head_img) {
         if (0 != launch_head_softmax_tc(b->d_X[cur], b->total_cols, H, m.head_img, m.FF_W + (size_t)1024 * H, m.FF_b,
@@ -685,6 +713,7 @@ extern "C" int sb2_batch_decode(sb2_batch *b, const sb2_params *p) {
     if (nullptr == b || nullptr == p) return -1;
     const sb2_host_model &h = b->m->host;
     CUDA_OK(cudaSetDevice(b->eng->device));
+    NvtxRange range("sb2_batch_decode");
     if (h.head == 0)
         launch_decode_transducer(b->d_post, b->dims, (int)h.nstate, (int)h.ostride, p->stay_pen, p->skip_pen,
                                  p->local_pen, p->allow_slip, b->d_tb, b->d_tbE, b->d_path, b->d_score, b->stream);
@@ -887,6 +916,7 @@ static int finish_buffers(sb2_batch *b) {
 
 // The tail of calculate_post (src/scrappie_raw.c:290-312) for a whole batch on the device.
 static int finish_on_device(sb2_batch *b, const sb2_params *p, sb2_call *out) {
+    NvtxRange range("finish reads: homopolymer + bases, D2H");
     const sb2_host_model &h = b->m->host;
     if (0 != finish_buffers(b)) return -1;
     const int klen = (h.head == 0) ? (int)(logf((float)h.nstate) / logf(4.0f)) : 1;
@@ -1011,6 +1041,7 @@ extern "C" int sb2_batch_basecall(sb2_batch *b, const float *concat, int pinned,
     for (int r = 0; r < nread; r++) out[r] = sb2_call{nullptr, NAN, 0, 0};
     static const bool timing = getenv("SCRAPPIE_B200_TIMING") != nullptr;
     const double t0 = now_ms();
+    NvtxRange range("sb2_batch_basecall");
     CUDA_OK(cudaSetDevice(b->eng->device));
     if (nullptr != concat && 0 != sb2_batch_upload_concat(b, concat, pinned)) return -1;
     // SCRAPPIE_B200_FINISH=host keeps the homopolymer fix-up and the overlapper on the CPU (cross-check path)
@@ -1128,6 +1159,7 @@ static size_t min_read_samples(sb2_engine *eng, enum raw_model_type model) {
 // Signals from ordinary (pageable) host memory: gathered into the workspace's pinned staging area in the batch's
 // padded layout (pads zeroed), then one asynchronous H2D copy.
 static int stage_signals(sb2_batch *b, const float *const *signals, const std::vector<size_t> &keep) {
+    NvtxRange range("stage signals: pageable -> pinned -> device");
     const size_t total = (size_t)b->total_samples;
     if (total > b->stage_cap) {
         if (b->h_stage) cudaFreeHost(b->h_stage);
@@ -1195,6 +1227,7 @@ struct RawStage {
 // Upload the untrimmed signals and run the trimmer; start/end per read (end = 0: nothing left).
 static int stage_and_trim(sb2_engine *eng, const float *const *raws, const size_t *nsample, size_t nread,
                           const sb2_trim *t, RawStage &st, std::vector<int> &start, std::vector<int> &end) {
+    NvtxRange range("upload raw signals + trim");
     CUDA_OK(cudaSetDevice(eng->device));
     st.off.resize(nread);
     std::vector<int64_t> moff(nread);

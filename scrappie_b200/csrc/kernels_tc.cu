@@ -1006,8 +1006,12 @@ struct ScanV6Cfg {
 template <int H, int MATH, int NG, int RPG, bool RESID>
 __global__ void __launch_bounds__(ScanV6Cfg<H, NG, RPG, RESID>::NTHREADS, 1)
 gru_scan_v6_kernel(const float *__restrict__ Xin, const float *__restrict__ sW, const float *__restrict__ sW2,
-                   const float *__restrict__ resid, float *__restrict__ out, BatchDims d, int backward) {
+                   const float *__restrict__ resid, float *__restrict__ out, BatchDims d, int backward,
+                   long long *__restrict__ trace) {
     using C = ScanV6Cfg<H, NG, RPG, RESID>;
+    // diagnostic (SCRAPPIE_B200_TRACE=1): clock64() of CTA 0 at the hand-over points of steps 100..103, per group:
+    // trace[(grp * 4 + step - 100) * 16 + slot]; slots 0-4 issuer, 5-11 gate warp of lane quarter 0
+#define V6_TRACE(slot) do { if (trace != nullptr && blockIdx.x == 0 && lane == 0 && s >= 100 && s < 104) trace[((grp * 4) + (s - 100)) * 16 + (slot)] = clock64(); } while (0)
     constexpr int NM = C::NM, NP = RPG / 2, NQ = C::NQ;
     static_assert(RPG == 4 || RPG == 8, "reads per group");
     constexpr uint32_t LBO_B = C::LBO_B, SBO_B = C::SBO_B, TILE_B = C::TILE_B;
@@ -1146,6 +1150,7 @@ gru_scan_v6_kernel(const float *__restrict__ Xin, const float *__restrict__ sW, 
         for (int s = 0; s < Tmax; s++) {
             if (s > 0) mbar_wait(bar_h, (s - 1) & 1);
             tc_fence_after();
+            V6_TRACE(0);
             if (elect_one()) {
 #pragma unroll
                 for (int g = 0; g < 2; g++) {
@@ -1159,13 +1164,16 @@ gru_scan_v6_kernel(const float *__restrict__ Xin, const float *__restrict__ sW, 
                 }
             }
             __syncwarp();
+            V6_TRACE(1);
             // Every gate warp has finished step s - 1 (bar_h): its result row is staged and the input slot it used is
             // free.  The staging row step s will overwrite was last read by the store issued one step ago.
             bulk_wait_read0();
             if (s > 0) store(s - 1);
             fill(s + V5_RING - 1);
+            V6_TRACE(2);
             mbar_wait(bar_rh, s & 1);
             tc_fence_after();
+            V6_TRACE(3);
             if (elect_one()) {
                 const uint32_t dcol = acc0 + 2 * NM;
                 const uint32_t w_hi = tmem + 4 * KH, w_lo = w_hi + KH;
@@ -1176,6 +1184,7 @@ gru_scan_v6_kernel(const float *__restrict__ Xin, const float *__restrict__ sW, 
                 umma_commit(bar_c);
             }
             __syncwarp();
+            V6_TRACE(4);
         }
         if (Tmax > 0) {
             mbar_wait(bar_h, (Tmax - 1) & 1);
@@ -1234,10 +1243,12 @@ gru_scan_v6_kernel(const float *__restrict__ Xin, const float *__restrict__ sW, 
             const int slot = s % V5_RING;
             const float *xs_ = reinterpret_cast<const float *>(gring + slot * C::SLOT_B) + jj;
             mbar_wait(&bar_x[slot], (s / V5_RING) & 1);            // this step's input columns have landed
+            if (q == 0) V6_TRACE(5);
 
             // reset gate -> (r * h) operand
             mbar_wait(bar_r, s & 1);
             tc_fence_after();
+            if (q == 0) V6_TRACE(6);
             {
                 f32x2 t[NP], gr[NP], rh[NP];
                 preact(0, xs_ + H, k_sig, t);
@@ -1250,12 +1261,14 @@ gru_scan_v6_kernel(const float *__restrict__ Xin, const float *__restrict__ sW, 
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_rh);
+            if (q == 0) V6_TRACE(7);
 
             // update gate (its UMMAs ran while the reset gate was being evaluated).  MATH 5 keeps u = e^-a and 1 + u
             // instead of z: the state update below needs ONE reciprocal for z and tanh together.
             f32x2 gz[NP], gu[NP];
             mbar_wait(bar_z, s & 1);
             tc_fence_after();
+            if (q == 0) V6_TRACE(8);
             {
                 f32x2 t[NP];
                 preact(NM, xs_, k_sig, t);
@@ -1266,15 +1279,17 @@ gru_scan_v6_kernel(const float *__restrict__ Xin, const float *__restrict__ sW, 
                     for (int p = 0; p < NP; p++) {
                         float t0, t1;
                         upk2(t[p], t0, t1);
-                        gu[p] = pk2(ex2_approx(fminf(t0, 63.0f)), ex2_approx(fminf(t1, 63.0f)));
+                        gu[p] = pk2(ex2_approx(fminf(t0, 40.0f)), ex2_approx(fminf(t1, 40.0f)));
                         gz[p] = add2(gu[p], splat2(1.0f));                  // A = 1 + u (not z)
                     }
                 }
             }
 
+            if (q == 0) V6_TRACE(9);
             // candidate, state update, next step's operand, result row
             mbar_wait(bar_c, s & 1);
             tc_fence_after();
+            if (q == 0) V6_TRACE(10);
             {
                 f32x2 t[NP];
                 preact(2 * NM, xs_ + 2 * H, k_tanh, t);
@@ -1290,25 +1305,27 @@ gru_scan_v6_kernel(const float *__restrict__ Xin, const float *__restrict__ sW, 
                         hs[p] = fma2(gz[p], hs[p], mul2(omz, mul2(cand, splat2(OPERAND_SCALE))));
                     }
                 } else {
-                    // z = 1 / (1 + u), tanh = (1 - v) / (1 + v) with v = e^-2b:
-                    //   h' = z h + (1 - z) tanh = [h (1 + v) + u (1 - v)] / [(1 + u)(1 + v)]
-                    // -- one refined reciprocal for both gates (5 MUFU per element and step instead of 6).  The
-                    // exponents are clamped at 2^63 so the product of the two denominators stays finite.
+                    // z = 1 / (1 + u), tanh = (1 - v) / (1 + v) with u = e^-a, v = e^-2b:
+                    //   h' = h + (1 - z)(tanh - h) = h + u [(1 - v) - h (1 + v)] / [(1 + u)(1 + v)]
+                    // -- one refined reciprocal for both gates (5 MUFU per element and step instead of 6), written as
+                    // a CORRECTION to h: a unit whose update gate is shut (u below 2^-24 of the bracket) keeps its
+                    // state bit for bit, as with z h + (1 - z) c where z rounds to 1; a quotient form would re-round a
+                    // persistent state at every step and let it drift.  Exponents are clamped at 2^40 (sigmoid exact to
+                    // 1e-12) so that every intermediate, times the 2^8 operand scale, stays finite.
 #pragma unroll
                     for (int p = 0; p < NP; p++) {
                         float t0, t1;
                         upk2(t[p], t0, t1);
-                        const f32x2 v = pk2(ex2_approx(fminf(t0, 63.0f)), ex2_approx(fminf(t1, 63.0f)));
-                        const f32x2 B = add2(v, splat2(1.0f));
+                        const f32x2 v = pk2(ex2_approx(fminf(t0, 40.0f)), ex2_approx(fminf(t1, 40.0f)));
                         const f32x2 Bn = fma2(v, splat2(-1.0f), splat2(-1.0f));        // -(1 + v)
                         const f32x2 Dn = mul2(gz[p], Bn);                                 // -(1 + u)(1 + v)
                         float d0, d1;
                         upk2(Dn, d0, d1);
                         const f32x2 q0 = pk2(rcp_approx(-d0), rcp_approx(-d1));
                         const f32x2 q = fma2(q0, fma2(Dn, q0, splat2(1.0f)), q0);       // Newton step
-                        const f32x2 uw = mul2(gu[p], add2(Bn, splat2(2.0f)));             // u (1 - v)
-                        const f32x2 num = fma2(hs[p], B, mul2(uw, splat2(OPERAND_SCALE)));
-                        hs[p] = mul2(num, q);
+                        const f32x2 w256 = mul2(add2(Bn, splat2(2.0f)), splat2(OPERAND_SCALE));   // 256 (1 - v)
+                        const f32x2 br = fma2(hs[p], Bn, w256);                           // 256 (1 - v) - hs (1 + v)
+                        hs[p] = fma2(mul2(gu[p], br), q, hs[p]);
                     }
                 }
 #pragma unroll
@@ -1325,8 +1342,10 @@ gru_scan_v6_kernel(const float *__restrict__ Xin, const float *__restrict__ sW, 
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_h);
+            if (q == 0) V6_TRACE(11);
         }
     }
+#undef V6_TRACE
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, TCOLS);
@@ -1358,14 +1377,14 @@ static int launch_scan_v5(const float *Xin, const float *sW, const float *sW2, c
 
 template <int H, int MATH, int NG, int RPG>
 static int launch_scan_v6(const float *Xin, const float *sW, const float *sW2, const float *resid, float *out,
-                          const BatchDims &d, int backward, cudaStream_t s) {
+                          const BatchDims &d, int backward, long long *trace, cudaStream_t s) {
     const int grid = (d.nread + RPG * NG - 1) / (RPG * NG);
     if (resid != nullptr)
         gru_scan_v6_kernel<H, MATH, NG, RPG, true><<<grid, ScanV6Cfg<H, NG, RPG, true>::NTHREADS, ScanV6Cfg<H, NG, RPG, true>::SMEM_REQ, s>>>(
-            Xin, sW, sW2, resid, out, d, backward);
+            Xin, sW, sW2, resid, out, d, backward, trace);
     else
         gru_scan_v6_kernel<H, MATH, NG, RPG, false><<<grid, ScanV6Cfg<H, NG, RPG, false>::NTHREADS, ScanV6Cfg<H, NG, RPG, false>::SMEM_REQ, s>>>(
-            Xin, sW, sW2, resid, out, d, backward);
+            Xin, sW, sW2, resid, out, d, backward, trace);
     return 0;
 }
 
@@ -1381,10 +1400,10 @@ static int scan_env(const char *name) {
 int launch_gru_scan_tc(const float *Xin, const float *sW, const float *sW2, const float *resid, float *out,
                        const BatchDims &d, int H, int backward, int math, int gen, long long *trace, cudaStream_t s) {
     static const int groups = scan_env("SCRAPPIE_B200_SCAN_GROUPS");
-    if ((gen == 0 || gen == 6) && trace == nullptr && (math == 5 || math == 0)) {
+    if ((gen == 0 || gen == 6) && (math == 5 || math == 0)) {
         // v6: eight reads per group once a batch fills at least one and a half CTAs that way, four below
         const bool big = d.nread >= 48;
-#define SB2_V6(HH, MM, GG, RR) if (H == HH && math == MM) return launch_scan_v6<HH, MM, GG, RR>(Xin, sW, sW2, resid, out, d, backward, s)
+#define SB2_V6(HH, MM, GG, RR) if (H == HH && math == MM) return launch_scan_v6<HH, MM, GG, RR>(Xin, sW, sW2, resid, out, d, backward, trace, s)
         if (big) { SB2_V6(96, 5, 4, 8); SB2_V6(96, 0, 4, 8); SB2_V6(112, 5, 3, 8); SB2_V6(112, 0, 3, 8); }
         else { SB2_V6(96, 5, 2, 4); SB2_V6(96, 0, 2, 4); SB2_V6(112, 5, 2, 4); SB2_V6(112, 0, 2, 4); }
 #undef SB2_V6

@@ -9,6 +9,7 @@ for GEN in 6 5; do
   SCRAPPIE_B200_SCAN_GEN=$GEN timeout 600 python bench.py --no-cpu-baseline --no-other-configs --sustained-seconds 0 > $OUT/${TAG}_bench_gen$GEN.json 2> $OUT/${TAG}_bench_gen$GEN.err; echo "bench gen$GEN rc=$?"
   SCRAPPIE_B200_SCAN_GEN=$GEN timeout 600 python bench.py --no-cpu-baseline --no-other-configs --sustained-seconds 0 --model rnnrf_r94 --steps 8 --warmup 4 > $OUT/${TAG}_bench_rnnrf_gen$GEN.json 2>> $OUT/${TAG}_bench_gen$GEN.err; echo "rnnrf gen$GEN rc=$?"
 done
+timeout 300 python tools/scan_trace.py 256 > $OUT/${TAG}_scan_trace.log 2>&1; cat $OUT/${TAG}_scan_trace.log
 timeout 600 python tools/mixed_probe.py > $OUT/${TAG}_mixed_probe.log 2>&1; echo "probe rc=$?"; cat $OUT/${TAG}_mixed_probe.log | cut -c1-1500
 python - <<PY
 import json, glob
