@@ -484,7 +484,7 @@ def measure(eng, ranks, args, model, workload, steps, warmup, nsets, detail):
     # one call each, exactly what INTEGRATION.md section 2.1 tells a maintainer to do.
     order = sorted(range(nbatch), key=lambda k: -sum(len(s) for s in groups[k]))
     prepared = [eng.prepare_call(g) for g in groups]
-    nworker = min(nbatch * nsets, 16)
+    nworker = min(nbatch * max(nsets, 8), 32)          # calls in flight (each sleeps on its batch's completion event)
     last = [None] * nbatch
 
     def run_documented(nstep):
@@ -617,14 +617,9 @@ def main_b200(args, rank, world, local_rank):
     scan_avg_ms = float(np.mean([solo["scan%d" % l] for l in range(1, 6)]))
     flop_per_launch = FLOP_PER_READ_STEP_RECURRENT[model] * cols
     achieved = flop_per_launch / (scan_avg_ms * 1e-3) / 1e12
-    gen = int(os.environ.get("SCRAPPIE_B200_SCAN_GEN", "0"))
-    v5 = gen == 5 or (gen != 4 and b0["nread"] >= 48)
-    if v5:
-        reads_per_cta = 24 if H == 112 else 32
-    elif H == 112:
-        reads_per_cta = 12 if b0["nread"] >= 96 else 8
-    else:
-        reads_per_cta = 16 if b0["nread"] >= 128 else 8
+    # reads per scan CTA: groups of 8 reads (4 groups at H = 96, 3 at H = 112) for batches of >= 48 reads, else 2 x 4
+    big = b0["nread"] >= 48
+    reads_per_cta = (24 if H == 112 else 32) if big else 8
     scan_ctas = (b0["nread"] + reads_per_cta - 1) // reads_per_cta
     peak = pk["bf16_tflops"]
     traffic = None
@@ -666,7 +661,7 @@ def main_b200(args, rank, world, local_rank):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": head["workload"], "l2": head["l2"], "buffer_sets": head["buffer_sets"],
                    "scan_impl": os.environ.get("SCRAPPIE_B200_SCAN", "default"),
-                   "scan_generation": "v5 (8 reads per group, TMA input ring)" if v5 else "v4 (4 reads per group)",
+                   "scan_groups": "%d reads per CTA, %d per group" % (reads_per_cta, 8 if big else 4),
                    "parallelism": "reads sharded, %d rank(s), NCCL weight broadcast at init only" % world},
         "kbases_per_s": head["kbases_per_s"],
         "blocks_per_s": head["blocks_per_s"],

@@ -201,9 +201,6 @@ void sb2_engine_destroy(sb2_engine *eng);
 int sb2_engine_load_blob(sb2_engine *eng, enum raw_model_type model, const void *blob, size_t nbytes);
 /* Last error message of the calling thread ("" if none). */
 const char *sb2_last_error(void);
-/* GRU scan kernel generation: 0 automatic (v5 = 8 reads per group for batches of >= 48 reads, v4 = 4 reads per
- * group below), 4 / 5 forced -- the parity tests run both generations on the same batch. */
-int sb2_engine_set_scan_generation(sb2_engine *eng, int gen);
 /* Number of kernel launches this engine has issued so far. */
 uint64_t sb2_engine_launch_count(const sb2_engine *eng);
 

@@ -157,7 +157,6 @@ def lib():
         "sb2_engine_load_blob": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
         "sb2_last_error": (C.c_char_p, []),
         "sb2_engine_launch_count": (C.c_uint64, [C.c_void_p]),
-        "sb2_engine_set_scan_generation": (C.c_int, [C.c_void_p, C.c_int]),
         "sb2_engine_trim_pool": (C.c_int, [C.c_void_p]),
         "sb2_batch_create": (C.c_void_p, [C.c_void_p, C.c_int, C.POINTER(C.c_size_t), C.c_size_t]),
         "sb2_batch_destroy": (None, [C.c_void_p]),
@@ -544,11 +543,6 @@ class Engine(object):
     def trim_pool(self):
         """Free the idle workspaces basecall_batch keeps between calls; returns how many."""
         return int(lib().sb2_engine_trim_pool(self._h))
-
-    def set_scan_generation(self, gen):
-        """0 automatic, 4 / 5: force the GRU scan kernel generation (affects batches that have not run yet)."""
-        if lib().sb2_engine_set_scan_generation(self._h, int(gen)):
-            raise ValueError("scan generation must be 0, 4 or 5")
 
     def batch(self, model, nsample):
         return Batch(self, model, nsample)

@@ -58,13 +58,16 @@ struct sb2_engine {
     size_t flush_n = 0;
     std::mutex mu;
     int scan_impl = 5;      // gate math of the tcgen05 scan (5 / 2 / 0), or -1 = fp32 CUDA-core scan
-    std::atomic<int> scan_gen{0};   // 0 automatic (v5 for >= 48 reads), 4 / 5 forced
     int gemm_impl = 0;
     long long *d_trace = nullptr;   // diagnostic: hand-over timestamps of the scan kernel (SCRAPPIE_B200_TRACE=1)
     int head_exact = 0;     // 1: cephes exp / log in the fused head (bit-level mirror of the reference's maths)
     // idle workspaces of sb2_basecall_batch / sb2_basecall_raw_batch, per model: device buffers, pinned staging and
     // CUDA graphs survive between calls, so the documented drop-in call allocates nothing in steady state
     std::vector<struct sb2_batch *> pool[SB2_NMODEL];
+    // largest shape any pooled call of a model has needed so far: pooled workspaces are sized to it, so that after one
+    // pass over a mixed workload every workspace fits every batch and nothing is re-allocated any more (cudaFree
+    // synchronises the whole device -- with long-read batches in flight on other streams that stalls every caller)
+    std::atomic<size_t> hw_reads[SB2_NMODEL]{}, hw_cols[SB2_NMODEL]{}, hw_samples[SB2_NMODEL]{}, hw_bases[SB2_NMODEL]{}, hw_xrows[SB2_NMODEL]{};
 };
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -216,7 +219,6 @@ extern "C" sb2_engine *sb2_engine_create(int device, const char *weights_dir) {
     if (scan && (0 == strcmp(scan, "poly") || 0 == strcmp(scan, "v4_poly"))) eng->scan_impl = 2;
     if (scan && (0 == strcmp(scan, "cephes") || 0 == strcmp(scan, "v4_cephes"))) eng->scan_impl = 0;
     if (scan && 0 == strcmp(scan, "ffma")) eng->scan_impl = -1;
-    if (const char *g = getenv("SCRAPPIE_B200_SCAN_GEN")) eng->scan_gen = atoi(g);
     eng->gemm_impl = (gemm && 0 == strcmp(gemm, "ffma")) ? 0 : 1;    // 1 = tcgen05 (default), 0 = fp32 CUDA cores
     const char *headm = getenv("SCRAPPIE_B200_HEAD");
     eng->head_exact = (headm && 0 == strcmp(headm, "exact")) ? 1 : 0;
@@ -253,14 +255,6 @@ extern "C" int sb2_engine_read_trace(sb2_engine *eng, long long *out, int n) {
     CUDA_OK(cudaSetDevice(eng->device));
     CUDA_OK(cudaDeviceSynchronize());
     CUDA_OK(cudaMemcpy(out, eng->d_trace, sizeof(long long) * (size_t)std::min(n, 512), cudaMemcpyDeviceToHost));
-    return 0;
-}
-
-// Force a GRU scan kernel generation (4: four reads per group, 5: eight reads per group + TMA input ring; 0 = automatic).
-// Batches that already captured a CUDA graph keep replaying it: set this before their first run.
-extern "C" int sb2_engine_set_scan_generation(sb2_engine *eng, int gen) {
-    if (nullptr == eng || (gen != 0 && gen != 4 && gen != 5 && gen != 6)) return -1;
-    eng->scan_gen = gen;
     return 0;
 }
 
@@ -335,6 +329,14 @@ struct sb2_batch {
     float *h_stage = nullptr;                           // pinned staging of the signals in the padded layout
     size_t stage_cap = 0;
     int64_t *d_src = nullptr;                           // raw-signal basecall: source offset of every kept read
+    // Scan-ordered Xin (kernels_tc.cu): reads are grouped `rpg` at a time; group g owns rows [xgrp[g], xgrp[g] + rpg *
+    // Tmax_g) of Xin, step-major.  d_xrow[0 / 1][col] = row of column `col` for forward / backward layers.
+    int rpg = 4;
+    bool xil = false;
+    std::vector<long long> xgrp;
+    size_t xrows = 0, cap_xrows = 0;                    // rows of Xin the layout needs / the buffer holds
+    long long *d_xgrp = nullptr;
+    int *d_xrow[2]{};
     int graph_dims[3]{};                                // (nread, total_cols, max_cols) the captured graph was made for
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[ST_COUNT + 1]{};
@@ -353,8 +355,9 @@ static int dev_alloc(T **p, size_t n) {
 static void batch_free_device(sb2_batch *b) {
     void *ptrs[] = {b->d_raw, b->d_X[0], b->d_X[1], b->d_Xin, b->d_post, b->d_score, b->d_layers, b->d_tbE, b->d_path,
                     b->d_tb, b->d_meta, b->d_path2, b->d_nbase, b->d_bases, b->d_bprob, b->d_Xin2, b->d_FF, b->d_gidx,
-                    b->d_gval, b->d_src};
+                    b->d_gval, b->d_src, b->d_xrow[0], b->d_xrow[1]};
     for (void *p : ptrs) if (p) cudaFree(p);
+    b->d_xrow[0] = b->d_xrow[1] = nullptr; b->d_xgrp = nullptr;
     b->d_raw = b->d_X[0] = b->d_X[1] = b->d_Xin = b->d_post = b->d_score = b->d_layers = nullptr;
     b->d_tbE = b->d_path = nullptr; b->d_tb = nullptr; b->d_meta = nullptr; b->d_path2 = b->d_nbase = nullptr;
     b->d_bases = nullptr; b->d_bprob = b->d_Xin2 = b->d_FF = nullptr; b->d_gidx = nullptr; b->d_gval = nullptr; b->d_src = nullptr;
@@ -363,7 +366,7 @@ static void batch_free_device(sb2_batch *b) {
     b->h_paths = nullptr; b->h_scores = nullptr; b->h_gidx = nullptr; b->h_gval = nullptr; b->h_nbase = nullptr;
     b->h_bases = nullptr; b->h_meta = nullptr;
     if (b->graph) { cudaGraphExecDestroy(b->graph); b->graph = nullptr; }
-    b->cap_reads = b->cap_cols = b->cap_samples = b->cap_bases = b->cap_finish_cols = b->cap_finish_reads = 0;
+    b->cap_reads = b->cap_cols = b->cap_samples = b->cap_bases = b->cap_finish_cols = b->cap_finish_reads = b->cap_xrows = 0;
     b->gcap = 0;
     b->eager_runs = 0;
 }
@@ -404,16 +407,30 @@ static int batch_layout(sb2_batch *b, const size_t *nsample, size_t nread, std::
     b->col_off[nread] = (int)co;
     b->total_cols = (int)co;
     b->total_samples = so;
+    // read groups of the GRU scan and their rows in the scan-ordered Xin
+    b->rpg = scan_reads_per_group((int)nread);
+    const size_t ngroup = (nread + b->rpg - 1) / b->rpg;
+    b->xgrp.assign(ngroup + 1, 0);
+    for (size_t g = 0; g < ngroup; g++) {
+        int tmax = 0;
+        for (size_t r = g * b->rpg; r < std::min(nread, (g + 1) * b->rpg); r++) tmax = std::max(tmax, b->nblock[r]);
+        b->xgrp[g + 1] = b->xgrp[g] + (long long)b->rpg * tmax;
+    }
+    b->xrows = (size_t)b->xgrp[ngroup];
+    // tensor-core scan fed by the tensor-core affine map (the rgrgr / rnnrf topology); row numbers are 32-bit
+    b->xil = (h.arch == 0) && b->eng->gemm_impl != 0 && b->eng->scan_impl >= 0 && b->xrows < ((size_t)1 << 31);
+    if (!b->xil) b->xrows = (size_t)co;
     return 0;
 }
 
-static size_t meta_offsets(size_t cap_reads, size_t off[5]) {
+static size_t meta_offsets(size_t cap_reads, size_t off[6]) {
     size_t o = 0;
     off[0] = o; o += align_up(cap_reads * sizeof(int), 16);               // nsample
     off[1] = o; o += align_up(cap_reads * sizeof(int), 16);               // nblock
     off[2] = o; o += align_up((cap_reads + 1) * sizeof(int), 16);         // col_off
     off[3] = o; o += align_up(cap_reads * sizeof(int64_t), 16);           // samp_off
     off[4] = o; o += align_up(cap_reads * sizeof(sb2_conv_tail), 16);     // conv tails
+    off[5] = o; o += align_up((cap_reads / 4 + 2) * sizeof(long long), 16);  // first Xin row of every read group
     return o;
 }
 
@@ -423,16 +440,30 @@ static int batch_reserve(sb2_batch *b) {
     const sb2_host_model &h = b->m->host;
     const size_t H = h.H;
     const size_t nread = (size_t)b->nread, ncol_need = (size_t)b->total_cols, nsamp_need = (size_t)b->total_samples;
-    if (nread <= b->cap_reads && ncol_need <= b->cap_cols && nsamp_need <= b->cap_samples) return 0;
+    if (nread <= b->cap_reads && ncol_need <= b->cap_cols && nsamp_need <= b->cap_samples && b->xrows <= b->cap_xrows) return 0;
     if (b->stream) CUDA_OK(cudaStreamSynchronize(b->stream));
     const bool keep_layers = b->keep_layers;
-    auto grow = [&](size_t need, size_t have) { return std::max(have, b->pooled ? need + need / 8 : need); };
-    const size_t cap_reads = grow(nread, b->cap_reads), ncol = grow(ncol_need, b->cap_cols), nsamp = grow(nsamp_need, b->cap_samples);
+    auto raise_to = [](std::atomic<size_t> &hw, size_t v) {
+        size_t cur = hw.load();
+        while (cur < v && !hw.compare_exchange_weak(cur, v)) { }
+        return std::max(cur, v);
+    };
+    size_t cap_reads = std::max(nread, b->cap_reads), ncol = std::max(ncol_need, b->cap_cols), nsamp = std::max(nsamp_need, b->cap_samples);
+    size_t xrows = std::max(std::max(b->xrows, ncol_need), b->cap_xrows);
+    if (b->pooled) {
+        sb2_engine *eng = b->eng;
+        const int mt = (int)b->model_type;
+        cap_reads = raise_to(eng->hw_reads[mt], cap_reads);
+        ncol = raise_to(eng->hw_cols[mt], ncol + ncol / 16);
+        nsamp = raise_to(eng->hw_samples[mt], nsamp + nsamp / 16);
+        xrows = raise_to(eng->hw_xrows[mt], xrows + xrows / 16);
+    }
+    xrows = std::max(xrows, ncol);
     batch_free_device(b);
     // raw_r94 keeps both directions of a bidirectional pair alive and merges them into `ffw` features
     if (h.arch == 1 && (dev_alloc(&b->d_Xin2, ncol * 3 * H) || dev_alloc(&b->d_FF, ncol * std::max(h.ffw, h.nfilter)))) return -1;
     if (dev_alloc(&b->d_raw, nsamp) || dev_alloc(&b->d_X[0], ncol * H) || dev_alloc(&b->d_X[1], ncol * H) ||
-        dev_alloc(&b->d_Xin, ncol * 3 * H) || dev_alloc(&b->d_post, ncol * h.ostride) ||
+        dev_alloc(&b->d_Xin, xrows * 3 * H) || dev_alloc(&b->d_post, ncol * h.ostride) ||
         dev_alloc(&b->d_score, cap_reads) || dev_alloc(&b->d_path, ncol + cap_reads))
         return -1;
     if (h.head == 0) {
@@ -440,7 +471,7 @@ static int batch_reserve(sb2_batch *b) {
     } else {
         if (dev_alloc(&b->d_tb, ncol * 8)) return -1;
     }
-    size_t off[5];
+    size_t off[6];
     b->meta_bytes = meta_offsets(cap_reads, off);
     if (dev_alloc(&b->d_meta, b->meta_bytes)) return -1;
     CUDA_OK(cudaMallocHost(reinterpret_cast<void **>(&b->h_meta), b->meta_bytes));
@@ -449,8 +480,11 @@ static int batch_reserve(sb2_batch *b) {
     b->d_coloff = reinterpret_cast<int *>(b->d_meta + off[2]);
     b->d_sampoff = reinterpret_cast<int64_t *>(b->d_meta + off[3]);
     b->d_tails = reinterpret_cast<sb2_conv_tail *>(b->d_meta + off[4]);
+    b->d_xgrp = reinterpret_cast<long long *>(b->d_meta + off[5]);
+    if (dev_alloc(&b->d_xrow[0], ncol) || dev_alloc(&b->d_xrow[1], ncol)) return -1;
     CUDA_OK(cudaMemset(b->d_raw, 0, nsamp * sizeof(float)));
-    b->cap_reads = cap_reads; b->cap_cols = ncol; b->cap_samples = nsamp;
+    CUDA_OK(cudaMemset(b->d_Xin, 0, xrows * 3 * H * sizeof(float)));   // rows of a ragged group's shorter reads are read, never written
+    b->cap_reads = cap_reads; b->cap_cols = ncol; b->cap_samples = nsamp; b->cap_xrows = xrows;
     if (keep_layers && dev_alloc(&b->d_layers, (size_t)6 * ncol * H)) return -1;
     return 0;
 }
@@ -458,9 +492,10 @@ static int batch_reserve(sb2_batch *b) {
 // One H2D copy of the batch's dimension tables (asynchronous on the batch's stream: h_meta is pinned and is not
 // touched again before the next re-shape, which only happens after the stream has been synchronised).
 static int batch_upload_meta(sb2_batch *b, const std::vector<sb2_conv_tail> &tails) {
-    size_t off[5];
+    size_t off[6];
     meta_offsets(b->cap_reads, off);
     const size_t nread = (size_t)b->nread;
+    memcpy(b->h_meta + off[5], b->xgrp.data(), b->xgrp.size() * sizeof(long long));
     memcpy(b->h_meta + off[0], b->nsample.data(), nread * sizeof(int));
     memcpy(b->h_meta + off[1], b->nblock.data(), nread * sizeof(int));
     memcpy(b->h_meta + off[2], b->col_off.data(), (nread + 1) * sizeof(int));
@@ -490,6 +525,11 @@ static int batch_shape(sb2_batch *b, const size_t *nsample, size_t nread) {
     }
     if (0 != batch_reserve(b)) return -1;
     if (0 != batch_upload_meta(b, tails)) return -1;
+    if (b->xil) {
+        launch_scan_rows(b->dims, b->d_xgrp, b->rpg, b->d_xrow[0], b->d_xrow[1], b->stream);
+        b->eng->launches += 1;
+        CUDA_OK(cudaGetLastError());
+    }
     // A captured graph bakes in grid sizes and the dimension arguments: it is kept only for an identical shape, and a
     // new shape runs eagerly once before it is captured (a stream of differently shaped batches never pays for
     // capture + instantiation).
@@ -567,8 +607,8 @@ static inline void stage_mark(sb2_batch *b, int i) { if (b->timing) cudaEventRec
     } while (0)
 
 // One GRU layer scan with the engine's selected kernel generation.
-static int run_scan(sb2_batch *b, const float *Xin, const DevModel &m, int l, const float *resid, float *out, int backward,
-                    long long *trace) {
+static int run_scan(sb2_batch *b, const float *Xin, const long long *xgrp, const DevModel &m, int l, const float *resid,
+                    float *out, int backward, long long *trace) {
     const int H = (int)b->m->host.H;
     cudaStream_t s = b->stream;
     const int impl = b->eng->scan_impl;
@@ -576,7 +616,7 @@ static int run_scan(sb2_batch *b, const float *Xin, const DevModel &m, int l, co
         launch_gru_scan_ffma(Xin, m.sW[l], m.sW2[l], resid, out, b->dims, H, backward, s);
         return 0;
     }
-    const int rc = launch_gru_scan_tc(Xin, m.sW[l], m.sW2[l], resid, out, b->dims, H, backward, impl, b->eng->scan_gen.load(), trace, s);
+    const int rc = launch_gru_scan_tc(Xin, xgrp, m.sW[l], m.sW2[l], resid, out, b->dims, H, backward, impl, trace, s);
     if (0 != rc) sb2_set_error("tensor-core scan: unsupported configuration");
     return rc;
 }
@@ -602,10 +642,10 @@ static int forward_raw_r94(sb2_batch *b, const sb2_params *p, bool return_log) {
         launch_affine(in, ncol, K, m.iW[lf], K, m.b[lf], 3 * H, b->d_Xin, 3 * H, 1.0f, 1.0f, 0, 0, s);
         launch_affine(in, ncol, K, m.iW[lb], K, m.b[lb], 3 * H, b->d_Xin2, 3 * H, 1.0f, 1.0f, 0, 0, s);
         stage_mark(b, ST_SCAN(2 * pair));
-        if (0 != run_scan(b, b->d_Xin, m, lf, nullptr, b->d_X[0], 0, nullptr)) return -1;
+        if (0 != run_scan(b, b->d_Xin, nullptr, m, lf, nullptr, b->d_X[0], 0, nullptr)) return -1;
         stage_mark(b, ST_AFFINE(2 * pair + 1));
         stage_mark(b, ST_SCAN(2 * pair + 1));
-        if (0 != run_scan(b, b->d_Xin2, m, lb, nullptr, b->d_X[1], 1, nullptr)) return -1;
+        if (0 != run_scan(b, b->d_Xin2, nullptr, m, lb, nullptr, b->d_X[1], 1, nullptr)) return -1;
         // feedforward2_tanh: tanh(b + Wf gruF + Wb gruB)
         launch_affine(b->d_X[0], ncol, H, m.comb_Wf[pair], H, m.comb_b[pair], FW, b->d_FF, FW, 1.0f, 1.0f, 0, 0, s);
         launch_affine(b->d_X[1], ncol, H, m.comb_Wb[pair], H, nullptr, FW, b->d_FF, FW, 1.0f, 1.0f, 2, 1, s);
@@ -638,7 +678,7 @@ extern "C" int sb2_batch_forward(sb2_batch *b, const sb2_params *p, bool return_
     }
     CUDA_OK(cudaSetDevice(b->eng->device));
     NvtxRange range("sb2_batch_forward");
-    LAUNCH_OK("(an earlier call on this thread)");
+    cudaGetLastError();     // a stale error of an unrelated earlier runtime call on this thread must not fail this pass
     if (h.arch == 1) return forward_raw_r94(b, p, return_log);
     const int H = (int)h.H;
     cudaStream_t s = b->stream;
@@ -657,13 +697,14 @@ extern "C" int sb2_batch_forward(sb2_batch *b, const sb2_params *p, bool return_
         stage_mark(b, ST_AFFINE(l));
         if (b->eng->gemm_impl == 0) {
             launch_affine(b->d_X[cur], b->total_cols, H, m.iW[l], H, m.b[l], 3 * H, b->d_Xin, 3 * H, 1.0f, 1.0f, 0, 0, s);
-        } else if (0 != launch_affine_tc(b->d_X[cur], b->total_cols, H, m.iw_img[l], m.b[l], b->d_Xin, s)) {
+        } else if (0 != launch_affine_tc(b->d_X[cur], b->total_cols, H, m.iw_img[l], m.b[l], b->d_Xin,
+                                         b->xil ? b->d_xrow[(l % 2) == 0 ? 1 : 0] : nullptr, s)) {
             sb2_set_error("tensor-core affine kernel could not be configured");
             return -1;
         }
         LAUNCH_OK("affine (GRU input transform)");
         stage_mark(b, ST_SCAN(l));
-        if (0 != run_scan(b, b->d_Xin, m, l, h.residual ? b->d_X[cur] : nullptr, b->d_X[cur ^ 1], (l % 2) == 0,
+        if (0 != run_scan(b, b->d_Xin, b->xil ? b->d_xgrp : nullptr, m, l, h.residual ? b->d_X[cur] : nullptr, b->d_X[cur ^ 1], (l % 2) == 0,
                           (l == 1) ? b->eng->d_trace : nullptr))
             return -1;
         LAUNCH_OK("gru_scan");
@@ -906,7 +947,14 @@ static int finish_buffers(sb2_batch *b) {
     }
     if (nbytes > b->cap_bases) {
         if (b->d_bases) { CUDA_OK(cudaStreamSynchronize(b->stream)); cudaFree(b->d_bases); cudaFreeHost(b->h_bases); b->d_bases = nullptr; b->h_bases = nullptr; }
-        const size_t cap = b->pooled ? nbytes + nbytes / 4 : nbytes;
+        size_t cap = nbytes;
+        if (b->pooled) {                                // engine-wide high-water mark, as for the activations
+            std::atomic<size_t> &hw = b->eng->hw_bases[(int)b->model_type];
+            size_t cur = hw.load();
+            cap = nbytes + nbytes / 4;
+            while (cur < cap && !hw.compare_exchange_weak(cur, cap)) { }
+            cap = std::max(cur, cap);
+        }
         if (dev_alloc(&b->d_bases, cap)) return -1;
         CUDA_OK(cudaMallocHost(reinterpret_cast<void **>(&b->h_bases), cap));
         b->cap_bases = cap;
@@ -1146,6 +1194,7 @@ extern "C" int sb2_engine_trim_pool(sb2_engine *eng) {
         }
     }
     for (sb2_batch *b : idle) sb2_batch_destroy(b);
+    for (int m = 0; m < SB2_NMODEL; m++) { eng->hw_reads[m] = 0; eng->hw_cols[m] = 0; eng->hw_samples[m] = 0; eng->hw_bases[m] = 0; eng->hw_xrows[m] = 0; }
     return (int)idle.size();
 }
 
@@ -1168,8 +1217,9 @@ static int stage_signals(sb2_batch *b, const float *const *signals, const std::v
         CUDA_OK(cudaMallocHost(reinterpret_cast<void **>(&b->h_stage), cap * sizeof(float)));
         b->stage_cap = cap;
     }
+    // plain loop: the callers are already one host thread per batch in flight; an OpenMP team per caller would leave
+    // dozens of spinning workers behind every call
     const int n = b->nread;
-#pragma omp parallel for schedule(static) num_threads(host_threads()) if (total > (size_t)1 << 18)
     for (int r = 0; r < n; r++) {
         float *dst = b->h_stage + b->samp_off[r];
         const size_t len = (size_t)b->nsample[r], padded = (len + 3) / 4 * 4;

@@ -100,12 +100,16 @@ void launch_small_head(const float *X, int ncol, int K, const float *W, const fl
 void launch_gather(const float *post, int ostride, const int *col_state_pairs, int n, float *out, cudaStream_t s);
 
 // ---- tensor-core path (kernels_tc.cu) ----
-// gru_forward / gru_backward on tcgen05 with the recurrent weights resident in TMEM (A operand from tensor memory).
-// math: 0 cephes gates, 2 polynomial exp2, 5 SFU ex2 + Newton-refined reciprocal.  Batches of >= 48 reads run the
-// v5 kernel (8 reads per group, inputs through a TMA ring), smaller ones v4 (4 reads per group).
-// gen: 0 automatic, 4 / 5 force a kernel generation (parity tests run both on the same batch)
-int launch_gru_scan_tc(const float *Xin, const float *sW, const float *sW2, const float *resid, float *out,
-                       const BatchDims &d, int H, int backward, int math, int gen, long long *trace, cudaStream_t s);
+// gru_forward / gru_backward (+ residual) on tcgen05 with the recurrent weights resident in TMEM.
+// math: 0 cephes gates, 5 SFU ex2 + Newton-refined reciprocal.  Batches of >= 48 reads run eight reads per group,
+// smaller ones four (scan_reads_per_group).  xgrp != nullptr: Xin is in SCAN ORDER -- read r, step s (s = t forward,
+// T - 1 - t backward) at row xgrp[r / RPG] + s * RPG + r % RPG -- and every group-step is one TMA copy; nullptr: Xin is
+// read-major like every other activation matrix.
+int scan_reads_per_group(int nread);
+int launch_gru_scan_tc(const float *Xin, const long long *xgrp, const float *sW, const float *sW2, const float *resid,
+                       float *out, const BatchDims &d, int H, int backward, int math, long long *trace, cudaStream_t s);
+// dst_row tables of the scan-ordered Xin: row_f[col] / row_b[col] for every column of the batch (forward / backward layers)
+void launch_scan_rows(const BatchDims &d, const long long *xgrp, int rpg, int *row_f, int *row_b, cudaStream_t s);
 // per-device kernel attributes (dynamic shared-memory limits); called by sb2_engine_create for its device
 int configure_scan_kernels();
 int configure_gemm_kernels();
@@ -119,7 +123,9 @@ int launch_tc_selftest(const float *A, const float *B, float *D, int K, int N, i
 size_t gemm_image_bytes(int ntile, int rows, int K);
 void build_gemm_image(const float *W, int ldw, int M, int K, int rows, int ntile, uint8_t *img);
 // feedforward_linear for a GRU layer: C[col][0:3H] = b + iW^T X[col]  (src/layers.c:248-252)
-int launch_affine_tc(const float *X, int ncol, int H, const uint8_t *wimg, const float *bias, float *C, cudaStream_t s);
+// dst_row (may be null): output row of every input column -- the scan-ordered Xin layout; null = row = column
+int launch_affine_tc(const float *X, int ncol, int H, const uint8_t *wimg, const float *bias, float *C, const int *dst_row,
+                     cudaStream_t s);
 
 // fused output head for 1025-state models: FF GEMM -> softmax with temperature -> robust log
 // (src/layers.c:340-357, :79-94); wimg = build_gemm_image(FF_W, K, 1024, K, 128, 8, .), w_stay = FF_W row 1024

@@ -100,7 +100,7 @@ __device__ __forceinline__ void split8(const float4 &a, const float4 &b, float s
 template <int K, int ROWS, int NTILE, int NT, int LDC>
 __global__ void __launch_bounds__(416, 1)
 affine_tc_kernel(const float *__restrict__ X, int ncol, const uint8_t *__restrict__ wimg, const float *__restrict__ bias,
-                 int M, float *__restrict__ C) {
+                 int M, float *__restrict__ C, const int *__restrict__ dst_row) {
     using G = GemmCfg<K, ROWS, NTILE, NT>;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t *w_img = smem;
@@ -262,7 +262,7 @@ affine_tc_kernel(const float *__restrict__ X, int ncol, const uint8_t *__restric
                 tc_fence_after();
                 // written by the producers before they released this chunk's operand; 2^-16 unless the chunk held |x| >= 128
                 const float rscale = *reinterpret_cast<volatile float *>(&cscale[it & 3]);
-                if (warp_valid) {
+                if (warp_valid && dst_row == nullptr) {
                     // ldc is a compile-time constant: every store address is base + immediate
                     float *dst = C + (size_t)col0 * LDC + g * ROWS + m;
                     const bool full = (col0 + NT <= ncol);
@@ -283,6 +283,23 @@ affine_tc_kernel(const float *__restrict__ X, int ncol, const uint8_t *__restric
                             }
                         }
                     }
+                } else if (warp_valid) {
+                    // scan-ordered output: column c goes to row dst_row[c] (one coalesced load of 32 row numbers, then a
+                    // shuffle per column); a warp's store is still 128 contiguous bytes of one row
+                    float *dst = C + g * ROWS + m;
+#pragma unroll 1
+                    for (int n0 = 0; n0 < NT; n0 += 32) {
+                        float v[32];
+                        tmem_ld32(lane_base + a * NT + n0, v);
+                        const int cmine = col0 + n0 + lane;
+                        const int rmine = (cmine < ncol) ? __ldg(dst_row + cmine) : -1;
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            const int row = __shfl_sync(0xffffffffu, rmine, j);
+                            if (ok[g] && row >= 0) dst[(size_t)row * LDC] = fmaf(v[j], rscale, bg[g]);
+                        }
+                    }
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -297,22 +314,23 @@ affine_tc_kernel(const float *__restrict__ X, int ncol, const uint8_t *__restric
 
 template <int K, int ROWS, int NTILE, int NT, int LDC>
 static int launch_affine_cfg(const float *X, int ncol, const uint8_t *wimg, const float *bias, int M, float *C,
-                             cudaStream_t s) {
+                             const int *dst_row, cudaStream_t s) {
     using G = GemmCfg<K, ROWS, NTILE, NT>;
     // persistent CTAs: one per SM unless SCRAPPIE_B200_AFFINE_CTAS caps it (read once) -- the kernel is HBM-bound and
     // holds a whole SM (216 KB of shared memory) for as long as it runs
     static const int max_ctas = [] { const char *e = getenv("SCRAPPIE_B200_AFFINE_CTAS"); const int v = e ? atoi(e) : 0; return (v > 0 && v < 148) ? v : 148; }();
     const int nchunk = (ncol + NT - 1) / NT;
     const int grid = nchunk < max_ctas ? nchunk : max_ctas;
-    affine_tc_kernel<K, ROWS, NTILE, NT, LDC><<<grid, 416, G::SMEM, s>>>(X, ncol, wimg, bias, M, C);
+    affine_tc_kernel<K, ROWS, NTILE, NT, LDC><<<grid, 416, G::SMEM, s>>>(X, ncol, wimg, bias, M, C, dst_row);
     return 0;
 }
 
 // GRU input transform: M = 3H rows as three tiles (z, r, candidate) of H rows, K = H.
-int launch_affine_tc(const float *X, int ncol, int H, const uint8_t *wimg, const float *bias, float *C, cudaStream_t s) {
+int launch_affine_tc(const float *X, int ncol, int H, const uint8_t *wimg, const float *bias, float *C, const int *dst_row,
+                     cudaStream_t s) {
     if (ncol <= 0) return 0;
-    if (H == 96) return launch_affine_cfg<96, 96, 3, 128, 288>(X, ncol, wimg, bias, 3 * H, C, s);
-    if (H == 112) return launch_affine_cfg<112, 112, 3, 64, 336>(X, ncol, wimg, bias, 3 * H, C, s);
+    if (H == 96) return launch_affine_cfg<96, 96, 3, 128, 288>(X, ncol, wimg, bias, 3 * H, C, dst_row, s);
+    if (H == 112) return launch_affine_cfg<112, 112, 3, 64, 336>(X, ncol, wimg, bias, 3 * H, C, dst_row, s);
     return -1;
 }
 

@@ -654,14 +654,13 @@ def _ragged_lengths(n, lo, hi, seed):
     return [int(x) for x in rng.integers(lo, hi, size=n)]
 
 
-@pytest.mark.parametrize("gen", [6, 5, 4])
-def test_rnnrf_batch_size_kernels(sb, oracle, gen):
-    """BASELINE config 3's hot kernels: rnnrf_r94 (src/networks.c:567-615) with >= 96 ragged reads, so that the scan
-    runs with 8 reads per group / 3 groups per CTA (v5) or 12 reads per CTA (gru_scan_v4<112, ., 3>) instead of the
-    two-group kernel every small test uses.  Posterior vs oracle, per-layer activations for reads in every group
-    position (incl. indices 8-11 and the ragged last CTA), decode_crf exact, bases == the reference algorithm."""
+def test_rnnrf_batch_size_kernels(sb, oracle):
+    """BASELINE config 3's hot kernels: rnnrf_r94 (src/networks.c:567-615) with 100 ragged reads, so that the scan runs
+    with 8 reads per group and 3 groups per CTA (gru_scan_kernel<112, ., 3, 8, true, true>, inputs in scan order)
+    instead of the 4-read groups every small test uses.  Posterior vs oracle, per-layer activations for reads in every
+    group position (incl. indices 8-11 and the ragged last CTA), decode_crf exact, bases == the reference algorithm."""
     eng = sb.Engine(0)
-    eng.set_scan_generation(gen)
+    gen = "rpg8"
     lens = _ragged_lengths(100, 1000, 1400, 11)
     lens[9] = 1399
     lens[10] = 1000
@@ -690,14 +689,14 @@ def test_rnnrf_batch_size_kernels(sb, oracle, gen):
     eng.close()
 
 
-@pytest.mark.parametrize("gen", [6, 5, 4])
-def test_rgrgr_ragged_large_batch(sb, oracle, gen):
-    """rgrgr_r94 with 130 RAGGED reads (src/networks.c:250-296): different lengths inside every read group and
-    across groups, last CTA partly empty -- 8-read groups of v5 and the four-group v4 kernel.  Posterior and layers
-    vs oracle, decoder exact on the GPU's posterior, bases == reference algorithm, and every read equal to the same
-    read basecalled alone (batch composition must not change a bit)."""
+def test_rgrgr_ragged_large_batch(sb, oracle):
+    """rgrgr_r94 with 130 RAGGED reads (src/networks.c:250-296): different lengths inside every 8-read group and across
+    groups, last CTA partly empty (gru_scan_kernel<96, ., 4, 8, false, true>; ragged groups leave unused rows in the
+    scan-ordered Xin).  Posterior and layers vs oracle, decoder exact on the GPU's posterior, bases == reference
+    algorithm, and every read equal to the same read basecalled alone in a 4-read-group batch (batch composition must
+    not change a bit)."""
     eng = sb.Engine(0)
-    eng.set_scan_generation(gen)
+    gen = "rpg8"
     lens = _ragged_lengths(130, 1000, 4000, 5)
     lens[3], lens[64], lens[129] = 19, 3999, 1003
     sigs = [synthetic_read(3000 + i, n) for i, n in enumerate(lens)]
@@ -717,7 +716,7 @@ def test_rgrgr_ragged_large_batch(sb, oracle, gen):
         assert np.array_equal(opath, paths[i]) and oscore == float(scores[i])
     post64, post129 = b.posterior(64).copy(), b.posterior(129).copy()
     b.close()
-    for i, want in ((64, post64), (129, post129)):       # solo batches run the small-batch (v4, two groups) kernel
+    for i, want in ((64, post64), (129, post129)):       # solo batches run the small-batch configuration (4 reads per group)
         solo = eng.batch("rgrgr_r94", [lens[i]])
         solo.upload([sigs[i]])
         solo.forward()

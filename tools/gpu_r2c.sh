@@ -1,16 +1,16 @@
 #!/bin/bash
+# Round-2 GPU visit: parity tests (every failure is wanted), smoke, headline + rnnrf bench, scan timeline, mixed probe.
 TAG=${1:-r2c}
 OUT=gpurun_out
 mkdir -p $OUT
 timeout 1500 python -m pytest tests -m gpu -q --maxfail=12 > $OUT/${TAG}_tests.log 2>&1; echo "tests rc=$?"
 grep -E "^(FAILED|ERROR)|passed|failed" $OUT/${TAG}_tests.log | tail -20
 timeout 300 python __graft_entry__.py smoke > $OUT/${TAG}_smoke.log 2>&1; echo "smoke rc=$?"; tail -2 $OUT/${TAG}_smoke.log
-for GEN in 6 5; do
-  SCRAPPIE_B200_SCAN_GEN=$GEN timeout 600 python bench.py --no-cpu-baseline --no-other-configs --sustained-seconds 0 > $OUT/${TAG}_bench_gen$GEN.json 2> $OUT/${TAG}_bench_gen$GEN.err; echo "bench gen$GEN rc=$?"
-  SCRAPPIE_B200_SCAN_GEN=$GEN timeout 600 python bench.py --no-cpu-baseline --no-other-configs --sustained-seconds 0 --model rnnrf_r94 --steps 8 --warmup 4 > $OUT/${TAG}_bench_rnnrf_gen$GEN.json 2>> $OUT/${TAG}_bench_gen$GEN.err; echo "rnnrf gen$GEN rc=$?"
-done
-timeout 300 python tools/scan_trace.py 256 > $OUT/${TAG}_scan_trace.log 2>&1; cat $OUT/${TAG}_scan_trace.log
-timeout 600 python tools/mixed_probe.py > $OUT/${TAG}_mixed_probe.log 2>&1; echo "probe rc=$?"; cat $OUT/${TAG}_mixed_probe.log | cut -c1-1500
+timeout 600 python bench.py --no-cpu-baseline --no-other-configs --sustained-seconds 0 > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench rc=$?"
+timeout 600 python bench.py --no-cpu-baseline --no-other-configs --sustained-seconds 0 --model rnnrf_r94 --steps 8 --warmup 4 > $OUT/${TAG}_bench_rnnrf.json 2>> $OUT/${TAG}_bench.err; echo "rnnrf rc=$?"
+timeout 300 python tools/scan_trace.py 256 > $OUT/${TAG}_scan_trace.log 2>&1; head -16 $OUT/${TAG}_scan_trace.log
+timeout 300 python tools/debug_rnnrf.py > $OUT/${TAG}_debug_rnnrf.log 2>&1; tail -7 $OUT/${TAG}_debug_rnnrf.log | cut -c1-400
+timeout 600 python tools/mixed_probe.py > $OUT/${TAG}_mixed_probe.log 2>&1; echo "probe rc=$?"; tail -9 $OUT/${TAG}_mixed_probe.log | cut -c1-600
 python - <<PY
 import json, glob
 for f in sorted(glob.glob("$OUT/${TAG}_bench*.json")):
