@@ -255,6 +255,12 @@ affine_tc_kernel(const float *__restrict__ X, int ncol, const uint8_t *__restric
         uint32_t acc_it = 0, it = 0;
         for (int c = blockIdx.x; c < nchunk; c += gridDim.x, it++) {
             const int col0 = c * NT;
+            int rrow[NT / 32];                          // scan-ordered output: rows of this chunk's columns (-1 past the end)
+#pragma unroll
+            for (int k = 0; k < NT / 32; k++) {
+                const int cmine = col0 + 32 * k + lane;
+                rrow[k] = (dst_row != nullptr && cmine < ncol) ? __ldg(dst_row + cmine) : -1;
+            }
 #pragma unroll
             for (int g = 0; g < NTILE; g++, acc_it++) {
                 const uint32_t a = acc_it & 1;
@@ -284,16 +290,16 @@ affine_tc_kernel(const float *__restrict__ X, int ncol, const uint8_t *__restric
                         }
                     }
                 } else if (warp_valid) {
-                    // scan-ordered output: column c goes to row dst_row[c] (one coalesced load of 32 row numbers, then a
-                    // shuffle per column); a warp's store is still 128 contiguous bytes of one row
+                    // scan-ordered output: column c goes to row dst_row[c].  The row numbers of the chunk's columns were
+                    // fetched (coalesced, one register per 32 columns) before the accumulators were waited for; a
+                    // shuffle hands each column's row to the warp, whose store is still 128 contiguous bytes of one row
                     float *dst = C + g * ROWS + m;
-#pragma unroll 1
+#pragma unroll
                     for (int n0 = 0; n0 < NT; n0 += 32) {
                         float v[32];
                         tmem_ld32(lane_base + a * NT + n0, v);
-                        const int cmine = col0 + n0 + lane;
-                        const int rmine = (cmine < ncol) ? __ldg(dst_row + cmine) : -1;
                         tmem_ld_wait();
+                        const int rmine = rrow[n0 / 32];
 #pragma unroll
                         for (int j = 0; j < 32; j++) {
                             const int row = __shfl_sync(0xffffffffu, rmine, j);

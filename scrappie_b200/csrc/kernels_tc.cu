@@ -363,7 +363,8 @@ gru_scan_kernel(const float *__restrict__ Xin, const long long *__restrict__ xgr
         const int myT = (lane < RPG) ? gmeta[8 + lane] : 0;
         const int mycol = (lane < RPG) ? gmeta[lane] : 0;
         float *odst = out + (size_t)mycol * H;
-        const float *xsrc = XIL ? (Xin + (size_t)xgrp[blockIdx.x * NG + grp] * (3 * H)) : (Xin + (size_t)mycol * (3 * H));
+        // (groups past the end of the batch exist in the last CTA: Tmax = 0, nothing is copied, no table entry is read)
+        const float *xsrc = XIL ? (Xin + (size_t)(Tmax > 0 ? xgrp[blockIdx.x * NG + grp] : 0) * (3 * H)) : (Xin + (size_t)mycol * (3 * H));
         auto fill = [&](int st) {                       // request the inputs of step st (all lanes call it)
             if (st < Tmax) {
                 const int slot = st % SCAN_RING;
