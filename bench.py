@@ -484,7 +484,7 @@ def measure(eng, ranks, args, model, workload, steps, warmup, nsets, detail):
     # one call each, exactly what INTEGRATION.md section 2.1 tells a maintainer to do.
     order = sorted(range(nbatch), key=lambda k: -sum(len(s) for s in groups[k]))
     prepared = [eng.prepare_call(g) for g in groups]
-    nworker = min(nbatch * max(nsets, 8), int(os.environ.get("BENCH_E2E_WORKERS", "16")))   # calls in flight (each sleeps on its batch's completion event)
+    nworker = min(nbatch * max(nsets, 8), int(os.environ.get("BENCH_E2E_WORKERS", "8")))   # calls in flight (each sleeps on its batch's completion event)
     last = [None] * nbatch
 
     def run_documented(nstep):

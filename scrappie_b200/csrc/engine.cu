@@ -330,7 +330,7 @@ struct sb2_batch {
     size_t stage_cap = 0;
     int64_t *d_src = nullptr;                           // raw-signal basecall: source offset of every kept read
     // Scan-ordered Xin (kernels_tc.cu): reads are grouped `rpg` at a time; group g owns rows [xgrp[g], xgrp[g] + rpg *
-    // Tmax_g) of Xin, step-major.  d_xrow[0 / 1][col] = row of column `col` for forward / backward layers.
+    // Tmax_g) of Xin, step-major.  d_xrow[0 / 1][row] = input column of Xin row `row` for forward / backward layers.
     int rpg = 4;
     bool xil = false;
     std::vector<long long> xgrp;
@@ -481,7 +481,7 @@ static int batch_reserve(sb2_batch *b) {
     b->d_sampoff = reinterpret_cast<int64_t *>(b->d_meta + off[3]);
     b->d_tails = reinterpret_cast<sb2_conv_tail *>(b->d_meta + off[4]);
     b->d_xgrp = reinterpret_cast<long long *>(b->d_meta + off[5]);
-    if (dev_alloc(&b->d_xrow[0], ncol) || dev_alloc(&b->d_xrow[1], ncol)) return -1;
+    if (dev_alloc(&b->d_xrow[0], xrows) || dev_alloc(&b->d_xrow[1], xrows)) return -1;
     CUDA_OK(cudaMemset(b->d_raw, 0, nsamp * sizeof(float)));
     CUDA_OK(cudaMemset(b->d_Xin, 0, xrows * 3 * H * sizeof(float)));   // rows of a ragged group's shorter reads are read, never written
     b->cap_reads = cap_reads; b->cap_cols = ncol; b->cap_samples = nsamp; b->cap_xrows = xrows;
@@ -515,6 +515,13 @@ static int batch_upload_meta(sb2_batch *b, const std::vector<sb2_conv_tail> &tai
 
 // (Re-)shape a batch for `nread` reads of the given lengths.
 static int batch_shape(sb2_batch *b, const size_t *nsample, size_t nread) {
+    // same lengths as this workspace's last use (a caller streaming equal-sized batches): every table on the device is
+    // still valid -- nothing to compute, nothing to upload, and the captured graph stays
+    if (nullptr != b->stream && b->cap_reads > 0 && (size_t)b->nread == nread) {
+        bool same = true;
+        for (size_t r = 0; r < nread && same; r++) same = (size_t)b->nsample[r] == nsample[r];
+        if (same) return 0;
+    }
     std::vector<sb2_conv_tail> tails;
     const int prev[3] = {b->nread, b->total_cols, b->max_cols};
     if (0 != batch_layout(b, nsample, nread, tails)) return -1;
@@ -526,7 +533,7 @@ static int batch_shape(sb2_batch *b, const size_t *nsample, size_t nread) {
     if (0 != batch_reserve(b)) return -1;
     if (0 != batch_upload_meta(b, tails)) return -1;
     if (b->xil) {
-        launch_scan_rows(b->dims, b->d_xgrp, b->rpg, b->d_xrow[0], b->d_xrow[1], b->stream);
+        if (0 != launch_scan_rows(b->dims, b->d_xgrp, b->rpg, b->xrows, b->d_xrow[0], b->d_xrow[1], b->stream)) return -1;
         b->eng->launches += 1;
         CUDA_OK(cudaGetLastError());
     }
@@ -697,7 +704,7 @@ extern "C" int sb2_batch_forward(sb2_batch *b, const sb2_params *p, bool return_
         stage_mark(b, ST_AFFINE(l));
         if (b->eng->gemm_impl == 0) {
             launch_affine(b->d_X[cur], b->total_cols, H, m.iW[l], H, m.b[l], 3 * H, b->d_Xin, 3 * H, 1.0f, 1.0f, 0, 0, s);
-        } else if (0 != launch_affine_tc(b->d_X[cur], b->total_cols, H, m.iw_img[l], m.b[l], b->d_Xin,
+        } else if (0 != launch_affine_tc(b->d_X[cur], b->xil ? (int)b->xrows : b->total_cols, H, m.iw_img[l], m.b[l], b->d_Xin,
                                          b->xil ? b->d_xrow[(l % 2) == 0 ? 1 : 0] : nullptr, s)) {
             sb2_set_error("tensor-core affine kernel could not be configured");
             return -1;

@@ -108,8 +108,9 @@ void launch_gather(const float *post, int ostride, const int *col_state_pairs, i
 int scan_reads_per_group(int nread);
 int launch_gru_scan_tc(const float *Xin, const long long *xgrp, const float *sW, const float *sW2, const float *resid,
                        float *out, const BatchDims &d, int H, int backward, int math, long long *trace, cudaStream_t s);
-// dst_row tables of the scan-ordered Xin: row_f[col] / row_b[col] for every column of the batch (forward / backward layers)
-void launch_scan_rows(const BatchDims &d, const long long *xgrp, int rpg, int *row_f, int *row_b, cudaStream_t s);
+// src_col tables of the scan-ordered Xin: src_f[row] / src_b[row] = input column of every Xin row for forward / backward
+// layers (-1 for the unused rows of ragged groups); nrow = rows of the layout
+int launch_scan_rows(const BatchDims &d, const long long *xgrp, int rpg, size_t nrow, int *src_f, int *src_b, cudaStream_t s);
 // per-device kernel attributes (dynamic shared-memory limits); called by sb2_engine_create for its device
 int configure_scan_kernels();
 int configure_gemm_kernels();
@@ -123,8 +124,9 @@ int launch_tc_selftest(const float *A, const float *B, float *D, int K, int N, i
 size_t gemm_image_bytes(int ntile, int rows, int K);
 void build_gemm_image(const float *W, int ldw, int M, int K, int rows, int ntile, uint8_t *img);
 // feedforward_linear for a GRU layer: C[col][0:3H] = b + iW^T X[col]  (src/layers.c:248-252)
-// dst_row (may be null): output row of every input column -- the scan-ordered Xin layout; null = row = column
-int launch_affine_tc(const float *X, int ncol, int H, const uint8_t *wimg, const float *bias, float *C, const int *dst_row,
+// src_col (may be null): the kernel makes `ncol` OUTPUT rows; row i is computed from input column src_col[i] (-1: the
+// row is not used) -- the scan-ordered Xin layout; null = row i from column i
+int launch_affine_tc(const float *X, int ncol, int H, const uint8_t *wimg, const float *bias, float *C, const int *src_col,
                      cudaStream_t s);
 
 // fused output head for 1025-state models: FF GEMM -> softmax with temperature -> robust log

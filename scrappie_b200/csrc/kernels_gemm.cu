@@ -100,7 +100,7 @@ __device__ __forceinline__ void split8(const float4 &a, const float4 &b, float s
 template <int K, int ROWS, int NTILE, int NT, int LDC>
 __global__ void __launch_bounds__(416, 1)
 affine_tc_kernel(const float *__restrict__ X, int ncol, const uint8_t *__restrict__ wimg, const float *__restrict__ bias,
-                 int M, float *__restrict__ C, const int *__restrict__ dst_row) {
+                 int M, float *__restrict__ C, const int *__restrict__ src_col) {
     using G = GemmCfg<K, ROWS, NTILE, NT>;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t *w_img = smem;
@@ -183,23 +183,38 @@ affine_tc_kernel(const float *__restrict__ X, int ncol, const uint8_t *__restric
         constexpr int UNITS = NT * K8;
         constexpr int NPROD = 256;
         constexpr int PER = (UNITS + NPROD - 1) / NPROD;
+        // Source column of every unit this thread converts.  src_col == nullptr: output row = input column (read-major
+        // Xin).  Otherwise the kernel runs over the rows of the SCAN-ORDERED Xin ([group][step][read], kernels_tc.cu) and
+        // src_col[row] names the input column that row is made from (-1: a ragged group's unused row): the output
+        // stays one contiguous block per chunk, the input becomes a gather of 16-step pieces of 8 reads.  The row
+        // numbers of a chunk are fetched while the previous chunk is converted, so no load waits for another.
         uint32_t it = 0;
+        int scol[PER];
+        auto fetch_cols = [&](int c) {
+#pragma unroll
+            for (int i = 0; i < PER; i++) {
+                const int u = pt + i * NPROD;
+                const int row = c * NT + u / K8;
+                scol[i] = -1;
+                if (u < UNITS && c < nchunk && row < ncol) scol[i] = (src_col != nullptr) ? __ldg(src_col + row) : row;
+            }
+        };
+        fetch_cols(blockIdx.x);
         for (int c = blockIdx.x; c < nchunk; c += gridDim.x, it++) {
             const uint32_t s = it & 1;
-            const int col0 = c * NT;
-            const float *src = X + (size_t)col0 * K;
-            const int nvalid = min(NT, ncol - col0) * K8;
             float4 va[PER], vb[PER];
 #pragma unroll
             for (int i = 0; i < PER; i++) {
                 const int u = pt + i * NPROD;
                 va[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                 vb[i] = va[i];
-                if (u < nvalid) {
-                    va[i] = __ldg(reinterpret_cast<const float4 *>(src + (size_t)u * 8));
-                    vb[i] = __ldg(reinterpret_cast<const float4 *>(src + (size_t)u * 8 + 4));
+                if (scol[i] >= 0) {
+                    const float *src = X + (size_t)scol[i] * K + (u % K8) * 8;
+                    va[i] = __ldg(reinterpret_cast<const float4 *>(src));
+                    vb[i] = __ldg(reinterpret_cast<const float4 *>(src + 4));
                 }
             }
+            fetch_cols(c + (int)gridDim.x);
             // chunk-wide max |x| (integer compare of the sign-stripped bits; NaN / inf sort above every finite value)
             uint32_t mx = 0;
 #pragma unroll
@@ -255,12 +270,6 @@ affine_tc_kernel(const float *__restrict__ X, int ncol, const uint8_t *__restric
         uint32_t acc_it = 0, it = 0;
         for (int c = blockIdx.x; c < nchunk; c += gridDim.x, it++) {
             const int col0 = c * NT;
-            int rrow[NT / 32];                          // scan-ordered output: rows of this chunk's columns (-1 past the end)
-#pragma unroll
-            for (int k = 0; k < NT / 32; k++) {
-                const int cmine = col0 + 32 * k + lane;
-                rrow[k] = (dst_row != nullptr && cmine < ncol) ? __ldg(dst_row + cmine) : -1;
-            }
 #pragma unroll
             for (int g = 0; g < NTILE; g++, acc_it++) {
                 const uint32_t a = acc_it & 1;
@@ -268,7 +277,7 @@ affine_tc_kernel(const float *__restrict__ X, int ncol, const uint8_t *__restric
                 tc_fence_after();
                 // written by the producers before they released this chunk's operand; 2^-16 unless the chunk held |x| >= 128
                 const float rscale = *reinterpret_cast<volatile float *>(&cscale[it & 3]);
-                if (warp_valid && dst_row == nullptr) {
+                if (warp_valid) {
                     // ldc is a compile-time constant: every store address is base + immediate
                     float *dst = C + (size_t)col0 * LDC + g * ROWS + m;
                     const bool full = (col0 + NT <= ncol);
@@ -289,23 +298,6 @@ affine_tc_kernel(const float *__restrict__ X, int ncol, const uint8_t *__restric
                             }
                         }
                     }
-                } else if (warp_valid) {
-                    // scan-ordered output: column c goes to row dst_row[c].  The row numbers of the chunk's columns were
-                    // fetched (coalesced, one register per 32 columns) before the accumulators were waited for; a
-                    // shuffle hands each column's row to the warp, whose store is still 128 contiguous bytes of one row
-                    float *dst = C + g * ROWS + m;
-#pragma unroll
-                    for (int n0 = 0; n0 < NT; n0 += 32) {
-                        float v[32];
-                        tmem_ld32(lane_base + a * NT + n0, v);
-                        tmem_ld_wait();
-                        const int rmine = rrow[n0 / 32];
-#pragma unroll
-                        for (int j = 0; j < 32; j++) {
-                            const int row = __shfl_sync(0xffffffffu, rmine, j);
-                            if (ok[g] && row >= 0) dst[(size_t)row * LDC] = fmaf(v[j], rscale, bg[g]);
-                        }
-                    }
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -320,23 +312,23 @@ affine_tc_kernel(const float *__restrict__ X, int ncol, const uint8_t *__restric
 
 template <int K, int ROWS, int NTILE, int NT, int LDC>
 static int launch_affine_cfg(const float *X, int ncol, const uint8_t *wimg, const float *bias, int M, float *C,
-                             const int *dst_row, cudaStream_t s) {
+                             const int *src_col, cudaStream_t s) {
     using G = GemmCfg<K, ROWS, NTILE, NT>;
     // persistent CTAs: one per SM unless SCRAPPIE_B200_AFFINE_CTAS caps it (read once) -- the kernel is HBM-bound and
     // holds a whole SM (216 KB of shared memory) for as long as it runs
     static const int max_ctas = [] { const char *e = getenv("SCRAPPIE_B200_AFFINE_CTAS"); const int v = e ? atoi(e) : 0; return (v > 0 && v < 148) ? v : 148; }();
     const int nchunk = (ncol + NT - 1) / NT;
     const int grid = nchunk < max_ctas ? nchunk : max_ctas;
-    affine_tc_kernel<K, ROWS, NTILE, NT, LDC><<<grid, 416, G::SMEM, s>>>(X, ncol, wimg, bias, M, C, dst_row);
+    affine_tc_kernel<K, ROWS, NTILE, NT, LDC><<<grid, 416, G::SMEM, s>>>(X, ncol, wimg, bias, M, C, src_col);
     return 0;
 }
 
 // GRU input transform: M = 3H rows as three tiles (z, r, candidate) of H rows, K = H.
-int launch_affine_tc(const float *X, int ncol, int H, const uint8_t *wimg, const float *bias, float *C, const int *dst_row,
+int launch_affine_tc(const float *X, int ncol, int H, const uint8_t *wimg, const float *bias, float *C, const int *src_col,
                      cudaStream_t s) {
     if (ncol <= 0) return 0;
-    if (H == 96) return launch_affine_cfg<96, 96, 3, 128, 288>(X, ncol, wimg, bias, 3 * H, C, dst_row, s);
-    if (H == 112) return launch_affine_cfg<112, 112, 3, 64, 336>(X, ncol, wimg, bias, 3 * H, C, dst_row, s);
+    if (H == 96) return launch_affine_cfg<96, 96, 3, 128, 288>(X, ncol, wimg, bias, 3 * H, C, src_col, s);
+    if (H == 112) return launch_affine_cfg<112, 112, 3, 64, 336>(X, ncol, wimg, bias, 3 * H, C, src_col, s);
     return -1;
 }
 

@@ -593,21 +593,25 @@ gru_scan_kernel(const float *__restrict__ Xin, const long long *__restrict__ xgr
     if (warp == 0) tmem_dealloc(tmem, TCOLS);
 }
 
-// dst_row tables for affine_tc_kernel: where column (read r, time t) of a layer's input transform goes in the
-// scan-ordered Xin, for forward layers (step = t) and backward layers (step = T - 1 - t).  One CTA per read.
-__global__ void scan_rows_kernel(BatchDims d, const long long *__restrict__ xgrp, int rpg, int *__restrict__ row_f,
-                                 int *__restrict__ row_b) {
+// src_col tables for affine_tc_kernel: which input column (read r, time t) each row of the scan-ordered Xin is made
+// from, for forward layers (step = t) and backward layers (step = T - 1 - t).  One CTA per read; rows of a ragged group
+// that no read reaches keep the -1 the tables were filled with.
+__global__ void scan_rows_kernel(BatchDims d, const long long *__restrict__ xgrp, int rpg, int *__restrict__ src_f,
+                                 int *__restrict__ src_b) {
     const int r = blockIdx.x;
     const int T = d.nblock[r], col = d.col_off[r];
     const long long base = xgrp[r / rpg] + (r % rpg);
     for (int t = threadIdx.x; t < T; t += blockDim.x) {
-        row_f[col + t] = (int)(base + (long long)t * rpg);
-        row_b[col + t] = (int)(base + (long long)(T - 1 - t) * rpg);
+        src_f[base + (long long)t * rpg] = col + t;
+        src_b[base + (long long)(T - 1 - t) * rpg] = col + t;
     }
 }
 
-void launch_scan_rows(const BatchDims &d, const long long *xgrp, int rpg, int *row_f, int *row_b, cudaStream_t s) {
-    if (d.nread > 0) scan_rows_kernel<<<d.nread, 256, 0, s>>>(d, xgrp, rpg, row_f, row_b);
+int launch_scan_rows(const BatchDims &d, const long long *xgrp, int rpg, size_t nrow, int *src_f, int *src_b, cudaStream_t s) {
+    if (cudaMemsetAsync(src_f, 0xFF, nrow * sizeof(int), s) != cudaSuccess || cudaMemsetAsync(src_b, 0xFF, nrow * sizeof(int), s) != cudaSuccess)
+        return -1;
+    if (d.nread > 0) scan_rows_kernel<<<d.nread, 256, 0, s>>>(d, xgrp, rpg, src_f, src_b);
+    return 0;
 }
 
 template <int H, int MATH, int NG, int RPG, bool RESID>
@@ -623,7 +627,7 @@ static int launch_scan_cfg(const float *Xin, const long long *xgrp, const float 
 }
 
 // math: 0 cephes-identical gates, 5 SFU ex2 + Newton-refined reciprocal (default).  xgrp: first Xin row of every read
-// group when Xin is in scan order (see affine_tc_kernel's dst_row), nullptr when Xin is read-major.  Instantiated for
+// group when Xin is in scan order (see affine_tc_kernel's src_col), nullptr when Xin is read-major.  Instantiated for
 // the shapes the models have: H = 96 without and H = 112 with the residual input.
 int launch_gru_scan_tc(const float *Xin, const long long *xgrp, const float *sW, const float *sW2, const float *resid,
                        float *out, const BatchDims &d, int H, int backward, int math, long long *trace, cudaStream_t s) {

@@ -2,14 +2,16 @@
 TAG=${1:-r2g}
 OUT=gpurun_out
 mkdir -p $OUT
-timeout 900 python -m pytest tests -m gpu -q --maxfail=12 -k "layerwise or ragged or batch_size or full_size" > $OUT/${TAG}_tests.log 2>&1; echo "tests rc=$?"
+timeout 900 python -m pytest tests -m gpu -q --maxfail=12 > $OUT/${TAG}_tests.log 2>&1; echo "tests rc=$?"
 grep -E "^(FAILED|ERROR)|passed|failed" $OUT/${TAG}_tests.log | tail -5
-for W in 16 8 24; do
+for W in 8 6 12; do
   BENCH_E2E_WORKERS=$W timeout 600 python bench.py --no-cpu-baseline --no-other-configs --sustained-seconds 0 > $OUT/${TAG}_bench_w$W.json 2> $OUT/${TAG}_bench_w$W.err; echo "bench w$W rc=$?"
 done
-for W in 16 8; do
-  BENCH_E2E_WORKERS=$W timeout 600 python bench.py --no-cpu-baseline --no-other-configs --sustained-seconds 0 --model rnnrf_r94 --steps 8 --warmup 4 > $OUT/${TAG}_bench_rnnrf_w$W.json 2>> $OUT/${TAG}_bench_w$W.err; echo "rnnrf w$W rc=$?"
+for S in 6 8; do
+  timeout 600 python bench.py --no-cpu-baseline --no-other-configs --sustained-seconds 0 --sets $S --steps 24 > $OUT/${TAG}_bench_sets$S.json 2> $OUT/${TAG}_bench_sets$S.err; echo "bench sets$S rc=$?"
 done
+timeout 600 python bench.py --no-cpu-baseline --no-other-configs --sustained-seconds 0 --model rnnrf_r94 --steps 8 --warmup 4 > $OUT/${TAG}_bench_rnnrf.json 2>> $OUT/${TAG}_bench_w8.err; echo "rnnrf rc=$?"
+timeout 600 python bench.py --no-cpu-baseline --no-other-configs --sustained-seconds 0 --workload mixed --sets 6 --steps 12 --warmup 6 > $OUT/${TAG}_bench_mixed.json 2>> $OUT/${TAG}_bench_w8.err; echo "mixed rc=$?"
 python - <<PY
 import json, glob
 for f in sorted(glob.glob("$OUT/${TAG}_bench*.json")):
