@@ -484,7 +484,9 @@ def measure(eng, ranks, args, model, workload, steps, warmup, nsets, detail):
     # one call each, exactly what INTEGRATION.md section 2.1 tells a maintainer to do.
     order = sorted(range(nbatch), key=lambda k: -sum(len(s) for s in groups[k]))
     prepared = [eng.prepare_call(g) for g in groups]
-    nworker = min(nbatch * max(nsets, 8), int(os.environ.get("BENCH_E2E_WORKERS", "8")))   # calls in flight (each sleeps on its batch's completion event)
+    # calls in flight (each worker sleeps on its batch's completion event).  Eight keep the GPU busy when every call takes
+    # the same ~12 ms; the mixed workload's calls take 3 .. 200 ms and want more of them in flight
+    nworker = min(nbatch * max(nsets, 8), int(os.environ.get("BENCH_E2E_WORKERS", "16" if workload == "mixed" else "8")))
     last = [None] * nbatch
 
     def run_documented(nstep):

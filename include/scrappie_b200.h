@@ -288,6 +288,9 @@ void sb2_calls_free(sb2_call *calls, size_t n);     /* free() every calls[i].bas
  * per-engine pool between calls, so a steady stream of calls allocates nothing; concurrent callers each get their own.
  * sb2_engine_trim_pool releases the idle ones (returns how many); sb2_engine_destroy releases all. */
 int sb2_engine_trim_pool(sb2_engine *eng);
+/* how often a workspace (device buffers, pinned staging, base-string area) was (re)allocated so far: constant once the
+ * pool is warm */
+uint64_t sb2_engine_realloc_count(const sb2_engine *eng);
 /* Same on an existing batch workspace (no device allocation per call).  concat: signals in
  * the batch's padded layout (pinned != 0 if it came from sb2_host_alloc_pinned), or NULL
  * when the signals are already resident. */

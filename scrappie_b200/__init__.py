@@ -158,6 +158,7 @@ def lib():
         "sb2_last_error": (C.c_char_p, []),
         "sb2_engine_launch_count": (C.c_uint64, [C.c_void_p]),
         "sb2_engine_trim_pool": (C.c_int, [C.c_void_p]),
+        "sb2_engine_realloc_count": (C.c_uint64, [C.c_void_p]),
         "sb2_batch_create": (C.c_void_p, [C.c_void_p, C.c_int, C.POINTER(C.c_size_t), C.c_size_t]),
         "sb2_batch_destroy": (None, [C.c_void_p]),
         "sb2_batch_nblock": (C.c_size_t, [C.c_void_p, C.c_size_t]),
@@ -539,6 +540,10 @@ class Engine(object):
     @property
     def launches(self):
         return int(lib().sb2_engine_launch_count(self._h))
+
+    @property
+    def reallocs(self):
+        return int(lib().sb2_engine_realloc_count(self._h))
 
     def trim_pool(self):
         """Free the idle workspaces basecall_batch keeps between calls; returns how many."""

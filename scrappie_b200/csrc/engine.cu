@@ -54,6 +54,7 @@ struct sb2_engine {
     DevModel models[SB2_NMODEL + 1];            // [SB2_NMODEL] = the events (LSTM) model of nanonet_posterior
     char weights_dir[1024]{};
     std::atomic<uint64_t> launches{0};
+    std::atomic<uint64_t> reallocs{0};          // (re)allocations of batch workspaces: 0 in steady state
     float *flush_buf = nullptr;
     size_t flush_n = 0;
     std::mutex mu;
@@ -258,6 +259,10 @@ extern "C" int sb2_engine_read_trace(sb2_engine *eng, long long *out, int n) {
     return 0;
 }
 
+// Number of times a batch workspace (device buffers, pinned staging, base-string area) had to be (re)allocated: grows
+// while the pool warms up, stays constant in steady state.
+extern "C" uint64_t sb2_engine_realloc_count(const sb2_engine *eng) { return eng ? eng->reallocs.load() : 0; }
+
 extern "C" uint64_t sb2_engine_launch_count(const sb2_engine *eng) { return eng ? eng->launches.load() : 0; }
 
 extern "C" sb2_params sb2_default_params(void) {
@@ -460,6 +465,7 @@ static int batch_reserve(sb2_batch *b) {
     }
     xrows = std::max(xrows, ncol);
     batch_free_device(b);
+    b->eng->reallocs += 1;
     // raw_r94 keeps both directions of a bidirectional pair alive and merges them into `ffw` features
     if (h.arch == 1 && (dev_alloc(&b->d_Xin2, ncol * 3 * H) || dev_alloc(&b->d_FF, ncol * std::max(h.ffw, h.nfilter)))) return -1;
     if (dev_alloc(&b->d_raw, nsamp) || dev_alloc(&b->d_X[0], ncol * H) || dev_alloc(&b->d_X[1], ncol * H) ||
@@ -953,6 +959,7 @@ static int finish_buffers(sb2_batch *b) {
         if (nullptr == b->h_scores) CUDA_OK(cudaMallocHost(reinterpret_cast<void **>(&b->h_scores), b->cap_reads * sizeof(float)));
     }
     if (nbytes > b->cap_bases) {
+        b->eng->reallocs += 1;
         if (b->d_bases) { CUDA_OK(cudaStreamSynchronize(b->stream)); cudaFree(b->d_bases); cudaFreeHost(b->h_bases); b->d_bases = nullptr; b->h_bases = nullptr; }
         size_t cap = nbytes;
         if (b->pooled) {                                // engine-wide high-water mark, as for the activations
@@ -1218,6 +1225,7 @@ static int stage_signals(sb2_batch *b, const float *const *signals, const std::v
     NvtxRange range("stage signals: pageable -> pinned -> device");
     const size_t total = (size_t)b->total_samples;
     if (total > b->stage_cap) {
+        b->eng->reallocs += 1;
         if (b->h_stage) cudaFreeHost(b->h_stage);
         b->h_stage = nullptr;
         const size_t cap = total + total / 8;

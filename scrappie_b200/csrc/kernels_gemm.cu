@@ -65,6 +65,11 @@ void build_gemm_image(const float *W, int ldw, int M, int K, int rows, int ntile
 // ---------------------------------------------------------------------------------
 // device
 // ---------------------------------------------------------------------------------
+// Columns per chunk of the H = 96 input transform.  64 (159 KB of shared memory) measures the same as 128 (216 KB) and
+// lets the CTA share an SM with a decode CTA of another batch instead of waiting for an empty one.
+#ifndef SB2_AFFINE_NT
+#define SB2_AFFINE_NT 64
+#endif
 template <int K, int ROWS, int NTILE, int NT>
 struct GemmCfg {
     static constexpr uint32_t LBO_A = 128, SBO_A = (K / 8) * 128;
@@ -327,7 +332,7 @@ static int launch_affine_cfg(const float *X, int ncol, const uint8_t *wimg, cons
 int launch_affine_tc(const float *X, int ncol, int H, const uint8_t *wimg, const float *bias, float *C, const int *src_col,
                      cudaStream_t s) {
     if (ncol <= 0) return 0;
-    if (H == 96) return launch_affine_cfg<96, 96, 3, 128, 288>(X, ncol, wimg, bias, 3 * H, C, src_col, s);
+    if (H == 96) return launch_affine_cfg<96, 96, 3, SB2_AFFINE_NT, 288>(X, ncol, wimg, bias, 3 * H, C, src_col, s);
     if (H == 112) return launch_affine_cfg<112, 112, 3, 64, 336>(X, ncol, wimg, bias, 3 * H, C, src_col, s);
     return -1;
 }
@@ -350,7 +355,12 @@ int launch_affine_tc(const float *X, int ncol, int H, const uint8_t *wimg, const
 // warp  8    UMMA issuer        warp 9  TMA weight streamer       warps 10-13  activation producers
 template <int K>
 struct HeadCfg {
-    static constexpr int NT = 64, NTILE = 8, WSTAGES = 3;
+// Weight ring depth.  Two stages (153 KB of shared memory in all) measure the same as three (202 KB) and leave room for a
+// co-resident decode CTA (44 KB): the kernel then does not have to wait for a completely empty SM.
+#ifndef SB2_HEAD_WSTAGES
+#define SB2_HEAD_WSTAGES 2
+#endif
+    static constexpr int NT = 64, NTILE = 8, WSTAGES = SB2_HEAD_WSTAGES;
     static constexpr uint32_t LBO_A = 128, SBO_A = (K / 8) * 128;
     static constexpr uint32_t TILE_A = 128 * K * 2, WTILE = 2 * TILE_A;
     static constexpr uint32_t LBO_B = 16 * NT + 16, SBO_B = 128;
@@ -679,7 +689,7 @@ int launch_head_softmax_tc(const float *X, int ncol, int K, const uint8_t *wimg,
 // attribute belongs to the device, so a process-wide "configured" flag would leave a second GPU unconfigured.
 int configure_gemm_kernels() {
     const cudaFuncAttribute A = cudaFuncAttributeMaxDynamicSharedMemorySize;
-    bool ok = cudaFuncSetAttribute(affine_tc_kernel<96, 96, 3, 128, 288>, A, (int)GemmCfg<96, 96, 3, 128>::SMEM) == cudaSuccess;
+    bool ok = cudaFuncSetAttribute(affine_tc_kernel<96, 96, 3, SB2_AFFINE_NT, 288>, A, (int)GemmCfg<96, 96, 3, SB2_AFFINE_NT>::SMEM) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(affine_tc_kernel<112, 112, 3, 64, 336>, A, (int)GemmCfg<112, 112, 3, 64>::SMEM) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(head_softmax_tc_kernel<96, true, 2>, A, (int)HeadCfg<96>::SMEM) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(head_softmax_tc_kernel<96, true, 4>, A, (int)HeadCfg<96>::SMEM) == cudaSuccess;

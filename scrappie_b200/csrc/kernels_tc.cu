@@ -163,7 +163,10 @@ __device__ __forceinline__ uint32_t pack_half2(__half lo16, __half hi16) {
 // Arithmetic: split fp16 operands, fp32 accumulation (tc_common.cuh); MATH 5 = ex2.approx + Newton-refined rcp.approx
 // (default), MATH 0 = the reference's cephes polynomials element by element (SCRAPPIE_B200_SCAN=cephes).  The same
 // code serves RPG = 4 and 8, so a read's result does not depend on the batch it travels in.
-constexpr int SCAN_RING = 3;            // input slots: the copy for step s + 2 is issued while step s runs
+// Input slots: the copy for step s + RING - 1 is issued while step s runs.  Eight-read groups step every ~1.4 us, so two
+// steps of lead cover HBM latency under load; four-read groups (small batches, long reads) step every ~0.7 us and get
+// five steps of lead.
+template <int RPG> struct ScanRing { static constexpr int N = (RPG == 8) ? 3 : 6; };
 
 typedef unsigned long long f32x2;
 __device__ __forceinline__ f32x2 pk2(float a, float b) {
@@ -238,6 +241,7 @@ struct ScanCfg {
     static constexpr uint32_t SLOT_B = RPG * XCOL_B;                               // one group, one step
     static constexpr uint32_t OUT_B = RPG * H * 4;                                 // one group, one step of results
     static constexpr uint32_t OFF_RING = (NG * 2 * TILE_B + 127) / 128 * 128;
+    static constexpr int SCAN_RING = ScanRing<RPG>::N;
     static constexpr uint32_t OFF_OUT = OFF_RING + NG * SCAN_RING * SLOT_B;
     static constexpr uint32_t OFF_BAR = OFF_OUT + NG * 2 * OUT_B;
     static constexpr uint32_t NBAR = NG * (5 + SCAN_RING);
@@ -261,7 +265,7 @@ gru_scan_kernel(const float *__restrict__ Xin, const long long *__restrict__ xgr
     // diagnostic (SCRAPPIE_B200_TRACE=1): clock64() of CTA 0 at the hand-over points of steps 100..103, per group:
     // trace[(grp * 4 + step - 100) * 16 + slot]; slots 0-4 issuer, 5-11 gate warp of lane quarter 0
 #define SCAN_TRACE(slot) do { if (trace != nullptr && blockIdx.x == 0 && lane == 0 && s >= 100 && s < 104) trace[((grp * 4) + (s - 100)) * 16 + (slot)] = clock64(); } while (0)
-    constexpr int NM = C::NM, NP = RPG / 2, NQ = C::NQ;
+    constexpr int NM = C::NM, NP = RPG / 2, NQ = C::NQ, SCAN_RING = C::SCAN_RING;
     static_assert(RPG == 4 || RPG == 8, "reads per group");
     constexpr uint32_t LBO_B = C::LBO_B, SBO_B = C::SBO_B, TILE_B = C::TILE_B;
     constexpr int NKS = H / 16;

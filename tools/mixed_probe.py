@@ -35,8 +35,8 @@ for name in ("cold", "warm", "warm2"):
     dt = time.perf_counter() - t_all
     print(name, "sequential: %.1f ms total, %.3g samples/s" % (dt * 1e3, total / dt), rows)
 order = sorted(range(len(groups)), key=lambda k: -sum(len(s) for s in groups[k]))
-for nworker in (4, 8, 16):
-    for rep in range(2):
+for nworker in (8, 16, 24, 32, 48):
+    for rep in range(3):
         q = queue.Queue()
         for _ in range(6):
             for k in order:
@@ -56,4 +56,4 @@ for nworker in (4, 8, 16):
         for t in th:
             t.join()
         dt = (time.perf_counter() - t0) / 6
-        print("threads %d pass %d: %.1f ms per step, %.3g samples/s" % (nworker, rep, dt * 1e3, total / dt))
+        print("threads %d pass %d: %.1f ms per step, %.3g samples/s, reallocs so far %d" % (nworker, rep, dt * 1e3, total / dt, eng.reallocs))
