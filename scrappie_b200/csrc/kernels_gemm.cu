@@ -180,9 +180,8 @@ affine_tc_kernel(const float *__restrict__ X, int ncol, const uint8_t *__restric
         }
     } else if (warp >= 5) {
         // ---- producers: fp32 activations -> split fp16 canonical B operand ---------------
-        // eight producer warps, and every load of a thread's share of the chunk is issued before the first value is
-        // converted: the whole 49 KB chunk is in flight at once (the kernel was bound by the exposed latency of
-        // these loads, profiles/r24)
+        // eight producer warps, and every load of a thread's share of a chunk is issued before the first value is
+        // converted (the kernel was bound by the exposed latency of these loads, profiles/r24)
         const int pt = tid - 160;                       // 0..255
         constexpr int K8 = K / 8;
         constexpr int UNITS = NT * K8;
@@ -193,9 +192,12 @@ affine_tc_kernel(const float *__restrict__ X, int ncol, const uint8_t *__restric
         // src_col[row] names the input column that row is made from (-1: a ragged group's unused row): the output
         // stays one contiguous block per chunk, the input becomes a gather of 16-step pieces of 8 reads.  The row
         // numbers of a chunk are fetched while the previous chunk is converted, so no load waits for another.
-        uint32_t it = 0;
-        int scol[PER];
-        auto fetch_cols = [&](int c) {
+        // TWO chunks of loads are in flight per thread (register sets A and B, the loop is unrolled by two): while chunk
+        // c is converted, the loads of chunk c + grid are already out and the source columns of chunk c + 2 grid are
+        // being fetched.  A CTA then pulls twice the bytes per unit of time, so the same HBM bandwidth needs fewer SMs --
+        // which is what counts when the scans of other batches hold part of the GPU.
+        struct Chunk { float4 va[PER], vb[PER]; };
+        auto fetch_cols = [&](int c, int (&scol)[PER]) {
 #pragma unroll
             for (int i = 0; i < PER; i++) {
                 const int u = pt + i * NPROD;
@@ -204,27 +206,26 @@ affine_tc_kernel(const float *__restrict__ X, int ncol, const uint8_t *__restric
                 if (u < UNITS && c < nchunk && row < ncol) scol[i] = (src_col != nullptr) ? __ldg(src_col + row) : row;
             }
         };
-        fetch_cols(blockIdx.x);
-        for (int c = blockIdx.x; c < nchunk; c += gridDim.x, it++) {
-            const uint32_t s = it & 1;
-            float4 va[PER], vb[PER];
+        auto load_chunk = [&](const int (&scol)[PER], Chunk &ch) {
 #pragma unroll
             for (int i = 0; i < PER; i++) {
                 const int u = pt + i * NPROD;
-                va[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                vb[i] = va[i];
+                ch.va[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                ch.vb[i] = ch.va[i];
                 if (scol[i] >= 0) {
                     const float *src = X + (size_t)scol[i] * K + (u % K8) * 8;
-                    va[i] = __ldg(reinterpret_cast<const float4 *>(src));
-                    vb[i] = __ldg(reinterpret_cast<const float4 *>(src + 4));
+                    ch.va[i] = __ldg(reinterpret_cast<const float4 *>(src));
+                    ch.vb[i] = __ldg(reinterpret_cast<const float4 *>(src + 4));
                 }
             }
-            fetch_cols(c + (int)gridDim.x);
+        };
+        auto convert_chunk = [&](const Chunk &ch, uint32_t it) {
+            const uint32_t s = it & 1;
             // chunk-wide max |x| (integer compare of the sign-stripped bits; NaN / inf sort above every finite value)
             uint32_t mx = 0;
 #pragma unroll
             for (int i = 0; i < PER; i++) {
-                const float4 a = va[i], b = vb[i];
+                const float4 a = ch.va[i], b = ch.vb[i];
                 const float m = fmaxf(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))),
                                       fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w))));
                 mx = max(mx, __float_as_uint(m));
@@ -250,7 +251,7 @@ affine_tc_kernel(const float *__restrict__ X, int ncol, const uint8_t *__restric
                 if (u < UNITS) {
                     const int n = u / K8, k8 = u % K8;
                     uint4 hi, lo;
-                    split8(va[i], vb[i], opscale, hi, lo);
+                    split8(ch.va[i], ch.vb[i], opscale, hi, lo);
                     const uint32_t off = (uint32_t)(n >> 3) * G::SBO_B + (uint32_t)k8 * G::LBO_B + (uint32_t)(n & 7) * 16;
                     *reinterpret_cast<uint4 *>(b_hi + off) = hi;
                     *reinterpret_cast<uint4 *>(b_lo + off) = lo;
@@ -259,6 +260,25 @@ affine_tc_kernel(const float *__restrict__ X, int ncol, const uint8_t *__restric
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&full[s]);
+        };
+        const int G_ = (int)gridDim.x;
+        Chunk A, B;
+        int colsA[PER], colsB[PER];
+        uint32_t it = 0;
+        int c = blockIdx.x;
+        fetch_cols(c, colsA);
+        fetch_cols(c + G_, colsB);
+        load_chunk(colsA, A);
+        while (c < nchunk) {
+            load_chunk(colsB, B);                       // chunk c + G (all zeros past the end)
+            fetch_cols(c + 2 * G_, colsA);
+            convert_chunk(A, it++);
+            c += G_;
+            if (c >= nchunk) break;
+            load_chunk(colsA, A);                       // chunk c + G
+            fetch_cols(c + 2 * G_, colsB);
+            convert_chunk(B, it++);
+            c += G_;
         }
     } else {
         // ---- epilogue: accumulator + bias -> global ---------------------------------------
