@@ -68,7 +68,7 @@ struct sb2_engine {
     // largest shape any pooled call of a model has needed so far: pooled workspaces are sized to it, so that after one
     // pass over a mixed workload every workspace fits every batch and nothing is re-allocated any more (cudaFree
     // synchronises the whole device -- with long-read batches in flight on other streams that stalls every caller)
-    std::atomic<size_t> hw_reads[SB2_NMODEL]{}, hw_cols[SB2_NMODEL]{}, hw_samples[SB2_NMODEL]{}, hw_bases[SB2_NMODEL]{}, hw_xrows[SB2_NMODEL]{};
+    std::atomic<size_t> hw_reads[SB2_NMODEL]{}, hw_cols[SB2_NMODEL]{}, hw_samples[SB2_NMODEL]{}, hw_bases[SB2_NMODEL]{}, hw_xrows[SB2_NMODEL]{}, hw_stage[SB2_NMODEL]{};
 };
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -232,6 +232,14 @@ extern "C" sb2_engine *sb2_engine_create(int device, const char *weights_dir) {
         delete eng;
         return nullptr;
     }
+    {   // stream-ordered allocator: keep freed workspace memory in the device's pool instead of returning it to the driver
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep_all = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep_all);
+        }
+        cudaGetLastError();
+    }
     if (getenv("SCRAPPIE_B200_TRACE") && cudaMalloc(&eng->d_trace, 512 * sizeof(long long)) == cudaSuccess)
         cudaMemset(eng->d_trace, 0, 512 * sizeof(long long));
     return eng;
@@ -361,7 +369,7 @@ static void batch_free_device(sb2_batch *b) {
     void *ptrs[] = {b->d_raw, b->d_X[0], b->d_X[1], b->d_Xin, b->d_post, b->d_score, b->d_layers, b->d_tbE, b->d_path,
                     b->d_tb, b->d_meta, b->d_path2, b->d_nbase, b->d_bases, b->d_bprob, b->d_Xin2, b->d_FF, b->d_gidx,
                     b->d_gval, b->d_src, b->d_xrow[0], b->d_xrow[1]};
-    for (void *p : ptrs) if (p) cudaFree(p);
+    for (void *p : ptrs) if (p) cudaFreeAsync(p, b->stream);
     b->d_xrow[0] = b->d_xrow[1] = nullptr; b->d_xgrp = nullptr;
     b->d_raw = b->d_X[0] = b->d_X[1] = b->d_Xin = b->d_post = b->d_score = b->d_layers = nullptr;
     b->d_tbE = b->d_path = nullptr; b->d_tb = nullptr; b->d_meta = nullptr; b->d_path2 = b->d_nbase = nullptr;
@@ -376,11 +384,22 @@ static void batch_free_device(sb2_batch *b) {
     b->eager_runs = 0;
 }
 
+// Batch buffers come from the device's stream-ordered memory pool (cudaMallocAsync / cudaFreeAsync on the batch's own
+// stream; the pool keeps what is freed, see sb2_engine_create): re-sizing a workspace then never synchronises the
+// device.  cudaFree would -- it waits for every kernel in flight on every stream, and with long-read batches of other
+// callers running that is hundreds of milliseconds per freed buffer.
+template <typename T>
+static int batch_alloc(sb2_batch *b, T **p, size_t n) {
+    CUDA_OK(cudaMallocAsync(reinterpret_cast<void **>(p), (n ? n : 1) * sizeof(T), b->stream));
+    return 0;
+}
+
 extern "C" void sb2_batch_destroy(sb2_batch *b) {
     if (nullptr == b) return;
     cudaSetDevice(b->eng->device);
     if (b->stream) cudaStreamSynchronize(b->stream);
     batch_free_device(b);
+    if (b->stream) cudaStreamSynchronize(b->stream);    // the stream-ordered frees above
     if (b->h_stage) cudaFreeHost(b->h_stage);
     for (auto &e : b->ev) if (e) cudaEventDestroy(e);
     if (b->ev_done) cudaEventDestroy(b->ev_done);
@@ -467,19 +486,19 @@ static int batch_reserve(sb2_batch *b) {
     batch_free_device(b);
     b->eng->reallocs += 1;
     // raw_r94 keeps both directions of a bidirectional pair alive and merges them into `ffw` features
-    if (h.arch == 1 && (dev_alloc(&b->d_Xin2, ncol * 3 * H) || dev_alloc(&b->d_FF, ncol * std::max(h.ffw, h.nfilter)))) return -1;
-    if (dev_alloc(&b->d_raw, nsamp) || dev_alloc(&b->d_X[0], ncol * H) || dev_alloc(&b->d_X[1], ncol * H) ||
-        dev_alloc(&b->d_Xin, xrows * 3 * H) || dev_alloc(&b->d_post, ncol * h.ostride) ||
-        dev_alloc(&b->d_score, cap_reads) || dev_alloc(&b->d_path, ncol + cap_reads))
+    if (h.arch == 1 && (batch_alloc(b, &b->d_Xin2, ncol * 3 * H) || batch_alloc(b, &b->d_FF, ncol * std::max(h.ffw, h.nfilter)))) return -1;
+    if (batch_alloc(b, &b->d_raw, nsamp) || batch_alloc(b, &b->d_X[0], ncol * H) || batch_alloc(b, &b->d_X[1], ncol * H) ||
+        batch_alloc(b, &b->d_Xin, xrows * 3 * H) || batch_alloc(b, &b->d_post, ncol * h.ostride) ||
+        batch_alloc(b, &b->d_score, cap_reads) || batch_alloc(b, &b->d_path, ncol + cap_reads))
         return -1;
     if (h.head == 0) {
-        if (dev_alloc(&b->d_tb, ncol * (h.nstate - 1)) || dev_alloc(&b->d_tbE, ncol)) return -1;
+        if (batch_alloc(b, &b->d_tb, ncol * (h.nstate - 1)) || batch_alloc(b, &b->d_tbE, ncol)) return -1;
     } else {
-        if (dev_alloc(&b->d_tb, ncol * 8)) return -1;
+        if (batch_alloc(b, &b->d_tb, ncol * 8)) return -1;
     }
     size_t off[6];
     b->meta_bytes = meta_offsets(cap_reads, off);
-    if (dev_alloc(&b->d_meta, b->meta_bytes)) return -1;
+    if (batch_alloc(b, &b->d_meta, b->meta_bytes)) return -1;
     CUDA_OK(cudaMallocHost(reinterpret_cast<void **>(&b->h_meta), b->meta_bytes));
     b->d_nsample = reinterpret_cast<int *>(b->d_meta + off[0]);
     b->d_nblock = reinterpret_cast<int *>(b->d_meta + off[1]);
@@ -487,11 +506,11 @@ static int batch_reserve(sb2_batch *b) {
     b->d_sampoff = reinterpret_cast<int64_t *>(b->d_meta + off[3]);
     b->d_tails = reinterpret_cast<sb2_conv_tail *>(b->d_meta + off[4]);
     b->d_xgrp = reinterpret_cast<long long *>(b->d_meta + off[5]);
-    if (dev_alloc(&b->d_xrow[0], xrows) || dev_alloc(&b->d_xrow[1], xrows)) return -1;
-    CUDA_OK(cudaMemset(b->d_raw, 0, nsamp * sizeof(float)));
-    CUDA_OK(cudaMemset(b->d_Xin, 0, xrows * 3 * H * sizeof(float)));   // rows of a ragged group's shorter reads are read, never written
+    if (batch_alloc(b, &b->d_xrow[0], xrows) || batch_alloc(b, &b->d_xrow[1], xrows)) return -1;
+    CUDA_OK(cudaMemsetAsync(b->d_raw, 0, nsamp * sizeof(float), b->stream));
+    CUDA_OK(cudaMemsetAsync(b->d_Xin, 0, xrows * 3 * H * sizeof(float), b->stream));   // rows of a ragged group's shorter reads are read, never written
     b->cap_reads = cap_reads; b->cap_cols = ncol; b->cap_samples = nsamp; b->cap_xrows = xrows;
-    if (keep_layers && dev_alloc(&b->d_layers, (size_t)6 * ncol * H)) return -1;
+    if (keep_layers && batch_alloc(b, &b->d_layers, (size_t)6 * ncol * H)) return -1;
     return 0;
 }
 
@@ -581,7 +600,7 @@ extern "C" int sb2_batch_keep_layers(sb2_batch *b, int keep) {
     if (nullptr == b) return -1;
     if (b->m->host.arch != 0) { sb2_set_error("per-layer dumps are only available for the rgrgr / rnnrf topology"); return -1; }
     CUDA_OK(cudaSetDevice(b->eng->device));
-    if (keep && nullptr == b->d_layers && dev_alloc(&b->d_layers, (size_t)6 * b->cap_cols * b->m->host.H)) return -1;
+    if (keep && nullptr == b->d_layers && batch_alloc(b, &b->d_layers, (size_t)6 * b->cap_cols * b->m->host.H)) return -1;
     b->keep_layers = keep != 0;
     return 0;
 }
@@ -943,7 +962,7 @@ static int basecall_buffers(sb2_batch *b) {
     if (nullptr == b->h_scores) CUDA_OK(cudaMallocHost(reinterpret_cast<void **>(&b->h_scores), b->cap_reads * sizeof(float)));
     CUDA_OK(cudaMallocHost(reinterpret_cast<void **>(&b->h_gidx), b->gcap * 2 * sizeof(int)));
     CUDA_OK(cudaMallocHost(reinterpret_cast<void **>(&b->h_gval), b->gcap * sizeof(float)));
-    if (dev_alloc(&b->d_gidx, b->gcap * 2) || dev_alloc(&b->d_gval, b->gcap)) return -1;
+    if (batch_alloc(b, &b->d_gidx, b->gcap * 2) || batch_alloc(b, &b->d_gval, b->gcap)) return -1;
     return 0;
 }
 
@@ -954,13 +973,13 @@ static int finish_buffers(sb2_batch *b) {
     b->bases_stride = (int)align_up((size_t)klen * ((size_t)b->max_cols + 1) + 1, 16);
     const size_t nbytes = (size_t)b->nread * b->bases_stride;
     if (nullptr == b->d_path2) {
-        if (dev_alloc(&b->d_path2, b->cap_cols + b->cap_reads) || dev_alloc(&b->d_nbase, b->cap_reads)) return -1;
+        if (batch_alloc(b, &b->d_path2, b->cap_cols + b->cap_reads) || batch_alloc(b, &b->d_nbase, b->cap_reads)) return -1;
         CUDA_OK(cudaMallocHost(reinterpret_cast<void **>(&b->h_nbase), b->cap_reads * sizeof(int)));
         if (nullptr == b->h_scores) CUDA_OK(cudaMallocHost(reinterpret_cast<void **>(&b->h_scores), b->cap_reads * sizeof(float)));
     }
     if (nbytes > b->cap_bases) {
         b->eng->reallocs += 1;
-        if (b->d_bases) { CUDA_OK(cudaStreamSynchronize(b->stream)); cudaFree(b->d_bases); cudaFreeHost(b->h_bases); b->d_bases = nullptr; b->h_bases = nullptr; }
+        if (b->d_bases) { CUDA_OK(cudaStreamSynchronize(b->stream)); cudaFreeAsync(b->d_bases, b->stream); cudaFreeHost(b->h_bases); b->d_bases = nullptr; b->h_bases = nullptr; }
         size_t cap = nbytes;
         if (b->pooled) {                                // engine-wide high-water mark, as for the activations
             std::atomic<size_t> &hw = b->eng->hw_bases[(int)b->model_type];
@@ -969,7 +988,7 @@ static int finish_buffers(sb2_batch *b) {
             while (cur < cap && !hw.compare_exchange_weak(cur, cap)) { }
             cap = std::max(cur, cap);
         }
-        if (dev_alloc(&b->d_bases, cap)) return -1;
+        if (batch_alloc(b, &b->d_bases, cap)) return -1;
         CUDA_OK(cudaMallocHost(reinterpret_cast<void **>(&b->h_bases), cap));
         b->cap_bases = cap;
     }
@@ -1049,12 +1068,12 @@ static int homopolymer_fixup(sb2_batch *b, int *paths) {
     int rc = bad ? -1 : 0;
     if (0 == rc && nent > b->gcap) {                    // overlapping runs can exceed the estimate: grow, do not fail
         cudaStreamSynchronize(b->stream);
-        cudaFreeHost(b->h_gidx); cudaFreeHost(b->h_gval); cudaFree(b->d_gidx); cudaFree(b->d_gval);
+        cudaFreeHost(b->h_gidx); cudaFreeHost(b->h_gval); cudaFreeAsync(b->d_gidx, b->stream); cudaFreeAsync(b->d_gval, b->stream);
         b->h_gidx = nullptr; b->h_gval = nullptr; b->d_gidx = nullptr; b->d_gval = nullptr;
         b->gcap = nent + nent / 2;
         if (cudaMallocHost(reinterpret_cast<void **>(&b->h_gidx), b->gcap * 2 * sizeof(int)) != cudaSuccess ||
             cudaMallocHost(reinterpret_cast<void **>(&b->h_gval), b->gcap * sizeof(float)) != cudaSuccess ||
-            dev_alloc(&b->d_gidx, b->gcap * 2) || dev_alloc(&b->d_gval, b->gcap)) {
+            batch_alloc(b, &b->d_gidx, b->gcap * 2) || batch_alloc(b, &b->d_gval, b->gcap)) {
             sb2_set_error("homopolymer gather buffers: out of memory");
             rc = -1;
         }
@@ -1208,7 +1227,15 @@ extern "C" int sb2_engine_trim_pool(sb2_engine *eng) {
         }
     }
     for (sb2_batch *b : idle) sb2_batch_destroy(b);
-    for (int m = 0; m < SB2_NMODEL; m++) { eng->hw_reads[m] = 0; eng->hw_cols[m] = 0; eng->hw_samples[m] = 0; eng->hw_bases[m] = 0; eng->hw_xrows[m] = 0; }
+    {   // hand the pooled device memory back to the driver (other allocators of the process may want it)
+        cudaMemPool_t pool = nullptr;
+        if (cudaSetDevice(eng->device) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, eng->device) == cudaSuccess) {
+            cudaDeviceSynchronize();
+            cudaMemPoolTrimTo(pool, 0);
+        }
+        cudaGetLastError();
+    }
+    for (int m = 0; m < SB2_NMODEL; m++) { eng->hw_reads[m] = 0; eng->hw_cols[m] = 0; eng->hw_samples[m] = 0; eng->hw_bases[m] = 0; eng->hw_xrows[m] = 0; eng->hw_stage[m] = 0; }
     return (int)idle.size();
 }
 
@@ -1228,7 +1255,13 @@ static int stage_signals(sb2_batch *b, const float *const *signals, const std::v
         b->eng->reallocs += 1;
         if (b->h_stage) cudaFreeHost(b->h_stage);
         b->h_stage = nullptr;
-        const size_t cap = total + total / 8;
+        size_t cap = total + total / 8;
+        {   // engine-wide high-water mark: a workspace that starts with a small batch is sized for the largest seen
+            std::atomic<size_t> &hw = b->eng->hw_stage[(int)b->model_type];
+            size_t cur = hw.load();
+            while (cur < cap && !hw.compare_exchange_weak(cur, cap)) { }
+            cap = std::max(cur, cap);
+        }
         CUDA_OK(cudaMallocHost(reinterpret_cast<void **>(&b->h_stage), cap * sizeof(float)));
         b->stage_cap = cap;
     }
@@ -1391,7 +1424,7 @@ extern "C" int sb2_basecall_raw_batch(sb2_engine *eng, enum raw_model_type model
     int ncalled = -1;
     std::vector<sb2_call> calls(keep.size(), sb2_call{nullptr, NAN, 0, 0});
     bool ok = 0 == batch_shape(b, len.data(), len.size());
-    if (ok && (nullptr == b->d_src || keep.size() > b->cap_reads)) ok = 0 == dev_alloc(&b->d_src, b->cap_reads);
+    if (ok && (nullptr == b->d_src || keep.size() > b->cap_reads)) ok = 0 == batch_alloc(b, &b->d_src, b->cap_reads);
     // the trimmer ran on the legacy stream: order this workspace's stream after it
     ok = ok && cudaStreamSynchronize(0) == cudaSuccess;
     ok = ok && cudaMemcpyAsync(b->d_src, src.data(), keep.size() * sizeof(int64_t), cudaMemcpyHostToDevice, b->stream) == cudaSuccess;
@@ -1663,7 +1696,7 @@ extern "C" int sb2_batch_posterior_crf(sb2_batch *b) {
     const sb2_host_model &h = b->m->host;
     if (h.head != 1 || h.nstate != 25) { sb2_set_error("posterior_crf needs a CRF model (rnnrf_r94)"); return -1; }
     CUDA_OK(cudaSetDevice(b->eng->device));
-    if (nullptr == b->d_bprob && dev_alloc(&b->d_bprob, (b->cap_cols + b->cap_reads) * 8)) return -1;
+    if (nullptr == b->d_bprob && batch_alloc(b, &b->d_bprob, (b->cap_cols + b->cap_reads) * 8)) return -1;
     launch_posterior_crf(b->d_post, b->dims, (int)h.ostride, b->d_bprob, b->stream);
     b->eng->launches += 1;
     CUDA_OK(cudaGetLastError());
