@@ -480,67 +480,38 @@ def measure(eng, ranks, args, model, workload, steps, warmup, nsets, detail):
     batches, pinned = None, None
 
     # ---- end to end through the documented call: sb2_basecall_batch from pageable host arrays ----------------------
-    # Work items = (step, batch); worker threads (one per concurrent batch slot) take them longest batch first and make
-    # one call each, exactly what INTEGRATION.md section 2.1 tells a maintainer to do.
+    # A team of C host threads (examples/batch_caller.c -> scrappie_b200/libsb2_caller.so), each taking the next batch
+    # -- work items (step, batch), a step's batches longest first -- and making ONE sb2_basecall_batch call on it, exactly
+    # what INTEGRATION.md section 2.1 tells a maintainer of `scrappie raw` to do.  No Python inside the timed region.
     order = sorted(range(nbatch), key=lambda k: -sum(len(s) for s in groups[k]))
-    prepared = [eng.prepare_call(g) for g in groups]
-    # calls in flight (each worker sleeps on its batch's completion event).  Eight keep the GPU busy when every call takes
-    # the same ~12 ms; the mixed workload's calls take 3 .. 200 ms and want more of them in flight
+    job = sb.CallerJob(eng, model, groups, order)
+    # calls in flight (each caller sleeps on its batch's completion event).  Eight keep the GPU busy when every call
+    # takes the same ~12 ms; the mixed workload's calls take 3 .. 200 ms and want more of them in flight
     nworker = min(nbatch * max(nsets, 8), int(os.environ.get("BENCH_E2E_WORKERS", "16" if workload == "mixed" else "8")))
-    last = [None] * nbatch
-
-    def run_documented(nstep):
-        q = queue.Queue()
-        for _ in range(nstep):
-            for k in order:
-                q.put(k)
-        err = []
-
-        def worker():
-            while True:
-                try:
-                    k = q.get_nowait()
-                except queue.Empty:
-                    return
-                try:
-                    last[k] = eng.basecall_prepared(model, prepared[k], params)
-                except Exception as e:      # noqa: BLE001 - re-raised on the main thread
-                    err.append(e)
-                    return
-        th = [threading.Thread(target=worker) for _ in range(nworker)]
-        for t in th:
-            t.start()
-        for t in th:
-            t.join()
-        if err:
-            raise err[0]
-
-    run_documented(max(2, (warmup + 1) // 2))           # pool warm-up: workspaces, pinned staging, graphs
+    job.run(max(2, (warmup + 1) // 2), nworker, params)          # pool warm-up: workspaces, pinned staging, graphs
     ranks.barrier()
     reallocs0 = eng.reallocs
-    t0 = time.perf_counter()
-    run_documented(steps)
+    e2e_total_s, nbases_doc, doc_bases, _ = job.run(steps, nworker, params, want_bases=(rank == 0))
     torch.cuda.synchronize()
-    e2e_s = (time.perf_counter() - t0) / steps
+    e2e_s = e2e_total_s / steps
     reallocs_timed = eng.reallocs - reallocs0           # 0: the documented call allocates nothing in steady state
     ranks.barrier()
 
     # ---- parity gate on the base strings the timed run produced -----------------------------------------------------
-    pick = []
+    starts = np.concatenate([[0], np.cumsum([len(g) for g in groups])])
     if workload == "fixed":
         pick = [(0, r) for r in range(len(groups[0]))] + [(k, r) for k in range(1, nbatch) for r in range(0, len(groups[k]), 8)]
     else:
         rng = np.random.default_rng(17)
         flat = [(k, r) for k in range(nbatch) for r in range(len(groups[k]))]
         pick = [flat[i] for i in sorted(rng.choice(len(flat), size=min(48, len(flat)), replace=False))]
-    pool_workspaces = None
     if rank == 0:
-        got = [last[k].bases(r) for k, r in pick]
+        got = [doc_bases[int(starts[k]) + r] for k, r in pick]
         parity = check_parity(model, [groups[k][r] for k, r in pick], got)
-        parity["persistent_path_agrees"] = (persistent_bases == last[0].bases(0))
+        parity["persistent_path_agrees"] = (persistent_bases == doc_bases[0])
         out["parity"] = parity
-
-    last = None
+    doc_bases = None
+    job = None
     eng.trim_pool()                                     # the next workload sizes its own workspaces
     step_all = ranks.gather(step_ms)
     e2e_all = ranks.gather(e2e_s)
@@ -550,10 +521,10 @@ def measure(eng, ranks, args, model, workload, steps, warmup, nsets, detail):
         "ms_per_step": max(step_all), "value": W * total_samples / (max(step_all) * 1e-3),
         "ms_per_step_ranks": spread(step_all),
         "blocks_per_s": W * total_blocks / (max(step_all) * 1e-3),
-        "kbases_per_s": W * nbases / max(e2e_all) / 1e3,
+        "kbases_per_s": W * nbases_doc / max(e2e_all) / 1e3,
         "e2e": {"value": W * total_samples / max(e2e_all), "unit": "samples/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": max(e2e_all) * 1e3, "ms_per_step_ranks": spread([x * 1e3 for x in e2e_all]),
-                "api": "sb2_basecall_batch (pooled workspaces) from pageable host arrays, %d host threads" % nworker,
+                "api": "sb2_basecall_batch (pooled workspaces) from pageable host arrays, %d C host threads (examples/batch_caller.c)" % nworker,
                 "workspace_allocations_in_timed_region": reallocs_timed,
                 "persistent": {"value": W * total_samples / max(e2ep_all), "ms_per_step": max(e2ep_all) * 1e3,
                                "api": "sb2_batch_basecall on caller-owned batches, pre-filled pinned buffers"}},

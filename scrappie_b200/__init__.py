@@ -839,6 +839,63 @@ def multi_stream_time(batches, params=None, nrep=1):
     return float(ms[0])
 
 
+_caller = None
+
+
+def caller_lib():
+    """libsb2_caller.so: the C caller of the batch drop-in call (examples/batch_caller.c)."""
+    global _caller
+    if _caller is None:
+        lib()                                           # libscrappie_b200.so first: the caller links against it
+        L = C.CDLL(os.path.join(_HERE, "libsb2_caller.so"))
+        L.sb2_caller_run.restype = C.c_double
+        L.sb2_caller_run.argtypes = [C.c_void_p, C.c_int, C.POINTER(_f32p), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t),
+                                     C.c_int, _i32p, C.c_int, C.c_int, C.POINTER(Params), C.POINTER(C.c_void_p),
+                                     _f32p, C.POINTER(C.c_size_t)]
+        L.sb2_caller_free.argtypes = [C.c_void_p]
+        _caller = L
+    return _caller
+
+
+class CallerJob(object):
+    """A workload prepared for sb2_caller_run: batches of reads in ordinary host memory, handed to a team of C host
+    threads that each call sb2_basecall_batch (the documented drop-in call) on the next batch -- what `scrappie raw`'s
+    OpenMP loop would do with the GPU library behind it.  No Python runs while the job does."""
+
+    def __init__(self, engine, model, groups, order=None):
+        self.engine, self.model = engine, model
+        self.sigs = [np.ascontiguousarray(s, dtype=np.float32) for g in groups for s in g]
+        n = len(self.sigs)
+        self.nread = n
+        self.ptrs = (_f32p * n)(*[_fp(s) for s in self.sigs])
+        self.lens = (C.c_size_t * n)(*[s.size for s in self.sigs])
+        starts = np.concatenate([[0], np.cumsum([len(g) for g in groups])]).astype(np.uintp)
+        self.starts = np.ascontiguousarray(starts)
+        self.nbatch = len(groups)
+        self.order = None if order is None else np.ascontiguousarray(order, dtype=np.int32)
+
+    def run(self, nstep, nthread, params=None, want_bases=False):
+        """Returns (seconds, bases called in the last step, [base strings of the last step])."""
+        params = params or default_params()
+        out = (C.c_void_p * self.nread)() if want_bases else None
+        scores = np.zeros(self.nread, dtype=np.float32)
+        nb = C.c_size_t(0)
+        secs = caller_lib().sb2_caller_run(self.engine._h, _MODEL_ENUM[self.model], self.ptrs, self.lens,
+                                           self.starts.ctypes.data_as(C.POINTER(C.c_size_t)), self.nbatch,
+                                           _ip(self.order) if self.order is not None else None, int(nstep), int(nthread),
+                                           C.byref(params), out, _fp(scores), C.byref(nb))
+        if secs < 0:
+            raise RuntimeError("sb2_caller_run failed: %s" % last_error())
+        bases = None
+        if want_bases:
+            bases = []
+            for p in out:
+                bases.append(C.string_at(p).decode() if p else None)
+                if p:
+                    caller_lib().sb2_caller_free(p)
+        return secs, int(nb.value), bases, scores
+
+
 class PinnedBuffer(object):
     """Page-locked host float32 buffer (cudaMallocHost) exposed as a numpy array."""
 

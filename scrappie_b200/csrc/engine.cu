@@ -1210,6 +1210,15 @@ static sb2_batch *pool_acquire(sb2_engine *eng, enum raw_model_type model, const
 static void pool_release(sb2_engine *eng, sb2_batch *b, bool healthy) {
     if (nullptr == b) return;
     if (!healthy) { sb2_batch_destroy(b); return; }    // never recycle a workspace a CUDA error went through
+    // A workspace made before the high-water marks reached their present values would be passed over by the best-fit
+    // search until, much later, nothing else is idle and it has to grow in the middle of steady state: let it go now
+    // (stream-ordered frees: cheap), the next caller that finds the pool short makes a full-sized one.
+    const int mt = (int)b->model_type;
+    if (b->cap_cols < eng->hw_cols[mt] || b->cap_samples < eng->hw_samples[mt] || b->cap_xrows < eng->hw_xrows[mt] ||
+        b->cap_reads < eng->hw_reads[mt]) {
+        sb2_batch_destroy(b);
+        return;
+    }
     std::lock_guard<std::mutex> lock(eng->mu);
     eng->pool[b->model_type].push_back(b);
 }

@@ -844,3 +844,19 @@ def test_two_engines_in_one_process(sb, oracle):
     assert out[1][5][0] == oracle.basecall_raw("rgrgr_r94", sigs[5])[2]
     for e in engines:
         e.close()
+
+
+def test_c_caller_thread_team(sb, engine, oracle):
+    """examples/batch_caller.c (libsb2_caller.so): a team of C host threads, each calling sb2_basecall_batch on the next
+    batch -- the OpenMP loop of src/scrappie_raw.c:355-387 with the GPU library behind it, and what bench.py times as
+    `e2e`.  Every read must come back as from a single call, whatever the number of threads and passes."""
+    groups = [[synthetic_read(1200 + 10 * k + i, 700 + 41 * i + 13 * k) for i in range(5 + k)] for k in range(6)]
+    flat = [s for g in groups for s in g]
+    want = engine.basecall_batch("rgrgr_r94", flat)
+    job = sb.CallerJob(engine, "rgrgr_r94", groups, order=[5, 4, 3, 2, 1, 0])
+    for nthread, nstep in ((1, 1), (4, 3), (12, 2)):
+        secs, nbases, bases, scores = job.run(nstep, nthread, want_bases=True)
+        assert secs > 0 and bases == [w[0] for w in want]
+        assert nbases == sum(len(w[0]) for w in want)
+        assert np.array_equal(scores, np.array([w[1] for w in want], dtype=np.float32))
+    assert bases[3] == oracle.basecall_raw("rgrgr_r94", flat[3])[2]
