@@ -487,8 +487,10 @@ def measure(eng, ranks, args, model, workload, steps, warmup, nsets, detail):
     job = sb.CallerJob(eng, model, groups, order)
     # calls in flight (each caller sleeps on its batch's completion event).  Eight keep the GPU busy when every call
     # takes the same ~12 ms; the mixed workload's calls take 3 .. 200 ms and want more of them in flight
-    nworker = min(nbatch * max(nsets, 8), int(os.environ.get("BENCH_E2E_WORKERS", "16" if workload == "mixed" else "8")))
-    job.run(max(2, (warmup + 1) // 2), nworker, params)          # pool warm-up: workspaces, pinned staging, graphs
+    nworker = min(nbatch * max(nsets, 8), int(os.environ.get("BENCH_E2E_WORKERS", "16" if workload == "mixed" else "12")))
+    # pool warm-up: every caller must have had a workspace made for it (device buffers, pinned staging, graphs) and the
+    # workspaces must have seen the largest batch -- enough passes that each caller gets at least two calls
+    job.run(max(2, (warmup + 1) // 2, (2 * nworker + nbatch - 1) // nbatch), nworker, params)
     ranks.barrier()
     reallocs0 = eng.reallocs
     e2e_total_s, nbases_doc, doc_bases, _ = job.run(steps, nworker, params, want_bases=(rank == 0))
