@@ -422,19 +422,6 @@ def measure(eng, ranks, args, model, workload, steps, warmup, nsets, detail):
     out = {"workload": desc, "l2": l2_note, "buffer_sets": nsets, "steps": steps, "nbatch": nbatch,
            "total_samples": total_samples, "total_blocks": total_blocks, "launches": int(launches), "clocks": clocks}
 
-    # ---- sustained: the same streaming loop for >= N seconds (power-capped clocks instead of the burst's) ---------
-    if detail and args.sustained_seconds > 0:
-        n_long = int(np.ceil(args.sustained_seconds * 1e3 / step_ms / nsets)) * nsets
-        sampler = ClockSampler(torch.cuda.current_device()) if rank == 0 else None
-        ranks.barrier()
-        long_ms = sb.multi_stream_time(batches, params, nrep=[n_long // nsets] * len(batches))
-        ranks.barrier()
-        lc = sampler.stop() if sampler else None
-        long_all = ranks.gather(long_ms)
-        out["sustained"] = {"value": ranks.world * total_samples * n_long / (max(long_all) * 1e-3), "unit": "samples/s",
-                            "steps": n_long, "seconds": max(long_all) * 1e-3, "ms_per_step": max(long_all) / n_long,
-                            "clocks": lc}
-
     # stage intervals of one synchronised step of the first set (diagnostics, outside the timed region)
     if detail:
         sb.multi_time(batches[:nbatch], params, nrep=1, flush_l2=True)
@@ -465,19 +452,37 @@ def measure(eng, ranks, args, model, workload, steps, warmup, nsets, detail):
     d2h = sum(d2h_bytes(model, b.nread, max(b.nblock), int(res.nbase.max())) for b, res in zip(batches[:nbatch], results[:nbatch]))
     persistent_bases = results[0].bases(0)
 
-    if detail:
+    def sustained_and_solo():
+        # ---- sustained: the streaming loop for >= N seconds (power-capped clocks instead of the burst's).  Runs AFTER
+        # the short timed regions, so that those see the clocks a fresh job sees.
+        if args.sustained_seconds > 0:
+            n_long = int(np.ceil(args.sustained_seconds * 1e3 / step_ms / nsets)) * nsets
+            smp = ClockSampler(torch.cuda.current_device()) if rank == 0 else None
+            ranks.barrier()
+            long_ms = sb.multi_stream_time(batches, params, nrep=[n_long // nsets] * len(batches))
+            ranks.barrier()
+            lc = smp.stop() if smp else None
+            long_all = ranks.gather(long_ms)
+            out["sustained"] = {"value": ranks.world * total_samples * n_long / (max(long_all) * 1e-3), "unit": "samples/s",
+                                "steps": n_long, "seconds": max(long_all) * 1e-3, "ms_per_step": max(long_all) / n_long,
+                                "clocks": lc}
         # Per-kernel figures from ONE batch timed alone (CUDA events on its stream, L2 flushed), after the timed region:
         # in the concurrent step the stage intervals of different batches overlap, so they are not launch durations.
         batches[0].time(params, nrep=3, flush_l2=True)
         out["stage_solo"] = batches[0].stage_ms()
         out["batch0"] = {"nread": batches[0].nread, "cols": batches[0].total_blocks, "ostride": batches[0].ostride,
                          "nsamp": batches[0].total_samples_padded}
+
+    def close_batches():
+        for b in batches:
+            b.close()
+        for pb in pinned:
+            pb.close()
+        del batches[:], pinned[:]
+
     results = None
-    for b in batches:
-        b.close()
-    for pb in pinned:
-        pb.close()
-    batches, pinned = None, None
+    if not detail:
+        close_batches()                                 # the larger workloads need the memory for the pooled workspaces
 
     # ---- end to end through the documented call: sb2_basecall_batch from pageable host arrays ----------------------
     # A team of C host threads (examples/batch_caller.c -> scrappie_b200/libsb2_caller.so), each taking the next batch
@@ -514,6 +519,9 @@ def measure(eng, ranks, args, model, workload, steps, warmup, nsets, detail):
         out["parity"] = parity
     doc_bases = None
     job = None
+    if detail:
+        sustained_and_solo()
+        close_batches()
     eng.trim_pool()                                     # the next workload sizes its own workspaces
     step_all = ranks.gather(step_ms)
     e2e_all = ranks.gather(e2e_s)

@@ -346,6 +346,10 @@ struct sb2_batch {
     // Tmax_g) of Xin, step-major.  d_xrow[0 / 1][row] = input column of Xin row `row` for forward / backward layers.
     int rpg = 4;
     bool xil = false;
+    // Column stride of the posterior ON THE DEVICE.  The reference's stride (4 * ceil(nstate / 4) = 1028 floats = 4112
+    // bytes) leaves every other column misaligned to the 128-byte lines the head's stores and the decoder's loads move;
+    // the 1025-state models therefore use 1056 floats (33 lines) in HBM and the download re-strides to the reference's.
+    int pstride = 0;
     std::vector<long long> xgrp;
     size_t xrows = 0, cap_xrows = 0;                    // rows of Xin the layout needs / the buffer holds
     long long *d_xgrp = nullptr;
@@ -431,6 +435,7 @@ static int batch_layout(sb2_batch *b, const size_t *nsample, size_t nread, std::
     b->col_off[nread] = (int)co;
     b->total_cols = (int)co;
     b->total_samples = so;
+    b->pstride = (h.head == 0 && h.nstate == 1025) ? 1056 : (int)h.ostride;
     // read groups of the GRU scan and their rows in the scan-ordered Xin
     b->rpg = scan_reads_per_group((int)nread);
     const size_t ngroup = (nread + b->rpg - 1) / b->rpg;
@@ -488,7 +493,7 @@ static int batch_reserve(sb2_batch *b) {
     // raw_r94 keeps both directions of a bidirectional pair alive and merges them into `ffw` features
     if (h.arch == 1 && (batch_alloc(b, &b->d_Xin2, ncol * 3 * H) || batch_alloc(b, &b->d_FF, ncol * std::max(h.ffw, h.nfilter)))) return -1;
     if (batch_alloc(b, &b->d_raw, nsamp) || batch_alloc(b, &b->d_X[0], ncol * H) || batch_alloc(b, &b->d_X[1], ncol * H) ||
-        batch_alloc(b, &b->d_Xin, xrows * 3 * H) || batch_alloc(b, &b->d_post, ncol * h.ostride) ||
+        batch_alloc(b, &b->d_Xin, xrows * 3 * H) || batch_alloc(b, &b->d_post, ncol * std::max((size_t)h.ostride, (size_t)1056)) ||
         batch_alloc(b, &b->d_score, cap_reads) || batch_alloc(b, &b->d_path, ncol + cap_reads))
         return -1;
     if (h.head == 0) {
@@ -688,10 +693,10 @@ static int forward_raw_r94(sb2_batch *b, const sb2_params *p, bool return_log) {
     stage_mark(b, ST_AFFINE(4));
     stage_mark(b, ST_SCAN(4));
     stage_mark(b, ST_HEAD);
-    launch_affine(b->d_FF, ncol, FW, m.FF_W, FW, m.FF_b, (int)h.nstate, b->d_post, (int)h.ostride,
+    launch_affine(b->d_FF, ncol, FW, m.FF_W, FW, m.FF_b, (int)h.nstate, b->d_post, b->pstride,
                   p->tempW / p->tempb, p->tempb, 1, 0, s);
     stage_mark(b, ST_FINISH);
-    launch_softmax_finish(b->d_post, ncol, (int)h.nstate, (int)h.ostride, p->min_prob, return_log ? 1 : 0, s);
+    launch_softmax_finish(b->d_post, ncol, (int)h.nstate, b->pstride, p->min_prob, return_log ? 1 : 0, s);
     nl += 2;
     stage_mark(b, ST_DECODE);
     b->eng->launches += nl;
@@ -751,7 +756,7 @@ extern "C" int sb2_batch_forward(sb2_batch *b, const sb2_params *p, bool return_
     stage_mark(b, ST_HEAD);
     if (h.head == 0 && b->eng->gemm_impl != 0 && nullptr != m.head_img) {
         if (0 != launch_head_softmax_tc(b->d_X[cur], b->total_cols, H, m.head_img, m.FF_W + (size_t)1024 * H, m.FF_b,
-                                        b->d_post, (int)h.ostride, p->tempW / p->tempb, p->tempb, p->min_prob,
+                                        b->d_post, b->pstride, p->tempW / p->tempb, p->tempb, p->min_prob,
                                         return_log ? 1 : 0, b->eng->head_exact, s)) {
             sb2_set_error("tensor-core head kernel could not be configured");
             return -1;
@@ -759,21 +764,21 @@ extern "C" int sb2_batch_forward(sb2_batch *b, const sb2_params *p, bool return_
         stage_mark(b, ST_FINISH);
         nl += 1;
     } else if (h.head == 0) {
-        launch_affine(b->d_X[cur], b->total_cols, H, m.FF_W, H, m.FF_b, (int)h.nstate, b->d_post, (int)h.ostride,
+        launch_affine(b->d_X[cur], b->total_cols, H, m.FF_W, H, m.FF_b, (int)h.nstate, b->d_post, b->pstride,
                       p->tempW / p->tempb, p->tempb, 1, 0, s);
         stage_mark(b, ST_FINISH);
-        launch_softmax_finish(b->d_post, b->total_cols, (int)h.nstate, (int)h.ostride, p->min_prob, return_log ? 1 : 0, s);
+        launch_softmax_finish(b->d_post, b->total_cols, (int)h.nstate, b->pstride, p->min_prob, return_log ? 1 : 0, s);
         nl += 2;
     } else {
         if (h.nstate <= 32 && h.ostride <= 32 && b->eng->gemm_impl != 0) {
-            launch_small_head(b->d_X[cur], b->total_cols, H, m.FF_W, m.FF_b, (int)h.nstate, b->d_post, (int)h.ostride, s);
+            launch_small_head(b->d_X[cur], b->total_cols, H, m.FF_W, m.FF_b, (int)h.nstate, b->d_post, b->pstride, s);
         } else {
-            CUDA_OK(cudaMemsetAsync(b->d_post, 0, (size_t)b->total_cols * h.ostride * sizeof(float), s));
-            launch_affine(b->d_X[cur], b->total_cols, H, m.FF_W, H, m.FF_b, (int)h.nstate, b->d_post, (int)h.ostride,
+            CUDA_OK(cudaMemsetAsync(b->d_post, 0, (size_t)b->total_cols * b->pstride * sizeof(float), s));
+            launch_affine(b->d_X[cur], b->total_cols, H, m.FF_W, H, m.FF_b, (int)h.nstate, b->d_post, b->pstride,
                           1.0f, 1.0f, 0, 0, s);
         }
         stage_mark(b, ST_FINISH);
-        launch_globalnorm(b->d_post, b->dims, (int)h.ostride, s);
+        launch_globalnorm(b->d_post, b->dims, b->pstride, s);
         nl += 2;
     }
     stage_mark(b, ST_DECODE);
@@ -788,10 +793,10 @@ extern "C" int sb2_batch_decode(sb2_batch *b, const sb2_params *p) {
     CUDA_OK(cudaSetDevice(b->eng->device));
     NvtxRange range("sb2_batch_decode");
     if (h.head == 0)
-        launch_decode_transducer(b->d_post, b->dims, (int)h.nstate, (int)h.ostride, p->stay_pen, p->skip_pen,
+        launch_decode_transducer(b->d_post, b->dims, (int)h.nstate, b->pstride, p->stay_pen, p->skip_pen,
                                  p->local_pen, p->allow_slip, b->d_tb, b->d_tbE, b->d_path, b->d_score, b->stream);
     else
-        launch_decode_crf(b->d_post, b->dims, (int)h.ostride, b->d_tb, b->d_path, b->d_score, b->stream);
+        launch_decode_crf(b->d_post, b->dims, b->pstride, b->d_tb, b->d_path, b->d_score, b->stream);
     b->eng->launches += 1;
     stage_mark(b, ST_COUNT);
     CUDA_OK(cudaGetLastError());
@@ -847,8 +852,8 @@ extern "C" int sb2_batch_download_posterior(sb2_batch *b, size_t read, float *ds
     const sb2_host_model &h = b->m->host;
     CUDA_OK(cudaSetDevice(b->eng->device));
     CUDA_OK(cudaStreamSynchronize(b->stream));
-    const float *src = b->d_post + (size_t)b->col_off[read] * h.ostride;
-    CUDA_OK(cudaMemcpy2D(dst, dst_stride * sizeof(float), src, h.ostride * sizeof(float),
+    const float *src = b->d_post + (size_t)b->col_off[read] * b->pstride;
+    CUDA_OK(cudaMemcpy2D(dst, dst_stride * sizeof(float), src, b->pstride * sizeof(float),
                          std::min((size_t)h.ostride, dst_stride) * sizeof(float), (size_t)b->nblock[read],
                          cudaMemcpyDeviceToHost));
     return 0;
@@ -1001,7 +1006,7 @@ static int finish_on_device(sb2_batch *b, const sb2_params *p, sb2_call *out) {
     const sb2_host_model &h = b->m->host;
     if (0 != finish_buffers(b)) return -1;
     const int klen = (h.head == 0) ? (int)(logf((float)h.nstate) / logf(4.0f)) : 1;
-    launch_finish_reads(b->d_post, b->dims, (int)h.nstate, (int)h.ostride, (int)h.head,
+    launch_finish_reads(b->d_post, b->dims, (int)h.nstate, b->pstride, (int)h.head,
                         (h.head == 0 && p->homopolymer == HOMOPOLYMER_MEAN) ? 1 : 0, klen, b->d_path, b->d_path2,
                         b->d_bases, b->bases_stride, b->d_nbase, b->stream);
     b->eng->launches += 1;
@@ -1090,7 +1095,7 @@ static int homopolymer_fixup(sb2_batch *b, int *paths) {
                 }
         }
         if (cudaMemcpyAsync(b->d_gidx, b->h_gidx, nent * 2 * sizeof(int), cudaMemcpyHostToDevice, b->stream) != cudaSuccess) rc = -1;
-        launch_gather(b->d_post, (int)h.ostride, b->d_gidx, (int)nent, b->d_gval, b->stream);
+        launch_gather(b->d_post, b->pstride, b->d_gidx, (int)nent, b->d_gval, b->stream);
         b->eng->launches += 1;
         if (cudaMemcpyAsync(b->h_gval, b->d_gval, nent * sizeof(float), cudaMemcpyDeviceToHost, b->stream) != cudaSuccess) rc = -1;
         if (cudaStreamSynchronize(b->stream) != cudaSuccess) rc = -1;
@@ -1706,7 +1711,7 @@ extern "C" int sb2_batch_posterior_crf(sb2_batch *b) {
     if (h.head != 1 || h.nstate != 25) { sb2_set_error("posterior_crf needs a CRF model (rnnrf_r94)"); return -1; }
     CUDA_OK(cudaSetDevice(b->eng->device));
     if (nullptr == b->d_bprob && batch_alloc(b, &b->d_bprob, (b->cap_cols + b->cap_reads) * 8)) return -1;
-    launch_posterior_crf(b->d_post, b->dims, (int)h.ostride, b->d_bprob, b->stream);
+    launch_posterior_crf(b->d_post, b->dims, b->pstride, b->d_bprob, b->stream);
     b->eng->launches += 1;
     CUDA_OK(cudaGetLastError());
     return 0;

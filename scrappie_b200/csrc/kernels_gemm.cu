@@ -427,7 +427,10 @@ head_softmax_tc_kernel(const float *__restrict__ X, int ncol, const uint8_t *__r
     constexpr int KSPLIT = 32 / CW;                     // lanes per column: they split the stay dot product
     constexpr int NEW = 4 * EW;                         // epilogue warps
     static_assert(CW == 32 || CW == 16, "column slice");
-    constexpr int OSTRIDE = NTILE * 128 + 4;            // 1028 = 4 * ceil(1025 / 4), the reference's column stride
+    // column stride on the device: 1056 floats = 33 lines of 128 bytes, so that a warp's store of 32 consecutive states
+    // is ONE aligned line (with the reference's 1028 every column starts 16 bytes later than the one before and most
+    // stores straddle two lines); the stay state and the three padding lanes sit at 1024..1027, 1028..1055 are unused
+    constexpr int OSTRIDE = 1056;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t *w_ring = smem;
     uint8_t *b_ring = smem + G::OFF_B;
@@ -690,7 +693,7 @@ int launch_head_softmax_tc(const float *X, int ncol, int K, const uint8_t *wimg,
                            float *post, int ostride, float xdiv, float cdiv, float min_prob, int return_log,
                            int exact_math, cudaStream_t s) {
     if (ncol <= 0) return 0;
-    if (K != 96 || ostride != 1028) return -1;
+    if (K != 96 || ostride != 1056) return -1;
     using G = HeadCfg<96>;
     static const int ew = [] { const char *e = getenv("SCRAPPIE_B200_HEAD_SLICES"); return (e && atoi(e) == 2) ? 2 : 4; }();
     static const int max_ctas = [] { const char *e = getenv("SCRAPPIE_B200_HEAD_CTAS"); const int v = e ? atoi(e) : 0; return (v > 0 && v < 148) ? v : 148; }();

@@ -17,7 +17,7 @@ fi
 timeout 900 python bench.py > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench rc=$?"
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/${TAG}_bench_ref.json 2>> $OUT/${TAG}_bench.err; echo "ref rc=$?"; cat $OUT/${TAG}_bench_ref.json | cut -c1-400
 if [ "$DO_PROF" = "prof" ]; then
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/${TAG}_launches.csv \
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file $OUT/${TAG}_launches.csv \
       python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-other-configs --sustained-seconds 0 > $OUT/${TAG}_ncu_bench.log 2>&1; echo "ncu list rc=$?"
   for K in ${KERNELS:-gru_scan_kernel affine_tc head_softmax decode_transducer_warp conv_act}; do
     timeout 600 ncu --set full --clock-control none --import-source on -k regex:$K -s 1 -c 1 -f -o $OUT/${TAG}_${K} \
