@@ -20,7 +20,14 @@ RAW_KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write
             "launch__grid_size", "launch__block_size", "sm__cycles_elapsed.max", "smsp__inst_executed.sum",
             "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
             "launch__shared_mem_per_block_dynamic", "launch__shared_mem_per_block_static",
-            "lts__t_bytes.sum", "l1tex__data_bank_conflicts_pipe_lsu.sum"]
+            "lts__t_bytes.sum", "l1tex__data_bank_conflicts_pipe_lsu.sum", "lts__t_sector_hit_rate.pct",
+            "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+            "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+            "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+            "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+            "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+            "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+            "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio"]
 
 
 def launches(path):
@@ -74,6 +81,23 @@ def main():
                 i = hdr.index(key)
                 out.append("| %s | %s | %s |" % (key, units[i], " | ".join(r[i] for r in rows[2:])))
         out.append("")
+    # DRAM traffic per launch of every captured kernel (bench.py's roofline.traffic reads the newest *_traffic.json)
+    traffic = {}
+    for rep in reps:
+        if not os.path.exists(rep):
+            continue
+        txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(txt.splitlines()))
+        hdr, units = rows[0], rows[1]
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        for r in rows[2:]:
+            name = r[hdr.index("Kernel Name")].split("(")[0].replace("void ", "")
+            ir, iw, it = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("gpu__time_duration.sum")
+            traffic[name] = {"dram_read_bytes": float(r[ir]) * scale.get(units[ir], 1.0), "dram_write_bytes": float(r[iw]) * scale.get(units[iw], 1.0),
+                             "duration_us": float(r[it]) * {"us": 1.0, "ms": 1e3, "ns": 1e-3, "s": 1e6}.get(units[it], 1.0),
+                             "source": os.path.basename(rep) + " (ncu --set full, one launch of a 256 x 4000-sample batch)"}
+    if traffic:
+        json.dump(traffic, open(os.path.join(ROOT, "profiles", tag + "_traffic.json"), "w"), indent=1)
     dst = os.path.join(ROOT, "profiles", tag + "_summary.md")
     open(dst, "w").write("\n".join(out) + "\n")
     print(open(dst).read())
