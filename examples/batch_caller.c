@@ -18,6 +18,7 @@
 #include <math.h>
 #include <pthread.h>
 #include <stdatomic.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
@@ -37,7 +38,18 @@ typedef struct {
     float *score_out;
     atomic_long next;               /* next work item: step * nbatch + position in `order` */
     atomic_long nbase, failed;
+    char errmsg[512];               /* sb2_last_error() of the first call that failed (the library's message is per thread) */
 } caller_job;
+
+static char caller_error[512];
+const char *sb2_caller_last_error(void) { return caller_error; }
+
+static void caller_fail(caller_job *job, const char *what) {
+    if (0 == atomic_fetch_add(&job->failed, 1)) {
+        const char *msg = sb2_last_error();
+        snprintf(job->errmsg, sizeof(job->errmsg), "%s: %s", what, (msg && msg[0]) ? msg : "(no message)");
+    }
+}
 
 static void *caller_worker(void *arg) {
     caller_job *job = arg;
@@ -54,10 +66,10 @@ static void *caller_worker(void *arg) {
             free(calls);
             calls = malloc(n * sizeof(sb2_call));
             cap = n;
-            if (NULL == calls) { atomic_fetch_add(&job->failed, 1); break; }
+            if (NULL == calls) { caller_fail(job, "out of host memory"); break; }
         }
         const int ncalled = sb2_basecall_batch(job->eng, job->model, job->signals + r0, job->nsample + r0, n, job->params, calls);
-        if (ncalled < 0) { atomic_fetch_add(&job->failed, 1); break; }
+        if (ncalled < 0) { caller_fail(job, "sb2_basecall_batch"); break; }
         long nb = 0;
         const int keep = (step == job->nstep - 1);
         for (size_t i = 0; i < n; i++) {
@@ -80,6 +92,7 @@ double sb2_caller_run(sb2_engine *eng, int model, const float *const *signals, c
         return -1.0;
     caller_job job = {eng, (enum raw_model_type)model, signals, nsample, batch_start, order, nbatch, nstep, params,
                       bases_out, score_out};
+    job.errmsg[0] = '\0';
     atomic_init(&job.next, 0);
     atomic_init(&job.nbase, 0);
     atomic_init(&job.failed, 0);
@@ -93,7 +106,10 @@ double sb2_caller_run(sb2_engine *eng, int model, const float *const *signals, c
     for (int i = 0; i < started; i++) pthread_join(th[i], NULL);
     clock_gettime(CLOCK_MONOTONIC, &t1);
     if (nbase_total) *nbase_total = (size_t)atomic_load(&job.nbase);
-    if (0 == started || atomic_load(&job.failed) > 0) return -1.0;
+    if (0 == started || atomic_load(&job.failed) > 0) {
+        snprintf(caller_error, sizeof(caller_error), "%s", 0 == started ? "could not start a host thread" : job.errmsg);
+        return -1.0;
+    }
     return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
 }
 

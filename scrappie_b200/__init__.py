@@ -853,6 +853,7 @@ def caller_lib():
                                      C.c_int, _i32p, C.c_int, C.c_int, C.POINTER(Params), C.POINTER(C.c_void_p),
                                      _f32p, C.POINTER(C.c_size_t)]
         L.sb2_caller_free.argtypes = [C.c_void_p]
+        L.sb2_caller_last_error.restype = C.c_char_p
         _caller = L
     return _caller
 
@@ -885,7 +886,7 @@ class CallerJob(object):
                                            _ip(self.order) if self.order is not None else None, int(nstep), int(nthread),
                                            C.byref(params), out, _fp(scores), C.byref(nb))
         if secs < 0:
-            raise RuntimeError("sb2_caller_run failed: %s" % last_error())
+            raise RuntimeError("sb2_caller_run failed: %s" % caller_lib().sb2_caller_last_error().decode())
         bases = None
         if want_bases:
             bases = []

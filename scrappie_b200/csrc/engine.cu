@@ -545,6 +545,7 @@ static int batch_upload_meta(sb2_batch *b, const std::vector<sb2_conv_tail> &tai
 
 // (Re-)shape a batch for `nread` reads of the given lengths.
 static int batch_shape(sb2_batch *b, const size_t *nsample, size_t nread) {
+    CUDA_OK(cudaSetDevice(b->eng->device));             // callers are arbitrary host threads: their current device is not ours
     // same lengths as this workspace's last use (a caller streaming equal-sized batches): every table on the device is
     // still valid -- nothing to compute, nothing to upload, and the captured graph stays
     if (nullptr != b->stream && b->cap_reads > 0 && (size_t)b->nread == nread) {
@@ -1264,6 +1265,7 @@ static size_t min_read_samples(sb2_engine *eng, enum raw_model_type model) {
 // padded layout (pads zeroed), then one asynchronous H2D copy.
 static int stage_signals(sb2_batch *b, const float *const *signals, const std::vector<size_t> &keep) {
     NvtxRange range("stage signals: pageable -> pinned -> device");
+    CUDA_OK(cudaSetDevice(b->eng->device));
     const size_t total = (size_t)b->total_samples;
     if (total > b->stage_cap) {
         b->eng->reallocs += 1;
