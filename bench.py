@@ -376,18 +376,28 @@ def measure(eng, ranks, args, model, workload, steps, warmup, nsets, detail):
     rank = ranks.rank
     sigs, groups, desc = build_groups(args, model, workload, rank, ranks.world)
     nbatch = len(groups)
+    # resident batch objects of one buffer set, and how often each of them runs per step.  The sharded workload streams
+    # its (up to 100 000 / N reads = hundreds of batches) through at most 16 resident full-size batches plus the shard's
+    # last partial one: every batch of the shard is computed in every step, but only 17 workspaces are held in HBM.
+    res_idx, mult = list(range(nbatch)), [1] * nbatch
     if workload == "sharded":
         nsets, steps, warmup = 1, max(1, min(steps, 2)), 1          # one pass = the whole shard, already many batches
+        full = [k for k, g in enumerate(groups) if len(g) == args.batch]
+        tail = [k for k, g in enumerate(groups) if len(g) != args.batch]
+        keep = full[:16]
+        res_idx = keep + tail
+        mult = [len(full) // len(keep) + (1 if j < len(full) % len(keep) else 0) for j in range(len(keep))] + [1] * len(tail)
+    nres = len(res_idx)
     nsets = max(1, min(nsets, steps))
     params = sb.default_params()
     total_samples = sum(len(s) for s in sigs)
 
     # ---- device-resident throughput -------------------------------------------------------------------------------
-    # Set k = batches[k * nbatch : (k + 1) * nbatch] (same reads).  The steps alternate between the sets and run back
+    # Set k = batches[k * nres : (k + 1) * nres] (same reads).  The steps alternate between the sets and run back
     # to back on the batches' own streams with no synchronisation in between (a continuously fed basecaller): step
     # n + 1 starts while step n is still decoding.  A step streams GBs of activations, far more than L2 holds.
     batches, pinned = [], []
-    for g in groups * nsets:
+    for g in [groups[k] for k in res_idx] * nsets:
         b = eng.batch(model, [len(s) for s in g])
         pb = sb.PinnedBuffer(b.total_samples_padded)
         pb.array[:] = 0
@@ -396,12 +406,12 @@ def measure(eng, ranks, args, model, workload, steps, warmup, nsets, detail):
         b.upload_concat(pb.ptr, pinned_async=False)
         batches.append(b)
         pinned.append(pb)
-    total_blocks = sum(b.total_blocks for b in batches[:nbatch])
+    total_blocks = sum(b.total_blocks * m for b, m in zip(batches[:nres], mult))
     set_reps = [steps // nsets + (1 if k < steps % nsets else 0) for k in range(nsets)]
-    reps = [set_reps[i // nbatch] for i in range(len(batches))]
+    reps = [set_reps[i // nres] * mult[i % nres] for i in range(len(batches))]
     sampler = ClockSampler(torch.cuda.current_device()) if rank == 0 else None
     if nsets > 1 or workload == "sharded":
-        sb.multi_stream_time(batches, params, nrep=max(1 if workload == "sharded" else 3, (warmup + nsets - 1) // nsets))
+        sb.multi_stream_time(batches, params, nrep=max(1 if workload == "sharded" else 3, (warmup + nsets - 1) // nsets))   # per object
         ranks.barrier()
         launches0 = eng.launches
         step_ms = sb.multi_stream_time(batches, params, nrep=reps) / steps
@@ -420,12 +430,13 @@ def measure(eng, ranks, args, model, workload, steps, warmup, nsets, detail):
         l2_note = "flushed between timed steps (384 MB overwrite, outside the timed region)"
     clocks = sampler.stop() if sampler else None
     out = {"workload": desc, "l2": l2_note, "buffer_sets": nsets, "steps": steps, "nbatch": nbatch,
-           "total_samples": total_samples, "total_blocks": total_blocks, "launches": int(launches), "clocks": clocks}
+           "total_samples": total_samples, "total_blocks": total_blocks, "launches": int(launches), "clocks": clocks,
+           "resident_batches": "%d workspaces per buffer set for the step's %d batches" % (nres, nbatch)}
 
     # stage intervals of one synchronised step of the first set (diagnostics, outside the timed region)
     if detail:
-        sb.multi_time(batches[:nbatch], params, nrep=1, flush_l2=True)
-        out["stage_concurrent"] = [b.stage_ms() for b in batches[:nbatch]]
+        sb.multi_time(batches[:nres], params, nrep=1, flush_l2=True)
+        out["stage_concurrent"] = [b.stage_ms() for b in batches[:nres]]
 
     # ---- end to end, persistent batch objects + pre-filled pinned buffers (round 1's e2e) ---------------------------
     results = [None] * len(batches)
@@ -447,9 +458,8 @@ def measure(eng, ranks, args, model, workload, steps, warmup, nsets, detail):
     run_threads(work_persistent, reps)
     torch.cuda.synchronize()
     e2e_persistent_s = (time.perf_counter() - t0) / steps
-    nbases = int(sum(int(res.nbase.sum()) for res in results[:nbatch]))
-    h2d = sum(b.total_samples_padded * 4 for b in batches[:nbatch])
-    d2h = sum(d2h_bytes(model, b.nread, max(b.nblock), int(res.nbase.max())) for b, res in zip(batches[:nbatch], results[:nbatch]))
+    h2d = sum(b.total_samples_padded * 4 * m for b, m in zip(batches[:nres], mult))
+    d2h = sum(d2h_bytes(model, b.nread, max(b.nblock), int(res.nbase.max())) * m for b, res, m in zip(batches[:nres], results[:nres], mult))
     persistent_bases = results[0].bases(0)
 
     def sustained_and_solo():
@@ -579,7 +589,7 @@ def main_b200(args, rank, world, local_rank):
     others = {}
     if default_run:
         def brief(m):
-            keys = ("workload", "value", "ms_per_step", "ms_per_step_ranks", "kbases_per_s", "steps", "buffer_sets", "parity", "launches")
+            keys = ("workload", "value", "ms_per_step", "ms_per_step_ranks", "kbases_per_s", "steps", "buffer_sets", "parity", "launches", "resident_batches")
             d = {k: m[k] for k in keys if k in m}
             d["e2e"] = {k: m["e2e"][k] for k in ("value", "ms_per_step", "api", "workspace_allocations_in_timed_region",
                                                  "h2d_bytes_per_step", "d2h_bytes_per_step")}

@@ -833,6 +833,9 @@ def test_two_engines_in_one_process(sb, oracle):
     out = [None, None]
 
     def work(k):
+        # twice: the second call finds the workspace's shape unchanged and skips the set-up -- from a fresh host thread
+        # whose current device is 0, whatever the engine's device is
+        engines[k].basecall_batch("rgrgr_r94", sigs)
         out[k] = engines[k].basecall_batch("rgrgr_r94", sigs)
 
     threads = [threading.Thread(target=work, args=(k,)) for k in range(2)]
