@@ -42,7 +42,7 @@ def main():
     names = demangle(list(counts))
     rows = []
     for fn, c in counts.items():
-        short = re.sub(r"\(.*", "", names.get(fn, fn)).replace("void ", "").replace("sb2::", "").replace("(anonymous namespace)::", "")
+        short = re.sub(r"\(.*", "", names.get(fn, fn).replace("(anonymous namespace)::", "")).replace("void ", "").replace("sb2::", "")
         r = regs.get(fn, ("?", "?"))
         rows.append((short, c["_total"], r[0], r[1]) + tuple(c[o] for o in OPS))
     rows.sort(key=lambda r: (-r[4], r[0]))
