@@ -35,6 +35,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# hardware work queues of the CUDA context (default 8): every batch in flight has its own stream and wants its own queue
+# (scrappie_b200 sets the same default; here because torch creates the context first)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 FLOP_PER_READ_STEP_RECURRENT = {"rgrgr_r94": 55296, "rgrgr_r941": 55296, "rgrgr_r10": 55296, "rnnrf_r94": 75264}
 # algorithmic HBM bytes per block when every intermediate is materialised once:
@@ -502,10 +505,11 @@ def measure(eng, ranks, args, model, workload, steps, warmup, nsets, detail):
     job = sb.CallerJob(eng, model, groups, order)
     # calls in flight (each caller sleeps on its batch's completion event).  Eight keep the GPU busy when every call
     # takes the same ~12 ms; the mixed workload's calls take 3 .. 200 ms and want more of them in flight
-    nworker = min(nbatch * max(nsets, 8), int(os.environ.get("BENCH_E2E_WORKERS", "16" if workload == "mixed" else "12")))
+    nworker = min(nbatch * max(nsets, 8), int(os.environ.get("BENCH_E2E_WORKERS", "48" if workload == "mixed" else "12")))
     # pool warm-up: every caller must have had a workspace made for it (device buffers, pinned staging, graphs) and the
-    # workspaces must have seen the largest batch -- enough passes that each caller gets at least two calls
-    job.run(max(2, (warmup + 1) // 2, (2 * nworker + nbatch - 1) // nbatch), nworker, params)
+    # workspaces must have seen the largest batch.  A workspace made before the pool's high-water marks were final is
+    # let go when it is handed back, so a caller reaches its steady state with its third call: enough passes for that
+    job.run(max(2, (warmup + 1) // 2, (3 * nworker + nbatch - 1) // nbatch + 1), nworker, params)
     ranks.barrier()
     reallocs0 = eng.reallocs
     e2e_total_s, nbases_doc, doc_bases, _ = job.run(steps, nworker, params, want_bases=(rank == 0))
@@ -658,6 +662,7 @@ def main_b200(args, rank, world, local_rank):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": head["workload"], "l2": head["l2"], "buffer_sets": head["buffer_sets"],
                    "scan_impl": os.environ.get("SCRAPPIE_B200_SCAN", "default"),
+                   "cuda_device_max_connections": os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS"),
                    "scan_groups": "%d reads per CTA, %d per group" % (reads_per_cta, 8 if big else 4),
                    "parallelism": "reads sharded, %d rank(s), NCCL weight broadcast at init only" % world},
         "kbases_per_s": head["kbases_per_s"],

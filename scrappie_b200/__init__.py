@@ -18,6 +18,9 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # SCRAPPIE_B200_LIB selects an alternative build of the library (A/B measurements); the weights stay where they are
+# one hardware work queue per batch in flight instead of 8 shared ones (see sb2_engine_create); must be in the environment
+# before anything in the process creates a CUDA context
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 LIB_PATH = os.environ.get("SCRAPPIE_B200_LIB") or os.path.join(_HERE, "libscrappie_b200.so")
 WEIGHTS_DIR = os.path.join(_HERE, "weights")
 if os.environ.get("SCRAPPIE_B200_LIB"):

@@ -196,6 +196,13 @@ static DevModel *get_model(sb2_engine *eng, enum raw_model_type model) {
 }
 
 extern "C" sb2_engine *sb2_engine_create(int device, const char *weights_dir) {
+    // Streams are mapped onto CUDA_DEVICE_MAX_CONNECTIONS hardware work queues (default 8); streams that share a queue
+    // are served in order, so one batch's kernels wait behind another batch's dependent chain (measured: with every
+    // batch in flight on its own stream, 32 queues give +7 % end to end on equal-length reads and 1.3-2x on mixed
+    // lengths, where a long read's scan blocks its queue for tens of ms).  The variable is read when the process creates
+    // its CUDA context: it only takes effect if nothing in the process has used CUDA before (a host application that
+    // initialises CUDA itself should export it).  An explicit setting of the caller is kept.
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) {
@@ -478,14 +485,18 @@ static int batch_reserve(sb2_batch *b) {
         return std::max(cur, v);
     };
     size_t cap_reads = std::max(nread, b->cap_reads), ncol = std::max(ncol_need, b->cap_cols), nsamp = std::max(nsamp_need, b->cap_samples);
-    size_t xrows = std::max(std::max(b->xrows, ncol_need), b->cap_xrows);
+    const size_t xrows_need = std::max(b->xrows, ncol_need);
+    size_t xrows = std::max(xrows_need, b->cap_xrows);
     if (b->pooled) {
+        // The 1/16 head room goes on what this call NEEDS, never on the capacity the workspace already has: a re-reserve
+        // caused by one dimension (say, more reads) must not push the other dimensions' high-water marks up by another
+        // 6 % -- every other workspace of the pool would fall below the marks and be re-made when it is handed back.
         sb2_engine *eng = b->eng;
         const int mt = (int)b->model_type;
         cap_reads = raise_to(eng->hw_reads[mt], cap_reads);
-        ncol = raise_to(eng->hw_cols[mt], ncol + ncol / 16);
-        nsamp = raise_to(eng->hw_samples[mt], nsamp + nsamp / 16);
-        xrows = raise_to(eng->hw_xrows[mt], xrows + xrows / 16);
+        ncol = raise_to(eng->hw_cols[mt], std::max(ncol_need + ncol_need / 16, b->cap_cols));
+        nsamp = raise_to(eng->hw_samples[mt], std::max(nsamp_need + nsamp_need / 16, b->cap_samples));
+        xrows = raise_to(eng->hw_xrows[mt], std::max(xrows_need + xrows_need / 16, b->cap_xrows));
     }
     xrows = std::max(xrows, ncol);
     batch_free_device(b);
