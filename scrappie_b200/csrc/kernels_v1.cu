@@ -887,9 +887,9 @@ void launch_decode_transducer(const float *post, const BatchDims &d, int nstate,
 // ---------------------------------------------------------------------------------
 // read finishing on the device: homopolymer fix-up + overlapper / crfpath_to_basecall
 // ---------------------------------------------------------------------------------
-// One thread per read walks that read's Viterbi path exactly as homopolymer_path
+// One warp per read walks that read's Viterbi path with the results of homopolymer_path
 // (src/homopolymer.c:67-235: runs are detected on the ORIGINAL path, base-major, and applied in that
-// order to the working copy) and overlapper (src/decode.c:367-382, :449-509) do on the host.  Only the
+// order to the working copy) and overlapper (src/decode.c:367-382, :449-509) on the host.  Only the
 // base strings travel back over PCIe.  The host implementations (host_decode.c) remain the library's
 // single-read entry points and the cross-check of this kernel (tests/test_gpu_parity.py).
 __device__ __forceinline__ int dev_kmer_shift(int prev, int next, int nkmer) {
@@ -928,106 +928,51 @@ __device__ void dev_apply_run(const float *post, int ostride, int col0, int stay
     for (int i = 0; i < length; i++) pw[start + i] = (i < nnew) ? state : -1;
 }
 
-__global__ void __launch_bounds__(32)
-finish_reads_kernel(const float *__restrict__ post, BatchDims d, int nstate, int ostride, int head, int homopolymer,
-                    int klen, const int *__restrict__ path_in, int *__restrict__ path_work, char *__restrict__ bases,
-                    int bases_stride, int *__restrict__ nbase_out) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= d.nread) return;
-    const int nb = d.nblock[r];
-    const int col0 = d.col_off[r];
-    const int *pin = path_in + col0 + r;
-    int *pw = path_work + col0 + r;
-    char *out = bases + (size_t)r * bases_stride;
-    const char base_of[4] = {'A', 'C', 'G', 'T'};
-    if (head == 1) {                                    // crfpath_to_basecall, src/decode.c:895-918
-        int n = 0;
-        for (int i = 0; i < nb; i++)
-            if (pin[i] < 4) out[n++] = base_of[pin[i]];
-        out[n] = 0;
-        nbase_out[r] = n;
-        return;
-    }
-    for (int i = 0; i <= nb; i++) pw[i] = pin[i];
-    const int nkmer = nstate - 1;
-    if (homopolymer == 1) {
-        const int pathlen = nb;                         // homopolymer_path scans post->nc entries
-        const int mod1 = 1 << (2 * (klen - 1)), mod2 = 1 << (2 * (klen - 2));
-        const int stay = nstate - 1;
-        for (int base = 0; base < 4; base++) {
-            const int full = dev_homopolymer_kmer(base, klen);
-            const int tail1 = dev_homopolymer_kmer(base, klen - 1);
-            const int tail2 = dev_homopolymer_kmer(base, klen - 2);
-            for (int i = 1; i < pathlen - 2; i++) {
-                const int before = pin[i - 1], here = pin[i];
-                const bool here_ok = (here == -1) || (here == full);
-                if (before == -1 || !here_ok) continue;
-                if ((before % mod1 == tail1) && before != full) {
-                    int e = i + 1;
-                    while (e < pathlen && (pin[e] == -1 || pin[e] == full)) e++;
-                    dev_apply_run(post, ostride, col0, stay, pw, i, e - i, full);
-                }
-                if ((before % mod2 == tail2) && (before % mod1 != tail1)) {
-                    int j = i;
-                    while (j < pathlen && pin[j] == -1) j++;
-                    if (pin[j] == full && j < pathlen - 1) {
-                        int e = j + 1;
-                        while (e < pathlen && (pin[e] == -1 || pin[e] == full)) e++;
-                        dev_apply_run(post, ostride, col0, stay, pw, j, e - j, full);
-                    }
-                }
-            }
-        }
-    }
-    // overlapper
-    const int n = nb + 1;
-    int first = 0;
-    while (first < n && pw[first] < 0) first++;
-    if (first == n) { out[0] = 0; nbase_out[r] = -1; return; }      // all stays: the host returns NULL
-    for (int j = 0, kmer = pw[first]; j < klen; j++, kmer >>= 2) out[klen - 1 - j] = base_of[kmer & 3];
-    int tail = klen - 1;
-    int prev = pw[first];
-    for (int i = first + 1; i < n; i++) {
-        const int cur = pw[i];
-        if (cur < 0) continue;
-        const int shift = dev_kmer_shift(prev, cur, nkmer);
-        int kmer = cur;
-        for (int j = 0; j < shift; j++, kmer >>= 2) out[tail + shift - j] = base_of[kmer & 3];
-        tail += shift;
-        prev = cur;
-    }
-    out[tail + 1] = 0;
-    nbase_out[r] = tail + 1;
-}
-
-// Same, one WARP per read with the path staged in shared memory: run detection is evaluated for 32
-// positions at a time (ballot), hits are processed in ascending position order -- rule "XYYYY" before
-// rule "ZXYYY" at the same position, bases outermost -- i.e. in exactly the host's order.  Used when a
-// read's path fits the staging area; longer reads take finish_reads_kernel.
+// One WARP per read.  Run detection is evaluated for 32 positions at a time (ballot); hits are processed in ascending
+// position order -- rule "XYYYY" before rule "ZXYYY" at the same position, bases outermost -- i.e. in exactly the
+// host's order.  The overlapper is warp-parallel as well: 32 path entries per round, every move finds the k-mer before it
+// with a ballot, the shifts are prefix-summed and every lane writes its own bases -- the same string as the serial
+// loop of src/decode.c:449-509, 32 entries at a time.
+// STAGED: original path, working copy and base string live in shared memory (reads of up to ~940 blocks: the fixed-length
+// configurations).  Otherwise they stay in global memory (path_in, path_work, bases): no shared memory at all, so a
+// batch of long reads neither waits for an SM with 200 KB free nor walks a 26 000-block path with a single thread.
 constexpr int FIN_WARPS = 4;
-constexpr size_t FIN_SMEM_MAX = 200 * 1024;
+constexpr size_t FIN_SMEM_MAX = 48 * 1024;
 
+template <bool STAGED>
 __global__ void __launch_bounds__(32 * FIN_WARPS)
 finish_reads_warp_kernel(const float *__restrict__ post, BatchDims d, int nstate, int ostride, int head, int homopolymer,
-                         int klen, int maxb, const int *__restrict__ path_in, char *__restrict__ bases, int bases_stride,
-                         int *__restrict__ nbase_out) {
+                         int klen, int maxb, const int *__restrict__ path_in, int *__restrict__ path_work,
+                         char *__restrict__ bases, int bases_stride, int *__restrict__ nbase_out) {
     extern __shared__ __align__(16) uint8_t fin_smem[];
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int r = blockIdx.x * FIN_WARPS + warp;
     if (r >= d.nread) return;
-    const int bcap = klen * (maxb + 1) + 1;
-    const size_t per_warp = (size_t)2 * (maxb + 1) * sizeof(int) + (size_t)((bcap + 15) / 16 * 16);
-    int *po = reinterpret_cast<int *>(fin_smem + warp * per_warp);      // original path
-    int *pw = po + (maxb + 1);                                           // working copy
-    char *sb = reinterpret_cast<char *>(pw + (maxb + 1));
     const int nb = d.nblock[r];
     const int col0 = d.col_off[r];
     const int *pin = path_in + col0 + r;
     char *out = bases + (size_t)r * bases_stride;
-    for (int i = lane; i <= nb; i += 32) { const int v = pin[i]; po[i] = v; pw[i] = v; }
+    const int *po;                                      // original path
+    int *pw;                                            // working copy
+    char *sb;                                           // base string under construction
+    if (STAGED) {
+        const int bcap = klen * (maxb + 1) + 1;
+        const size_t per_warp = (size_t)2 * (maxb + 1) * sizeof(int) + (size_t)((bcap + 15) / 16 * 16);
+        int *ps = reinterpret_cast<int *>(fin_smem + warp * per_warp);
+        pw = ps + (maxb + 1);
+        sb = reinterpret_cast<char *>(pw + (maxb + 1));
+        for (int i = lane; i <= nb; i += 32) { const int v = pin[i]; ps[i] = v; pw[i] = v; }
+        po = ps;
+    } else {
+        po = pin;
+        pw = path_work + col0 + r;
+        sb = out;
+        if (head != 1)
+            for (int i = lane; i <= nb; i += 32) pw[i] = pin[i];
+    }
     __syncwarp();
     int nbase = 0;
-    if (head == 1) {                                    // crfpath_to_basecall
+    if (head == 1) {                                    // crfpath_to_basecall, src/decode.c:895-918
         for (int i0 = 0; i0 < nb; i0 += 32) {
             const int i = i0 + lane;
             const int st = (i < nb) ? po[i] : 4;
@@ -1038,7 +983,7 @@ finish_reads_warp_kernel(const float *__restrict__ post, BatchDims d, int nstate
     } else {
         const int nkmer = nstate - 1;
         if (homopolymer == 1) {
-            const int pathlen = nb;
+            const int pathlen = nb;                     // homopolymer_path scans post->nc entries
             const int mod1 = 1 << (2 * (klen - 1)), mod2 = 1 << (2 * (klen - 2));
             const int stay = nstate - 1;
             for (int base = 0; base < 4; base++) {
@@ -1080,35 +1025,50 @@ finish_reads_warp_kernel(const float *__restrict__ post, BatchDims d, int nstate
             }
         }
         __syncwarp();
-        // overlapper: serial over the path (lane 0), bases staged in shared memory
-        if (lane == 0) {
-            const char base_of[4] = {'A', 'C', 'G', 'T'};
-            const int n = nb + 1;
-            int first = 0;
-            while (first < n && pw[first] < 0) first++;
-            if (first == n) {
-                nbase = -1;
-            } else {
-                for (int j = 0, kmer = pw[first]; j < klen; j++, kmer >>= 2) sb[klen - 1 - j] = base_of[kmer & 3];
-                int tail = klen - 1;
-                int prev = pw[first];
-                for (int i = first + 1; i < n; i++) {
-                    const int cur = pw[i];
-                    if (cur < 0) continue;
-                    const int shift = dev_kmer_shift(prev, cur, nkmer);
-                    int kmer = cur;
-                    for (int j = 0; j < shift; j++, kmer >>= 2) sb[tail + shift - j] = base_of[kmer & 3];
-                    tail += shift;
-                    prev = cur;
-                }
-                nbase = tail + 1;
-            }
+        // overlapper (src/decode.c:449-509), 32 path entries per round
+        const int n = nb + 1;
+        int first = n;
+        for (int i0 = 0; i0 < n; i0 += 32) {
+            const int i = i0 + lane;
+            const unsigned m = __ballot_sync(0xffffffffu, i < n && pw[i] >= 0);
+            if (m) { first = i0 + __ffs(m) - 1; break; }
         }
-        nbase = __shfl_sync(0xffffffffu, nbase, 0);
+        if (first == n) {
+            nbase = -1;                                 // all stays: the host returns NULL
+        } else {
+            int prev_carry = pw[first];
+            if (lane < klen) sb[klen - 1 - lane] = "ACGT"[(prev_carry >> (2 * lane)) & 3];
+            int tail = klen - 1;
+            for (int i0 = first + 1; i0 < n; i0 += 32) {
+                const int i = i0 + lane;
+                const int cur = (i < n) ? pw[i] : -1;
+                const bool moved = cur >= 0;
+                const unsigned m = __ballot_sync(0xffffffffu, moved);
+                if (0 == m) continue;
+                // the k-mer before this one: the nearest move below in this round, else the last move of earlier rounds
+                const unsigned below = m & ((1u << lane) - 1u);
+                const int src = below ? (31 - __clz(below)) : 0;
+                const int pv = __shfl_sync(0xffffffffu, cur, src);
+                const int prev = below ? pv : prev_carry;
+                const int shift = moved ? dev_kmer_shift(prev, cur, nkmer) : 0;
+                int incl = shift;
+#pragma unroll
+                for (int dl = 1; dl < 32; dl <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, dl);
+                    if (lane >= dl) incl += t;
+                }
+                const int at = tail + (incl - shift);   // this move appends bases at at + 1 .. at + shift
+                for (int j = 0, kmer = cur; j < shift; j++, kmer >>= 2) sb[at + shift - j] = "ACGT"[kmer & 3];
+                tail += __shfl_sync(0xffffffffu, incl, 31);
+                prev_carry = __shfl_sync(0xffffffffu, cur, 31 - __clz(m));
+            }
+            nbase = tail + 1;
+        }
     }
     __syncwarp();
     const int nout = (nbase > 0) ? nbase : 0;
-    for (int i = lane; i < nout; i += 32) out[i] = sb[i];
+    if (STAGED)
+        for (int i = lane; i < nout; i += 32) out[i] = sb[i];
     if (lane == 0) { out[nout] = 0; nbase_out[r] = nbase; }
 }
 
@@ -1118,13 +1078,13 @@ void launch_finish_reads(const float *post, const BatchDims &d, int nstate, int 
     const int maxb = d.max_cols;
     const size_t per_warp = (size_t)2 * (maxb + 1) * sizeof(int) + (size_t)((klen * (maxb + 1) + 1 + 15) / 16 * 16);
     const size_t smem = per_warp * FIN_WARPS;
-    if (smem <= FIN_SMEM_MAX) {     // the attribute is set for every device in configure_v1_kernels()
-        finish_reads_warp_kernel<<<(d.nread + FIN_WARPS - 1) / FIN_WARPS, 32 * FIN_WARPS, smem, s>>>(
-            post, d, nstate, ostride, head, homopolymer, klen, maxb, path_in, bases, bases_stride, nbase);
-        return;
-    }
-    finish_reads_kernel<<<(d.nread + 31) / 32, 32, 0, s>>>(post, d, nstate, ostride, head, homopolymer, klen, path_in,
-                                                        path_work, bases, bases_stride, nbase);
+    const int grid = (d.nread + FIN_WARPS - 1) / FIN_WARPS;
+    if (smem <= FIN_SMEM_MAX)       // within the default dynamic shared-memory limit: no function attribute needed
+        finish_reads_warp_kernel<true><<<grid, 32 * FIN_WARPS, smem, s>>>(post, d, nstate, ostride, head, homopolymer, klen, maxb,
+                                                                         path_in, path_work, bases, bases_stride, nbase);
+    else
+        finish_reads_warp_kernel<false><<<grid, 32 * FIN_WARPS, 0, s>>>(post, d, nstate, ostride, head, homopolymer, klen, maxb,
+                                                                       path_in, path_work, bases, bases_stride, nbase);
 }
 
 // ---------------------------------------------------------------------------------
@@ -1153,7 +1113,7 @@ void launch_flush(float *buf, size_t nfloat, cudaStream_t s) { flush_kernel<<<14
 
 // Per-device function attributes of this file's kernels (called once per engine, after cudaSetDevice).
 int configure_v1_kernels() {
-    return cudaFuncSetAttribute(finish_reads_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FIN_SMEM_MAX) == cudaSuccess ? 0 : -1;
+    return cudaFuncSetAttribute(finish_reads_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FIN_SMEM_MAX) == cudaSuccess ? 0 : -1;
 }
 
 }  // namespace sb2

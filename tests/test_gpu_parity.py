@@ -321,6 +321,17 @@ def test_long_and_mixed_length_reads(sb, engine, oracle):
     calls = engine.basecall_batch("rgrgr_r94", sigs)
     assert calls[2][0] == oracle.basecall_raw("rgrgr_r94", sigs[2])[2]
     assert all(c[0] for c in calls)
+    # device finishing of long reads (paths kept in global memory, warp-parallel overlapper) == the host functions on
+    # the downloaded path and posterior
+    mine = b.basecall()
+    paths, scores = b.paths()
+    for i in range(len(sigs)):
+        post = sb.ScrappyMatrix.from_numpy(b.posterior(i), b.nstate)
+        path = paths[i].copy()
+        assert sb.lib().homopolymer_path(post.data(), path.ctypes.data_as(sb._i32p), 1) == 0
+        pos = np.zeros(len(path), dtype=np.int32)
+        want = sb._take_string(sb.lib().overlapper(path.ctypes.data_as(sb._i32p), len(path), 1024, pos.ctypes.data_as(sb._i32p)))
+        assert mine[i][0] == want == calls[i][0]
     b.close()
 
 
