@@ -399,8 +399,25 @@ def measure(eng, ranks, args, model, workload, steps, warmup, nsets, detail):
     # Set k = batches[k * nres : (k + 1) * nres] (same reads).  The steps alternate between the sets and run back
     # to back on the batches' own streams with no synchronisation in between (a continuously fed basecaller): step
     # n + 1 starts while step n is still decoding.  A step streams GBs of activations, far more than L2 holds.
+    # Resident objects: `nsets` copies of every resident batch -- except for the mixed-length workload, where a batch of
+    # 130 000-sample reads takes 16 x as long as a batch of 4 000-sample reads with as many samples (the scan is
+    # serial in time): there the same number of objects is dealt out in proportion to the batches' estimated duration,
+    # so that the step's long batches are in flight as often as a continuously fed basecaller would have them.
+    obj_group = res_idx * nsets
+    set_reps = [steps // nsets + (1 if k < steps % nsets else 0) for k in range(nsets)]
+    reps = [set_reps[i // nres] * mult[i % nres] for i in range(len(obj_group))]
+    if workload == "mixed":
+        est = [2.0 + 0.006 * max(len(x) for x in groups[k]) / 5.0 for k in res_idx]          # ms, from the longest read
+        copies = [int(min(steps, max(1, round(nsets * nres * e / sum(est))))) for e in est]
+        obj_group = list(res_idx) + [k for k, c in zip(res_idx, copies) for _ in range(c - 1)]
+        seen, reps = {}, []
+        for k in obj_group:
+            j = seen.get(k, 0)
+            seen[k] = j + 1
+            c = copies[res_idx.index(k)]
+            reps.append(steps // c + (1 if j < steps % c else 0))
     batches, pinned = [], []
-    for g in [groups[k] for k in res_idx] * nsets:
+    for g in [groups[k] for k in obj_group]:
         b = eng.batch(model, [len(s) for s in g])
         pb = sb.PinnedBuffer(b.total_samples_padded)
         pb.array[:] = 0
@@ -410,8 +427,6 @@ def measure(eng, ranks, args, model, workload, steps, warmup, nsets, detail):
         batches.append(b)
         pinned.append(pb)
     total_blocks = sum(b.total_blocks * m for b, m in zip(batches[:nres], mult))
-    set_reps = [steps // nsets + (1 if k < steps % nsets else 0) for k in range(nsets)]
-    reps = [set_reps[i // nres] * mult[i % nres] for i in range(len(batches))]
     sampler = ClockSampler(torch.cuda.current_device()) if rank == 0 else None
     if nsets > 1 or workload == "sharded":
         sb.multi_stream_time(batches, params, nrep=max(1 if workload == "sharded" else 3, (warmup + nsets - 1) // nsets))   # per object
@@ -434,7 +449,7 @@ def measure(eng, ranks, args, model, workload, steps, warmup, nsets, detail):
     clocks = sampler.stop() if sampler else None
     out = {"workload": desc, "l2": l2_note, "buffer_sets": nsets, "steps": steps, "nbatch": nbatch,
            "total_samples": total_samples, "total_blocks": total_blocks, "launches": int(launches), "clocks": clocks,
-           "resident_batches": "%d workspaces per buffer set for the step's %d batches" % (nres, nbatch)}
+           "resident_batches": "%d workspaces for the step's %d batches" % (len(obj_group), nbatch)}
 
     # stage intervals of one synchronised step of the first set (diagnostics, outside the timed region)
     if detail:
@@ -469,10 +484,11 @@ def measure(eng, ranks, args, model, workload, steps, warmup, nsets, detail):
         # ---- sustained: the streaming loop for >= N seconds (power-capped clocks instead of the burst's).  Runs AFTER
         # the short timed regions, so that those see the clocks a fresh job sees.
         if args.sustained_seconds > 0:
-            n_long = int(np.ceil(args.sustained_seconds * 1e3 / step_ms / nsets)) * nsets
+            k_long = int(np.ceil(args.sustained_seconds * 1e3 / (step_ms * steps)))
+            n_long = steps * k_long
             smp = ClockSampler(torch.cuda.current_device()) if rank == 0 else None
             ranks.barrier()
-            long_ms = sb.multi_stream_time(batches, params, nrep=[n_long // nsets] * len(batches))
+            long_ms = sb.multi_stream_time(batches, params, nrep=[r * k_long for r in reps])
             ranks.barrier()
             lc = smp.stop() if smp else None
             long_all = ranks.gather(long_ms)
@@ -505,11 +521,14 @@ def measure(eng, ranks, args, model, workload, steps, warmup, nsets, detail):
     job = sb.CallerJob(eng, model, groups, order)
     # calls in flight (each caller sleeps on its batch's completion event).  Eight keep the GPU busy when every call
     # takes the same ~12 ms; the mixed workload's calls take 3 .. 200 ms and want more of them in flight
-    nworker = min(nbatch * max(nsets, 8), int(os.environ.get("BENCH_E2E_WORKERS", "48" if workload == "mixed" else "12")))
+    nworker = min(nbatch * max(nsets, 8), int(os.environ.get("BENCH_MIXED_WORKERS", "48") if workload == "mixed" else os.environ.get("BENCH_E2E_WORKERS", "12")))
     # pool warm-up: every caller must have had a workspace made for it (device buffers, pinned staging, graphs) and the
     # workspaces must have seen the largest batch.  A workspace made before the pool's high-water marks were final is
     # let go when it is handed back, so a caller reaches its steady state with its third call: enough passes for that
-    job.run(max(2, (warmup + 1) // 2, (3 * nworker + nbatch - 1) // nbatch + 1), nworker, params)
+    # -- in two runs: when the first one returns every workspace has been handed back, the high-water marks are final
+    # and the workspaces made before they were are gone; the second one makes the missing ones at their final size
+    job.run(2, nworker, params)
+    job.run(max(2, (warmup + 1) // 2, (2 * nworker + nbatch - 1) // nbatch), nworker, params)
     ranks.barrier()
     reallocs0 = eng.reallocs
     e2e_total_s, nbases_doc, doc_bases, _ = job.run(steps, nworker, params, want_bases=(rank == 0))
