@@ -163,16 +163,18 @@ void launch_conv_act(const float *raw, const BatchDims &d, const sb2_conv_tail *
                      cudaStream_t s) {
     const int nfp = (nf + 31) / 32 * 32;
     dim3 grid((d.max_cols + CONV_CPB - 1) / CONV_CPB, d.nread);
+    // whole column lanes only: 96 filters -> 192 threads (two lanes), not 256 with a quarter of the CTA idle
+    const int nthr = (nfp <= 256) ? nfp * (256 / nfp) : 256;
     if (winlen == 19 && stride == 5) {
-        conv_act_v2_kernel<19, 5><<<grid, 256, 0, s>>>(raw, d, tails, taps, bias, nf, nfp, act, out);
+        conv_act_v2_kernel<19, 5><<<grid, nthr, 0, s>>>(raw, d, tails, taps, bias, nf, nfp, act, out);
         return;
     }
     if (winlen == 11 && stride == 1) {
-        conv_act_v2_kernel<11, 1><<<grid, 256, 0, s>>>(raw, d, tails, taps, bias, nf, nfp, act, out);
+        conv_act_v2_kernel<11, 1><<<grid, nthr, 0, s>>>(raw, d, tails, taps, bias, nf, nfp, act, out);
         return;
     }
     if (winlen == 11 && stride == 5) {
-        conv_act_v2_kernel<11, 5><<<grid, 256, 0, s>>>(raw, d, tails, taps, bias, nf, nfp, act, out);
+        conv_act_v2_kernel<11, 5><<<grid, nthr, 0, s>>>(raw, d, tails, taps, bias, nf, nfp, act, out);
         return;
     }
     const size_t smem = (size_t)(winlen * nf + (CONV_CPB - 1) * stride + winlen) * sizeof(float);
