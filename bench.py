@@ -370,6 +370,47 @@ def build_groups(args, model, workload, rank, world):
     return sigs, groups, desc
 
 
+def plan_resident(group_lens, workload, steps, warmup, nsets, batch):
+    """Which batch objects are held in HBM for the device-resident measurement and how often each of them runs.
+    `group_lens[k]` = the read lengths of the step's batch k.  Returns (obj_group, reps, mult, nsets, steps, warmup):
+    object i is a workspace of batch obj_group[i] that runs reps[i] times in the timed region; the first len(mult)
+    objects are one copy of every resident batch, and copy j of them stands for mult[j] batches of the step.  Over the
+    timed region every batch of the step is computed exactly `steps` times.
+
+    fixed    `nsets` copies ("buffer sets") of every batch, the steps alternating between them.
+    sharded  (config 5) the shard's hundreds of batches stream through at most 16 resident full-size batches plus the
+             shard's last partial one: every batch is computed in every step, but only 17 workspaces are held.
+    mixed    (config 4) a batch of 130 000-sample reads takes 16 x as long as a batch of 4 000-sample reads with as many
+             samples (the scan is serial in time): the nsets * nbatch objects are dealt out in proportion to the batches'
+             estimated duration, so that the long batches are in flight as often as a continuously fed basecaller
+             would have them."""
+    nbatch = len(group_lens)
+    res_idx, mult = list(range(nbatch)), [1] * nbatch
+    if workload == "sharded":
+        nsets, steps, warmup = 1, max(1, min(steps, 2)), 1          # one pass = the whole shard, already many batches
+        full = [k for k, g in enumerate(group_lens) if len(g) == batch]
+        tail = [k for k, g in enumerate(group_lens) if len(g) != batch]
+        keep = full[:16]
+        res_idx = keep + tail
+        mult = [len(full) // len(keep) + (1 if j < len(full) % len(keep) else 0) for j in range(len(keep))] + [1] * len(tail)
+    nres = len(res_idx)
+    nsets = max(1, min(nsets, steps))
+    obj_group = res_idx * nsets
+    set_reps = [steps // nsets + (1 if k < steps % nsets else 0) for k in range(nsets)]
+    reps = [set_reps[i // nres] * mult[i % nres] for i in range(len(obj_group))]
+    if workload == "mixed":
+        est = [2.0 + 0.006 * max(group_lens[k]) / 5.0 for k in res_idx]                      # ms, from the longest read
+        copies = [int(min(steps, max(1, round(nsets * nres * e / sum(est))))) for e in est]
+        obj_group = list(res_idx) + [k for k, c in zip(res_idx, copies) for _ in range(c - 1)]
+        seen, reps = {}, []
+        for k in obj_group:
+            j = seen.get(k, 0)
+            seen[k] = j + 1
+            c = copies[res_idx.index(k)]
+            reps.append(steps // c + (1 if j < steps % c else 0))
+    return obj_group, reps, mult, nsets, steps, warmup
+
+
 def measure(eng, ranks, args, model, workload, steps, warmup, nsets, detail):
     """One workload through all three measurements: device-resident streaming (`value`), the documented call from
     pageable host arrays (`e2e`), the persistent-batch path (`e2e.persistent`), plus the parity check of the e2e run's
@@ -379,43 +420,16 @@ def measure(eng, ranks, args, model, workload, steps, warmup, nsets, detail):
     rank = ranks.rank
     sigs, groups, desc = build_groups(args, model, workload, rank, ranks.world)
     nbatch = len(groups)
-    # resident batch objects of one buffer set, and how often each of them runs per step.  The sharded workload streams
-    # its (up to 100 000 / N reads = hundreds of batches) through at most 16 resident full-size batches plus the shard's
-    # last partial one: every batch of the shard is computed in every step, but only 17 workspaces are held in HBM.
-    res_idx, mult = list(range(nbatch)), [1] * nbatch
-    if workload == "sharded":
-        nsets, steps, warmup = 1, max(1, min(steps, 2)), 1          # one pass = the whole shard, already many batches
-        full = [k for k, g in enumerate(groups) if len(g) == args.batch]
-        tail = [k for k, g in enumerate(groups) if len(g) != args.batch]
-        keep = full[:16]
-        res_idx = keep + tail
-        mult = [len(full) // len(keep) + (1 if j < len(full) % len(keep) else 0) for j in range(len(keep))] + [1] * len(tail)
-    nres = len(res_idx)
-    nsets = max(1, min(nsets, steps))
+    obj_group, reps, mult, nsets, steps, warmup = plan_resident([[len(x) for x in g] for g in groups], workload, steps,
+                                                               warmup, nsets, args.batch)
+    nres = len(mult)                                    # the first nres objects are one copy of every resident batch
     params = sb.default_params()
     total_samples = sum(len(s) for s in sigs)
 
     # ---- device-resident throughput -------------------------------------------------------------------------------
-    # Set k = batches[k * nres : (k + 1) * nres] (same reads).  The steps alternate between the sets and run back
-    # to back on the batches' own streams with no synchronisation in between (a continuously fed basecaller): step
-    # n + 1 starts while step n is still decoding.  A step streams GBs of activations, far more than L2 holds.
-    # Resident objects: `nsets` copies of every resident batch -- except for the mixed-length workload, where a batch of
-    # 130 000-sample reads takes 16 x as long as a batch of 4 000-sample reads with as many samples (the scan is
-    # serial in time): there the same number of objects is dealt out in proportion to the batches' estimated duration,
-    # so that the step's long batches are in flight as often as a continuously fed basecaller would have them.
-    obj_group = res_idx * nsets
-    set_reps = [steps // nsets + (1 if k < steps % nsets else 0) for k in range(nsets)]
-    reps = [set_reps[i // nres] * mult[i % nres] for i in range(len(obj_group))]
-    if workload == "mixed":
-        est = [2.0 + 0.006 * max(len(x) for x in groups[k]) / 5.0 for k in res_idx]          # ms, from the longest read
-        copies = [int(min(steps, max(1, round(nsets * nres * e / sum(est))))) for e in est]
-        obj_group = list(res_idx) + [k for k, c in zip(res_idx, copies) for _ in range(c - 1)]
-        seen, reps = {}, []
-        for k in obj_group:
-            j = seen.get(k, 0)
-            seen[k] = j + 1
-            c = copies[res_idx.index(k)]
-            reps.append(steps // c + (1 if j < steps % c else 0))
+    # The resident batches run back to back on their own streams with no synchronisation in between (a continuously
+    # fed basecaller): step n + 1 starts while step n is still decoding.  A step streams GBs of activations, far more
+    # than L2 holds.
     batches, pinned = [], []
     for g in [groups[k] for k in obj_group]:
         b = eng.batch(model, [len(s) for s in g])

@@ -345,3 +345,44 @@ def test_bench_reference_arm_contract():
     assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert abs(line["e2e"]["value"] - line["value"]) < 1e-6 * line["value"]
+
+
+def test_bench_resident_plan():
+    """bench.py's plan of resident workspaces: whatever the workload, every batch of a step is computed exactly `steps`
+    times in the timed region, the sharded shard is streamed through a bounded number of workspaces (config 5 at N = 2
+    is 196 batches per rank: they do not fit in HBM at once), and the mixed-length workload gives its long batches more
+    copies than its short ones within the same object budget."""
+    import collections
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+
+    def runs(obj_group, reps):
+        c = collections.Counter()
+        for k, r in zip(obj_group, reps):
+            c[k] += r
+        return c
+
+    # fixed: 4 batches, 4 buffer sets, 20 steps
+    og, reps, mult, nsets, steps, warmup = bench.plan_resident([[4000] * 256] * 4, "fixed", 20, 5, 4, 256)
+    assert len(og) == 16 and mult == [1] * 4 and nsets == 4 and steps == 20
+    assert all(v == 20 for v in runs(og, reps).values()) and sorted(set(og)) == [0, 1, 2, 3] and og[:4] == [0, 1, 2, 3]
+    # fewer steps than sets
+    og, reps, mult, nsets, steps, _ = bench.plan_resident([[4000] * 256] * 4, "fixed", 2, 1, 4, 256)
+    assert nsets == 2 and all(v == 2 for v in runs(og, reps).values())
+    # sharded: 50 000 reads = 195 full batches + one of 80 reads
+    groups = [[4000] * 256] * 195 + [[4000] * 80]
+    og, reps, mult, nsets, steps, warmup = bench.plan_resident(groups, "sharded", 2, 1, 1, 256)
+    assert len(og) == 17 and nsets == 1 and steps == 2 and sum(mult) == 196 and mult[-1] == 1 and og[-1] == 195
+    assert reps == [m * steps for m in mult]
+    og, reps, mult, _, steps, _ = bench.plan_resident([[4000] * 100], "sharded", 2, 1, 1, 256)     # less than one batch
+    assert og == [0] and mult == [1] and reps == [steps]
+    # mixed: the long batch gets the most copies, every batch still runs `steps` times, object budget respected
+    groups = [[130000] * 10, [40000] * 26, [9000] * 120, [4900] * 256, [1700] * 66]
+    og, reps, mult, nsets, steps, _ = bench.plan_resident(groups, "mixed", 12, 6, 6, 256)
+    r = runs(og, reps)
+    assert all(r[k] == 12 for k in range(5)) and og[:5] == [0, 1, 2, 3, 4]
+    ncopy = collections.Counter(og)
+    assert ncopy[0] == 12 and ncopy[0] >= ncopy[1] >= ncopy[2] >= ncopy[3] >= ncopy[4] >= 1
+    assert len(og) <= 6 * 5 + 5

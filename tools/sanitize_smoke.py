@@ -23,6 +23,9 @@ for model in ("rgrgr_r94", "rnnrf_r94"):
     assert all(c[0] for c in calls), model
     calls2 = eng.basecall_batch(model, many)            # pooled workspace, second use
     assert calls == calls2
+longish = [synthetic_read(300 + i, n) for i, n in enumerate((6000, 5203))]   # > 940 blocks: read finishing with the paths in global memory
+calls = eng.basecall_batch("rgrgr_r94", longish)
+assert all(c[0] for c in calls)
 raws = [(synthetic_read(50 + i, n) * np.float32(10) + np.float32(90)).astype(np.float32) for i, n in enumerate((1500, 1300))]
 res = eng.basecall_raw_batch("rgrgr_r94", raws)
 assert all(r[0] for r in res)
