@@ -495,6 +495,14 @@ def measure(eng, ranks, args, model, workload, steps, warmup, nsets, detail):
     persistent_bases = results[0].bases(0)
 
     def sustained_and_solo():
+        # Per-kernel figures from ONE batch timed alone (CUDA events on its stream, L2 flushed), after the timed regions
+        # and BEFORE the sustained run (a kernel timed alone is compared with the burst peaks; after five seconds under
+        # the power cap the clocks are 20 % lower).  In the concurrent step the stage intervals of different batches
+        # overlap, so they are not launch durations.
+        batches[0].time(params, nrep=3, flush_l2=True)
+        out["stage_solo"] = batches[0].stage_ms()
+        out["batch0"] = {"nread": batches[0].nread, "cols": batches[0].total_blocks, "ostride": batches[0].ostride,
+                         "nsamp": batches[0].total_samples_padded}
         # ---- sustained: the streaming loop for >= N seconds (power-capped clocks instead of the burst's).  Runs AFTER
         # the short timed regions, so that those see the clocks a fresh job sees.
         if args.sustained_seconds > 0:
@@ -509,12 +517,6 @@ def measure(eng, ranks, args, model, workload, steps, warmup, nsets, detail):
             out["sustained"] = {"value": ranks.world * total_samples * n_long / (max(long_all) * 1e-3), "unit": "samples/s",
                                 "steps": n_long, "seconds": max(long_all) * 1e-3, "ms_per_step": max(long_all) / n_long,
                                 "clocks": lc}
-        # Per-kernel figures from ONE batch timed alone (CUDA events on its stream, L2 flushed), after the timed region:
-        # in the concurrent step the stage intervals of different batches overlap, so they are not launch durations.
-        batches[0].time(params, nrep=3, flush_l2=True)
-        out["stage_solo"] = batches[0].stage_ms()
-        out["batch0"] = {"nread": batches[0].nread, "cols": batches[0].total_blocks, "ostride": batches[0].ostride,
-                         "nsamp": batches[0].total_samples_padded}
 
     def close_batches():
         for b in batches:

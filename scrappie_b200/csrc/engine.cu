@@ -1018,6 +1018,9 @@ static int finish_on_device(sb2_batch *b, const sb2_params *p, sb2_call *out) {
     const sb2_host_model &h = b->m->host;
     if (0 != finish_buffers(b)) return -1;
     const int klen = (h.head == 0) ? (int)(logf((float)h.nstate) / logf(4.0f)) : 1;
+    // small batches fetch the whole base-string area in one copy (below): its unused tails are defined bytes
+    if ((size_t)b->nread * b->bases_stride <= ((size_t)2 << 20))
+        CUDA_OK(cudaMemsetAsync(b->d_bases, 0, (size_t)b->nread * b->bases_stride, b->stream));
     launch_finish_reads(b->d_post, b->dims, (int)h.nstate, b->pstride, (int)h.head,
                         (h.head == 0 && p->homopolymer == HOMOPOLYMER_MEAN) ? 1 : 0, klen, b->d_path, b->d_path2,
                         b->d_bases, b->bases_stride, b->d_nbase, b->stream);

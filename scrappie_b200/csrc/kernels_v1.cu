@@ -537,7 +537,7 @@ decode_crf_v2_kernel(const float *__restrict__ trans, BatchDims d, int ostride, 
                 const float c = e[f] + prev[f];
                 if (c > best) { best = c; arg = f; }       // strict: lowest `from` wins ties
             }
-            if (lane < 5) tbr[(size_t)(t0 + t) * 8 + lane] = (uint8_t)arg;
+            if (lane < 8) tbr[(size_t)(t0 + t) * 8 + lane] = (lane < 5) ? (uint8_t)arg : (uint8_t)0;   // 8-byte rows: pad written too
 #pragma unroll
             for (int q = 0; q < 5; q++) prev[q] = __shfl_sync(0xffffffffu, best, q);
         }
