@@ -72,6 +72,9 @@ def parse_args():
                          "log-normal lengths in [1k, 200k] samples, length-bucketed dynamic batching (config 4); sharded: "
                          "--total-reads reads of --samples samples dealt out to the ranks by shard_reads (config 5)")
     ap.add_argument("--total-reads", type=int, default=100000)
+    ap.add_argument("--shard-as", default=None, metavar="R/W",
+                    help="sharded workload only: take the shard rank R of W ranks would own, whatever this job's size is "
+                         "(reproduces one rank of an N-GPU run on one GPU)")
     return ap.parse_args()
 
 
@@ -220,9 +223,49 @@ def run_oracle_port(model, sigs):
     return time.time() - t0, nb, 0, 1, bases
 
 
-def check_parity(model, sigs, got_bases):
+# posterior tolerance of the parity tests (tests/test_gpu_parity.py): log space; rnnrf's CRF scores on |x| <= 14
+POSTERIOR_TOL = {"rnnrf_r94": 2.5e-4}
+
+
+def explain_mismatch(eng, model, sig, got):
+    """A read whose GPU base string differs from the reference's.  north_star's parity statement has two parts: the
+    Viterbi decode is bit-exact GIVEN the posterior, and the posterior is within a stated fp32 tolerance.  Posteriors
+    ~2e-5 apart (the distance the reference's own OpenBLAS build has from a plain-C fp32 evaluation) can resolve a
+    near-tie of the Viterbi recursion differently, so a differing base string is a defect only if one of the two parts
+    fails.  Checked here for this read: (1) the GPU posterior against the reference's, (2) the REFERENCE's decoder,
+    homopolymer fix-up and overlapper applied to the GPU posterior against the GPU's base string."""
+    from oracle.oracle import Reference
+    ref = Reference()
+    b = eng.batch(model, [len(sig)])
+    b.upload([sig])
+    b.forward()
+    b.decode()
+    gpost = b.posterior(0)
+    gscore = float(b.paths()[1][0])
+    b.close()
+    rpost = ref.posterior(model, sig)
+    ns = {"rnnrf_r94": 25, "rgrgr_r10": 4097}.get(model, 1025)
+    err = float(np.abs(gpost[:, :ns] - rpost[:, :ns]).max())
+    if model == "rnnrf_r94":
+        rscore, _ = ref.decode_crf(rpost)
+        _, path = ref.decode_crf(gpost)
+        bases = ref.crfpath_to_basecall(path, gpost.shape[0])
+    else:
+        rscore, _ = ref.decode_transducer(rpost, ns)
+        _, path = ref.decode_transducer(gpost, ns)
+        path = ref.homopolymer_path(gpost, ns, path)
+        bases, _ = ref.overlapper(path, ns - 1)
+    tol = POSTERIOR_TOL.get(model, 1e-4)
+    return {"posterior_max_abs_err": err, "posterior_tolerance": tol, "viterbi_score_gpu": gscore, "viterbi_score_reference": rscore,
+            "reference_decoder_on_gpu_posterior_gives_gpu_bases": bases == got,
+            "explained": bool(err <= tol and bases == got)}
+
+
+def check_parity(model, sigs, got_bases, eng=None):
     """Base strings of the GPU run vs the CPU reference on the same reads (python/test/test_scrappy.py:72-75 makes
-    the same comparison for the reference's own Python binding)."""
+    the same comparison for the reference's own Python binding).  `bases_identical` is the plain comparison; a read
+    that differs is examined by explain_mismatch, and `ok` is false -- the run exits non-zero -- unless every such
+    read is a Viterbi near-tie between posteriors that agree within the tolerance."""
     res = run_reference(model, sigs, want_bases=True)
     against = "reference (oracle/_ref)"
     if res is None:
@@ -230,8 +273,12 @@ def check_parity(model, sigs, got_bases):
         against = "oracle port"
     want = res[4]
     bad = [i for i, (g, w) in enumerate(zip(got_bases, want)) if g != w]
-    return {"reads_checked": len(sigs), "bases_identical": not bad, "mismatching_reads": bad[:8], "against": against,
-            "bases_checked": int(sum(len(w or "") for w in want))}
+    out = {"reads_checked": len(sigs), "bases_identical": not bad, "mismatching_reads": bad[:8], "against": against,
+           "bases_checked": int(sum(len(w or "") for w in want)), "ok": not bad}
+    if bad and eng is not None and against.startswith("reference"):
+        out["near_ties"] = [dict(read=i, **explain_mismatch(eng, model, sigs[i], got_bases[i])) for i in bad[:8]]
+        out["ok"] = len(bad) <= 8 and all(t["explained"] for t in out["near_ties"])
+    return out
 
 
 def cpu_baseline(model, sigs, nreads_sample):
@@ -356,6 +403,8 @@ def build_groups(args, model, workload, rank, world):
         # config 5 literally: read i of the job has seed 1000 + i; the job's reads are dealt out by shard_reads and each
         # rank batches what it owns.  Only 2048 distinct signals are synthesised (read i uses signal i % 2048): the
         # content of a read does not change what the path costs, generating 100 000 of them in Python would.
+        if args.shard_as:
+            rank, world = (int(x) for x in args.shard_as.split("/"))
         owned = shard_reads([args.samples] * args.total_reads, rank, world)
         distinct = make_workload(min(2048, args.total_reads), args.samples, 1000)
         sigs = [distinct[int(i) % len(distinct)] for i in owned]
@@ -566,7 +615,7 @@ def measure(eng, ranks, args, model, workload, steps, warmup, nsets, detail):
         pick = [flat[i] for i in sorted(rng.choice(len(flat), size=min(48, len(flat)), replace=False))]
     if rank == 0:
         got = [doc_bases[int(starts[k]) + r] for k, r in pick]
-        parity = check_parity(model, [groups[k][r] for k, r in pick], got)
+        parity = check_parity(model, [groups[k][r] for k, r in pick], got, eng)
         parity["persistent_path_agrees"] = (persistent_bases == doc_bases[0])
         out["parity"] = parity
     doc_bases = None
@@ -737,9 +786,9 @@ def main_b200(args, rank, world, local_rank):
     print(json.dumps(line))
     ranks.close()
     bad = [name for name, p in [("headline", line.get("parity"))] + [(k, v.get("parity")) for k, v in others.items()]
-           if p is not None and not p["bases_identical"]]
+           if p is not None and not p["ok"]]
     if bad:
-        sys.stderr.write("bench.py: base sequences differ from the reference in: %s\n" % ", ".join(bad))
+        sys.stderr.write("bench.py: base sequences differ from the reference (not a near-tie within the posterior tolerance) in: %s\n" % ", ".join(bad))
         sys.exit(3)
 
 

@@ -874,3 +874,31 @@ def test_c_caller_thread_team(sb, engine, oracle):
         assert nbases == sum(len(w[0]) for w in want)
         assert np.array_equal(scores, np.array([w[1] for w in want], dtype=np.float32))
     assert bases[3] == oracle.basecall_raw("rgrgr_r94", flat[3])[2]
+
+
+def test_near_tie_read_is_explained_by_posterior_rounding(sb, engine, reference):
+    """north_star: Viterbi bit-exact GIVEN the posterior, posterior within tolerance.  Synthetic read 2712 is a near-tie
+    (Viterbi scores of the two candidate paths 3e-5 apart): the GPU's base string may differ from the reference's, and
+    bench.py's parity gate must then find (1) the posteriors within tolerance and (2) the reference's own decoder +
+    homopolymer fix-up + overlapper on the GPU posterior reproducing the GPU's bases -- anything else is a defect."""
+    import importlib.util
+    if reference is None:
+        pytest.skip("oracle/_ref not built")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    sig = synthetic_read(2712, 4000)
+    got = engine.basecall_batch("rgrgr_r94", [sig])[0][0]
+    ex = bench.explain_mismatch(engine, "rgrgr_r94", sig, got)
+    assert ex["posterior_max_abs_err"] < LOG_TOL
+    assert ex["reference_decoder_on_gpu_posterior_gives_gpu_bases"] and ex["explained"]
+    assert abs(ex["viterbi_score_gpu"] - ex["viterbi_score_reference"]) < 1e-3
+    # the gate itself: identical reads pass, the near-tie passes as explained, a corrupted string does not
+    sigs = [synthetic_read(1000, 4000), sig]
+    calls = [c[0] for c in engine.basecall_batch("rgrgr_r94", sigs)]
+    par = bench.check_parity("rgrgr_r94", sigs, calls, engine)
+    assert par["ok"] and par["reads_checked"] == 2
+    broken = [calls[0][:50] + "A" + calls[0][50:], calls[1]]
+    par = bench.check_parity("rgrgr_r94", sigs, broken, engine)
+    assert not par["ok"] and not par["bases_identical"] and 0 in par["mismatching_reads"]
