@@ -326,9 +326,10 @@ def main_reference(args, rank, world):
     line = {"impl": "reference", "metric": "raw samples/sec (%s)" % args.model, "value": value, "unit": "samples/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "%s raw, %d synthetic %d-sample reads per GPU, batch=%d; CPU %s arm: bounded sample of "
-                                   "%d reads per step, one read per OpenMP thread"
-                                   % (args.model, args.reads, args.samples, args.batch, kind, len(sigs))},
+            # the same workload label as the GPU arm's line (build_groups); what is specific to this arm stands beside it
+            "config": {"workload": "%s raw, %d synthetic %d-sample reads per GPU, batch=%d (%d concurrent batches), forward + Viterbi decode"
+                                   % (args.model, args.reads, args.samples, args.batch, (args.reads + args.batch - 1) // args.batch),
+                       "cpu_arm": "%s: bounded sample of %d reads per step, one read per OpenMP thread, 1 BLAS thread" % (kind, len(sigs))},
             "kbases_per_s": nbases / (ms / 1e3) / 1e3,
             "cpu_baseline": cpu,
             "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
