@@ -585,8 +585,8 @@ def measure(eng, ranks, args, model, workload, steps, warmup, nsets, detail):
     # what INTEGRATION.md section 2.1 tells a maintainer of `scrappie raw` to do.  No Python inside the timed region.
     order = sorted(range(nbatch), key=lambda k: -sum(len(s) for s in groups[k]))
     job = sb.CallerJob(eng, model, groups, order)
-    # calls in flight (each caller sleeps on its batch's completion event).  Eight keep the GPU busy when every call
-    # takes the same ~12 ms; the mixed workload's calls take 3 .. 200 ms and want more of them in flight
+    # calls in flight (each caller sleeps on its batch's completion event): 16 when every call takes the same ~12 ms
+    # (12 callers measure 5 % less, 20 the same); the mixed workload's calls take 3 .. 250 ms and want 48 of them
     nworker = min(nbatch * max(nsets, 8), int(os.environ.get("BENCH_MIXED_WORKERS", "48") if workload == "mixed" else os.environ.get("BENCH_E2E_WORKERS", "16")))
     # pool warm-up: every caller must have had a workspace made for it (device buffers, pinned staging, graphs) and the
     # workspaces must have seen the largest batch.  A workspace made before the pool's high-water marks were final is
