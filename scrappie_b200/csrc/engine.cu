@@ -841,7 +841,9 @@ extern "C" int sb2_batch_run(sb2_batch *b, const sb2_params *p) {
         if (0 == rc) sb2_set_error("CUDA graph capture failed: %s", cudaGetErrorString(e));
         return -1;
     }
-    const cudaError_t ei = cudaGraphInstantiate(&b->graph, g, 0);
+    // per-node launch priorities (the scan's, when enabled) are honoured only with this flag
+    static const unsigned long long gflags = (scan_launch_priority() != 0) ? cudaGraphInstantiateFlagUseNodePriority : 0;
+    const cudaError_t ei = cudaGraphInstantiate(&b->graph, g, gflags);
     cudaGraphDestroy(g);
     if (ei != cudaSuccess) { b->graph = nullptr; sb2_set_error("CUDA graph instantiation failed: %s", cudaGetErrorString(ei)); return -1; }
     b->graph_params = *p;

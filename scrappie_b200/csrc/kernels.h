@@ -106,6 +106,7 @@ void launch_gather(const float *post, int ostride, const int *col_state_pairs, i
 // T - 1 - t backward) at row xgrp[r / RPG] + s * RPG + r % RPG -- and every group-step is one TMA copy; nullptr: Xin is
 // read-major like every other activation matrix.
 int scan_reads_per_group(int nread);
+int scan_launch_priority();
 int launch_gru_scan_tc(const float *Xin, const long long *xgrp, const float *sW, const float *sW2, const float *resid,
                        float *out, const BatchDims &d, int H, int backward, int math, long long *trace, cudaStream_t s);
 // src_col tables of the scan-ordered Xin: src_f[row] / src_b[row] = input column of every Xin row for forward / backward

@@ -618,16 +618,37 @@ int launch_scan_rows(const BatchDims &d, const long long *xgrp, int rpg, size_t 
     return 0;
 }
 
+// 0 = launches inherit their stream's priority; otherwise the device's greatest priority (a negative number)
+int scan_launch_priority() {
+    const char *e = getenv("SCRAPPIE_B200_SCAN_PRIO");
+    if (e == nullptr || atoi(e) == 0) return 0;
+    int least = 0, greatest = 0;
+    if (cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess) return 0;
+    return greatest;
+}
+
 template <int H, int MATH, int NG, int RPG, bool RESID>
 static int launch_scan_cfg(const float *Xin, const long long *xgrp, const float *sW, const float *sW2, const float *resid,
                            float *out, const BatchDims &d, int backward, long long *trace, cudaStream_t s) {
     using C = ScanCfg<H, NG, RPG, RESID>;
     const int grid = (d.nread + RPG * NG - 1) / (RPG * NG);
+    // SCRAPPIE_B200_SCAN_PRIO=1 (experiment, read once): the scan's CTAs are dispatched ahead of other batches' pending
+    // CTAs -- the scans are the long pole of every batch's chain and need a completely free SM each
+    static const int prio = scan_launch_priority();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(C::NTHREADS); cfg.dynamicSmemBytes = C::SMEM_REQ; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    if (prio != 0) {
+        attr[0].id = cudaLaunchAttributePriority;
+        attr[0].val.priority = prio;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+    }
+    cudaError_t e;
     if (xgrp != nullptr)
-        gru_scan_kernel<H, MATH, NG, RPG, RESID, true><<<grid, C::NTHREADS, C::SMEM_REQ, s>>>(Xin, xgrp, sW, sW2, resid, out, d, backward, trace);
+        e = cudaLaunchKernelEx(&cfg, gru_scan_kernel<H, MATH, NG, RPG, RESID, true>, Xin, xgrp, sW, sW2, resid, out, d, backward, trace);
     else
-        gru_scan_kernel<H, MATH, NG, RPG, RESID, false><<<grid, C::NTHREADS, C::SMEM_REQ, s>>>(Xin, xgrp, sW, sW2, resid, out, d, backward, trace);
-    return 0;
+        e = cudaLaunchKernelEx(&cfg, gru_scan_kernel<H, MATH, NG, RPG, RESID, false>, Xin, xgrp, sW, sW2, resid, out, d, backward, trace);
+    return e == cudaSuccess ? 0 : -1;
 }
 
 // math: 0 cephes-identical gates, 5 SFU ex2 + Newton-refined reciprocal (default).  xgrp: first Xin row of every read
