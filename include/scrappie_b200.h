@@ -291,6 +291,12 @@ int sb2_engine_trim_pool(sb2_engine *eng);
 /* how often a workspace (device buffers, pinned staging, base-string area) was (re)allocated so far: constant once the
  * pool is warm */
 uint64_t sb2_engine_realloc_count(const sb2_engine *eng);
+/* Fault injection for tests of the error paths (the reference tests its own with a failing allocator,
+ * src/scrappie_stdlib.h:10-37): the workspace allocation number `nth` from now on (0 = the next one; device and pinned
+ * host allocations of batch workspaces both count) fails with "injected allocation failure"; a negative value switches
+ * the hook off.  Every entry point must then return its error value (NULL / NAN / -1) with sb2_last_error set, release
+ * what the failed call had allocated and leave the engine -- and a caller-owned batch -- usable.  Process-wide. */
+void sb2_debug_fail_alloc(long nth);
 /* Same on an existing batch workspace (no device allocation per call).  concat: signals in
  * the batch's padded layout (pinned != 0 if it came from sb2_host_alloc_pinned), or NULL
  * when the signals are already resident. */

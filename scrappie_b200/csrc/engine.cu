@@ -395,12 +395,35 @@ static void batch_free_device(sb2_batch *b) {
     b->eager_runs = 0;
 }
 
+// Fault injection (sb2_debug_fail_alloc): countdown to the workspace allocation that is made to fail; < 0 = off.
+static std::atomic<long> g_fault_countdown{-1};
+extern "C" void sb2_debug_fail_alloc(long nth) { g_fault_countdown.store(nth); }
+static bool fault_now() {
+    if (g_fault_countdown.load(std::memory_order_relaxed) < 0) return false;
+    return g_fault_countdown.fetch_sub(1) == 0;
+}
+#define FAULT_POINT()                                                                             \
+    do {                                                                                          \
+        if (fault_now()) { sb2_set_error("injected allocation failure (%s:%d)", __FILE__, __LINE__); return -1; } \
+    } while (0)
+
+// pinned host memory of a batch workspace
+template <typename T>
+static int pinned_alloc(T **p, size_t n) {
+    *p = nullptr;
+    FAULT_POINT();
+    CUDA_OK(cudaMallocHost(reinterpret_cast<void **>(p), (n ? n : 1) * sizeof(T)));
+    return 0;
+}
+
 // Batch buffers come from the device's stream-ordered memory pool (cudaMallocAsync / cudaFreeAsync on the batch's own
 // stream; the pool keeps what is freed, see sb2_engine_create): re-sizing a workspace then never synchronises the
 // device.  cudaFree would -- it waits for every kernel in flight on every stream, and with long-read batches of other
 // callers running that is hundreds of milliseconds per freed buffer.
 template <typename T>
 static int batch_alloc(sb2_batch *b, T **p, size_t n) {
+    *p = nullptr;
+    FAULT_POINT();
     CUDA_OK(cudaMallocAsync(reinterpret_cast<void **>(p), (n ? n : 1) * sizeof(T), b->stream));
     return 0;
 }
@@ -515,7 +538,7 @@ static int batch_reserve(sb2_batch *b) {
     size_t off[6];
     b->meta_bytes = meta_offsets(cap_reads, off);
     if (batch_alloc(b, &b->d_meta, b->meta_bytes)) return -1;
-    CUDA_OK(cudaMallocHost(reinterpret_cast<void **>(&b->h_meta), b->meta_bytes));
+    if (pinned_alloc(&b->h_meta, b->meta_bytes)) return -1;
     b->d_nsample = reinterpret_cast<int *>(b->d_meta + off[0]);
     b->d_nblock = reinterpret_cast<int *>(b->d_meta + off[1]);
     b->d_coloff = reinterpret_cast<int *>(b->d_meta + off[2]);
@@ -973,15 +996,18 @@ static int host_threads() {
 }
 
 static int basecall_buffers(sb2_batch *b) {
-    if (nullptr != b->h_paths) return 0;                // freed together with the device buffers when a workspace grows
+    // (all of these are freed together with the device buffers when a workspace grows; each is checked on its own so
+    // that a call that failed half-way through can simply be repeated)
     const size_t np = b->cap_cols + b->cap_reads;
     // every run position needs (stay, repeat k-mer) of one column; runs can overlap, so leave head room
-    b->gcap = 4 * b->cap_cols + 64;
-    CUDA_OK(cudaMallocHost(reinterpret_cast<void **>(&b->h_paths), np * sizeof(int)));
-    if (nullptr == b->h_scores) CUDA_OK(cudaMallocHost(reinterpret_cast<void **>(&b->h_scores), b->cap_reads * sizeof(float)));
-    CUDA_OK(cudaMallocHost(reinterpret_cast<void **>(&b->h_gidx), b->gcap * 2 * sizeof(int)));
-    CUDA_OK(cudaMallocHost(reinterpret_cast<void **>(&b->h_gval), b->gcap * sizeof(float)));
-    if (batch_alloc(b, &b->d_gidx, b->gcap * 2) || batch_alloc(b, &b->d_gval, b->gcap)) return -1;
+    const size_t gcap = b->gcap ? b->gcap : 4 * b->cap_cols + 64;
+    if (nullptr == b->h_paths && pinned_alloc(&b->h_paths, np)) return -1;
+    if (nullptr == b->h_scores && pinned_alloc(&b->h_scores, b->cap_reads)) return -1;
+    if (nullptr == b->h_gidx && pinned_alloc(&b->h_gidx, gcap * 2)) return -1;
+    if (nullptr == b->h_gval && pinned_alloc(&b->h_gval, gcap)) return -1;
+    if (nullptr == b->d_gidx && batch_alloc(b, &b->d_gidx, gcap * 2)) return -1;
+    if (nullptr == b->d_gval && batch_alloc(b, &b->d_gval, gcap)) return -1;
+    b->gcap = gcap;
     return 0;
 }
 
@@ -991,11 +1017,10 @@ static int finish_buffers(sb2_batch *b) {
     // worst case: every block moves by a full k-mer
     b->bases_stride = (int)align_up((size_t)klen * ((size_t)b->max_cols + 1) + 1, 16);
     const size_t nbytes = (size_t)b->nread * b->bases_stride;
-    if (nullptr == b->d_path2) {
-        if (batch_alloc(b, &b->d_path2, b->cap_cols + b->cap_reads) || batch_alloc(b, &b->d_nbase, b->cap_reads)) return -1;
-        CUDA_OK(cudaMallocHost(reinterpret_cast<void **>(&b->h_nbase), b->cap_reads * sizeof(int)));
-        if (nullptr == b->h_scores) CUDA_OK(cudaMallocHost(reinterpret_cast<void **>(&b->h_scores), b->cap_reads * sizeof(float)));
-    }
+    if (nullptr == b->d_path2 && batch_alloc(b, &b->d_path2, b->cap_cols + b->cap_reads)) return -1;
+    if (nullptr == b->d_nbase && batch_alloc(b, &b->d_nbase, b->cap_reads)) return -1;
+    if (nullptr == b->h_nbase && pinned_alloc(&b->h_nbase, b->cap_reads)) return -1;
+    if (nullptr == b->h_scores && pinned_alloc(&b->h_scores, b->cap_reads)) return -1;
     if (nbytes > b->cap_bases) {
         b->eng->reallocs += 1;
         if (b->d_bases) { CUDA_OK(cudaStreamSynchronize(b->stream)); cudaFreeAsync(b->d_bases, b->stream); cudaFreeHost(b->h_bases); b->d_bases = nullptr; b->h_bases = nullptr; }
@@ -1008,7 +1033,7 @@ static int finish_buffers(sb2_batch *b) {
             cap = std::max(cur, cap);
         }
         if (batch_alloc(b, &b->d_bases, cap)) return -1;
-        CUDA_OK(cudaMallocHost(reinterpret_cast<void **>(&b->h_bases), cap));
+        if (pinned_alloc(&b->h_bases, cap)) { cudaFreeAsync(b->d_bases, b->stream); b->d_bases = nullptr; return -1; }
         b->cap_bases = cap;
     }
     return 0;
@@ -1294,7 +1319,8 @@ static int stage_signals(sb2_batch *b, const float *const *signals, const std::v
             while (cur < cap && !hw.compare_exchange_weak(cur, cap)) { }
             cap = std::max(cur, cap);
         }
-        CUDA_OK(cudaMallocHost(reinterpret_cast<void **>(&b->h_stage), cap * sizeof(float)));
+        b->stage_cap = 0;
+        if (pinned_alloc(&b->h_stage, cap)) return -1;
         b->stage_cap = cap;
     }
     // plain loop: the callers are already one host thread per batch in flight; an OpenMP team per caller would leave

@@ -902,3 +902,69 @@ def test_near_tie_read_is_explained_by_posterior_rounding(sb, engine, reference)
     broken = [calls[0][:50] + "A" + calls[0][50:], calls[1]]
     par = bench.check_parity("rgrgr_r94", sigs, broken, engine)
     assert not par["ok"] and not par["bases_identical"] and 0 in par["mismatching_reads"]
+
+
+def test_injected_allocation_failures_unwind(sb, engine):
+    """Error paths under a failing allocator (the reference tests its own this way: src/scrappie_stdlib.h:10-37).
+    sb2_debug_fail_alloc(n) makes the n-th workspace allocation from now on fail.  Whatever n: the call reports an
+    error (never crashes, never returns wrong bases), the engine stays usable, and a caller-owned batch on which a call
+    failed half-way can simply be called again."""
+    import ctypes as C
+    L = sb.lib()
+    L.sb2_debug_fail_alloc.argtypes = [C.c_long]
+    L.sb2_debug_fail_alloc.restype = None
+    sigs = [synthetic_read(40 + i, 1500 + 11 * i) for i in range(5)]
+    want = engine.basecall_batch("rgrgr_r94", sigs)
+    try:
+        # the pooled drop-in call on a fresh workspace: every allocation of the call fails once
+        nfail = 0
+        for n in range(80):
+            engine.trim_pool()
+            L.sb2_debug_fail_alloc(n)
+            try:
+                got = engine.basecall_batch("rgrgr_r94", sigs)
+            except RuntimeError as e:
+                assert "injected allocation failure" in str(e)
+                nfail += 1
+                continue
+            finally:
+                L.sb2_debug_fail_alloc(-1)
+            assert got == want                            # the countdown outlived the call: nothing failed
+            break
+        else:
+            raise AssertionError("the call never got through")
+        assert nfail >= 15, nfail
+        assert engine.basecall_batch("rgrgr_r94", sigs) == want
+        # batch creation
+        for n in range(40):
+            L.sb2_debug_fail_alloc(n)
+            try:
+                b = engine.batch("rgrgr_r94", [len(s) for s in sigs])
+            except RuntimeError:
+                continue
+            finally:
+                L.sb2_debug_fail_alloc(-1)
+            break
+        # a caller-owned batch: a call that failed half-way through its own (lazy) allocations is repeatable
+        b.upload(sigs)
+        nfail = 0
+        for n in range(20):
+            L.sb2_debug_fail_alloc(n)
+            try:
+                calls = b.basecall()
+            except RuntimeError:
+                nfail += 1
+                continue
+            finally:
+                L.sb2_debug_fail_alloc(-1)
+            break
+        assert nfail >= 3 and calls == want and b.basecall() == want
+        b.close()
+        # the single-read symbols return their error value
+        L.sb2_debug_fail_alloc(0)
+        with pytest.raises(RuntimeError):
+            sb.calc_post(sb.RawTable(sigs[0]), "rgrgr_r94")
+    finally:
+        L.sb2_debug_fail_alloc(-1)
+    post = sb.calc_post(sb.RawTable(sigs[0]), "rgrgr_r94")
+    assert post is not None
